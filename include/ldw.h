@@ -1,0 +1,179 @@
+/*
+ * libldwgpu -- C ABI of the B200-native LDWeaver hot path (encoding -> Hamming-distance weights ->
+ * weighted pairwise-MI scan -> short-range / long-range link filter).
+ *
+ * Pure C, no R / torch / C++ types in any signature.  Inputs are BORROWED, read-only host buffers
+ * (R vectors, numpy arrays); fixed-size outputs are caller-allocated; variable-size link lists are
+ * library-owned pinned host buffers that stay valid until the next scan on the same plan or until
+ * ldw_mi_plan_destroy().  Every entry point returns 0 on success or a nonzero LDW_ERR_* code;
+ * ldw_last_error() gives the message (thread-local).  Nothing is ever printed to stdout and no
+ * exception or longjmp crosses this boundary, so an R shim can turn a nonzero code into
+ * Rf_error(ldw_last_error()) after releasing its own resources (reference convention:
+ * BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:17,24).
+ *
+ * There is NO CPU fallback behind these functions: without a CUDA device they fail with
+ * LDW_ERR_CUDA.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the LDWeaver
+ * source tree, v1.5.2).
+ */
+#ifndef LDW_H
+#define LDW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDW_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define LDW_API __attribute__((visibility("default")))
+#else
+#define LDW_API
+#endif
+
+enum {
+  LDW_OK = 0,
+  LDW_ERR_ARG = 1,         /* invalid argument (message says which) */
+  LDW_ERR_CUDA = 2,        /* CUDA runtime / driver failure, or no device */
+  LDW_ERR_NOMEM = 3,       /* host or device allocation failed */
+  LDW_ERR_UNSUPPORTED = 4, /* input outside what this round implements (message says what) */
+  LDW_ERR_INTERNAL = 5
+};
+
+/* flags for ldw_mi_scan */
+enum {
+  LDW_SCAN_SR_ONLY = 1,   /* perform_SR_analysis_only = TRUE (R/computePairwiseMI.R:179-189, quirk Q12) */
+  LDW_SCAN_IDEAL_Q = 2,   /* opt-out of quirk Q1: use 0.25*r_i*r_j on off-diagonal blocks too (NOT reference behaviour) */
+  LDW_SCAN_NO_LINKS = 4   /* compute everything but skip host materialisation of SR columns (bench: device-only timing) */
+};
+
+typedef struct ldw_ctx ldw_ctx;         /* one per device; owns stream + scratch */
+typedef struct ldw_mi_plan ldw_mi_plan; /* device-resident packed operands for one snp.dat + hdw */
+
+LDW_API int ldw_abi_version(void);
+LDW_API const char* ldw_last_error(void);
+
+/* Create / destroy a context on CUDA device `device` (0-based). */
+LDW_API int ldw_create(int device, ldw_ctx** out);
+LDW_API void ldw_destroy(ldw_ctx* ctx);
+/* Number of visible CUDA devices (0 if none / no driver). */
+LDW_API int ldw_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoding.
+ *
+ * ldw_aln_param replaces `.extractAlnParam(file, filter, gap_thresh, maf_thresh)`
+ *   (R/RcppExports.R:32-34 -> _LDWeaver_extractAlnParam, src/RcppExports.cpp:109;
+ *    body src/getACGTNsites.cpp:13-176) for an alignment already tokenised into a byte matrix.
+ *   aln        : nseq x seq_len bytes, row-major (one FASTA record per row, raw characters)
+ *   filter     : 0 = "default", 1 = "relaxed" (R/extractSNPs.R:29-36)
+ *   pos_out    : capacity seq_len int32; receives the 1-based retained columns (ascending)
+ *   n_snp_out  : number retained
+ *   counts_out : optional (may be NULL) 5 x seq_len doubles, column-major (A,C,G,T,other per column)
+ *
+ * ldw_extract_snps replaces `.extractSNPs(file, n_seq, n_snp, POS)`
+ *   (R/RcppExports.R:36-38 -> _LDWeaver_extractSNPs, src/RcppExports.cpp:123;
+ *    body src/getACGTNsites.cpp:179-291).  The reference's 15 COO vectors partition the
+ *   nseq x nsnp grid; they are returned as ONE uint8 class matrix:
+ *   codes_out  : nsnp x nseq bytes (codes_out[k*nseq + s] in 0..4 = A,C,G,T,N/other)
+ *   table_out  : 5 x nsnp doubles, column-major (ACGTN_table)
+ *
+ * ldw_read_fasta is the host-side tokeniser (gz or plain multi-FASTA -> byte matrix); it stays on
+ *   the CPU like the reference's kseq/zlib reader (src/kseq2.h, src/getACGTNsites.cpp:33-45).
+ *   Call with aln_out == NULL to query nseq / seq_len (seq_len = -1 if records differ in length,
+ *   as src/getACGTNsites.cpp:54-56), then again with aln_out (capacity aln_cap bytes) and the queried
+ *   seq_len left in *seq_len_out (it is the row stride); names_out receives nseq NUL-terminated names
+ *   back to back (capacity names_cap bytes; may be NULL).
+ */
+LDW_API int ldw_aln_param(ldw_ctx* ctx, const uint8_t* aln, int64_t nseq, int64_t seq_len, int filter, double gap_thresh,
+                  double maf_thresh, int32_t* pos_out, int64_t* n_snp_out, double* counts_out);
+LDW_API int ldw_extract_snps(ldw_ctx* ctx, const uint8_t* aln, int64_t nseq, int64_t seq_len, const int32_t* pos,
+                     int64_t n_snp, uint8_t* codes_out, double* table_out);
+LDW_API int ldw_read_fasta(const char* path, int64_t* nseq_out, int64_t* seq_len_out, uint8_t* aln_out, int64_t aln_cap,
+                   char* names_out, int64_t names_cap);
+
+/* ldw_acgtn2num replaces `.ACGTN2num(nv, cv, ncores)` (R/RcppExports.R:4-6 -> _LDWeaver_ACGTN2num,
+ *   src/RcppExports.cpp:16; body src/ACGTN2num_parallel.cpp:10-43).  In place on nv (5 x n doubles,
+ *   column-major); ref holds one character per SNP. */
+LDW_API int ldw_acgtn2num(ldw_ctx* ctx, double* nv, const char* ref, int64_t n);
+
+/* ------------------------------------------------------------------------------------------------
+ * Population-structure weights.
+ * ldw_hdw replaces the body of estimate_Hamming_distance_weights(snp.dat, threshold)
+ *   (R/performPopulationStuctureCorrection.R:20-81; the five Matrix::crossprod calls :49-74 and
+ *   the threshold/colSums/reciprocal :76).
+ *   codes      : nsnp x nseq class matrix (== the five snp.matrix_* slots)
+ *   threshold  : fraction; thresh = (int)(nsnp*threshold) (truncation, :23)
+ *   cnt_out    : nseq int32, #sequences (incl. self) with Hamming distance < thresh
+ *   hdw_out    : nseq doubles, 1/(cnt+1)
+ *   dist_out   : optional (may be NULL) nseq x nseq int32 Hamming distances, column-major
+ */
+LDW_API int ldw_hdw(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, double threshold, int32_t* cnt_out,
+            double* hdw_out, int32_t* dist_out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Weighted pairwise-MI scan + sr/lr link filter.
+ * Replaces the scan part of perform_MI_computation (R/computePairwiseMI.R:46-116: make_blocks :147-165,
+ *   perform_MI_computation_ACGTN :167-386, computeMI_Sprase :390-398, .fastHadamard
+ *   src/computeMI.cpp:11-21, .compareToRow src/computeMI.cpp:25-41).  mergeNsort_sr_links, ARACNE and
+ *   the tsv writers stay in R and consume the link columns returned here.
+ *
+ * ldw_mi_plan_create uploads one snp.dat (codes, uqe-derived allele sets, POS) and the weights, and
+ * packs the tensor-core operands on the device.  `blk` is round(max_blk_sz, -3) (R/computePairwiseMI.R:69).
+ */
+typedef struct ldw_links {
+  int64_t n;             /* rows */
+  const int32_t* pos1;   /* POS of the column ("to") SNP   (R/computePairwiseMI.R:320) */
+  const int32_t* pos2;   /* POS of the row ("from") SNP    (:319) */
+  const int32_t* clust1; /* paint of the column SNP        (:323) */
+  const int32_t* clust2; /* paint of the row SNP           (:322) */
+  const int32_t* len;    /* circular distance              (:330), integer-valued */
+  const double* MI;      /* mutual information             (:331) */
+  const int32_t* block;  /* 0-based make_blocks row the link came from */
+} ldw_links;
+
+typedef struct ldw_scan_stats {
+  int64_t n_blocks;
+  int64_t n_pairs;       /* pairs evaluated == rows the reference's MI_df would hold, summed over blocks */
+  int64_t n_sr;          /* len <= sr_dist */
+  int64_t n_lr_total;    /* len > sr_dist (before the quantile filter) */
+  int64_t n_lr_kept;
+  int64_t n_borderline;  /* LR candidates within borderline_tol of their block threshold (listed in `borderline`) */
+  int64_t n_reruns;      /* blocks re-run because the candidate threshold guess was too high */
+  double t_pack_ms, t_scan_ms, t_select_ms, t_d2h_ms; /* device / host phase timings of the last scan */
+} ldw_scan_stats;
+
+LDW_API int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, const double* hdw,
+                       const int32_t* pos, const int32_t* paint, int64_t blk, ldw_mi_plan** out);
+LDW_API void ldw_mi_plan_destroy(ldw_mi_plan* plan);
+
+/* Run the scan over all make_blocks() blocks whose index b satisfies b % n_parts == part
+ * (multi-GPU: one plan per device, blocks dealt round-robin; n_parts = 1, part = 0 for everything).
+ *   g               : genome length (snp.dat$g)
+ *   sr_dist         : short-range cut-off (len <= sr_dist is SR, R/computePairwiseMI.R:333)
+ *   lr_retain_links, lr_links_approx : as R/computePairwiseMI.R:352 (lr_links_approx computed by the
+ *                     caller, it depends on R's RNG, :94-97); ignored with LDW_SCAN_SR_ONLY
+ *   thr_out / prob_out : optional arrays of n_blocks doubles (NaN where the block had no LR branch)
+ * Link lists are in reference order (blocks in make_blocks order; rows inside a block as
+ * R/computePairwiseMI.R:306-310), LR rows being those that pass `MI >= disc_thresh` (:358).
+ */
+LDW_API int ldw_mi_scan(ldw_mi_plan* plan, double g, double sr_dist, double lr_retain_links, double lr_links_approx,
+                int flags, int n_parts, int part, ldw_links* sr_out, ldw_links* lr_out, ldw_links* borderline_out,
+                double* thr_out, double* prob_out, ldw_scan_stats* stats_out);
+
+/* Dense MI matrix of one block (debug / parity aid; nf x nt doubles, column-major, fp32-accurate values).
+ * from/to are 0-based ascending global SNP ids, as `from`/`to` of perform_MI_computation_ACGTN. */
+LDW_API int ldw_mi_block_dense(ldw_mi_plan* plan, int64_t block_index, double* mi_out, int64_t* nf_out, int64_t* nt_out);
+
+/* Exact (fp64) MI of explicit pairs of one block: pair k = (from_local[k], to_local[k]). */
+LDW_API int ldw_mi_pairs_exact(ldw_mi_plan* plan, int64_t block_index, const int32_t* from_local, const int32_t* to_local,
+                       int64_t n_pairs, double* mi_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDW_H */

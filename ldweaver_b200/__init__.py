@@ -1,0 +1,9 @@
+"""ldweaver_b200 -- B200-native drop-in for LDWeaver's genome-wide pairwise-LD hot path.
+
+Only what the path needs lives here: ``csrc/`` (hand-written sm_100a CUDA kernels + the C ABI of
+``include/ldw.h``) and the host-side mirror of the reference's R interface (``api``)."""
+from .api import (SnpDat, acgtn2num, estimate_Hamming_distance_weights, parse_fasta_alignment,  # noqa: F401
+                  parse_fasta_SNP_alignment, snp_dat_from_alignment_matrix, snp_dat_from_codes)
+
+__all__ = ["SnpDat", "acgtn2num", "estimate_Hamming_distance_weights", "parse_fasta_alignment",
+           "parse_fasta_SNP_alignment", "snp_dat_from_alignment_matrix", "snp_dat_from_codes"]

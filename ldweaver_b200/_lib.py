@@ -1,0 +1,123 @@
+"""ctypes loader for libldwgpu.so (the C-ABI of include/ldw.h).
+
+The product path has NO CPU fallback: if the shared library is missing, or no CUDA device is
+present, loading / context creation raises loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libldwgpu.so")
+
+i64 = C.c_int64
+f64 = C.c_double
+P = C.POINTER
+
+
+class LdwError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libldwgpu error {code}: {msg}")
+        self.code = code
+
+
+class Links(C.Structure):
+    """struct ldw_links (include/ldw.h)."""
+    _fields_ = [("n", i64), ("pos1", P(C.c_int32)), ("pos2", P(C.c_int32)), ("clust1", P(C.c_int32)),
+                ("clust2", P(C.c_int32)), ("len", P(C.c_int32)), ("MI", P(f64)), ("block", P(C.c_int32))]
+
+    def to_dict(self) -> dict:
+        n = int(self.n)
+        out = {}
+        for name, ct, dt in (("pos1", C.c_int32, np.int32), ("pos2", C.c_int32, np.int32), ("clust1", C.c_int32, np.int32),
+                             ("clust2", C.c_int32, np.int32), ("len", C.c_int32, np.int32), ("MI", f64, np.float64),
+                             ("block", C.c_int32, np.int32)):
+            ptr = getattr(self, name)
+            if n == 0 or not ptr:
+                out[name] = np.zeros(0, dtype=dt)
+            else:
+                out[name] = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+        return out
+
+
+class ScanStats(C.Structure):
+    """struct ldw_scan_stats (include/ldw.h)."""
+    _fields_ = [("n_blocks", i64), ("n_pairs", i64), ("n_sr", i64), ("n_lr_total", i64), ("n_lr_kept", i64),
+                ("n_borderline", i64), ("n_reruns", i64), ("t_pack_ms", f64), ("t_scan_ms", f64), ("t_select_ms", f64),
+                ("t_d2h_ms", f64)]
+
+    def to_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def lib():
+    """Load libldwgpu.so (built by ``python __graft_entry__.py`` / ``make -C ldweaver_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                          "ldweaver_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.ldw_last_error.restype = C.c_char_p
+    L.ldw_create.argtypes = [C.c_int, P(C.c_void_p)]
+    L.ldw_destroy.argtypes = [C.c_void_p]
+    L.ldw_destroy.restype = None
+    L.ldw_aln_param.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_int, f64, f64, C.c_void_p, P(i64), C.c_void_p]
+    L.ldw_extract_snps.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    L.ldw_read_fasta.argtypes = [C.c_char_p, P(i64), P(i64), C.c_void_p, i64, C.c_void_p, i64]
+    L.ldw_acgtn2num.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, i64]
+    L.ldw_hdw.argtypes = [C.c_void_p, C.c_void_p, i64, i64, f64, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ldw_mi_plan_create.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, i64,
+                                     P(C.c_void_p)]
+    L.ldw_mi_plan_destroy.argtypes = [C.c_void_p]
+    L.ldw_mi_plan_destroy.restype = None
+    L.ldw_mi_scan.argtypes = [C.c_void_p, f64, f64, f64, f64, C.c_int, C.c_int, C.c_int, P(Links), P(Links), P(Links),
+                              C.c_void_p, C.c_void_p, P(ScanStats)]
+    L.ldw_mi_block_dense.argtypes = [C.c_void_p, i64, C.c_void_p, P(i64), P(i64)]
+    L.ldw_mi_pairs_exact.argtypes = [C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise LdwError(rc, lib().ldw_last_error().decode(errors="replace"))
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """Owns one ldw_ctx (one CUDA device)."""
+
+    def __init__(self, device: int = 0):
+        self.handle = C.c_void_p()
+        check(lib().ldw_create(device, C.byref(self.handle)))
+        self.device = device
+
+    def close(self):
+        if self.handle:
+            lib().ldw_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]

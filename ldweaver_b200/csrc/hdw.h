@@ -1,0 +1,15 @@
+// Internal (C++) interface of the Hamming-distance-weights stage; see hdw.cu.
+#pragma once
+#include "host_util.h"
+
+namespace ldw {
+
+// codes: device [n x S] uint8.  table: device int32 [n x 5] class counts; mask: observed-allele bitmask; r: popcount.
+int snp_allele_stats(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, int32_t* d_table, uint8_t* d_mask,
+                     uint8_t* d_r);
+int exclusive_scan_i32(cudaStream_t st, const int32_t* d_in, int64_t n, int32_t* d_out, int32_t* d_total);
+// d_neigh: int32[S] neighbour counts (incl. self); d_hdw: double[S]; d_dist: optional int32 [S x S] (column-major).
+int hdw_device(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, int32_t thresh, int32_t* d_neigh,
+               double* d_hdw, int32_t* d_dist, int num_sms);
+
+}  // namespace ldw

@@ -1,0 +1,95 @@
+// Host-side plumbing shared by the C-ABI entry points: error capture (no exceptions or aborts cross the
+// ABI), CUDA checks, device buffers, TMA tensor-map encoding through the driver entry point (so the
+// library needs no -lcuda at link time).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ldw.h"
+
+namespace ldw {
+
+std::string& last_error_ref();
+int set_error(int code, const char* fmt, ...);
+
+#define LDW_CUDA(call)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t e__ = (call);                                                                              \
+    if (e__ != cudaSuccess)                                                                                \
+      return ldw::set_error(LDW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+#define LDW_TRY(call)        \
+  do {                       \
+    int rc__ = (call);       \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// Simple owning device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  int alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return set_error(LDW_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+    }
+    bytes = n;
+    return 0;
+  }
+  int ensure(size_t n) { return (n <= bytes && p) ? 0 : alloc(n); }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  PinnedBuf() {}
+  PinnedBuf(const PinnedBuf&) = delete;
+  PinnedBuf& operator=(const PinnedBuf&) = delete;
+  ~PinnedBuf() { release(); }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  int ensure(size_t n) {
+    if (n <= bytes && p) return 0;
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMallocHost(&p, n);
+    if (e != cudaSuccess) {
+      p = nullptr;
+      return set_error(LDW_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", n, cudaGetErrorString(e));
+    }
+    bytes = n;
+    return 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// 2-D uint8 tensor [rows][kbytes] (kbytes contiguous), box = 128 bytes x box_rows, 128B swizzle.
+int make_tmap_u8_sw128(CUtensorMap* out, const void* gptr, uint64_t rows, uint64_t kbytes, uint32_t box_rows);
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+}  // namespace ldw

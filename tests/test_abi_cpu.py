@@ -1,0 +1,59 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/ldw.h declares, and
+fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "ldw.h")).read()
+    return sorted(set(re.findall(r"LDW_API [a-z0-9_ \*]+?\b(ldw_[a-z0-9_]+)\(", hdr)))
+
+
+def test_header_declares_expected_entry_points():
+    syms = _declared_symbols()
+    for s in ("ldw_create", "ldw_destroy", "ldw_aln_param", "ldw_extract_snps", "ldw_acgtn2num", "ldw_hdw",
+              "ldw_mi_plan_create", "ldw_mi_scan", "ldw_last_error", "ldw_read_fasta"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from ldweaver_b200 import _lib
+    L = _lib.lib()
+    for s in _declared_symbols():
+        assert hasattr(L, s), f"{s} declared in include/ldw.h but not exported"
+    assert L.ldw_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    from ldweaver_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.LdwError) as ei:
+        _lib.Context(0)
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_host_fasta_reader(tmp_path):
+    import gzip
+    import numpy as np
+    from ldweaver_b200 import api
+    p = tmp_path / "x.fa.gz"
+    with gzip.open(p, "wt") as fh:
+        fh.write(">s1 some description\nACGT\nac-n\n>s2\nTTTTGGGG\n>s3\nAC\nGTAC\nGT\n")
+    names, aln = api.read_fasta_matrix(str(p))
+    assert names == ["s1", "s2", "s3"]
+    assert [bytes(r) for r in aln] == [b"ACGTac-n", b"TTTTGGGG", b"ACGTACGT"]
+    q = tmp_path / "bad.fa"
+    q.write_text(">a\nACGT\n>b\nACG\n")
+    with pytest.raises(ValueError, match="different lengths"):
+        api.read_fasta_matrix(str(q))
+    e = tmp_path / "empty.fa"
+    e.write_text("")
+    with pytest.raises(ValueError, match="any sequences"):
+        api.read_fasta_matrix(str(e))

@@ -1,0 +1,99 @@
+"""GPU parity tests (through the C ABI): encoding and Hamming-distance weights vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    import ldweaver_b200 as ldw
+    return ldw
+
+
+def test_encode_fixture_bit_exact(fixture_input, fixture_expected):
+    import ldw_oracle as O
+    ldw = _lib()
+    aln, pos = fixture_input["aln"], fixture_input["pos"]
+    for method in ("default", "relaxed"):
+        snp = ldw.snp_dat_from_alignment_matrix(aln, fixture_input["names"], pos=pos, method=method)
+        assert snp.nsnp == 1268 and snp.nseq == 400 and snp.g is None
+        np.testing.assert_array_equal(snp.POS, fixture_expected[f"{method}_POS"])
+        np.testing.assert_array_equal(snp.r, fixture_expected[f"{method}_r"])
+        np.testing.assert_array_equal(snp.uqe, fixture_expected[f"{method}_uqe"])
+        np.testing.assert_array_equal(snp.codes, fixture_expected["codes"])
+
+
+def test_encode_filters_vs_oracle_ragged():
+    """Filters that bite, lower case, gaps, IUPAC, odd sizes (unaligned rows)."""
+    import c_oracle as CO
+    import ldw_oracle as O
+    ldw = _lib()
+    rng = np.random.default_rng(11)
+    for (S, L) in ((37, 1001), (128, 4096), (301, 777)):
+        alphabet = np.frombuffer(b"ACGTacgtNn-RYK", dtype=np.uint8)
+        base = rng.integers(0, 4, size=L)
+        aln = alphabet[base][None, :].repeat(S, axis=0).copy()
+        mut = rng.random((S, L)) < rng.random(L)[None, :] * 0.3
+        aln[mut] = alphabet[rng.integers(0, len(alphabet), size=int(mut.sum()))]
+        for filt, method in ((0, "default"), (1, "relaxed")):
+            for gap, maf in ((0.15, 0.01), (0.05, 0.1)):
+                pos_c, counts_c = CO.aln_param(aln, filt, gap, maf)
+                if len(pos_c) == 0:
+                    with pytest.raises(ValueError):
+                        ldw.snp_dat_from_alignment_matrix(aln, method=method, gap_freq=gap, maf_freq=maf)
+                    continue
+                snp = ldw.snp_dat_from_alignment_matrix(aln, method=method, gap_freq=gap, maf_freq=maf)
+                np.testing.assert_array_equal(snp.POS, pos_c)
+                codes_c, table_c = CO.extract_snps(aln, pos_c)
+                np.testing.assert_array_equal(snp.codes, codes_c)
+                np.testing.assert_array_equal(snp.uqe, (table_c > 0).T.astype(float))
+                assert snp.g == L
+
+
+def test_acgtn2num_vs_oracle():
+    import c_oracle as CO
+    ldw = _lib()
+    cv = ("ACGTN-acgtnXR" * 50)[:601]
+    nv = np.ones((5, len(cv)), order="F")
+    nv2 = nv.copy(order="F")
+    ldw.acgtn2num(nv, list(cv))
+    CO.acgtn2num(nv2, cv.encode())
+    np.testing.assert_array_equal(nv, nv2)
+
+
+def test_hdw_fixture_bit_exact(fixture_snp, fixture_expected):
+    ldw = _lib()
+    snp = ldw.snp_dat_from_codes(fixture_snp.codes, fixture_snp.POS, 50000)
+    hdw, cnt, dist = ldw.estimate_Hamming_distance_weights(snp, 0.1, return_parts=True)
+    np.testing.assert_array_equal(dist, fixture_expected["hdw_dist"])
+    np.testing.assert_array_equal(cnt, fixture_expected["hdw_cnt"])
+    np.testing.assert_array_equal(hdw, fixture_expected["hdw"])
+    # fused path (no distance matrix requested) must give the same weights
+    hdw2 = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    np.testing.assert_array_equal(hdw2, fixture_expected["hdw"])
+    # Q7: threshold 0 -> all weights 1
+    assert np.all(ldw.estimate_Hamming_distance_weights(snp, 0.0) == 1.0)
+
+
+@pytest.mark.parametrize("S,n,seed", [(130, 900, 1), (616, 3000, 2), (1000, 5000, 3), (2500, 1200, 4)])
+def test_hdw_synthetic_vs_c_oracle(S, n, seed):
+    """Multi-allelic, N-rich synthetic codes; sizes that exercise split-K, the fused epilogue (several
+    column tiles) and padding."""
+    import c_oracle as CO
+    ldw = _lib()
+    rng = np.random.default_rng(seed)
+    founders = rng.integers(0, 5, size=(n, 12)).astype(np.uint8)
+    assign = rng.integers(0, 12, size=S)
+    codes = founders[:, assign]
+    flip = rng.random((n, S)) < 0.04
+    codes[flip] = rng.integers(0, 5, size=int(flip.sum()))
+    codes[: n // 10] = codes[: n // 10] % 2          # biallelic block
+    codes[n // 10: n // 10 + 7] = 3                  # monomorphic sites (own no plane)
+    w_ref, cnt_ref, dist_ref = CO.hdw(codes, 0.1, want_dist=True)
+    snp = ldw.snp_dat_from_codes(codes, np.arange(1, n + 1), n)
+    w, cnt, dist = ldw.estimate_Hamming_distance_weights(snp, 0.1, return_parts=True)
+    np.testing.assert_array_equal(dist, dist_ref)
+    np.testing.assert_array_equal(cnt, cnt_ref)
+    np.testing.assert_array_equal(w, w_ref)
+    w2 = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    np.testing.assert_array_equal(w2, w_ref)
