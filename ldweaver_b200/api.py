@@ -184,3 +184,156 @@ def estimate_Hamming_distance_weights(snp_dat: SnpDat, threshold: float = 0.1, m
     if return_parts:
         return hdw, cnt, dist
     return hdw
+
+
+# --------------------------------------------------------------------------------------------------
+# perform_MI_computation (scan + sr/lr link filter)
+# --------------------------------------------------------------------------------------------------
+SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS = 1, 2, 4
+
+
+@dataclass
+class CdsVar:
+    """The two fields of ``cds_var`` the scan reads (R/computePairwiseMI.R:74,194-195,372)."""
+    paint: np.ndarray
+    nclust: int
+
+
+@dataclass
+class MIScanResult:
+    """Artefacts of the scan.  ``lr`` holds the rows the reference appends to lr_links.tsv
+    (R/computePairwiseMI.R:362), ``sr`` all short-range rows in block order, ``sr_links`` the per-cluster
+    routing of R/computePairwiseMI.R:372-376 (row indices into ``sr`` for cluster 1..nclust)."""
+    sr: dict
+    lr: dict
+    borderline: dict
+    sr_links: List[np.ndarray]
+    thr: np.ndarray
+    prob: np.ndarray
+    stats: dict
+    lr_links_approx: Optional[float]
+
+
+def round_half_even_thousands(x: float) -> int:
+    """``round(max_blk_sz, -3)`` (R/computePairwiseMI.R:69)."""
+    return int(np.round(x / 1000.0) * 1000)
+
+
+def make_blocks(nsnp: int, max_blk_sz: int):
+    """R/computePairwiseMI.R:147-165 (1-based inclusive from_s, from_e, to_s, to_e)."""
+    import math
+    p = int(math.ceil(nsnp / max_blk_sz))
+    fs = [(i - 1) * max_blk_sz + 1 for i in range(1, p + 1)]
+    fe = [min(i * max_blk_sz, nsnp) for i in range(1, p + 1)]
+    return [(fs[i], fe[i], fs[j], fe[j]) for i in range(p) for j in range(i, p)]
+
+
+class MIPlan:
+    """Device-resident operands for one (snp.dat, hdw): ldw_mi_plan_create / ldw_mi_scan."""
+
+    def __init__(self, snp_dat: SnpDat, hdw: np.ndarray, paint: np.ndarray, blk: int, device: int = 0):
+        self.ctx = _lib.default_context(device)
+        self.codes = np.ascontiguousarray(snp_dat.codes, dtype=np.uint8)
+        self.hdw = np.ascontiguousarray(hdw, dtype=np.float64)
+        self.pos = np.ascontiguousarray(snp_dat.POS, dtype=np.int32)
+        self.paint = np.ascontiguousarray(paint, dtype=np.int32)
+        n, S = self.codes.shape
+        if len(self.hdw) != S or len(self.pos) != n or len(self.paint) != n:
+            raise ValueError("snp.dat / hdw / cds_var size mismatch")
+        self.n, self.S, self.blk = n, S, int(blk)
+        self.handle = C.c_void_p()
+        check(_lib.lib().ldw_mi_plan_create(self.ctx.handle, ptr(self.codes), n, S, ptr(self.hdw), ptr(self.pos),
+                                            ptr(self.paint), int(blk), C.byref(self.handle)))
+        nr = -(-n // self.blk)
+        self.n_blocks = nr * (nr + 1) // 2
+
+    def close(self):
+        if self.handle:
+            _lib.lib().ldw_mi_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def scan(self, g: float, sr_dist: float, lr_retain_links: float, lr_links_approx: float, flags: int = 0,
+             n_parts: int = 1, part: int = 0, copy: bool = True):
+        sr, lr, bd = _lib.Links(), _lib.Links(), _lib.Links()
+        thr = np.full(self.n_blocks, np.nan)
+        prob = np.full(self.n_blocks, np.nan)
+        st = _lib.ScanStats()
+        check(_lib.lib().ldw_mi_scan(self.handle, float(g), float(sr_dist), float(lr_retain_links),
+                                     float(lr_links_approx if lr_links_approx else 0.0), int(flags), int(n_parts), int(part),
+                                     C.byref(sr), C.byref(lr), C.byref(bd), ptr(thr), ptr(prob), C.byref(st)))
+        if copy:
+            return sr.to_dict(), lr.to_dict(), bd.to_dict(), thr, prob, st.to_dict()
+        return sr, lr, bd, thr, prob, st.to_dict()
+
+    def block_dense(self, block_index: int) -> np.ndarray:
+        nf, nt = C.c_int64(), C.c_int64()
+        check(_lib.lib().ldw_mi_block_dense(self.handle, block_index, None, C.byref(nf), C.byref(nt)))
+        out = np.zeros((nf.value, nt.value), dtype=np.float64, order="F")
+        check(_lib.lib().ldw_mi_block_dense(self.handle, block_index, ptr(out), C.byref(nf), C.byref(nt)))
+        return out
+
+    def pairs_exact(self, block_index: int, from_local: np.ndarray, to_local: np.ndarray) -> np.ndarray:
+        f = np.ascontiguousarray(from_local, dtype=np.int32)
+        t = np.ascontiguousarray(to_local, dtype=np.int32)
+        out = np.zeros(len(f), dtype=np.float64)
+        check(_lib.lib().ldw_mi_pairs_exact(self.handle, block_index, ptr(f), ptr(t), len(f), ptr(out)))
+        return out
+
+
+def _format_r(x) -> str:
+    """write.table's number formatting (15 significant digits)."""
+    if float(x) == int(x) and abs(x) < 1e15:
+        return str(int(x))
+    return repr(float(f"{float(x):.15g}")) if "e" not in f"{float(x):.15g}" else f"{float(x):.15g}"
+
+
+def write_lr_tsv(path: str, lr: dict, append: bool = True) -> None:
+    """lr_links.tsv rows ``pos1 pos2 clust1 clust2 len MI`` (R/computePairwiseMI.R:362; no header, tab separated,
+    appended per block in the reference -- here once, in the same row order)."""
+    with open(path, "a" if append else "w") as fh:
+        for i in range(len(lr["MI"])):
+            fh.write(f"{lr['pos1'][i]}\t{lr['pos2'][i]}\t{lr['clust1'][i]}\t{lr['clust2'][i]}\t{lr['len'][i]}\t"
+                     f"{_format_r(lr['MI'][i])}\n")
+
+
+def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: int = 1, lr_save_path: Optional[str] = None,
+                           sr_save_path: Optional[str] = None, plt_folder: Optional[str] = None, sr_dist: float = 20000,
+                           lr_retain_links: float = 1e6, max_blk_sz: float = 10000, srp_cutoff: float = 3,
+                           runARACNE: bool = True, perform_SR_analysis_only: bool = False, order_links: bool = True,
+                           mega_dset: bool = False, lr_links_approx: Optional[float] = None, device: int = 0,
+                           write_tsv: bool = True, plan: Optional[MIPlan] = None) -> MIScanResult:
+    """Scan part of R/computePairwiseMI.R:46-116.  Same arguments as the reference (``ncores`` is accepted and
+    ignored by the GPU path; ``srp_cutoff``, ``runARACNE``, ``order_links``, ``plt_folder``, ``sr_save_path``
+    belong to the CPU post-processing that stays in R -- mergeNsort_sr_links / runARACNE, :118-143 -- and are
+    accepted for signature compatibility).  Extra keyword arguments are extensions: ``lr_links_approx`` overrides the
+    R-RNG based estimate of :94-97."""
+    if snp_dat.g is None:
+        raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
+    paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
+    nclust = int(cds_var.nclust if hasattr(cds_var, "nclust") else cds_var["nclust"])
+    if lr_save_path is None:
+        lr_save_path = os.path.join(os.getcwd(), "lr_links.tsv")  # :61
+    blk = round_half_even_thousands(max_blk_sz)  # :69
+    if not perform_SR_analysis_only and lr_links_approx is None:
+        from .rrng import lr_links_approx as _lra
+        lr_links_approx = _lra(np.asarray(snp_dat.POS), float(snp_dat.g), float(sr_dist))  # :94-97
+    own = plan is None
+    if own:
+        plan = MIPlan(snp_dat, hdw, paint, blk, device)
+    try:
+        flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
+        sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags)
+    finally:
+        if own:
+            plan.close()
+    if write_tsv and len(lr["MI"]):
+        write_lr_tsv(lr_save_path, lr, append=True)
+    by_cluster = [np.nonzero((sr["clust1"] == c) | (sr["clust2"] == c))[0] for c in range(1, nclust + 1)]  # :372-376
+    return MIScanResult(sr=sr, lr=lr, borderline=bd, sr_links=by_cluster, thr=thr, prob=prob, stats=stats,
+                        lr_links_approx=lr_links_approx)

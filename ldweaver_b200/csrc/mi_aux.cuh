@@ -1,0 +1,436 @@
+// Auxiliary kernels of the MI scan: operand packing, per-SNP records, exact (fp64) refinement of long-range
+// candidates, exact type-7 quantile selection, link materialisation.  All HBM-/latency-bound helpers; the hot
+// kernel is mi_kernel.cuh.
+#pragma once
+#include "mi_types.h"
+
+namespace ldw {
+
+// ------------------------------------------------------------------------------------------------
+// Per-slot records.  One warp per slot: class-wise exact fp64 marginals p^a = sum_s w_s [code = a] (kept per SNP for
+// the fp64 refinement) and the fixed-point marginals in the SAME digits the GEMM uses, so that
+// sum_b C^ab == P^a holds exactly in integers.
+__global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S, const int32_t* __restrict__ slot_snp,
+                                    int64_t nslots, const uint8_t* __restrict__ mask, const double* __restrict__ w,
+                                    const int32_t* __restrict__ wH, const int32_t* __restrict__ wL, Rec* rec,
+                                    int64_t vstride, double* p64 /*[n][5]*/) {
+  int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (slot >= nslots) return;
+  int32_t snp = slot_snp[slot];
+  if (snp < 0) {
+    if (lane < 4) {
+      Rec z;
+      for (int q = 0; q < 5; q++) { z.PH[q] = 0; z.PL[q] = 0; z.rp[q] = 0.f; }
+      z.pad = 0;
+      rec[lane * vstride + slot] = z;
+    }
+    return;
+  }
+  const uint8_t* row = codes + (int64_t)snp * S;
+  double p[5] = {0, 0, 0, 0, 0};
+  int h[5] = {0, 0, 0, 0, 0}, l[5] = {0, 0, 0, 0, 0};
+  for (int64_t s = lane; s < S; s += 32) {
+    int c = row[s];
+    double ws = w[s];
+    int hs = wH[s], ls = wL[s];
+#pragma unroll
+    for (int a = 0; a < 5; a++) {
+      bool m = (c == a);
+      p[a] += m ? ws : 0.0;
+      h[a] += m ? hs : 0;
+      l[a] += m ? ls : 0;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 5; a++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      p[a] += __shfl_xor_sync(0xffffffffu, p[a], o);
+      h[a] += __shfl_xor_sync(0xffffffffu, h[a], o);
+      l[a] += __shfl_xor_sync(0xffffffffu, l[a], o);
+    }
+  if (lane == 0)
+    for (int a = 0; a < 5; a++) p64[(int64_t)snp * 5 + a] = p[a];
+  if (lane < 4) {
+    // variant `lane`: partner SNP has r' = lane + 2 observed alleles
+    int m = mask[snp];
+    Rec z;
+    int q = 0;
+    for (int a = 0; a < 5; a++) {
+      if (m & (1 << a)) {
+        z.PH[q] = h[a];
+        z.PL[q] = l[a];
+        z.rp[q] = (float)(1.0 / (p[a] + 0.5 * (double)(lane + 2)));
+        q++;
+      }
+    }
+    for (; q < 5; q++) { z.PH[q] = 0; z.PL[q] = 0; z.rp[q] = 0.f; }
+    z.pad = 0;
+    rec[lane * vstride + slot] = z;
+  }
+}
+
+// Operand rows.  row_info[R] = snp | allele << 28, or 0xFFFFFFFF for padding rows.  Each thread writes one 16-byte
+// chunk (16 sequences) of the six arrays: X1 (0/1), X128 (0/128), D3..D0 (digit where the allele matches).
+__global__ void mi_pack_operands_kernel(const uint8_t* __restrict__ codes, int64_t S, int64_t Kpad,
+                                        const uint32_t* __restrict__ row_info, int64_t nrows,
+                                        const uint8_t* __restrict__ dig /*[4][Kpad]*/, uint8_t* X1, uint8_t* X128,
+                                        uint8_t* D3, uint8_t* D2, uint8_t* D1, uint8_t* D0) {
+  int64_t chunks = Kpad / 16;
+  int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= nrows * chunks) return;
+  int64_t R = id / chunks, ch = id % chunks;
+  uint32_t info = row_info[R];
+  uint32_t x1[4] = {0, 0, 0, 0}, x128[4] = {0, 0, 0, 0}, d[4][4];
+#pragma unroll
+  for (int t = 0; t < 4; t++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) d[t][k] = 0;
+  if (info != 0xFFFFFFFFu) {
+    const uint8_t* row = codes + (int64_t)(info & 0x0FFFFFFF) * S;
+    int al = info >> 28;
+    int64_t s0 = ch * 16;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      int64_t s = s0 + k;
+      uint32_t bit = (s < S && row[s] == al) ? 1u : 0u;
+      int sh = 8 * (k & 3);
+      x1[k >> 2] |= bit << sh;
+      x128[k >> 2] |= (bit << 7) << sh;
+      if (bit) {
+#pragma unroll
+        for (int t = 0; t < 4; t++) d[t][k >> 2] |= (uint32_t)dig[t * Kpad + s] << sh;
+      }
+    }
+  }
+  int64_t off = R * Kpad + ch * 16;
+  *reinterpret_cast<uint4*>(X1 + off) = make_uint4(x1[0], x1[1], x1[2], x1[3]);
+  *reinterpret_cast<uint4*>(X128 + off) = make_uint4(x128[0], x128[1], x128[2], x128[3]);
+  *reinterpret_cast<uint4*>(D3 + off) = make_uint4(d[0][0], d[0][1], d[0][2], d[0][3]);
+  *reinterpret_cast<uint4*>(D2 + off) = make_uint4(d[1][0], d[1][1], d[1][2], d[1][3]);
+  *reinterpret_cast<uint4*>(D1 + off) = make_uint4(d[2][0], d[2][1], d[2][2], d[2][3]);
+  *reinterpret_cast<uint4*>(D0 + off) = make_uint4(d[3][0], d[3][1], d[3][2], d[3][3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact fp64 MI of explicit pairs, following the reference arithmetic literally
+// (R/computePairwiseMI.R:260-263, :391-395 and src/computeMI.cpp:19), including quirk Q1.
+struct RefineParams {
+  const uint8_t* codes;
+  int64_t S;
+  const double* w;
+  const double* p64;      // [n][5]
+  const uint8_t* r;       // per SNP
+  const uint8_t* mask;    // per SNP
+  const int32_t* from_idx;  // local -> global SNP
+  const int32_t* to_idx;
+  const uint8_t* rfl_arr;   // r of from-list by local index
+  const uint8_t* rtl_arr;
+  int32_t nf, nt;
+  int32_t ideal_q;
+  double neff;
+};
+
+__device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int jl, int lane) {
+  const int gi = P.from_idx[il], gj = P.to_idx[jl];
+  const uint8_t* ci = P.codes + (int64_t)gi * P.S;
+  const uint8_t* cj = P.codes + (int64_t)gj * P.S;
+  double c[25];
+#pragma unroll
+  for (int k = 0; k < 25; k++) c[k] = 0.0;
+  for (int64_t s = lane; s < P.S; s += 32) {
+    int idx = (int)ci[s] * 5 + (int)cj[s];
+    double ws = P.w[s];
+#pragma unroll
+    for (int k = 0; k < 25; k++) c[k] += (idx == k) ? ws : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < 25; k++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+  const double ri = (double)P.r[gi], rj = (double)P.r[gj];
+  const int mi_ = P.mask[gi], mj_ = P.mask[gj];
+  const double den = P.neff + ri * rj * 0.5;
+  double Q;
+  if (P.ideal_q) {
+    Q = ri * rj * 0.25;
+  } else {
+    uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)P.nf;
+    uint32_t cdiv = (uint32_t)(lin / (uint32_t)P.nt), cmod = (uint32_t)(lin % (uint32_t)P.nt);
+    Q = (double)P.rfl_arr[cdiv] * (double)P.rtl_arr[cmod] * 0.25;
+  }
+  double mi = 0.0;
+#pragma unroll
+  for (int a = 0; a < 5; a++)
+#pragma unroll
+    for (int b = 0; b < 5; b++) {
+      if (((mi_ >> a) & 1) && ((mj_ >> b) & 1)) {
+        double pxy = c[a * 5 + b] + 0.5;
+        double pa = P.p64[(int64_t)gi * 5 + a], pb = P.p64[(int64_t)gj * 5 + b];
+        double dsum = pa * pb + Q + pa * (0.5 * ri) + pb * (0.5 * rj);
+        mi += pxy / den * log(pxy / dsum * den);
+      }
+    }
+  return mi;
+}
+
+__global__ void mi_refine_cand_kernel(RefineParams P, const Cand* __restrict__ cand, const uint32_t* __restrict__ count,
+                                      uint32_t cap, double* mi64) {
+  uint32_t n = *count < cap ? *count : cap;
+  int lane = threadIdx.x & 31;
+  for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+    double v = refine_pair(P, cand[i].il, cand[i].jl, lane);
+    if (lane == 0) mi64[i] = v;
+  }
+}
+
+__global__ void mi_refine_pairs_kernel(RefineParams P, const int32_t* __restrict__ il, const int32_t* __restrict__ jl,
+                                       int64_t n, double* out) {
+  int lane = threadIdx.x & 31;
+  for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n;
+       i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    double v = refine_pair(P, il[i], jl[i], lane);
+    if (lane == 0) out[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact per-block long-range selection: type-7 quantile over the block's long-range MI values from the
+// K largest refined candidates, then `MI >= thr` (R/computePairwiseMI.R:352-358, stats::quantile type 7).
+struct BlockResult {
+  double thr;
+  double v_lo;
+  uint32_t n_cand;
+  uint32_t n_kept;
+  uint32_t n_border;
+  uint32_t bad;  // 1: candidate buffer overflowed; 2: fewer candidates than needed; 4: threshold guess not provably safe
+};
+
+struct SelectParams {
+  const Cand* cand;
+  const double* mi64;
+  const uint32_t* count;
+  uint32_t cap;
+  const uint32_t* overflow;
+  const uint32_t* tcand_bits;
+  int32_t emit_all;
+  uint64_t k_lo, k_hi;  // ranks from the top (1-based) of x[lo], x[hi]
+  double h;             // interpolation weight (index - lo)
+  int32_t interpolate;  // index > lo
+  double tol_safe;      // margin between v_lo and the candidate threshold that proves the candidate set is complete
+  double tol_border;
+  const int32_t* from_idx;
+  const int32_t* to_idx;
+  int32_t nf, nt, diag;
+  int32_t block;
+  // outputs (global, appended)
+  uint64_t* kept_key;
+  int32_t* kept_gi;
+  int32_t* kept_gj;
+  double* kept_mi;
+  unsigned long long* kept_count;
+  uint64_t kept_cap;
+  uint32_t* kept_overflow;
+  BlockResult* result;
+};
+
+__device__ __forceinline__ uint64_t dkey(double v) {
+  uint64_t b = (uint64_t)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(uint64_t k) {
+  uint64_t b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
+// K-th largest (1-based) of n doubles by MSB-first radix select.  Whole CTA; returns the key to all threads.
+__device__ uint64_t select_kth_largest(const double* v, uint32_t n, uint64_t K, uint32_t* hist /*256 smem*/,
+                                       uint64_t* bcast /*smem*/) {
+  uint64_t prefix = 0, mask = 0, remaining = K;
+  for (int byte = 7; byte >= 0; byte--) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      uint64_t k = dkey(v[i]);
+      if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint64_t cum = 0;
+      int d = 255;
+      for (; d > 0; d--) {
+        if (cum + hist[d] >= remaining) break;
+        cum += hist[d];
+      }
+      bcast[0] = (uint64_t)d;
+      bcast[1] = remaining - cum;
+    }
+    __syncthreads();
+    prefix |= bcast[0] << (8 * byte);
+    mask |= 0xFFull << (8 * byte);
+    remaining = bcast[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// rank of pair (il, jl) in the reference's row order of a block (R/computePairwiseMI.R:306-310)
+__device__ __forceinline__ uint64_t pair_rank(int64_t il, int64_t jl, int64_t nf, int64_t nt, int diag) {
+  if (diag) {  // lower.tri(t(MI)): column-major over row > col
+    int64_t m = jl < nf ? jl : nf;
+    return (uint64_t)(m * (nf - 1) - m * (m - 1) / 2 + (il - jl - 1));
+  }
+  if (il < jl) {  // upper part first
+    int64_t U = jl <= nf ? jl * (jl - 1) / 2 : nf * (nf - 1) / 2 + (jl - nf) * nf;
+    return (uint64_t)(U + il);
+  }
+  int64_t n_upper = nt <= nf ? nt * (nt - 1) / 2 : nf * (nf - 1) / 2 + (nt - nf) * nf;
+  int64_t m = jl < nf ? jl : nf;
+  return (uint64_t)(n_upper + m * (nf - 1) - m * (m - 1) / 2 + (il - jl - 1));
+}
+
+__global__ void __launch_bounds__(1024) mi_select_kernel(SelectParams P) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint64_t bcast[2];
+  __shared__ uint32_t s_kept, s_border;
+  const uint32_t raw = *P.count;
+  const uint32_t n = raw < P.cap ? raw : P.cap;
+  uint32_t bad = 0;
+  if (*P.overflow || raw > P.cap) bad |= 1;
+  if ((uint64_t)n < P.k_lo) bad |= 2;
+  double thr = 0.0, v_lo = 0.0;
+  if (!(bad & 2) && n > 0) {
+    v_lo = dkey_inv(select_kth_largest(P.mi64, n, P.k_lo, hist, bcast));
+    thr = v_lo;
+    if (P.interpolate && P.k_hi >= 1 && P.k_hi != P.k_lo) {
+      double v_hi = dkey_inv(select_kth_largest(P.mi64, n, P.k_hi, hist, bcast));
+      if (v_hi != v_lo) thr = (1.0 - P.h) * v_lo + P.h * v_hi;  // stats::quantile type 7
+    }
+    if (!P.emit_all) {
+      double tc = (double)__uint_as_float(*P.tcand_bits);
+      if (!(v_lo >= tc + P.tol_safe)) bad |= 4;
+    }
+  }
+  if (threadIdx.x == 0) { s_kept = 0; s_border = 0; }
+  __syncthreads();
+  if (!bad) {
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      double v = P.mi64[i];
+      if (fabs(v - thr) <= P.tol_border) atomicAdd(&s_border, 1u);
+      if (v >= thr) {
+        unsigned long long o = atomicAdd(P.kept_count, 1ull);
+        atomicAdd(&s_kept, 1u);
+        if (o < P.kept_cap) {
+          int il = P.cand[i].il, jl = P.cand[i].jl;
+          P.kept_key[o] = ((uint64_t)P.block << 36) | pair_rank(il, jl, P.nf, P.nt, P.diag);
+          P.kept_gi[o] = P.from_idx[il];
+          P.kept_gj[o] = P.to_idx[jl];
+          P.kept_mi[o] = v;
+        } else {
+          *P.kept_overflow = 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BlockResult r;
+    r.thr = thr; r.v_lo = v_lo; r.n_cand = raw; r.n_kept = s_kept; r.n_border = s_border; r.bad = bad;
+    *P.result = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Link materialisation.
+struct ColInfo {  // per local column jl
+  int32_t a0, a1, b0, b1;
+  uint32_t baseU, baseL;
+};
+
+__device__ __forceinline__ int32_t circ_len_i32(int32_t p1, int32_t p2, int64_t g) {
+  int64_t d = (int64_t)p1 - (int64_t)p2;
+  if (d < 0) d = -d;
+  d %= g;
+  int64_t e = g - d;
+  return (int32_t)(d < e ? d : e);
+}
+
+struct SrMatParams {
+  const ColInfo* col;
+  const int32_t* from_idx;
+  const int32_t* to_idx;
+  const int32_t* pos;
+  const int32_t* paint;
+  const float* sr_mi;  // block's slots
+  int32_t nf, nt, diag, block;
+  int64_t g;
+  int32_t *o_pos1, *o_pos2, *o_c1, *o_c2, *o_len, *o_blk;  // already offset to the block's base
+  double* o_mi;
+};
+
+__global__ void mi_sr_materialize_kernel(SrMatParams P) {
+  int jl = blockIdx.x;
+  if (jl >= P.nt) return;
+  ColInfo c = P.col[jl];
+  int gj = P.to_idx[jl];
+  int32_t p1 = P.pos[gj], c1 = P.paint[gj];
+  // walk the column's short-range rows in ascending order: interval A then interval B, skipping il == jl,
+  // rows < jl go to the upper part (off-diagonal blocks only), rows > jl to the lower part
+  int la = c.a1 - c.a0, lb = c.b1 - c.b0;
+  int bj = min(max(jl + 1 - c.a0, 0), la) + min(max(jl + 1 - c.b0, 0), lb);  // SR rows <= jl
+  int bjm = min(max(jl - c.a0, 0), la) + min(max(jl - c.b0, 0), lb);          // SR rows < jl
+  for (int k = threadIdx.x; k < la + lb; k += blockDim.x) {
+    int il = k < la ? c.a0 + k : c.b0 + (k - la);
+    if (il == jl) continue;
+    int64_t slot;
+    if (il < jl) {
+      if (P.diag) continue;
+      slot = (int64_t)c.baseU + k;
+    } else {
+      slot = (int64_t)c.baseL + (k - bj);
+    }
+    (void)bjm;
+    int gi = P.from_idx[il];
+    int32_t p2 = P.pos[gi];
+    P.o_pos1[slot] = p1;
+    P.o_pos2[slot] = p2;
+    P.o_c1[slot] = c1;
+    P.o_c2[slot] = P.paint[gi];
+    P.o_len[slot] = circ_len_i32(p1, p2, P.g);
+    P.o_mi[slot] = (double)P.sr_mi[slot];
+    P.o_blk[slot] = P.block;
+  }
+}
+
+__global__ void mi_lr_materialize_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__ keys_sorted,
+                                         const int32_t* __restrict__ gi, const int32_t* __restrict__ gj,
+                                         const double* __restrict__ mi, const int32_t* __restrict__ pos,
+                                         const int32_t* __restrict__ paint, int64_t n, int64_t g, int32_t* o_pos1,
+                                         int32_t* o_pos2, int32_t* o_c1, int32_t* o_c2, int32_t* o_len, double* o_mi,
+                                         int32_t* o_blk) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t src = order[i];
+  int a = gi[src], b = gj[src];
+  int32_t p2 = pos[a], p1 = pos[b];
+  o_pos1[i] = p1;
+  o_pos2[i] = p2;
+  o_c1[i] = paint[b];
+  o_c2[i] = paint[a];
+  o_len[i] = circ_len_i32(p1, p2, g);
+  o_mi[i] = mi[src];
+  o_blk[i] = (int32_t)(keys_sorted[i] >> 36);
+}
+
+__global__ void iota_u32_kernel(uint32_t* p, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, double* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (double)in[i];
+}
+
+}  // namespace ldw

@@ -1,0 +1,438 @@
+// The weighted pairwise-MI scan kernel (sm_100a).
+//
+// What it replaces (reference, per make_blocks block): the ten sqrt(w)-weighted dense allele sub-matrices
+// (R/computePairwiseMI.R:238-256), the 25 calls of computeMI_Sprase (:270-298, :390-396: one dense x sparse product
+// and five rank-1 nf x nt temporaries each) with their .fastHadamard loop (src/computeMI.cpp:11-21), and the pair
+// enumeration / len / sr-lr split (:306-344).
+//
+// How.  The weighted joint allele counts  c_ij^ab = sum_s w_s [code(i,s)=a][code(j,s)=b]  are an integer GEMM:
+// weights are fixed-point (30 bits below the largest weight) split into two 15-bit halves, each half accumulated
+// exactly in an int32 TMEM accumulator by two K-passes of kind::i8 UMMA (A = one-hot plane x {128, 1}, B = one-hot
+// plane x {8-bit, 7-bit digit}).  Only the r-1 non-complement allele planes of a site enter the GEMM; the remaining
+// counts follow from the exact integer marginals (sum_b c^ab = p^a).  SNPs are grouped by plane count so a tile is
+// 128 row SNPs x NJ column SNPs with uniform (PA, PB).  Eight epilogue warps read the accumulators straight out of
+// TMEM (thread = row SNP), rebuild the (PA+1)x(PB+1) table, evaluate
+//     MI = sum_ab x/den * ln(x den / D),  x = c + 0.5,  D = (p_i^a + r_j/2)(p_j^b + r_i/2) + dQ   (dQ: quirk Q1)
+// in fp32 with one MUFU.LG2 per term (two with the Q1 correction), and emit: short-range links to their final,
+// position-determined output slot; long-range candidates above a monotonically rising candidate threshold.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue.
+#pragma once
+#include "mi_types.h"
+#include "umma.cuh"
+
+namespace ldw {
+
+constexpr int MI_THREADS = 384;
+constexpr int MI_STAGES = 2;
+constexpr uint32_t MI_ARR_BYTES = 128 * 128;              // one operand array slice: 128 rows x 128 K-bytes
+constexpr uint32_t MI_STAGE_BYTES = 6 * MI_ARR_BYTES;     // X1, X128, D3, D2, D1, D0
+constexpr uint32_t MI_JREC_BYTES = 128 * sizeof(Rec);     // per j-buffer
+constexpr uint32_t MI_JDYN_BYTES = 128 * sizeof(ColDyn);
+constexpr uint32_t MI_SMEM_BYTES = MI_STAGES * MI_STAGE_BYTES + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + 256 + 1024;
+
+__device__ __forceinline__ float lg2_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__host__ __device__ constexpr int mi_jc(int pa, int pb) {
+  return pa * pb <= 2 ? 16 : pa * pb <= 4 ? 8 : pa * pb <= 8 ? 4 : 2;
+}
+__host__ __device__ constexpr int mi_njlog2(int pa, int pb) {
+  return pa * pb == 1 ? 7 : pa * pb == 2 ? 6 : pa * pb <= 4 ? 5 : 4;
+}
+
+// Raise the long-range candidate threshold to the lower edge of the histogram bin above which at least
+// `kprime` already-emitted candidates lie.  Whole warp.  The threshold only ever rises, and every pair whose
+// MI was >= the threshold at the time it was evaluated has been emitted, so all pairs >= the final threshold
+// are in the candidate buffer.
+__device__ __noinline__ void lr_raise_threshold(const ScanParams& p, int lane) {
+  constexpr int PER = MI_HIST_BINS / 32;
+  uint32_t s = 0;
+  for (int k = 0; k < PER; k++) s += ld_volatile_u32(p.hist + lane * PER + k);
+  uint32_t suf = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t v = __shfl_down_sync(0xffffffffu, suf, o);
+    if (lane + o < 32) suf += v;
+  }
+  unsigned m = __ballot_sync(0xffffffffu, suf >= p.kprime);
+  if (m == 0) return;
+  int sel = 31 - __clz(m);
+  if (lane == sel) {
+    uint32_t run = suf - s;
+    for (int k = PER - 1; k >= 0; k--) {
+      run += ld_volatile_u32(p.hist + lane * PER + k);
+      if (run >= p.kprime) {
+        atomicMax(p.tcand_bits, (uint32_t)(lane * PER + k) << 19);
+        break;
+      }
+    }
+  }
+}
+
+struct EpiCtx {
+  int q, half, lane;
+  uint32_t tmem_base;  // lane-quarter offset already applied, column of this tile's accumulators
+  const Rec* jrec;     // shared
+  const ColDyn* jdyn;  // shared
+};
+
+// One term of the MI sum.  h,l: exact fixed-point joint count halves.
+template <bool QC>
+__device__ __forceinline__ float mi_term(float acc, int h, int l, float ra, float rb, float dq, float kH, float kL) {
+  float x = fmaf((float)h, kH, fmaf((float)l, kL, 0.5f));
+  float e = ra * rb;
+  float t = lg2_fast(x * e);
+  if (QC) t -= lg2_fast(fmaf(dq, e, 1.0f));
+  return fmaf(x, t, acc);
+}
+
+template <int PA, int PB, bool QC>
+__device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
+  constexpr int RA = PA + 1, RB = PB + 1;
+  constexpr int JC = mi_jc(PA, PB);
+  constexpr int NJ = 1 << mi_njlog2(PA, PB);
+  const int row = c.q * 32 + c.lane;
+  // ---- this thread's row SNP
+  const Rec* ri = p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row;
+  int PiH[RA], PiL[RA];
+  float rpad[RA];
+  const float den = p.den[RA - 2][RB - 2];
+#pragma unroll
+  for (int a = 0; a < RA; a++) {
+    PiH[a] = ri->PH[a];
+    PiL[a] = ri->PL[a];
+    rpad[a] = ri->rp[a] * den;
+  }
+  const RowDyn rd = p.rowdyn[td.i_dyn0 + row];
+  const int il = rd.il;
+  const float rtlq = rd.rtl * p.quarter_over_den[RA - 2][RB - 2];
+  const float q0 = p.q0[RA - 2][RB - 2];
+  const float scale = p.ln2_over_den[RA - 2][RB - 2];
+  const float kH = p.kH, kL = p.kL;
+  const bool has_sr = (td.flags & TILE_HAS_SR) != 0;
+  const bool do_lr = !p.sr_only && !p.dense;
+  const float tcand = (do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
+
+  const int jbeg = c.half * (NJ / 2);
+#pragma unroll 1
+  for (int j0 = jbeg; j0 < jbeg + NJ / 2; j0 += JC) {
+    uint32_t H[PA][PB][JC], L[PA][PB][JC];
+#pragma unroll
+    for (int a = 0; a < PA; a++)
+#pragma unroll
+      for (int b = 0; b < PB; b++) {
+        tmem_ldn<JC>(c.tmem_base + ((a * 2 + 0) * PB + b) * NJ + j0, H[a][b]);
+        tmem_ldn<JC>(c.tmem_base + ((a * 2 + 1) * PB + b) * NJ + j0, L[a][b]);
+      }
+    tmem_ld_wait();
+#pragma unroll
+    for (int jj = 0; jj < JC; jj++) {
+      const Rec& rj = c.jrec[j0 + jj];
+      const ColDyn& cd = c.jdyn[j0 + jj];
+      const int jl = cd.jl;
+      float dq = 0.f;
+      if (QC) {
+        if (p.ragged) {
+          // quirk Q1, general form: rft (nt x nf) is read by the linear index of the nf x nt matrix
+          float v = q0;
+          if (il >= 0 && jl >= 0) {
+            uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)p.nf;
+            uint32_t cdiv = (uint32_t)(lin / (uint32_t)p.nt), cmod = (uint32_t)(lin % (uint32_t)p.nt);
+            v = (float)p.rfl_arr[cdiv] * (float)p.rtl_arr[cmod] * p.quarter_over_den[RA - 2][RB - 2];
+          }
+          dq = v - q0;
+        } else {
+          dq = fmaf(rtlq, cd.rfl, -q0);
+        }
+      }
+      // ---- (PA+1) x (PB+1) joint table by exact integer complement, MI accumulated term by term
+      float acc = 0.f;
+      int colH[PB], colL[PB];
+#pragma unroll
+      for (int b = 0; b < PB; b++) colH[b] = colL[b] = 0;
+      int totH = 0, totL = 0;
+#pragma unroll
+      for (int a = 0; a < PA; a++) {
+        int rH = 0, rL = 0;
+#pragma unroll
+        for (int b = 0; b < PB; b++) {
+          int h = (int)H[a][b][jj], l = (int)L[a][b][jj];
+          rH += h; rL += l;
+          colH[b] += h; colL[b] += l;
+          acc = mi_term<QC>(acc, h, l, rpad[a], rj.rp[b], dq, kH, kL);
+        }
+        acc = mi_term<QC>(acc, PiH[a] - rH, PiL[a] - rL, rpad[a], rj.rp[PB], dq, kH, kL);
+        totH += rH; totL += rL;
+      }
+#pragma unroll
+      for (int b = 0; b < PB; b++)
+        acc = mi_term<QC>(acc, rj.PH[b] - colH[b], rj.PL[b] - colL[b], rpad[PA], rj.rp[b], dq, kH, kL);
+      {
+        int sjH = p.neffH - rj.PH[PB], sjL = p.neffL - rj.PL[PB];
+        acc = mi_term<QC>(acc, PiH[PA] - sjH + totH, PiL[PA] - sjL + totL, rpad[PA], rj.rp[PB], dq, kH, kL);
+      }
+      const float mi = acc * scale;
+
+      // ---- classification and emission
+      const bool valid = (il >= 0) && (jl >= 0) && (p.diag ? (il > jl) : (il != jl));
+      if (p.dense) {
+        if (il >= 0 && jl >= 0) p.dense_out[(size_t)il + (size_t)jl * (size_t)p.nf] = mi;
+        continue;
+      }
+      bool sr = false;
+      if (has_sr) {
+        const uint32_t la = (uint32_t)(cd.a1 - cd.a0), lb = (uint32_t)(cd.b1 - cd.b0);
+        sr = valid && (((uint32_t)(il - cd.a0) < la) || ((uint32_t)(il - cd.b0) < lb));
+        if (sr) {
+          // rows of this column that are short-range and precede `il`
+          int below = min(max(il - cd.a0, 0), (int)la) + min(max(il - cd.b0, 0), (int)lb);
+          uint32_t slot;
+          if (il < jl) {
+            slot = cd.baseU + (uint32_t)below;
+          } else {
+            int bj = min(max(jl + 1 - cd.a0, 0), (int)la) + min(max(jl + 1 - cd.b0, 0), (int)lb);
+            slot = cd.baseL + (uint32_t)(below - bj);
+          }
+          p.sr_out[slot] = mi;
+        }
+      }
+      if (do_lr) {
+        const bool em = valid && !sr && (mi >= tcand);
+        const unsigned bal = __ballot_sync(0xffffffffu, em);
+        if (bal) {
+          const int leader = __ffs(bal) - 1;
+          uint32_t base = 0;
+          if (c.lane == leader) base = atomicAdd(p.cand_count, (uint32_t)__popc(bal));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (em) {
+            uint32_t idx = base + (uint32_t)__popc(bal & ((1u << c.lane) - 1));
+            if (idx < p.cand_cap) {
+              Cand cc;
+              cc.il = il; cc.jl = jl; cc.mi = mi;
+              p.cand[idx] = cc;
+            } else {
+              *p.overflow = 1;
+            }
+            uint32_t bits = __float_as_uint(mi);
+            uint32_t bin = (bits & 0x80000000u) ? 0u : (bits >> 19);
+            atomicAdd(p.hist + bin, 1u);
+          }
+          if (!p.emit_all) {
+            const uint32_t n_new = (uint32_t)__popc(bal);
+            if ((base / p.delta) != ((base + n_new) / p.delta)) {
+              __threadfence();
+              lr_raise_threshold(p, c.lane);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+template <bool QC>
+__device__ __forceinline__ void epi_dispatch(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
+  switch (td.PA * 4 + td.PB - 5) {
+    case 0: epi_tile<1, 1, QC>(p, td, c); break;
+    case 1: epi_tile<1, 2, QC>(p, td, c); break;
+    case 2: epi_tile<1, 3, QC>(p, td, c); break;
+    case 3: epi_tile<1, 4, QC>(p, td, c); break;
+    case 4: epi_tile<2, 1, QC>(p, td, c); break;
+    case 5: epi_tile<2, 2, QC>(p, td, c); break;
+    case 6: epi_tile<2, 3, QC>(p, td, c); break;
+    case 7: epi_tile<2, 4, QC>(p, td, c); break;
+    case 8: epi_tile<3, 1, QC>(p, td, c); break;
+    case 9: epi_tile<3, 2, QC>(p, td, c); break;
+    case 10: epi_tile<3, 3, QC>(p, td, c); break;
+    case 11: epi_tile<3, 4, QC>(p, td, c); break;
+    case 12: epi_tile<4, 1, QC>(p, td, c); break;
+    case 13: epi_tile<4, 2, QC>(p, td, c); break;
+    case 14: epi_tile<4, 3, QC>(p, td, c); break;
+    case 15: epi_tile<4, 4, QC>(p, td, c); break;
+    default: break;
+  }
+}
+
+__global__ void __launch_bounds__(MI_THREADS, 1)
+mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* stage_base = smem;
+  Rec* jrec = reinterpret_cast<Rec*>(smem + MI_STAGES * MI_STAGE_BYTES);
+  ColDyn* jdyn = reinterpret_cast<ColDyn*>(smem + MI_STAGES * MI_STAGE_BYTES + 2 * MI_JREC_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MI_STAGES * MI_STAGE_BYTES + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES));
+  uint64_t* full = bars;            // [MI_STAGES]
+  uint64_t* empty = bars + 2;       // [MI_STAGES]
+  uint64_t* tfull = bars + 4;       // [2]
+  uint64_t* tempty = bars + 6;      // [2]
+  uint64_t* jfull = bars + 8;       // [2]
+  uint64_t* jempty = bars + 10;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; i++) tma_prefetch_desc(&tm.a[i]);
+    for (int i = 0; i < MI_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256);
+      mbar_init(&jfull[i], 1); mbar_init(&jempty[i], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
+        const TileDesc td = p.tiles[t];
+        const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
+        const int njidx = 7 - td.njlog2;  // 128,64,32,16 -> 0..3
+        const int jb = it & 1;
+        mbar_wait(&jempty[jb], ((it >> 1) & 1) ^ 1, 10);
+        mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (sizeof(Rec) + sizeof(ColDyn)));
+        bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
+        bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
+        for (int a = 0; a < PA; a++) {
+          const int arow = td.a_row0 + a * td.a_pstride;
+          for (int kb = 0; kb < p.nkb; kb++) {
+            mbar_wait(&empty[st], ph ^ 1, 11);
+            uint8_t* sb = stage_base + st * MI_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[st], 2 * MI_ARR_BYTES + (uint32_t)(4 * PB * NJ * 128));
+            tma_load_2d(sb, &tm.a[0], &full[st], kb * 128, arow);
+            tma_load_2d(sb + MI_ARR_BYTES, &tm.a[1], &full[st], kb * 128, arow);
+            for (int d = 0; d < 4; d++)
+              for (int b = 0; b < PB; b++)
+                tma_load_2d(sb + (2 + d) * MI_ARR_BYTES + b * NJ * 128, &tm.b[d][njidx], &full[st], kb * 128,
+                            td.b_row0 + b * td.b_pstride);
+            if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int st = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        const TileDesc td = p.tiles[t];
+        const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
+        const bool big = 2 * PA * PB * NJ > 256;
+        const uint32_t idesc = make_idesc_u8(128, (uint32_t)NJ);
+        uint32_t dbase;
+        if (big) {
+          for (int s = 0; s < 2; s++) {
+            mbar_wait(&tempty[as], aph ^ 1, 20);
+            if (++as == 2) { as = 0; aph ^= 1; }
+          }
+          dbase = tmem_base;
+        } else {
+          mbar_wait(&tempty[as], aph ^ 1, 21);
+          dbase = tmem_base + as * 256;
+        }
+        tc_fence_after();
+        for (int a = 0; a < PA; a++) {
+          for (int kb = 0; kb < p.nkb; kb++) {
+            mbar_wait(&full[st], ph, 22);
+            tc_fence_after();
+            const uint32_t sb = smem_u32(stage_base + st * MI_STAGE_BYTES);
+            const uint64_t dx1 = make_smem_desc_sw128(sb);
+            const uint64_t dx128 = make_smem_desc_sw128(sb + MI_ARR_BYTES);
+            for (int b = 0; b < PB; b++) {
+              const uint64_t d3 = make_smem_desc_sw128(sb + 2 * MI_ARR_BYTES + b * NJ * 128);
+              const uint64_t d2 = make_smem_desc_sw128(sb + 3 * MI_ARR_BYTES + b * NJ * 128);
+              const uint64_t d1 = make_smem_desc_sw128(sb + 4 * MI_ARR_BYTES + b * NJ * 128);
+              const uint64_t d0 = make_smem_desc_sw128(sb + 5 * MI_ARR_BYTES + b * NJ * 128);
+              const uint32_t dH = dbase + ((a * 2 + 0) * PB + b) * NJ;
+              const uint32_t dL = dbase + ((a * 2 + 1) * PB + b) * NJ;
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
+                umma_i8(dH, dx128 + 2 * k, d3 + 2 * k, idesc, first);
+                umma_i8(dH, dx1 + 2 * k, d2 + 2 * k, idesc, 1u);
+                umma_i8(dL, dx128 + 2 * k, d1 + 2 * k, idesc, first);
+                umma_i8(dL, dx1 + 2 * k, d0 + 2 * k, idesc, 1u);
+              }
+            }
+            umma_commit(&empty[st]);
+            if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+          }
+        }
+        if (big) {
+          umma_commit(&tfull[0]);
+          umma_commit(&tfull[1]);
+        } else {
+          umma_commit(&tfull[as]);
+          if (++as == 2) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================================== epilogue
+    EpiCtx c;
+    c.q = warp & 3;
+    c.half = (warp - 4) >> 2;
+    c.lane = lane;
+    int as = 0; uint32_t aph = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
+      const TileDesc td = p.tiles[t];
+      const int NJ = 1 << td.njlog2;
+      const bool big = 2 * td.PA * td.PB * NJ > 256;
+      const int jb = it & 1;
+      mbar_wait(&jfull[jb], (it >> 1) & 1, 30);
+      c.jrec = jrec + jb * 128;
+      c.jdyn = jdyn + jb * 128;
+      int s0 = as;
+      if (big) {
+        // both accumulator halves: wait for the two ring slots in order
+        uint32_t ph0 = aph;
+        mbar_wait(&tfull[as], ph0, 31);
+        int as1 = as ^ 1;
+        uint32_t ph1 = (as == 1) ? (aph ^ 1) : aph;
+        mbar_wait(&tfull[as1], ph1, 32);
+        c.tmem_base = tmem_base + ((uint32_t)(c.q * 32) << 16);
+      } else {
+        mbar_wait(&tfull[as], aph, 33);
+        c.tmem_base = tmem_base + ((uint32_t)(c.q * 32) << 16) + as * 256;
+      }
+      tc_fence_after();
+      if (p.qcorr) epi_dispatch<true>(p, td, c);
+      else epi_dispatch<false>(p, td, c);
+      tc_fence_before();
+      if (big) {
+        mbar_arrive(&tempty[0]);
+        mbar_arrive(&tempty[1]);
+        // two ring slots consumed: phase flips once
+        aph ^= 1;
+        (void)s0;
+      } else {
+        mbar_arrive(&tempty[as]);
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+      mbar_arrive(&jempty[jb]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace ldw

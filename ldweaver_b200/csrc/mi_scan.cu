@@ -1,10 +1,975 @@
+// Host driver + C ABI of the weighted pairwise-MI scan (see mi_kernel.cuh for the hot kernel).
+//
+// Reference semantics reproduced here (paths relative to the LDWeaver tree):
+//   make_blocks                     R/computePairwiseMI.R:147-165   (block list, row-major i, j >= i)
+//   perform_MI_computation_ACGTN    R/computePairwiseMI.R:167-386   (per block: MI, pair order Q2/Q5, len, sr/lr split,
+//                                                                     per-block type-7 quantile Q3, SR-only drop Q12)
+//   computeMI_Sprase/.fastHadamard  R/computePairwiseMI.R:390-398, src/computeMI.cpp:11-21 (incl. quirk Q1)
+#include <algorithm>
+#include <cmath>
+#include <cub/cub.cuh>
+#include <vector>
+
 #include "../../include/ldw.h"
 #include "ctx.h"
+#include "hdw.h"
+#include "mi_aux.cuh"
+#include "mi_kernel.cuh"
+
 using namespace ldw;
-extern "C" {
-int ldw_mi_plan_create(ldw_ctx*, const uint8_t*, int64_t, int64_t, const double*, const int32_t*, const int32_t*, int64_t, ldw_mi_plan**) { return set_error(LDW_ERR_UNSUPPORTED, "stub"); }
-void ldw_mi_plan_destroy(ldw_mi_plan*) {}
-int ldw_mi_scan(ldw_mi_plan*, double, double, double, double, int, int, int, ldw_links*, ldw_links*, ldw_links*, double*, double*, ldw_scan_stats*) { return set_error(LDW_ERR_UNSUPPORTED, "stub"); }
-int ldw_mi_block_dense(ldw_mi_plan*, int64_t, double*, int64_t*, int64_t*) { return set_error(LDW_ERR_UNSUPPORTED, "stub"); }
-int ldw_mi_pairs_exact(ldw_mi_plan*, int64_t, const int32_t*, const int32_t*, int64_t, double*) { return set_error(LDW_ERR_UNSUPPORTED, "stub"); }
+
+namespace {
+
+struct Group {
+  int32_t slot0 = 0, nslots = 0, row0 = 0, count = 0;
+};
+
+struct HostLinks {
+  PinnedBuf pos1, pos2, c1, c2, len, blk, mi;
+  int64_t n = 0;
+  int ensure(int64_t m) {
+    size_t b4 = (size_t)(m > 0 ? m : 1) * 4, b8 = (size_t)(m > 0 ? m : 1) * 8;
+    LDW_TRY(pos1.ensure(b4)); LDW_TRY(pos2.ensure(b4)); LDW_TRY(c1.ensure(b4)); LDW_TRY(c2.ensure(b4));
+    LDW_TRY(len.ensure(b4)); LDW_TRY(blk.ensure(b4)); LDW_TRY(mi.ensure(b8));
+    return 0;
+  }
+  void fill(ldw_links* o) const {
+    if (!o) return;
+    o->n = n;
+    o->pos1 = pos1.as<int32_t>(); o->pos2 = pos2.as<int32_t>(); o->clust1 = c1.as<int32_t>(); o->clust2 = c2.as<int32_t>();
+    o->len = len.as<int32_t>(); o->MI = mi.as<double>(); o->block = blk.as<int32_t>();
+  }
+};
+
+struct DevLinks {
+  DevBuf pos1, pos2, c1, c2, len, blk, mi;
+  int ensure(int64_t m) {
+    size_t b4 = (size_t)(m > 0 ? m : 1) * 4, b8 = (size_t)(m > 0 ? m : 1) * 8;
+    LDW_TRY(pos1.ensure(b4)); LDW_TRY(pos2.ensure(b4)); LDW_TRY(c1.ensure(b4)); LDW_TRY(c2.ensure(b4));
+    LDW_TRY(len.ensure(b4)); LDW_TRY(blk.ensure(b4)); LDW_TRY(mi.ensure(b8));
+    return 0;
+  }
+};
+
+// Everything one block needs on the device besides the static plan.
+struct BlockDev {
+  DevBuf rowdyn, coldyn, colinfo, tiles, from_idx, to_idx, rfl, rtl;
+  PinnedBuf stage;
+  cudaEvent_t done = nullptr;
+  bool used = false;
+};
+
+struct BlockHost {  // pageable staging reused per ring entry (kept alive until the async copies are issued)
+  std::vector<RowDyn> rowdyn;
+  std::vector<ColDyn> coldyn;
+  std::vector<ColInfo> colinfo;
+  std::vector<TileDesc> tiles;
+  std::vector<int32_t> from_idx, to_idx;
+  std::vector<uint8_t> rfl, rtl;
+  int32_t nf = 0, nt = 0;
+  int diag = 0, ragged = 0;
+  int64_t n_pairs = 0, n_sr = 0, n_lr = 0;
+};
+
+}  // namespace
+
+struct ldw_mi_plan {
+  ldw_ctx* ctx = nullptr;
+  int64_t n = 0, S = 0, blk = 0, Kpad = 0;
+  int nranges = 0;
+  std::vector<int32_t> pos, paint;
+  std::vector<uint8_t> r, mask;
+  std::vector<double> w;
+  std::vector<Group> groups;           // [nranges][4] (P = 1..4)
+  std::vector<int32_t> range_slot0;    // [nranges + 1]
+  std::vector<int32_t> slot_snp;       // global slot -> snp or -1
+  int64_t nslots = 0, nrows = 0;
+  double neff = 0, scale = 0;          // weight = W / scale
+  int32_t neffH = 0, neffL = 0;
+  bool pos_sorted = true;
+  // device, static
+  DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops[6];
+  TmapSet tm;
+  // scan workspace
+  static constexpr int RING = 4;
+  BlockDev ring[RING];
+  BlockHost hring[RING];
+  DevBuf d_cand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
+  DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
+  DevLinks d_sr, d_lr;
+  HostLinks h_sr, h_lr, h_border;
+  std::vector<BlockResult> results;
+  double t_pack_ms = 0;
+  ~ldw_mi_plan() {
+    for (auto& b : ring)
+      if (b.done) cudaEventDestroy(b.done);
+  }
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- plan
+int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const int32_t* pos, const int32_t* paint) {
+  ldw_ctx* ctx = P->ctx;
+  cudaStream_t st = ctx->stream;
+  const int64_t n = P->n, S = P->S, blk = P->blk;
+  cudaEvent_t e0, e1;
+  LDW_CUDA(cudaEventCreate(&e0));
+  LDW_CUDA(cudaEventCreate(&e1));
+  LDW_CUDA(cudaEventRecord(e0, st));
+  P->pos.assign(pos, pos + n);
+  P->paint.assign(paint, paint + n);
+  P->w.assign(hdw, hdw + S);
+  for (int64_t i = 1; i < n; i++)
+    if (pos[i] < pos[i - 1]) P->pos_sorted = false;
+  // ---- fixed-point weights: W_s = round(w_s * scale), scale = (2^30 - 1) / max(w); 15-bit halves H, L;
+  //      digits D3 (8 bit) D2 (7 bit) of H and D1, D0 of L
+  double wmax = 0, neff = 0;
+  for (int64_t s = 0; s < S; s++) {
+    if (!(hdw[s] > 0) || !std::isfinite(hdw[s])) return set_error(LDW_ERR_ARG, "hdw[%lld] = %g is not a positive finite weight", (long long)s, hdw[s]);
+    wmax = std::max(wmax, hdw[s]);
+    neff += hdw[s];
+  }
+  P->neff = neff;
+  P->scale = 1073741823.0 / wmax;
+  P->Kpad = round_up(S, 128);
+  std::vector<uint8_t> dig((size_t)4 * P->Kpad, 0);
+  std::vector<int32_t> wH(S), wL(S);
+  int64_t sumH = 0, sumL = 0;
+  for (int64_t s = 0; s < S; s++) {
+    int64_t W = (int64_t)std::llround(hdw[s] * P->scale);
+    if (W < 0) W = 0;
+    if (W > 1073741823) W = 1073741823;
+    int32_t H = (int32_t)(W >> 15), L = (int32_t)(W & 32767);
+    wH[s] = H; wL[s] = L;
+    sumH += H; sumL += L;
+    dig[0 * P->Kpad + s] = (uint8_t)(H >> 7);
+    dig[1 * P->Kpad + s] = (uint8_t)(H & 127);
+    dig[2 * P->Kpad + s] = (uint8_t)(L >> 7);
+    dig[3 * P->Kpad + s] = (uint8_t)(L & 127);
+  }
+  if (sumH > 0x7fffffffLL || sumL > 0x7fffffffLL) return set_error(LDW_ERR_UNSUPPORTED, "too many sequences for int32 accumulation (nseq=%lld)", (long long)S);
+  P->neffH = (int32_t)sumH;
+  P->neffL = (int32_t)sumL;
+
+  // ---- upload codes, per-SNP allele statistics
+  LDW_TRY(P->d_codes.alloc((size_t)n * S));
+  LDW_TRY(P->d_mask.alloc((size_t)n));
+  LDW_TRY(P->d_r.alloc((size_t)n));
+  DevBuf d_table;
+  LDW_TRY(d_table.alloc((size_t)n * 5 * 4));
+  LDW_CUDA(cudaMemcpyAsync(P->d_codes.p, codes, (size_t)n * S, cudaMemcpyHostToDevice, st));
+  LDW_TRY(snp_allele_stats(st, P->d_codes.as<uint8_t>(), n, S, d_table.as<int32_t>(), P->d_mask.as<uint8_t>(), P->d_r.as<uint8_t>()));
+  P->r.resize(n);
+  P->mask.resize(n);
+  LDW_CUDA(cudaMemcpyAsync(P->r.data(), P->d_r.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaMemcpyAsync(P->mask.data(), P->d_mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaStreamSynchronize(st));
+  for (int64_t i = 0; i < n; i++)
+    if (P->r[i] < 2)
+      return set_error(LDW_ERR_UNSUPPORTED, "SNP %lld is monomorphic (r=%d); the reference's filters never retain such sites "
+                       "and this implementation does not support them", (long long)i, (int)P->r[i]);
+
+  if (n >= (1 << 28)) return set_error(LDW_ERR_UNSUPPORTED, "nsnp >= 2^28 not supported");
+  // ---- slots: per block range, SNPs grouped by plane count P = r - 1, each group padded to 128
+  P->nranges = (int)((n + blk - 1) / blk);
+  P->groups.assign((size_t)P->nranges * 4, Group());
+  P->range_slot0.assign(P->nranges + 1, 0);
+  int64_t slot = 0, row = 0;
+  std::vector<int32_t> snp_slot(n);
+  for (int b = 0; b < P->nranges; b++) {
+    P->range_slot0[b] = (int32_t)slot;
+    int64_t lo = (int64_t)b * blk, hi = std::min<int64_t>(n, lo + blk);
+    for (int pc = 1; pc <= 4; pc++) {
+      Group& G = P->groups[(size_t)b * 4 + pc - 1];
+      G.slot0 = (int32_t)slot;
+      G.row0 = (int32_t)row;
+      int cnt = 0;
+      for (int64_t i = lo; i < hi; i++)
+        if (P->r[i] - 1 == pc) snp_slot[i] = (int32_t)(slot + cnt++);
+      G.count = cnt;
+      G.nslots = (int32_t)round_up(cnt, 128);
+      slot += G.nslots;
+      row += (int64_t)G.nslots * pc;
+      if (slot > 0x3fffffff || row > 0x3fffffff) return set_error(LDW_ERR_UNSUPPORTED, "problem too large for 32-bit slot indices");
+    }
+  }
+  P->range_slot0[P->nranges] = (int32_t)slot;
+  P->nslots = slot;
+  P->nrows = row;
+  P->slot_snp.assign(slot, -1);
+  for (int64_t i = 0; i < n; i++) P->slot_snp[snp_slot[i]] = (int32_t)i;
+  // operand row -> (snp, allele)
+  std::vector<uint32_t> row_info((size_t)std::max<int64_t>(row, 1), 0xFFFFFFFFu);
+  for (int b = 0; b < P->nranges; b++)
+    for (int pc = 1; pc <= 4; pc++) {
+      const Group& G = P->groups[(size_t)b * 4 + pc - 1];
+      for (int k = 0; k < G.count; k++) {
+        int32_t snp = P->slot_snp[G.slot0 + k];
+        int m = P->mask[snp], q = 0;
+        for (int a = 0; a < 5 && q < pc; a++)
+          if (m & (1 << a)) {
+            row_info[(size_t)G.row0 + (size_t)q * G.nslots + k] = (uint32_t)snp | ((uint32_t)a << 28);
+            q++;
+          }
+      }
+    }
+  // ---- device: weights, records, operands
+  DevBuf d_slot_snp, d_wH, d_wL, d_dig, d_row_info;
+  LDW_TRY(P->d_w.alloc((size_t)S * 8));
+  LDW_TRY(d_wH.alloc((size_t)S * 4));
+  LDW_TRY(d_wL.alloc((size_t)S * 4));
+  LDW_TRY(d_dig.alloc(dig.size()));
+  LDW_TRY(d_slot_snp.alloc((size_t)std::max<int64_t>(slot, 1) * 4));
+  LDW_TRY(d_row_info.alloc(row_info.size() * 4));
+  LDW_TRY(P->d_p64.alloc((size_t)n * 5 * 8));
+  LDW_TRY(P->d_rec.alloc((size_t)std::max<int64_t>(slot, 1) * 4 * sizeof(Rec)));
+  LDW_TRY(P->d_pos.alloc((size_t)n * 4));
+  LDW_TRY(P->d_paint.alloc((size_t)n * 4));
+  LDW_CUDA(cudaMemcpyAsync(P->d_w.p, hdw, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(d_wH.p, wH.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(d_wL.p, wL.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(d_dig.p, dig.data(), dig.size(), cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(d_slot_snp.p, P->slot_snp.data(), (size_t)slot * 4, cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(d_row_info.p, row_info.data(), row_info.size() * 4, cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(P->d_pos.p, pos, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(P->d_paint.p, paint, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  {
+    int wpb = 8;
+    mi_build_rec_kernel<<<(unsigned)((slot + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        P->d_codes.as<uint8_t>(), S, d_slot_snp.as<int32_t>(), slot, P->d_mask.as<uint8_t>(), P->d_w.as<double>(),
+        d_wH.as<int32_t>(), d_wL.as<int32_t>(), P->d_rec.as<Rec>(), slot, P->d_p64.as<double>());
+    LDW_CUDA(cudaGetLastError());
+  }
+  size_t op_bytes = (size_t)std::max<int64_t>(row, 128) * P->Kpad;
+  for (int k = 0; k < 6; k++) LDW_TRY(P->d_ops[k].alloc(op_bytes));
+  {
+    int64_t total = row * (P->Kpad / 16);
+    if (total > 0) {
+      mi_pack_operands_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+          P->d_codes.as<uint8_t>(), S, P->Kpad, d_row_info.as<uint32_t>(), row, d_dig.as<uint8_t>(), P->d_ops[0].as<uint8_t>(),
+          P->d_ops[1].as<uint8_t>(), P->d_ops[2].as<uint8_t>(), P->d_ops[3].as<uint8_t>(), P->d_ops[4].as<uint8_t>(),
+          P->d_ops[5].as<uint8_t>());
+      LDW_CUDA(cudaGetLastError());
+    }
+  }
+  uint64_t trows = (uint64_t)std::max<int64_t>(row, 128);
+  for (int k = 0; k < 2; k++) LDW_TRY(make_tmap_u8_sw128(&P->tm.a[k], P->d_ops[k].p, trows, (uint64_t)P->Kpad, 128));
+  for (int d = 0; d < 4; d++)
+    for (int j = 0; j < 4; j++)
+      LDW_TRY(make_tmap_u8_sw128(&P->tm.b[d][j], P->d_ops[2 + d].p, trows, (uint64_t)P->Kpad, 128u >> j));
+  for (auto& b : P->ring) LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+  LDW_CUDA(cudaEventRecord(e1, st));
+  LDW_CUDA(cudaStreamSynchronize(st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  P->t_pack_ms = ms;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  LDW_CUDA(cudaFuncSetAttribute(mi_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MI_SMEM_BYTES));
+  return 0;
 }
+
+// ---------------------------------------------------------------------------------------------- per-block host prep
+struct ScanCfg {
+  double g, sr_dist, lr_retain, lr_approx;
+  int flags;
+  int dense = 0;  // debug: every (row, col) cell is wanted, so no tile is skipped
+};
+
+// R's circular distance (R/computePairwiseMI.R:330) for integer positions
+inline double circ_len_d(double p1, double p2, double g) {
+  double m = std::fmod(p1 - p2, g);
+  if (m < 0) m += g;
+  return 0.5 * g - std::fabs(m - 0.5 * g);
+}
+
+// Builds the block's from/to lists (Q12 drop in SR-only mode), local-index maps, short-range column structure
+// and tile list.  Returns 1 if the block is empty (nothing to do).
+int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, BlockHost& H, bool sizes_only = false) {
+  const int64_t n = P->n, blk = P->blk;
+  const bool sr_only = (cfg.flags & LDW_SCAN_SR_ONLY) != 0;
+  const double g = cfg.g, sr = cfg.sr_dist;
+  int64_t flo = (int64_t)bf * blk, fhi = std::min<int64_t>(n, flo + blk);
+  int64_t tlo = (int64_t)bt * blk, thi = std::min<int64_t>(n, tlo + blk);
+  H.from_idx.clear();
+  H.to_idx.clear();
+  if (!sr_only) {
+    for (int64_t i = flo; i < fhi; i++) H.from_idx.push_back((int32_t)i);
+    for (int64_t i = tlo; i < thi; i++) H.to_idx.push_back((int32_t)i);
+  } else {
+    // R/computePairwiseMI.R:182-185: keep a SNP iff some SNP of the opposite list is strictly closer than sr_dist
+    auto keep = [&](int64_t lo, int64_t hi, int64_t olo, int64_t ohi, std::vector<int32_t>& out) {
+      for (int64_t i = lo; i < hi; i++) {
+        double x = P->pos[i];
+        bool k = false;
+        // positions are sorted: nearest candidates are around lower_bound(x) and, circularly, the two ends
+        auto it = std::lower_bound(P->pos.begin() + olo, P->pos.begin() + ohi, (int32_t)x);
+        int64_t c = it - P->pos.begin();
+        for (int64_t j : {c - 1, c, olo, ohi - 1})
+          if (j >= olo && j < ohi && std::fabs(circ_len_d(P->pos[j], x, g)) < sr) k = true;
+        if (k) out.push_back((int32_t)i);
+      }
+    };
+    keep(flo, fhi, tlo, thi, H.from_idx);
+    keep(tlo, thi, flo, fhi, H.to_idx);
+  }
+  const int32_t nf = (int32_t)H.from_idx.size(), nt = (int32_t)H.to_idx.size();
+  H.nf = nf; H.nt = nt;
+  H.diag = (nf == nt) && std::equal(H.from_idx.begin(), H.from_idx.end(), H.to_idx.begin());  // fromISto :198-202
+  H.ragged = (nf != nt);
+  H.n_pairs = H.n_sr = H.n_lr = 0;
+  if (nf == 0 || nt == 0) return 1;
+  H.n_pairs = H.diag ? (int64_t)nf * (nf - 1) / 2 : (int64_t)nf * nt - std::min(nf, nt);
+
+  const int32_t fs0 = P->range_slot0[bf], fs1 = P->range_slot0[bf + 1];
+  const int32_t ts0 = P->range_slot0[bt], ts1 = P->range_slot0[bt + 1];
+  // ---- short-range structure per column (two-pointer sweeps; positions ascending within both lists)
+  H.colinfo.assign(nt, ColInfo{0, 0, 0, 0, 0, 0});
+  const bool all_sr = !(sr < 0.5 * g);  // len <= g/2 always
+  {
+    int64_t a0 = 0, a1 = 0, w1 = 0, w0 = 0;
+    uint64_t accU = 0, accL = 0;
+    std::vector<uint32_t> cu(nt), cl(nt);
+    for (int j = 0; j < nt; j++) {
+      const double pj = P->pos[H.to_idx[j]];
+      int32_t ia0, ia1, ib0, ib1;
+      if (all_sr) {
+        ia0 = 0; ia1 = nf; ib0 = ib1 = 0;
+      } else {
+        while (a0 < nf && (double)P->pos[H.from_idx[a0]] < pj - sr) a0++;          // first row with pf >= pj - sr
+        while (a1 < nf && (double)P->pos[H.from_idx[a1]] <= pj + sr) a1++;         // first row with pf >  pj + sr
+        while (w1 < nf && (double)P->pos[H.from_idx[w1]] <= pj - (g - sr)) w1++;   // rows [0, w1): wrap from the left
+        while (w0 < nf && (double)P->pos[H.from_idx[w0]] < pj + (g - sr)) w0++;    // rows [w0, nf): wrap from the right
+        // intervals in ascending order: W1 = [0, w1), A = [a0, a1), W2 = [w0, nf); at most one wrap side is non-empty
+        int32_t x0 = (int32_t)a0, x1 = (int32_t)std::max(a0, a1);
+        if (w1 > 0) {
+          if ((int32_t)w1 >= x0) { ia0 = 0; ia1 = std::max<int32_t>((int32_t)w1, x1); ib0 = ib1 = 0; }
+          else { ia0 = 0; ia1 = (int32_t)w1; ib0 = x0; ib1 = x1; }
+        } else if (w0 < nf) {
+          if ((int32_t)w0 <= x1) { ia0 = x0; ia1 = nf; if ((int32_t)w0 < x0) ia0 = (int32_t)w0; ib0 = ib1 = 0; }
+          else { ia0 = x0; ia1 = x1; ib0 = (int32_t)w0; ib1 = nf; }
+        } else {
+          ia0 = x0; ia1 = x1; ib0 = ib1 = 0;
+        }
+      }
+      ColInfo& c = H.colinfo[j];
+      c.a0 = ia0; c.a1 = ia1; c.b0 = ib0; c.b1 = ib1;
+      auto below = [&](int x) {
+        return std::min(std::max(x - ia0, 0), ia1 - ia0) + std::min(std::max(x - ib0, 0), ib1 - ib0);
+      };
+      int tot = (ia1 - ia0) + (ib1 - ib0);
+      cu[j] = H.diag ? 0u : (uint32_t)below(std::min(j, nf));
+      cl[j] = (uint32_t)(tot - below(std::min(j + 1, nf)));
+      accU += cu[j];
+      accL += cl[j];
+    }
+    if (accU + accL > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "more than 2^32 short-range links in one block");
+    uint32_t ru = 0, rl = (uint32_t)accU;
+    for (int j = 0; j < nt; j++) {
+      H.colinfo[j].baseU = ru;
+      H.colinfo[j].baseL = rl;
+      ru += cu[j];
+      rl += cl[j];
+    }
+    H.n_sr = (int64_t)(accU + accL);
+    H.n_lr = H.n_pairs - H.n_sr;
+  }
+  if (sizes_only) return 0;
+  // ---- local-index maps over the slot ranges
+  H.rfl.resize(nf);
+  H.rtl.resize(nt);
+  for (int k = 0; k < nf; k++) H.rfl[k] = P->r[H.from_idx[k]];
+  for (int k = 0; k < nt; k++) H.rtl[k] = P->r[H.to_idx[k]];
+  std::vector<int32_t> il_of(fhi - flo, -1), jl_of(thi - tlo, -1);
+  for (int k = 0; k < nf; k++) il_of[H.from_idx[k] - flo] = k;
+  for (int k = 0; k < nt; k++) jl_of[H.to_idx[k] - tlo] = k;
+  H.rowdyn.assign(fs1 - fs0, RowDyn{-1, 0.f});
+  for (int32_t s = fs0; s < fs1; s++) {
+    int32_t snp = P->slot_snp[s];
+    if (snp < 0) continue;
+    int32_t il = il_of[snp - flo];
+    RowDyn rd;
+    rd.il = il;
+    rd.rtl = (il >= 0 && il < nt) ? (float)H.rtl[il] : 0.f;
+    H.rowdyn[s - fs0] = rd;
+  }
+  H.coldyn.assign(ts1 - ts0, ColDyn{-1, 0.f, 0, 0, 0, 0, 0, 0});
+  for (int32_t s = ts0; s < ts1; s++) {
+    int32_t snp = P->slot_snp[s];
+    if (snp < 0) continue;
+    int32_t jl = jl_of[snp - tlo];
+    ColDyn cd{-1, 0.f, 0, 0, 0, 0, 0, 0};
+    cd.jl = jl;
+    if (jl >= 0) {
+      cd.rfl = jl < nf ? (float)H.rfl[jl] : 0.f;
+      const ColInfo& c = H.colinfo[jl];
+      cd.a0 = c.a0; cd.a1 = c.a1; cd.b0 = c.b0; cd.b1 = c.b1; cd.baseU = c.baseU; cd.baseL = c.baseL;
+    }
+    H.coldyn[s - ts0] = cd;
+  }
+
+  // ---- tiles.  Per 16-slot chunk: first / last valid slot (SNP index and local index ascend with the slot
+  // inside a group), so a tile's extent costs a handful of look-ups.
+  const int nfc = (fs1 - fs0) / 16, ntc = (ts1 - ts0) / 16;
+  std::vector<int32_t> f_first(nfc, -1), f_last(nfc, -1), t_first(ntc, -1), t_last(ntc, -1);
+  for (int c = 0; c < nfc; c++)
+    for (int k = 0; k < 16; k++)
+      if (H.rowdyn[c * 16 + k].il >= 0) { if (f_first[c] < 0) f_first[c] = c * 16 + k; f_last[c] = c * 16 + k; }
+  for (int c = 0; c < ntc; c++)
+    for (int k = 0; k < 16; k++)
+      if (H.coldyn[c * 16 + k].jl >= 0) { if (t_first[c] < 0) t_first[c] = c * 16 + k; t_last[c] = c * 16 + k; }
+  auto extent = [](const std::vector<int32_t>& first, const std::vector<int32_t>& last, int off0, int nsl, int& lo, int& hi) {
+    lo = hi = -1;
+    for (int c = off0 / 16; c < (off0 + nsl) / 16; c++)
+      if (first[c] >= 0) { if (lo < 0) lo = first[c]; hi = last[c]; }
+  };
+  H.tiles.clear();
+  for (int pa = 1; pa <= 4; pa++) {
+    const Group& Gi = P->groups[(size_t)bf * 4 + pa - 1];
+    if (Gi.count == 0) continue;
+    for (int pb = 1; pb <= 4; pb++) {
+      const Group& Gj = P->groups[(size_t)bt * 4 + pb - 1];
+      if (Gj.count == 0) continue;
+      const int njl = mi_njlog2(pa, pb), NJ = 1 << njl;
+      for (int ti = 0; ti * 128 < Gi.count; ti++) {
+        int ilo, ihi;
+        extent(f_first, f_last, Gi.slot0 - fs0 + ti * 128, 128, ilo, ihi);
+        if (ilo < 0) continue;
+        const int il_min = H.rowdyn[ilo].il, il_max = H.rowdyn[ihi].il;
+        const double pi0 = P->pos[P->slot_snp[fs0 + ilo]], pi1 = P->pos[P->slot_snp[fs0 + ihi]];
+        for (int tj = 0; tj * NJ < Gj.count; tj++) {
+          int jlo, jhi;
+          extent(t_first, t_last, Gj.slot0 - ts0 + tj * NJ, NJ, jlo, jhi);
+          if (jlo < 0) continue;
+          const int jl_min = H.coldyn[jlo].jl, jl_max = H.coldyn[jhi].jl;
+          (void)jl_max; (void)il_min;
+          if (H.diag && !cfg.dense && il_max <= jl_min) continue;  // no pair with row > col
+          const double pj0 = P->pos[P->slot_snp[ts0 + jlo]], pj1 = P->pos[P->slot_snp[ts0 + jhi]];
+          const double gap = std::max(0.0, std::max(pi0, pj0) - std::min(pi1, pj1));
+          const double span = std::max(pi1, pj1) - std::min(pi0, pj0);
+          const bool has_sr = all_sr || gap <= sr || (g - span) <= sr;
+          if (sr_only && !has_sr) continue;
+          TileDesc td;
+          memset(&td, 0, sizeof(td));
+          td.a_row0 = Gi.row0 + ti * 128;
+          td.a_pstride = Gi.nslots;
+          td.b_row0 = Gj.row0 + tj * NJ;
+          td.b_pstride = Gj.nslots;
+          td.i_slot0 = Gi.slot0 + ti * 128;
+          td.j_slot0 = Gj.slot0 + tj * NJ;
+          td.i_dyn0 = td.i_slot0 - fs0;
+          td.j_dyn0 = td.j_slot0 - ts0;
+          td.PA = (uint8_t)pa; td.PB = (uint8_t)pb; td.njlog2 = (uint8_t)njl;
+          td.flags = has_sr ? TILE_HAS_SR : 0;
+          H.tiles.push_back(td);
+        }
+      }
+    }
+  }
+  return 0;
+}
+
+// All per-block arrays go through one pinned staging buffer per ring entry, so the copies are truly
+// asynchronous and the host can prepare the next block while the device works on this one.
+int upload_block(cudaStream_t st, BlockDev& D, const BlockHost& H) {
+  struct Part { DevBuf* d; const void* src; size_t bytes; };
+  Part parts[8] = {{&D.rowdyn, H.rowdyn.data(), H.rowdyn.size() * sizeof(RowDyn)},
+                   {&D.coldyn, H.coldyn.data(), H.coldyn.size() * sizeof(ColDyn)},
+                   {&D.colinfo, H.colinfo.data(), H.colinfo.size() * sizeof(ColInfo)},
+                   {&D.tiles, H.tiles.data(), H.tiles.size() * sizeof(TileDesc)},
+                   {&D.from_idx, H.from_idx.data(), H.from_idx.size() * 4},
+                   {&D.to_idx, H.to_idx.data(), H.to_idx.size() * 4},
+                   {&D.rfl, H.rfl.data(), H.rfl.size()},
+                   {&D.rtl, H.rtl.data(), H.rtl.size()}};
+  size_t total = 0;
+  for (auto& p : parts) total += (p.bytes + 255) & ~(size_t)255;
+  LDW_TRY(D.stage.ensure(total + 256));
+  size_t off = 0;
+  for (auto& p : parts) {
+    LDW_TRY(p.d->ensure(std::max<size_t>(p.bytes, 16)));
+    if (p.bytes) {
+      memcpy(D.stage.as<uint8_t>() + off, p.src, p.bytes);
+      LDW_CUDA(cudaMemcpyAsync(p.d->p, D.stage.as<uint8_t>() + off, p.bytes, cudaMemcpyHostToDevice, st));
+    }
+    off += (p.bytes + 255) & ~(size_t)255;
+  }
+  return 0;
+}
+
+void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& H, const ScanCfg& cfg, ScanParams& sp) {
+  memset(&sp, 0, sizeof(sp));
+  sp.tiles = D.tiles.as<TileDesc>();
+  sp.n_tiles = (int32_t)H.tiles.size();
+  sp.rec = P->d_rec.as<Rec>();
+  sp.rec_vstride = P->nslots;
+  sp.rowdyn = D.rowdyn.as<RowDyn>();
+  sp.coldyn = D.coldyn.as<ColDyn>();
+  sp.nkb = (int32_t)(P->Kpad / 128);
+  sp.nf = H.nf; sp.nt = H.nt;
+  sp.diag = H.diag; sp.ragged = H.ragged;
+  sp.qcorr = (!H.diag && !(cfg.flags & LDW_SCAN_IDEAL_Q)) ? 1 : 0;
+  sp.sr_only = (cfg.flags & LDW_SCAN_SR_ONLY) ? 1 : 0;
+  sp.rfl_arr = D.rfl.as<uint8_t>();
+  sp.rtl_arr = D.rtl.as<uint8_t>();
+  sp.kH = (float)(32768.0 / P->scale);
+  sp.kL = (float)(1.0 / P->scale);
+  sp.neffH = P->neffH; sp.neffL = P->neffL;
+  for (int a = 0; a < 4; a++)
+    for (int b = 0; b < 4; b++) {
+      double ri = a + 2, rj = b + 2;
+      double den = P->neff + 0.5 * ri * rj;
+      sp.den[a][b] = (float)den;
+      sp.ln2_over_den[a][b] = (float)(M_LN2 / den);
+      sp.q0[a][b] = (float)(0.25 * ri * rj / den);
+      sp.quarter_over_den[a][b] = (float)(0.25 / den);
+    }
+}
+
+RefineParams make_refine_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& H, const ScanCfg& cfg) {
+  RefineParams R;
+  R.codes = P->d_codes.as<uint8_t>();
+  R.S = P->S;
+  R.w = P->d_w.as<double>();
+  R.p64 = P->d_p64.as<double>();
+  R.r = P->d_r.as<uint8_t>();
+  R.mask = P->d_mask.as<uint8_t>();
+  R.from_idx = D.from_idx.as<int32_t>();
+  R.to_idx = D.to_idx.as<int32_t>();
+  R.rfl_arr = D.rfl.as<uint8_t>();
+  R.rtl_arr = D.rtl.as<uint8_t>();
+  R.nf = H.nf; R.nt = H.nt;
+  R.ideal_q = (cfg.flags & LDW_SCAN_IDEAL_Q) ? 1 : 0;
+  R.neff = P->neff;
+  return R;
+}
+
+int validate_scan(const ldw_mi_plan* P, const ScanCfg& cfg) {
+  if (!(cfg.g > 0) || cfg.g != std::floor(cfg.g) || cfg.g > 9.0e15) return set_error(LDW_ERR_ARG, "genome length g=%g must be a positive integer", cfg.g);
+  if (!(cfg.sr_dist >= 0)) return set_error(LDW_ERR_ARG, "sr_dist must be >= 0");
+  if (!P->pos_sorted) return set_error(LDW_ERR_UNSUPPORTED, "POS must be non-decreasing (the short-range slot layout relies on it)");
+  if (P->n > 0 && ((double)P->pos.back() - (double)P->pos.front()) >= cfg.g) return set_error(LDW_ERR_UNSUPPORTED, "POS span must be smaller than the genome length g");
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================== C ABI
+extern "C" {
+
+int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, const double* hdw,
+                       const int32_t* pos, const int32_t* paint, int64_t blk, ldw_mi_plan** out) {
+  LDW_TRY(ctx_bind(ctx));
+  if (!out) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: null out");
+  *out = nullptr;
+  if (!codes || !hdw || !pos || !paint) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: null argument");
+  if (n_snp < 2 || nseq < 1) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: need at least 2 SNPs and 1 sequence");
+  if (nseq > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: nseq > 65535 not supported by the 15-bit digit accumulation");
+  if (blk < 128 || blk > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: block size %lld outside [128, 65535]", (long long)blk);
+  for (int64_t i = 0; i < n_snp * nseq; i++)
+    if (codes[i] > 4) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: codes[%lld] = %d outside 0..4", (long long)i, (int)codes[i]);
+  ldw_mi_plan* P = new ldw_mi_plan();
+  P->ctx = ctx;
+  P->n = n_snp; P->S = nseq; P->blk = blk;
+  int rc = build_plan(P, codes, hdw, pos, paint);
+  if (rc != 0) { delete P; return rc; }
+  *out = P;
+  return 0;
+}
+
+void ldw_mi_plan_destroy(ldw_mi_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->ctx->device);
+  delete plan;
+}
+
+int ldw_mi_block_dense(ldw_mi_plan* P, int64_t block_index, double* mi_out, int64_t* nf_out, int64_t* nt_out) {
+  if (!P) return set_error(LDW_ERR_ARG, "null plan");
+  LDW_TRY(ctx_bind(P->ctx));
+  cudaStream_t st = P->ctx->stream;
+  // block_index -> (bf, bt) in make_blocks order
+  int bf = 0, bt = 0;
+  {
+    int64_t k = block_index;
+    bool found = false;
+    for (int i = 0; i < P->nranges && !found; i++)
+      for (int j = i; j < P->nranges; j++) {
+        if (k == 0) { bf = i; bt = j; found = true; break; }
+        k--;
+      }
+    if (!found) return set_error(LDW_ERR_ARG, "block index out of range");
+  }
+  ScanCfg cfg{1e15, 0.0, 0, 0, 0};
+  cfg.dense = 1;
+  BlockHost& H = P->hring[0];
+  BlockDev& D = P->ring[0];
+  int e = prepare_block(P, bf, bt, cfg, H);
+  if (e > 1) return e;
+  if (nf_out) *nf_out = H.nf;
+  if (nt_out) *nt_out = H.nt;
+  if (!mi_out) return 0;
+  LDW_TRY(upload_block(st, D, H));
+  size_t cells = (size_t)H.nf * H.nt;
+  LDW_TRY(P->d_dense.ensure(cells * 4));
+  LDW_CUDA(cudaMemsetAsync(P->d_dense.p, 0, cells * 4, st));
+  ScanParams sp;
+  fill_scan_params(P, D, H, cfg, sp);
+  sp.dense = 1;
+  sp.dense_out = P->d_dense.as<float>();
+  int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
+  if (grid > 0) {
+    mi_scan_kernel<<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
+    LDW_CUDA(cudaGetLastError());
+  }
+  DevBuf d64;
+  LDW_TRY(d64.alloc(cells * 8));
+  f32_to_f64_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(P->d_dense.as<float>(), (int64_t)cells, d64.as<double>());
+  LDW_CUDA(cudaMemcpyAsync(mi_out, d64.p, cells * 8, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int ldw_mi_pairs_exact(ldw_mi_plan* P, int64_t block_index, const int32_t* from_local, const int32_t* to_local,
+                       int64_t n_pairs, double* mi_out) {
+  if (!P) return set_error(LDW_ERR_ARG, "null plan");
+  LDW_TRY(ctx_bind(P->ctx));
+  cudaStream_t st = P->ctx->stream;
+  int bf = 0, bt = 0;
+  {
+    int64_t k = block_index;
+    bool found = false;
+    for (int i = 0; i < P->nranges && !found; i++)
+      for (int j = i; j < P->nranges; j++) {
+        if (k == 0) { bf = i; bt = j; found = true; break; }
+        k--;
+      }
+    if (!found) return set_error(LDW_ERR_ARG, "block index out of range");
+  }
+  if (n_pairs <= 0) return 0;
+  ScanCfg cfg{1e15, 0.0, 0, 0, 0};
+  BlockHost& H = P->hring[0];
+  BlockDev& D = P->ring[0];
+  int e = prepare_block(P, bf, bt, cfg, H);
+  if (e != 0) return e == 1 ? set_error(LDW_ERR_ARG, "empty block") : e;
+  for (int64_t k = 0; k < n_pairs; k++)
+    if (from_local[k] < 0 || from_local[k] >= H.nf || to_local[k] < 0 || to_local[k] >= H.nt)
+      return set_error(LDW_ERR_ARG, "pair %lld outside the block", (long long)k);
+  LDW_TRY(upload_block(st, D, H));
+  DevBuf di, dj, dout;
+  LDW_TRY(di.alloc((size_t)n_pairs * 4));
+  LDW_TRY(dj.alloc((size_t)n_pairs * 4));
+  LDW_TRY(dout.alloc((size_t)n_pairs * 8));
+  LDW_CUDA(cudaMemcpyAsync(di.p, from_local, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+  LDW_CUDA(cudaMemcpyAsync(dj.p, to_local, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
+  RefineParams R = make_refine_params(P, D, H, cfg);
+  int grid = (int)std::min<int64_t>((n_pairs + 7) / 8, 148 * 8);
+  mi_refine_pairs_kernel<<<grid, 256, 0, st>>>(R, di.as<int32_t>(), dj.as<int32_t>(), n_pairs, dout.as<double>());
+  LDW_CUDA(cudaGetLastError());
+  LDW_CUDA(cudaMemcpyAsync(mi_out, dout.p, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links, double lr_links_approx, int flags,
+                int n_parts, int part, ldw_links* sr_out, ldw_links* lr_out, ldw_links* borderline_out, double* thr_out,
+                double* prob_out, ldw_scan_stats* stats_out) {
+  if (!P) return set_error(LDW_ERR_ARG, "null plan");
+  LDW_TRY(ctx_bind(P->ctx));
+  cudaStream_t st = P->ctx->stream;
+  ScanCfg cfg{g, sr_dist, lr_retain_links, lr_links_approx, flags};
+  LDW_TRY(validate_scan(P, cfg));
+  const bool sr_only = (flags & LDW_SCAN_SR_ONLY) != 0;
+  if (!sr_only && !(lr_links_approx > 0)) return set_error(LDW_ERR_ARG, "lr_links_approx must be > 0");
+  if (n_parts < 1 || part < 0 || part >= n_parts) return set_error(LDW_ERR_ARG, "bad partition %d of %d", part, n_parts);
+
+  // ---- block list (make_blocks order), this part's share
+  struct Blk { int bf, bt; int64_t index; };
+  std::vector<Blk> blocks;
+  {
+    int64_t idx = 0;
+    for (int i = 0; i < P->nranges; i++)
+      for (int j = i; j < P->nranges; j++, idx++)
+        if (idx % n_parts == part) blocks.push_back({i, j, idx});
+  }
+  const int64_t nblk_total = (int64_t)P->nranges * (P->nranges + 1) / 2;
+  if (thr_out) for (int64_t b = 0; b < nblk_total; b++) thr_out[b] = NAN;
+  if (prob_out) for (int64_t b = 0; b < nblk_total; b++) prob_out[b] = NAN;
+
+  cudaEvent_t ev0, ev1, ev2, ev3;
+  LDW_CUDA(cudaEventCreate(&ev0)); LDW_CUDA(cudaEventCreate(&ev1)); LDW_CUDA(cudaEventCreate(&ev2)); LDW_CUDA(cudaEventCreate(&ev3));
+
+  // ---- pass 1 (host): per-block sizes -> output offsets and long-range selection ranks
+  struct Sel { int64_t n_lr = 0, n_sr = 0, n_pairs = 0; double prob = NAN; uint64_t k_lo = 0, k_hi = 0; double h = 0; int interp = 0;
+               int emit_all = 0; uint32_t kprime = 0, delta = 1, cap = 0; int64_t sr_base = 0; int skip = 0; };
+  std::vector<Sel> sel(blocks.size());
+  int64_t total_sr = 0, total_pairs = 0, total_lr = 0;
+  uint64_t max_cap = 1, sum_keep = 0;
+  {
+    BlockHost tmp;
+    for (size_t b = 0; b < blocks.size(); b++) {
+      int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, tmp, true);
+      if (e > 1) return e;
+      Sel& s = sel[b];
+      s.skip = (e == 1);
+      s.n_lr = tmp.n_lr; s.n_sr = tmp.n_sr; s.n_pairs = tmp.n_pairs;
+      s.sr_base = total_sr;
+      total_sr += tmp.n_sr; total_pairs += tmp.n_pairs; total_lr += tmp.n_lr;
+      if (!sr_only && tmp.n_lr > 0) {
+        const double m = (double)tmp.n_lr;
+        double prob = 1 - ((lr_retain_links * (m / lr_links_approx)) / m);  // R/computePairwiseMI.R:352
+        if (prob < 0) prob = 0;
+        s.prob = prob;
+        double index = 1 + (m - 1 > 0 ? m - 1 : 0) * prob;  // stats::quantile type 7
+        double lo = std::floor(index), hi = std::ceil(index);
+        s.k_lo = (uint64_t)(tmp.n_lr - (int64_t)lo + 1);
+        s.k_hi = (uint64_t)(tmp.n_lr - (int64_t)hi + 1);
+        s.h = index - lo;
+        s.interp = index > lo;
+        uint64_t K = s.k_lo;
+        if (2 * K + 65536 >= (uint64_t)tmp.n_lr) {
+          s.emit_all = 1;
+          if ((uint64_t)tmp.n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block keeps more than 2^32 long-range links");
+          s.cap = (uint32_t)tmp.n_lr;
+          s.kprime = (uint32_t)std::min<uint64_t>(K, 0xFFFFFFFFull);
+        } else {
+          uint64_t kp = K + std::max<uint64_t>(1024, K / 8);
+          uint64_t delta = std::max<uint64_t>(2 * kp, 32768);
+          uint64_t cap = std::min<uint64_t>((uint64_t)tmp.n_lr, 16 * kp + 2 * delta + 65536);
+          if (cap > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "long-range candidate buffer exceeds 2^32 entries");
+          s.kprime = (uint32_t)kp; s.delta = (uint32_t)delta; s.cap = (uint32_t)cap;
+        }
+        max_cap = std::max<uint64_t>(max_cap, s.cap);
+        sum_keep += K;
+      }
+    }
+  }
+  const uint64_t kept_cap = 2 * sum_keep + (1u << 20);
+
+  // ---- device workspace
+  LDW_TRY(P->d_cand.ensure(max_cap * sizeof(Cand)));
+  LDW_TRY(P->d_mi64.ensure(max_cap * 8));
+  LDW_TRY(P->d_state.ensure(64));
+  LDW_TRY(P->d_hist.ensure(MI_HIST_BINS * 4));
+  LDW_TRY(P->d_results.ensure(std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult)));
+  LDW_TRY(P->d_sr_f32.ensure((size_t)std::max<int64_t>(total_sr, 1) * 4));
+  LDW_TRY(P->d_kept_key.ensure(kept_cap * 8));
+  LDW_TRY(P->d_kept_gi.ensure(kept_cap * 4));
+  LDW_TRY(P->d_kept_gj.ensure(kept_cap * 4));
+  LDW_TRY(P->d_kept_mi.ensure(kept_cap * 8));
+  LDW_TRY(P->d_kept_count.ensure(16));
+  LDW_TRY(P->d_sr.ensure(total_sr));
+  LDW_CUDA(cudaMemsetAsync(P->d_kept_count.p, 0, 16, st));
+  LDW_CUDA(cudaMemsetAsync(P->d_results.p, 0, std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult), st));
+  uint32_t* d_count = P->d_state.as<uint32_t>();
+  uint32_t* d_tcand = d_count + 1;
+  uint32_t* d_overflow = d_count + 2;
+  uint32_t* d_kept_overflow = d_count + 3;
+  LDW_CUDA(cudaMemsetAsync(P->d_state.p, 0, 64, st));
+
+  LDW_CUDA(cudaEventRecord(ev0, st));
+  int64_t n_reruns = 0;
+  auto run_block = [&](size_t b, int force_emit_all, uint32_t cap_override) -> int {
+    Sel& s = sel[b];
+    if (s.skip) return 0;
+    int slot = (int)(b % ldw_mi_plan::RING);
+    BlockDev& D = P->ring[slot];
+    BlockHost& H = P->hring[slot];
+    if (D.used) LDW_CUDA(cudaEventSynchronize(D.done));  // host staging + device arrays of this ring entry are free again
+    int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, H);
+    if (e > 1) return e;
+    LDW_TRY(upload_block(st, D, H));
+    D.used = true;
+    ScanParams sp;
+    fill_scan_params(P, D, H, cfg, sp);
+    sp.sr_out = P->d_sr_f32.as<float>() + s.sr_base;
+    const bool lr = !sr_only && s.n_lr > 0;
+    const int emit_all = force_emit_all || s.emit_all;
+    uint32_t cap = cap_override ? cap_override : s.cap;
+    if (lr) {
+      LDW_CUDA(cudaMemsetAsync(P->d_state.p, 0, 12, st));  // count, tcand, overflow
+      LDW_CUDA(cudaMemsetAsync(P->d_hist.p, 0, MI_HIST_BINS * 4, st));
+      sp.cand = P->d_cand.as<Cand>();
+      sp.cand_cap = cap;
+      sp.cand_count = d_count;
+      sp.tcand_bits = d_tcand;
+      sp.hist = P->d_hist.as<uint32_t>();
+      sp.kprime = s.kprime;
+      sp.delta = s.delta ? s.delta : 1;
+      sp.overflow = d_overflow;
+      sp.emit_all = emit_all;
+    } else {
+      sp.sr_only = 1;  // nothing long-range to collect in this block
+    }
+    int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
+    if (grid > 0) {
+      mi_scan_kernel<<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
+      LDW_CUDA(cudaGetLastError());
+    }
+    if (lr) {
+      RefineParams R = make_refine_params(P, D, H, cfg);
+      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 256, 0, st>>>(R, P->d_cand.as<Cand>(), d_count, cap, P->d_mi64.as<double>());
+      LDW_CUDA(cudaGetLastError());
+      SelectParams q;
+      memset(&q, 0, sizeof(q));
+      q.cand = P->d_cand.as<Cand>(); q.mi64 = P->d_mi64.as<double>(); q.count = d_count; q.cap = cap;
+      q.overflow = d_overflow; q.tcand_bits = d_tcand; q.emit_all = emit_all;
+      q.k_lo = s.k_lo; q.k_hi = s.k_hi; q.h = s.h; q.interpolate = s.interp;
+      q.tol_safe = 4e-6; q.tol_border = 1e-9;
+      q.from_idx = D.from_idx.as<int32_t>(); q.to_idx = D.to_idx.as<int32_t>();
+      q.nf = H.nf; q.nt = H.nt; q.diag = H.diag; q.block = (int32_t)blocks[b].index;
+      q.kept_key = P->d_kept_key.as<uint64_t>(); q.kept_gi = P->d_kept_gi.as<int32_t>(); q.kept_gj = P->d_kept_gj.as<int32_t>();
+      q.kept_mi = P->d_kept_mi.as<double>(); q.kept_count = P->d_kept_count.as<unsigned long long>(); q.kept_cap = kept_cap;
+      q.kept_overflow = d_kept_overflow;
+      q.result = P->d_results.as<BlockResult>() + b;
+      mi_select_kernel<<<1, 1024, 0, st>>>(q);
+      LDW_CUDA(cudaGetLastError());
+    }
+    if (s.n_sr > 0 && !(flags & LDW_SCAN_NO_LINKS)) {
+      SrMatParams m;
+      m.col = D.colinfo.as<ColInfo>(); m.from_idx = D.from_idx.as<int32_t>(); m.to_idx = D.to_idx.as<int32_t>();
+      m.pos = P->d_pos.as<int32_t>(); m.paint = P->d_paint.as<int32_t>();
+      m.sr_mi = P->d_sr_f32.as<float>() + s.sr_base;
+      m.nf = H.nf; m.nt = H.nt; m.diag = H.diag; m.block = (int32_t)blocks[b].index; m.g = (int64_t)g;
+      m.o_pos1 = P->d_sr.pos1.as<int32_t>() + s.sr_base; m.o_pos2 = P->d_sr.pos2.as<int32_t>() + s.sr_base;
+      m.o_c1 = P->d_sr.c1.as<int32_t>() + s.sr_base; m.o_c2 = P->d_sr.c2.as<int32_t>() + s.sr_base;
+      m.o_len = P->d_sr.len.as<int32_t>() + s.sr_base; m.o_blk = P->d_sr.blk.as<int32_t>() + s.sr_base;
+      m.o_mi = P->d_sr.mi.as<double>() + s.sr_base;
+      mi_sr_materialize_kernel<<<H.nt, 128, 0, st>>>(m);
+      LDW_CUDA(cudaGetLastError());
+    }
+    LDW_CUDA(cudaEventRecord(D.done, st));
+    return 0;
+  };
+  for (size_t b = 0; b < blocks.size(); b++) LDW_TRY(run_block(b, 0, 0));
+  LDW_CUDA(cudaEventRecord(ev1, st));
+
+  // ---- verify the long-range selection of every block; re-run the (rare) blocks whose candidate set is not
+  //      provably complete with a plain "collect everything" pass
+  P->results.assign(blocks.size(), BlockResult());
+  if (!blocks.empty())
+    LDW_CUDA(cudaMemcpyAsync(P->results.data(), P->d_results.p, blocks.size() * sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaStreamSynchronize(st));
+  if (!sr_only) {
+    for (size_t b = 0; b < blocks.size(); b++) {
+      if (sel[b].skip || sel[b].n_lr == 0) continue;
+      if (P->results[b].bad) {
+        n_reruns++;
+        if ((uint64_t)sel[b].n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block %lld needs an exhaustive long-range pass over more than 2^32 links", (long long)blocks[b].index);
+        uint32_t cap = (uint32_t)sel[b].n_lr;
+        LDW_TRY(P->d_cand.ensure((size_t)cap * sizeof(Cand)));
+        LDW_TRY(P->d_mi64.ensure((size_t)cap * 8));
+        LDW_TRY(run_block(b, 1, cap));
+        LDW_CUDA(cudaMemcpyAsync(&P->results[b], P->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
+        LDW_CUDA(cudaStreamSynchronize(st));
+        if (P->results[b].bad) return set_error(LDW_ERR_INTERNAL, "long-range selection failed for block %lld (flags %u)", (long long)blocks[b].index, P->results[b].bad);
+      }
+    }
+  }
+  unsigned long long n_kept = 0;
+  uint32_t state[4];
+  LDW_CUDA(cudaMemcpyAsync(&n_kept, P->d_kept_count.p, 8, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaMemcpyAsync(state, P->d_state.p, 16, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaStreamSynchronize(st));
+  if (state[3] || n_kept > kept_cap) return set_error(LDW_ERR_UNSUPPORTED, "more long-range links pass their block thresholds (%llu) than the output buffer holds (%llu): massive ties at the threshold", n_kept, (unsigned long long)kept_cap);
+
+  // ---- long-range rows into reference order (block, then row order inside the block)
+  int64_t n_border = 0;
+  for (auto& r : P->results) n_border += r.n_border;
+  if (n_kept > 0 && !(flags & LDW_SCAN_NO_LINKS)) {
+    LDW_TRY(P->d_keys_sorted.ensure(n_kept * 8));
+    LDW_TRY(P->d_order_in.ensure(n_kept * 4));
+    LDW_TRY(P->d_order_out.ensure(n_kept * 4));
+    iota_u32_kernel<<<(unsigned)((n_kept + 255) / 256), 256, 0, st>>>(P->d_order_in.as<uint32_t>(), (int64_t)n_kept);
+    size_t tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, P->d_kept_key.as<uint64_t>(), P->d_keys_sorted.as<uint64_t>(),
+                                    P->d_order_in.as<uint32_t>(), P->d_order_out.as<uint32_t>(), (int)n_kept, 0, 64, st);
+    LDW_TRY(P->d_sort_tmp.ensure(tmp_bytes));
+    LDW_CUDA(cub::DeviceRadixSort::SortPairs(P->d_sort_tmp.p, tmp_bytes, P->d_kept_key.as<uint64_t>(), P->d_keys_sorted.as<uint64_t>(),
+                                             P->d_order_in.as<uint32_t>(), P->d_order_out.as<uint32_t>(), (int)n_kept, 0, 64, st));
+    LDW_TRY(P->d_lr.ensure((int64_t)n_kept));
+    mi_lr_materialize_kernel<<<(unsigned)((n_kept + 255) / 256), 256, 0, st>>>(
+        P->d_order_out.as<uint32_t>(), P->d_keys_sorted.as<uint64_t>(), P->d_kept_gi.as<int32_t>(), P->d_kept_gj.as<int32_t>(),
+        P->d_kept_mi.as<double>(), P->d_pos.as<int32_t>(), P->d_paint.as<int32_t>(), (int64_t)n_kept, (int64_t)g,
+        P->d_lr.pos1.as<int32_t>(), P->d_lr.pos2.as<int32_t>(), P->d_lr.c1.as<int32_t>(), P->d_lr.c2.as<int32_t>(),
+        P->d_lr.len.as<int32_t>(), P->d_lr.mi.as<double>(), P->d_lr.blk.as<int32_t>());
+    LDW_CUDA(cudaGetLastError());
+  }
+  LDW_CUDA(cudaEventRecord(ev2, st));
+
+  // ---- device -> pinned host
+  P->h_sr.n = 0; P->h_lr.n = 0; P->h_border.n = 0;
+  if (!(flags & LDW_SCAN_NO_LINKS)) {
+    auto d2h = [&](HostLinks& h, DevLinks& d, int64_t m) -> int {
+      LDW_TRY(h.ensure(m));
+      h.n = m;
+      if (m == 0) return 0;
+      LDW_CUDA(cudaMemcpyAsync(h.pos1.p, d.pos1.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(h.pos2.p, d.pos2.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(h.c1.p, d.c1.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(h.c2.p, d.c2.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(h.len.p, d.len.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(h.blk.p, d.blk.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(h.mi.p, d.mi.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+      return 0;
+    };
+    LDW_TRY(d2h(P->h_sr, P->d_sr, total_sr));
+    LDW_TRY(d2h(P->h_lr, P->d_lr, (int64_t)n_kept));
+  }
+  LDW_CUDA(cudaEventRecord(ev3, st));
+  LDW_CUDA(cudaStreamSynchronize(st));
+
+  // borderline list: kept-or-not candidates within tol of their block threshold are reported by count per block;
+  // the explicit rows are the LR rows whose MI is within tol of the block threshold
+  if (borderline_out) {
+    std::vector<int64_t> idx;
+    const int32_t* blkcol = P->h_lr.blk.as<int32_t>();
+    const double* micol = P->h_lr.mi.as<double>();
+    std::vector<double> thr_by_index(nblk_total, NAN);
+    for (size_t b = 0; b < blocks.size(); b++)
+      if (!sel[b].skip && sel[b].n_lr > 0 && !sr_only) thr_by_index[blocks[b].index] = P->results[b].thr;
+    for (int64_t i = 0; i < P->h_lr.n; i++)
+      if (std::fabs(micol[i] - thr_by_index[blkcol[i]]) <= 1e-9) idx.push_back(i);
+    LDW_TRY(P->h_border.ensure((int64_t)idx.size()));
+    P->h_border.n = (int64_t)idx.size();
+    for (size_t k = 0; k < idx.size(); k++) {
+      int64_t i = idx[k];
+      P->h_border.pos1.as<int32_t>()[k] = P->h_lr.pos1.as<int32_t>()[i];
+      P->h_border.pos2.as<int32_t>()[k] = P->h_lr.pos2.as<int32_t>()[i];
+      P->h_border.c1.as<int32_t>()[k] = P->h_lr.c1.as<int32_t>()[i];
+      P->h_border.c2.as<int32_t>()[k] = P->h_lr.c2.as<int32_t>()[i];
+      P->h_border.len.as<int32_t>()[k] = P->h_lr.len.as<int32_t>()[i];
+      P->h_border.blk.as<int32_t>()[k] = blkcol[i];
+      P->h_border.mi.as<double>()[k] = micol[i];
+    }
+    P->h_border.fill(borderline_out);
+  }
+  P->h_sr.fill(sr_out);
+  P->h_lr.fill(lr_out);
+  for (size_t b = 0; b < blocks.size(); b++) {
+    if (sel[b].skip || sel[b].n_lr == 0 || sr_only) continue;
+    if (thr_out) thr_out[blocks[b].index] = P->results[b].thr;
+    if (prob_out) prob_out[blocks[b].index] = sel[b].prob;
+  }
+  if (stats_out) {
+    memset(stats_out, 0, sizeof(*stats_out));
+    stats_out->n_blocks = (int64_t)blocks.size();
+    stats_out->n_pairs = total_pairs;
+    stats_out->n_sr = total_sr;
+    stats_out->n_lr_total = sr_only ? 0 : total_lr;
+    stats_out->n_lr_kept = (int64_t)n_kept;
+    stats_out->n_borderline = n_border;
+    stats_out->n_reruns = n_reruns;
+    float a = 0, b = 0, c = 0;
+    cudaEventElapsedTime(&a, ev0, ev1);
+    cudaEventElapsedTime(&b, ev1, ev2);
+    cudaEventElapsedTime(&c, ev2, ev3);
+    stats_out->t_pack_ms = P->t_pack_ms;
+    stats_out->t_scan_ms = a;
+    stats_out->t_select_ms = b;
+    stats_out->t_d2h_ms = c;
+  }
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Data layout shared by the host driver and the kernels of the weighted pairwise-MI scan (see mi_scan.cu).
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace ldw {
+
+// One record per (slot, variant): everything the epilogue needs to know about one SNP.
+//   PH/PL : fixed-point weighted marginals of the SNP's allele slots q = 0..r-1 (15-bit hi / lo digits of the
+//           30-bit weights), 0 for q >= r.  The last observed allele (slot r-1) is the "complement" slot whose
+//           joint counts are derived by subtraction instead of from the GEMM.
+//   rp    : 1/(p_q + 0.5 r') for r' = variant+2 (r of the partner SNP).
+struct __align__(16) Rec {
+  int32_t PH[5];
+  int32_t PL[5];
+  float rp[5];
+  int32_t pad;
+};
+static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
+
+// Per-block, per from-slot: local row index (or -1) and r of the TO-list SNP that sits at that local index
+// (quirk Q1: the reference reads the transposed rft by linear index).
+struct RowDyn {
+  int32_t il;
+  float rtl;
+};
+
+// Per-block, per to-slot: local column index (or -1), r of the FROM-list SNP at that local index (Q1), the
+// column's short-range row intervals [a0,a1) u [b0,b1) in local-row space and the column's output bases.
+struct __align__(16) ColDyn {
+  int32_t jl;
+  float rfl;
+  int32_t a0, a1, b0, b1;
+  uint32_t baseU, baseL;
+};
+static_assert(sizeof(ColDyn) == 32, "ColDyn must be 32 bytes");
+
+enum : uint32_t { TILE_HAS_SR = 1u };
+
+// One unit of work: 128 row SNPs (PA planes each) x NJ column SNPs (PB planes each).
+struct __align__(16) TileDesc {
+  int32_t a_row0, a_pstride;  // operand row of plane 0 of the row tile; rows between planes
+  int32_t b_row0, b_pstride;
+  int32_t i_slot0, j_slot0;   // global slot ids (index into Rec)
+  int32_t i_dyn0, j_dyn0;     // offsets into RowDyn / ColDyn
+  uint8_t PA, PB, njlog2, flags;
+  int32_t pad[3];
+};
+static_assert(sizeof(TileDesc) == 48, "TileDesc must be 48 bytes");
+
+struct Cand {
+  int32_t il, jl;
+  float mi;
+};
+
+constexpr int MI_HIST_BINS = 4096;  // positive-float bits >> 19
+
+struct ScanParams {
+  const TileDesc* tiles;
+  int32_t n_tiles;
+  const Rec* rec;
+  int64_t rec_vstride;
+  const RowDyn* rowdyn;
+  const ColDyn* coldyn;
+  int32_t nkb;  // K blocks of 128 sequences
+  int32_t nf, nt;
+  int32_t diag, ragged, qcorr, sr_only, dense, emit_all;
+  const uint8_t* rfl_arr;  // r of from-list by local index (ragged Q1 path)
+  const uint8_t* rtl_arr;  // r of to-list by local index
+  float kH, kL;
+  int32_t neffH, neffL;
+  float den[4][4];          // neff + 0.5 r_i r_j
+  float ln2_over_den[4][4];
+  float q0[4][4];           // 0.25 r_i r_j / den
+  float quarter_over_den[4][4];
+  float* sr_out;            // this block's SR slots
+  float* dense_out;         // debug: nf x nt, column-major
+  Cand* cand;
+  uint32_t cand_cap;
+  uint32_t* cand_count;
+  uint32_t* tcand_bits;
+  uint32_t* hist;
+  uint32_t kprime, delta;
+  uint32_t* overflow;
+};
+
+struct TmapSet {
+  CUtensorMap a[2];      // X1, X128  (box 128 rows)
+  CUtensorMap b[4][4];   // [digit array D3,D2,D1,D0][box rows 128,64,32,16]
+};
+
+}  // namespace ldw

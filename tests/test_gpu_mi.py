@@ -1,0 +1,184 @@
+"""GPU parity tests (through the C ABI): weighted pairwise-MI scan vs the oracle and the golden fixture."""
+import numpy as np
+import pytest
+
+from util import compare_lr_sets
+
+pytestmark = pytest.mark.gpu
+
+MI_TOL = 1e-6  # north star: MI within 1e-6 absolute of the reference double-precision result
+
+
+def _snp(fixture_snp, g=50000):
+    import ldweaver_b200 as ldw
+    return ldw.snp_dat_from_codes(fixture_snp.codes, fixture_snp.POS, g)
+
+
+def test_dense_block_mi_single_block(fixture_snp, fixture_expected):
+    """fp32 tensor-core path, one diagonal block (the whole fixture): every cell within 1e-6."""
+    import c_oracle as CO
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    snp = _snp(fixture_snp)
+    plan = ldw.MIPlan(snp, e["hdw"], e["paint"], 10000)
+    MI = plan.block_dense(0)
+    idx = np.arange(snp.nsnp)
+    ref = CO.block_mi(fixture_snp.codes, e["hdw"], fixture_snp.r, fixture_snp.uqe, idx, idx)
+    err = np.abs(MI - ref)
+    print("max abs err (diag block, fp32 path):", err.max())
+    assert err.max() < MI_TOL
+    plan.close()
+
+
+def test_dense_block_mi_offdiag_and_ragged(fixture_snp, fixture_expected):
+    """Quirk Q1 on a square off-diagonal block (blk=500 -> blocks of 500,500,268) and on ragged ones."""
+    import c_oracle as CO
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    snp = _snp(fixture_snp)
+    plan = ldw.MIPlan(snp, e["hdw"], e["paint"], 500)
+    blocks = O.make_blocks(snp.nsnp, 500)
+    worst = 0.0
+    for bi, (fs, fe, ts, te) in enumerate(blocks):
+        f, t = np.arange(fs - 1, fe), np.arange(ts - 1, te)
+        ref = CO.block_mi(fixture_snp.codes, e["hdw"], fixture_snp.r, fixture_snp.uqe, f, t)
+        MI = plan.block_dense(bi)
+        assert MI.shape == ref.shape
+        err = np.abs(MI - ref).max()
+        worst = max(worst, err)
+        assert err < MI_TOL, f"block {bi} ({fs}-{fe} x {ts}-{te}): {err}"
+    print("max abs err over blocks:", worst)
+    plan.close()
+
+
+def test_exact_pairs_fp64(fixture_snp, fixture_expected):
+    import c_oracle as CO
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    snp = _snp(fixture_snp)
+    plan = ldw.MIPlan(snp, e["hdw"], e["paint"], 1000)
+    rng = np.random.default_rng(3)
+    for bi, (fs, fe, ts, te) in enumerate(O.make_blocks(snp.nsnp, 1000)):
+        f, t = np.arange(fs - 1, fe), np.arange(ts - 1, te)
+        ref = CO.block_mi(fixture_snp.codes, e["hdw"], fixture_snp.r, fixture_snp.uqe, f, t)
+        il = rng.integers(0, len(f), 4000)
+        jl = rng.integers(0, len(t), 4000)
+        got = plan.pairs_exact(bi, il, jl)
+        assert np.abs(got - ref[il, jl]).max() < 1e-12
+    plan.close()
+
+
+@pytest.mark.parametrize("tag,g,blk,retain", [("g50k_b10000", 50000, 10000, 1e4), ("g50k_b1000", 50000, 1000, 1e4),
+                                               ("g2M_b1000", 2221315, 1000, 2e4)])
+def test_scan_vs_golden(fixture_snp, fixture_expected, tag, g, blk, retain):
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    snp = _snp(fixture_snp, g)
+    cds = ldw.CdsVar(paint=e["paint"], nclust=3)
+    res = ldw.perform_MI_computation(snp, e["hdw"], cds, ncores=1, sr_dist=20000, lr_retain_links=retain, max_blk_sz=blk,
+                                     lr_links_approx=1e5, write_tsv=False)
+    # ---- short-range rows: identical set, identical (reference) order, MI within tolerance
+    assert len(res.sr["MI"]) == int(e[f"{tag}_sr_n"])
+    np.testing.assert_array_equal(res.sr["pos1"], e[f"{tag}_sr_pos1"])
+    np.testing.assert_array_equal(res.sr["pos2"], e[f"{tag}_sr_pos2"])
+    assert np.abs(res.sr["MI"][::16] - e[f"{tag}_sr_MI_16"]).max() < MI_TOL
+    if f"{tag}_sr_MI" in e:
+        assert np.abs(res.sr["MI"] - e[f"{tag}_sr_MI"]).max() < MI_TOL
+    posmap = {int(p): i for i, p in enumerate(snp.POS)}
+    ln = 0.5 * g - np.abs(np.mod(res.sr["pos1"].astype(float) - res.sr["pos2"], g) - 0.5 * g)
+    np.testing.assert_array_equal(res.sr["len"], ln.astype(np.int64))
+    # ---- thresholds (exact type-7 quantile on fp64-refined values) and long-range rows
+    thr_ref = e[f"{tag}_thr"]
+    assert np.array_equal(np.isnan(res.thr), np.isnan(thr_ref))
+    ok = ~np.isnan(thr_ref)
+    assert np.abs(res.thr[ok] - thr_ref[ok]).max() < 1e-12
+    assert np.abs(res.prob[ok] - e[f"{tag}_prob"][ok]).max() == 0
+    g_p1, g_p2, g_mi = e[f"{tag}_lr_pos1"], e[f"{tag}_lr_pos2"], e[f"{tag}_lr_MI"]
+    nb = 0
+    blocks = O.make_blocks(snp.nsnp, O.r_round_to_thousands(blk))
+    POS = snp.POS.astype(np.float64)
+    for bi, (fs, fe, ts, te) in enumerate(blocks):
+        if np.isnan(thr_ref[bi]):
+            continue
+        f, t = np.arange(fs - 1, fe), np.arange(ts - 1, te)
+        in_blk = np.isin(g_p2, POS[f]) & np.isin(g_p1, POS[t])
+        if fs != ts:
+            in_blk &= (g_p2 < POS[t[0]]) & (g_p1 > POS[f[-1]])
+        else:
+            in_blk &= (g_p1 <= POS[f[-1]]) & (g_p2 <= POS[f[-1]]) & (g_p1 >= POS[f[0]]) & (g_p2 >= POS[f[0]])
+        k = res.lr["block"] == bi
+        _, a, b = compare_lr_sets(g_p1[in_blk], g_p2[in_blk], g_mi[in_blk], res.lr["pos1"][k], res.lr["pos2"][k],
+                                  res.lr["MI"][k], thr_ref[bi])
+        nb += len(a) + len(b)
+    print(tag, "LR kept", len(res.lr["MI"]), "golden", len(g_mi), "borderline differences", nb, "stats", res.stats)
+    assert nb < 0.02 * max(1, len(g_mi))
+    # long-range rows come out in reference order (block, then row order inside the block)
+    assert np.all(np.diff(res.lr["block"]) >= 0)
+    # cluster routing (R/computePairwiseMI.R:372-376)
+    for c in range(3):
+        m = (res.sr["clust1"] == c + 1) | (res.sr["clust2"] == c + 1)
+        np.testing.assert_array_equal(np.nonzero(m)[0], res.sr_links[c])
+
+
+def test_scan_lr_order_matches_reference(fixture_snp, fixture_expected):
+    """Order of the retained LR rows inside each block equals the reference's row order (non-borderline rows)."""
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    tag = "g50k_b1000"
+    snp = _snp(fixture_snp, 50000)
+    res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), lr_retain_links=1e4, max_blk_sz=1000,
+                                     lr_links_approx=1e5, write_tsv=False)
+    got = list(zip(res.lr["pos1"].tolist(), res.lr["pos2"].tolist()))
+    ref = list(zip(e[f"{tag}_lr_pos1"].astype(int).tolist(), e[f"{tag}_lr_pos2"].astype(int).tolist()))
+    common = set(got) & set(ref)
+    assert [x for x in got if x in common] == [x for x in ref if x in common]
+
+
+def test_sr_only_mode_vs_oracle(fixture_snp, fixture_expected):
+    """Q12: SR-only mode drops far SNPs first (local indices change, so Q1/Q2 act on the reduced lists)."""
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    g = 2221315
+    osnp = O.snp_dat_from_codes(fixture_snp.codes, fixture_snp.POS, g)
+    ref = O.perform_MI_scan(osnp, e["hdw"], e["paint"], 3, max_blk_sz=1000, perform_SR_analysis_only=True, sr_dist=2000)
+    snp = _snp(fixture_snp, g)
+    res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), sr_dist=2000, max_blk_sz=1000,
+                                     perform_SR_analysis_only=True, write_tsv=False)
+    assert len(res.lr["MI"]) == 0
+    np.testing.assert_array_equal(res.sr["pos1"], ref.sr["pos1"].astype(np.int32))
+    np.testing.assert_array_equal(res.sr["pos2"], ref.sr["pos2"].astype(np.int32))
+    assert np.abs(res.sr["MI"] - ref.sr["MI"]).max() < MI_TOL
+
+
+def test_multiallelic_nrich_vs_oracle():
+    """N-rich, multi-allelic synthetic data: every plane-count class (r = 2..5) and all tile kinds."""
+    import c_oracle as CO
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    rng = np.random.default_rng(42)
+    S, n = 300, 700
+    nall = rng.choice([2, 3, 4], size=n, p=[0.5, 0.3, 0.2])
+    founders = np.stack([rng.integers(0, k, size=10) for k in nall]).astype(np.uint8)
+    codes = founders[:, rng.integers(0, 10, size=S)]
+    flip = rng.random((n, S)) < 0.05
+    codes[flip] = (codes[flip] + 1) % np.repeat(nall, S).reshape(n, S)[flip]
+    codes[rng.random((n, S)) < 0.08] = 4  # N / gap class
+    osnp = O.snp_dat_from_codes(codes, np.sort(rng.choice(np.arange(1, 90000), n, replace=False)), 100000)
+    assert set(np.unique(osnp.r)) >= {2.0, 3.0, 4.0, 5.0} or osnp.r.max() >= 4
+    keep = osnp.r >= 2
+    codes, POS = codes[keep], osnp.POS[keep]
+    osnp = O.snp_dat_from_codes(codes, POS, 100000)
+    hdw = CO.hdw(codes, 0.1)[0]
+    snp = ldw.snp_dat_from_codes(codes, POS, 100000)
+    plan = ldw.MIPlan(snp, hdw, np.ones(len(POS), dtype=np.int32), 1000)
+    idx = np.arange(len(POS))
+    ref = CO.block_mi(codes, hdw, osnp.r, osnp.uqe, idx, idx)
+    MI = plan.block_dense(0)
+    err = np.abs(MI - ref).max()
+    print("multi-allelic max abs err:", err, "r histogram", np.unique(osnp.r, return_counts=True))
+    assert err < MI_TOL
+    plan.close()
