@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the LDWeaver hot path on B200: weighted SNP-pair MI/sec (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm's CPU path (oracle port)
+
+A "step" is one full weighted pairwise-MI scan (all make_blocks blocks: GEMM + fused MI epilogue + sr/lr link
+filter + per-block exact LR selection + link-column materialisation) of the synthetic 616 x 100k alignment
+(SURVEY.md 8d, config C2), blocks dealt round-robin over the ranks.  `value` is pairs/s with the packed operands
+already resident in HBM (device time from CUDA events on the library's stream, max over ranks); `e2e` is the same
+metric through the C ABI from host buffers: host->device upload + operand packing + scan + device->host copy of
+every link column, inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+SR_DIST = 20000.0
+LR_RETAIN = 1e6
+MAX_BLK = 10000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--nsnp", type=int, default=0, help="override the number of SNPs (debug only; invalidates the metric)")
+    ap.add_argument("--cpu-sample", type=int, default=4000, help="block edge of the bounded CPU-baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return {"hbm_gbs": d.get("hbm_gbs"), "bf16_tflops": d.get("bf16_tflops"),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(",") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if "Active" in r[5 + k] and "Not" not in r[5 + k]:
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_sample(sy, hdw, edge: int):
+    """The reference algorithm's CPU path (oracle C port, all host threads) on a bounded sample of the same workload:
+    one off-diagonal `edge` x `edge` block (25 weighted products + temporaries + fastHadamard, pair enumeration, len,
+    type-7 quantile, filter).  Returns (pairs, seconds, threads)."""
+    import c_oracle as CO
+    n = sy.codes.shape[0]
+    edge = min(edge, n // 2)
+    f = np.arange(0, edge)
+    t = np.arange(n - edge, n)
+    table = np.stack([(sy.codes == a).any(axis=1) for a in range(5)], axis=1).astype(np.float64)
+    r = table.sum(axis=1)
+    t0 = time.perf_counter()
+    MI = CO.block_mi(sy.codes, hdw, r, table, f, t)
+    L = CO.block_links(MI, sy.POS.astype(np.float64), f, t, float(sy.g), SR_DIST, LR_RETAIN, 4.9e9)
+    dt = time.perf_counter() - t0
+    return len(L["MI"]), dt, CO.lib().ldwo_num_threads()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from ldweaver_b200 import synth
+
+    S, n_cfg, seed, probs, nrate = synth.CONFIGS[args.config]
+    n = args.nsnp or n_cfg
+    workload = f"{args.config}: synthetic {S} seqs x {n} SNPs (seed {seed}), Hamming-weighted MI, sr_dist {int(SR_DIST)}, " \
+               f"lr_retain_links {int(LR_RETAIN)}, max_blk_sz {MAX_BLK}"
+    config = {"workload": workload, "nseq": S, "nsnp": n, "sr_dist": SR_DIST, "lr_retain_links": LR_RETAIN,
+              "max_blk_sz": MAX_BLK, "partition": f"make_blocks blocks round-robin over {world} rank(s)",
+              "l2": "operand arrays (6 x rows x Kpad bytes) exceed the 126 MB L2; no explicit flush"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import c_oracle as CO
+        sy = synth.generate(S, min(n, 4 * args.cpu_sample), seed, probs, nrate)
+        hdw, _ = CO.hdw(sy.codes, 0.1)
+        for _ in range(min(args.warmup, 1)):
+            cpu_reference_sample(sy, hdw, min(500, args.cpu_sample))
+        pairs = 0
+        secs = 0.0
+        for _ in range(args.steps):
+            p_, dt, thr = cpu_reference_sample(sy, hdw, args.cpu_sample)
+            pairs += p_
+            secs += dt
+        val = pairs / secs
+        sample = f"one off-diagonal {args.cpu_sample}x{args.cpu_sample} block of the workload per step (reference-shaped C/OpenMP port)"
+        line = {"impl": "reference", "metric": "weighted SNP-pair MI/sec", "value": val, "unit": "pairs/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": thr, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ldweaver_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import api
+
+    sy = synth.generate(S, n, seed, probs, nrate)
+    snp = ldw.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
+    # population-structure weights on rank 0, broadcast over NVLink with NCCL
+    hdw_t = torch.empty(S, dtype=torch.float64, device="cuda")
+    t_hdw = None
+    if rank == 0:
+        t0 = time.perf_counter()
+        hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1, device=local_rank)
+        t_hdw = time.perf_counter() - t0
+        hdw_t.copy_(torch.from_numpy(hdw))
+    if world > 1:
+        dist.broadcast(hdw_t, src=0)
+    hdw = hdw_t.cpu().numpy()
+    lra = synth.exact_lr_links_approx(sy.POS, sy.g, SR_DIST)
+    blk = api.round_half_even_thousands(MAX_BLK)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # pinned host copies of the inputs (what an R shim would hand over)
+    codes_pin = torch.from_numpy(sy.codes).pin_memory().numpy()
+    plan = ldw.MIPlan(ldw.snp_dat_from_codes(codes_pin, sy.POS, sy.g), hdw, sy.paint, blk, device=local_rank)
+    flags_dev = api.SCAN_NO_D2H
+    for _ in range(args.warmup):
+        plan.scan(sy.g, SR_DIST, LR_RETAIN, lra, flags_dev, world, rank, copy=False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    dev_ms = 0.0
+    kern_ms = 0.0
+    stats = None
+    agg = {"n_pairs": 0, "n_launches": 0, "n_scan_launches": 0, "exec_int8_ops": 0.0, "n_tiles": 0}
+    for _ in range(args.steps):
+        *_, stats = plan.scan(sy.g, SR_DIST, LR_RETAIN, lra, flags_dev, world, rank, copy=False)
+        dev_ms += stats["t_scan_ms"] + stats["t_select_ms"]
+        kern_ms += stats["t_kernel_ms"]
+        for k in agg:
+            agg[k] += stats[k]
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    dev_ms_max = allmax(dev_ms)
+    wall_max = allmax(t_wall)
+    pairs_all = allsum(float(agg["n_pairs"]))  # over all ranks and steps
+    launches_all = allsum(float(agg["n_launches"]))
+    value = pairs_all / (dev_ms_max * 1e-3)
+
+    # ------------------------------------------------------------------ end to end through the C ABI from host buffers
+    e2e = None
+    if not args.no_e2e:
+        snp_pin = ldw.snp_dat_from_codes(codes_pin, sy.POS, sy.g)
+        e_steps = max(1, min(args.steps, 3))
+        for _ in range(1):  # warm-up: pinned output buffers get allocated once
+            p2 = ldw.MIPlan(snp_pin, hdw, sy.paint, blk, device=local_rank)
+            p2.scan(sy.g, SR_DIST, LR_RETAIN, lra, 0, world, rank, copy=False)
+            p2.close()
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        pe = 0
+        for _ in range(e_steps):
+            p2 = ldw.MIPlan(snp_pin, hdw, sy.paint, blk, device=local_rank)
+            sr, lr, bd, thr, prob, st2 = p2.scan(sy.g, SR_DIST, LR_RETAIN, lra, 0, world, rank, copy=False)
+            d2h += (int(sr.n) + int(lr.n)) * 32
+            pe += st2["n_pairs"]
+            p2.close()
+        barrier()
+        te = allmax(time.perf_counter() - t0)
+        pe_all = allsum(float(pe))
+        h2d = codes_pin.nbytes + hdw.nbytes + sy.POS.nbytes + sy.paint.nbytes
+        e2e = {"value": pe_all / te, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // e_steps),
+               "ms_per_step": 1e3 * te / e_steps, "steps": e_steps,
+               "includes": "host->device upload, operand packing, scan, link materialisation, device->host copy of all link columns"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (mi_scan_kernel)
+    peaks = load_peaks()
+    peak_tf = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+    n_launch = max(1, agg["n_scan_launches"])
+    avg_launch_s = kern_ms * 1e-3 / n_launch
+    alg_flop_per_launch = 50.0 * S * (agg["n_pairs"] / n_launch)  # 50*S flop per SNP pair
+    achieved_tf = alg_flop_per_launch / avg_launch_s / 1e12
+    exec_tops = agg["exec_int8_ops"] / (kern_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                "kernel": "mi_scan_kernel", "avg_launch_ms": 1e3 * avg_launch_s, "launches": n_launch,
+                "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
+                "executed_int8_tops": exec_tops,
+                "executed_frac_of_int8_peak": exec_tops / (2.0 * (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])),
+                "note": "achieved = ALGORITHMIC 50*S flop/pair over the kernel's CUDA-event time; the kernel executes fewer "
+                        "tensor ops than that (only r-1 allele planes per site enter the GEMM, 4 int8 K-passes), see DESIGN.md"}
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        pr, dt, thr = cpu_reference_sample(sy, hdw, args.cpu_sample)
+        cpu = {"value": pr / dt, "unit": "pairs/s", "cores": thr, "kind": "port",
+               "sample": f"one off-diagonal {min(args.cpu_sample, n // 2)}x{min(args.cpu_sample, n // 2)} block of the same workload "
+                         f"({pr} pairs, {dt:.1f} s), reference-shaped C/OpenMP port of R/computePairwiseMI.R + src/computeMI.cpp"}
+
+    line = {"metric": "weighted SNP-pair MI/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int8 x int8 -> int32 (30-bit fixed-point weights), fp32 epilogue, fp64 LR refinement",
+            "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"],
+                       "pairs_per_step": pairs_all / args.steps, "n_sr": stats["n_sr"], "n_lr_kept": stats["n_lr_kept"],
+                       "n_reruns": stats["n_reruns"], "tiles_per_step_rank0": agg["n_tiles"] / args.steps,
+                       "lr_links_approx": lra}}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -4,8 +4,8 @@
  *
  * Pure C, no R / torch / C++ types in any signature.  Inputs are BORROWED, read-only host buffers
  * (R vectors, numpy arrays); fixed-size outputs are caller-allocated; variable-size link lists are
- * library-owned pinned host buffers that stay valid until the next scan on the same plan or until
- * ldw_mi_plan_destroy().  Every entry point returns 0 on success or a nonzero LDW_ERR_* code;
+ * library-owned pinned host buffers (owned by the context) that stay valid until the next scan on the
+ * same context or until ldw_destroy().  Every entry point returns 0 on success or a nonzero LDW_ERR_* code;
  * ldw_last_error() gives the message (thread-local).  Nothing is ever printed to stdout and no
  * exception or longjmp crosses this boundary, so an R shim can turn a nonzero code into
  * Rf_error(ldw_last_error()) after releasing its own resources (reference convention:
@@ -48,7 +48,9 @@ enum {
 enum {
   LDW_SCAN_SR_ONLY = 1,   /* perform_SR_analysis_only = TRUE (R/computePairwiseMI.R:179-189, quirk Q12) */
   LDW_SCAN_IDEAL_Q = 2,   /* opt-out of quirk Q1: use 0.25*r_i*r_j on off-diagonal blocks too (NOT reference behaviour) */
-  LDW_SCAN_NO_LINKS = 4   /* compute everything but skip host materialisation of SR columns (bench: device-only timing) */
+  LDW_SCAN_NO_LINKS = 4,  /* compute MI / thresholds only: no link columns are materialised or copied */
+  LDW_SCAN_NO_D2H = 8     /* materialise the link columns in device memory but do not copy them to the host
+                             (device-resident throughput measurement); link outputs come back with n rows and NULL pointers */
 };
 
 typedef struct ldw_ctx ldw_ctx;         /* one per device; owns stream + scratch */
@@ -144,7 +146,12 @@ typedef struct ldw_scan_stats {
   int64_t n_lr_kept;
   int64_t n_borderline;  /* LR candidates within borderline_tol of their block threshold (listed in `borderline`) */
   int64_t n_reruns;      /* blocks re-run because the candidate threshold guess was too high */
-  double t_pack_ms, t_scan_ms, t_select_ms, t_d2h_ms; /* device / host phase timings of the last scan */
+  double t_pack_ms, t_scan_ms, t_select_ms, t_d2h_ms; /* CUDA-event phase timings of the last scan (library stream) */
+  double t_kernel_ms;    /* sum of the scan kernel's own launch durations (CUDA events around each launch) */
+  int64_t n_scan_launches; /* launches of the scan kernel */
+  int64_t n_launches;    /* all kernels this library launched during the scan */
+  int64_t n_tiles;       /* tiles processed */
+  double exec_int8_ops;  /* int8 tensor operations actually issued (2 * MACs) */
 } ldw_scan_stats;
 
 LDW_API int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, const double* hdw,

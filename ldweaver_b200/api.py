@@ -189,7 +189,7 @@ def estimate_Hamming_distance_weights(snp_dat: SnpDat, threshold: float = 0.1, m
 # --------------------------------------------------------------------------------------------------
 # perform_MI_computation (scan + sr/lr link filter)
 # --------------------------------------------------------------------------------------------------
-SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS = 1, 2, 4
+SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS, SCAN_NO_D2H = 1, 2, 4, 8
 
 
 @dataclass

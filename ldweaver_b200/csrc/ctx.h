@@ -2,10 +2,30 @@
 #pragma once
 #include "host_util.h"
 
+// Link columns in pinned host memory (what ldw_links points into).  Owned by the context and reused by every
+// scan on it: allocating gigabytes of pinned memory costs far more than the scan itself.
+struct HostLinks {
+  ldw::PinnedBuf pos1, pos2, c1, c2, len, blk, mi;
+  int64_t n = 0;
+  int ensure(int64_t m) {
+    size_t b4 = (size_t)(m > 0 ? m : 1) * 4, b8 = (size_t)(m > 0 ? m : 1) * 8;
+    LDW_TRY(pos1.ensure(b4)); LDW_TRY(pos2.ensure(b4)); LDW_TRY(c1.ensure(b4)); LDW_TRY(c2.ensure(b4));
+    LDW_TRY(len.ensure(b4)); LDW_TRY(blk.ensure(b4)); LDW_TRY(mi.ensure(b8));
+    return 0;
+  }
+  void fill(ldw_links* o) const {
+    if (!o) return;
+    o->n = n;
+    o->pos1 = pos1.as<int32_t>(); o->pos2 = pos2.as<int32_t>(); o->clust1 = c1.as<int32_t>(); o->clust2 = c2.as<int32_t>();
+    o->len = len.as<int32_t>(); o->MI = mi.as<double>(); o->block = blk.as<int32_t>();
+  }
+};
+
 struct ldw_ctx {
   int device = 0;
   int num_sms = 0;
   cudaStream_t stream = nullptr;
+  HostLinks h_sr, h_lr, h_border;
 };
 
 namespace ldw {

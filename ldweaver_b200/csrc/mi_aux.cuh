@@ -175,13 +175,32 @@ __device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int
   return mi;
 }
 
+// Candidates below the FINAL candidate threshold are an incomplete sample of their MI range (the threshold rose
+// while they were being collected); they cannot take part in the selection and are not refined.
 __global__ void mi_refine_cand_kernel(RefineParams P, const Cand* __restrict__ cand, const uint32_t* __restrict__ count,
-                                      uint32_t cap, double* mi64) {
+                                      uint32_t cap, const uint32_t* __restrict__ tcand_bits, int emit_all, double* mi64) {
   uint32_t n = *count < cap ? *count : cap;
+  const float tc = emit_all ? -3.0e38f : __uint_as_float(*tcand_bits);
   int lane = threadIdx.x & 31;
   for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+    if (cand[i].mi < tc) {
+      if (lane == 0) mi64[i] = -1.0e300;
+      continue;
+    }
     double v = refine_pair(P, cand[i].il, cand[i].jl, lane);
     if (lane == 0) mi64[i] = v;
+  }
+}
+
+// Start of a block's long-range collection: counters cleared, histogram cleared, candidate threshold seeded from
+// the chained estimate of the previous block (or 0 = collect until the histogram can place a threshold).
+__global__ void mi_block_begin_kernel(uint32_t* state /*count, tcand, overflow*/, uint32_t* hist, const uint32_t* chain_bits,
+                                      int use_chain) {
+  for (int i = threadIdx.x; i < MI_HIST_BINS; i += blockDim.x) hist[i] = 0;
+  if (threadIdx.x == 0) {
+    state[0] = 0;
+    state[1] = use_chain ? *chain_bits : 0u;
+    state[2] = 0;
   }
 }
 
@@ -232,6 +251,7 @@ struct SelectParams {
   unsigned long long* kept_count;
   uint64_t kept_cap;
   uint32_t* kept_overflow;
+  uint32_t* chain_bits;  // seed of the next block's candidate threshold
   BlockResult* result;
 };
 
@@ -335,6 +355,13 @@ __global__ void __launch_bounds__(1024) mi_select_kernel(SelectParams P) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
+    // chain: the next block starts collecting at 0.8 x this block's threshold; after a failure fall back hard
+    if (!P.emit_all) {
+      float tc = __uint_as_float(*P.tcand_bits);
+      float nxt = bad ? 0.25f * tc : 0.8f * (float)v_lo;
+      if (!(nxt > 0.f)) nxt = 0.f;
+      *P.chain_bits = __float_as_uint(nxt);
+    }
     BlockResult r;
     r.thr = thr; r.v_lo = v_lo; r.n_cand = raw; r.n_kept = s_kept; r.n_border = s_border; r.bad = bad;
     *P.result = r;

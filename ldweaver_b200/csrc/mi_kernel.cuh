@@ -41,8 +41,10 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
   return v;
 }
 
+// columns handled per TMEM read batch: keeps the unrolled body near 32-64 MI terms (instruction cache) and the
+// accumulator registers at <= 32
 __host__ __device__ constexpr int mi_jc(int pa, int pb) {
-  return pa * pb <= 2 ? 16 : pa * pb <= 4 ? 8 : pa * pb <= 8 ? 4 : 2;
+  return (pa + 1) * (pb + 1) <= 4 ? 16 : (pa + 1) * (pb + 1) <= 6 ? 8 : (pa + 1) * (pb + 1) <= 9 ? 4 : (pa + 1) * (pb + 1) <= 12 ? 2 : 1;
 }
 __host__ __device__ constexpr int mi_njlog2(int pa, int pb) {
   return pa * pb == 1 ? 7 : pa * pb == 2 ? 6 : pa * pb <= 4 ? 5 : 4;
@@ -84,14 +86,52 @@ struct EpiCtx {
   const ColDyn* jdyn;  // shared
 };
 
-// One term of the MI sum.  h,l: exact fixed-point joint count halves.
+// Everything the per-pair code needs, held in registers (copied once per tile): reading it through the kernel
+// parameter struct inside the pair loop costs a generic load per use.
+struct EpiConst {
+  float kT, scale, q0, rtlq, qod, tcand;
+  int32_t neffH, neffL, nf, nt, il;
+  uint32_t sa, sb, rb;        // fixed-point count -> float: t = (H << sa) + ((L + rb) >> sb)
+  int32_t diag, ragged, dense, do_lr, has_sr;
+  float* sr_out;
+};
+
+// One term of the MI sum.  h,l: exact fixed-point halves of the joint count (both non-negative).
 template <bool QC>
-__device__ __forceinline__ float mi_term(float acc, int h, int l, float ra, float rb, float dq, float kH, float kL) {
-  float x = fmaf((float)h, kH, fmaf((float)l, kL, 0.5f));
+__device__ __forceinline__ float mi_term(float acc, int h, int l, float ra, float rb, float dq, const EpiConst& k) {
+  uint32_t t = ((uint32_t)h << k.sa) + (((uint32_t)l + k.rb) >> k.sb);
+  float x = fmaf(__uint2float_rn(t), k.kT, 0.5f);
   float e = ra * rb;
-  float t = lg2_fast(x * e);
-  if (QC) t -= lg2_fast(fmaf(dq, e, 1.0f));
-  return fmaf(x, t, acc);
+  float v = lg2_fast(x * e);
+  if (QC) v -= lg2_fast(fmaf(dq, e, 1.0f));
+  return fmaf(x, v, acc);
+}
+
+// Rare path (a long-range candidate somewhere in the warp): reads its parameters straight from the kernel parameters.
+__device__ __noinline__ void lr_emit(const ScanParams& p, bool em, int il, int jl, float mi, int lane) {
+  const unsigned bal = __ballot_sync(0xffffffffu, em);
+  if (bal == 0) return;
+  const int leader = __ffs(bal) - 1;
+  uint32_t base = 0;
+  const uint32_t n_new = (uint32_t)__popc(bal);
+  if (lane == leader) base = atomicAdd(p.cand_count, n_new);
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (em) {
+    uint32_t idx = base + (uint32_t)__popc(bal & ((1u << lane) - 1));
+    if (idx < p.cand_cap) {
+      Cand cc;
+      cc.il = il; cc.jl = jl; cc.mi = mi;
+      p.cand[idx] = cc;
+    } else {
+      *p.overflow = 1;
+    }
+    uint32_t bits = __float_as_uint(mi);
+    atomicAdd(p.hist + ((bits & 0x80000000u) ? 0u : (bits >> 19)), 1u);
+  }
+  if (!p.emit_all && (base / p.delta) != ((base + n_new) / p.delta)) {
+    __threadfence();
+    lr_raise_threshold(p, lane);
+  }
 }
 
 template <int PA, int PB, bool QC>
@@ -100,26 +140,34 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   constexpr int JC = mi_jc(PA, PB);
   constexpr int NJ = 1 << mi_njlog2(PA, PB);
   const int row = c.q * 32 + c.lane;
+  // ---- per-tile constants into registers
+  EpiConst k;
+  const float den = p.den[RA - 2][RB - 2];
+  k.kT = p.kT; k.scale = p.ln2_over_den[RA - 2][RB - 2]; k.q0 = p.q0[RA - 2][RB - 2];
+  k.qod = p.quarter_over_den[RA - 2][RB - 2];
+  k.neffH = p.neffH; k.neffL = p.neffL; k.nf = p.nf; k.nt = p.nt;
+  k.sa = p.sa; k.sb = p.sb; k.rb = p.rb;
+  k.diag = p.diag; k.ragged = p.ragged; k.dense = p.dense;
+  k.do_lr = (!p.sr_only && !p.dense) ? 1 : 0;
+  k.has_sr = (td.flags & TILE_HAS_SR) ? 1 : 0;
+  k.sr_out = p.sr_out;
+  k.tcand = (k.do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
   // ---- this thread's row SNP
   const Rec* ri = p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row;
   int PiH[RA], PiL[RA];
   float rpad[RA];
-  const float den = p.den[RA - 2][RB - 2];
 #pragma unroll
   for (int a = 0; a < RA; a++) {
-    PiH[a] = ri->PH[a];
-    PiL[a] = ri->PL[a];
-    rpad[a] = ri->rp[a] * den;
+    PiH[a] = __ldg(&ri->PH[a]);
+    PiL[a] = __ldg(&ri->PL[a]);
+    rpad[a] = __ldg(&ri->rp[a]) * den;
   }
   const RowDyn rd = p.rowdyn[td.i_dyn0 + row];
-  const int il = rd.il;
-  const float rtlq = rd.rtl * p.quarter_over_den[RA - 2][RB - 2];
-  const float q0 = p.q0[RA - 2][RB - 2];
-  const float scale = p.ln2_over_den[RA - 2][RB - 2];
-  const float kH = p.kH, kL = p.kL;
-  const bool has_sr = (td.flags & TILE_HAS_SR) != 0;
-  const bool do_lr = !p.sr_only && !p.dense;
-  const float tcand = (do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
+  k.il = rd.il;
+  k.rtlq = rd.rtl * k.qod;
+  const int il = k.il;
+  // validity of a pair: diagonal block -> 0 <= jl < il; otherwise 0 <= jl < nt, jl != il (quirk Q2); il must exist
+  const uint32_t jl_lim = il < 0 ? 0u : (k.diag ? (uint32_t)il : (uint32_t)k.nt);
 
   const int jbeg = c.half * (NJ / 2);
 #pragma unroll 1
@@ -140,19 +188,22 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
       const int jl = cd.jl;
       float dq = 0.f;
       if (QC) {
-        if (p.ragged) {
+        if (k.ragged) {
           // quirk Q1, general form: rft (nt x nf) is read by the linear index of the nf x nt matrix
-          float v = q0;
+          float v = k.q0;
           if (il >= 0 && jl >= 0) {
-            uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)p.nf;
-            uint32_t cdiv = (uint32_t)(lin / (uint32_t)p.nt), cmod = (uint32_t)(lin % (uint32_t)p.nt);
-            v = (float)p.rfl_arr[cdiv] * (float)p.rtl_arr[cmod] * p.quarter_over_den[RA - 2][RB - 2];
+            uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)k.nf;
+            uint32_t cdiv = (uint32_t)(lin / (uint32_t)k.nt), cmod = (uint32_t)(lin % (uint32_t)k.nt);
+            v = (float)p.rfl_arr[cdiv] * (float)p.rtl_arr[cmod] * k.qod;
           }
-          dq = v - q0;
+          dq = v - k.q0;
         } else {
-          dq = fmaf(rtlq, cd.rfl, -q0);
+          dq = fmaf(k.rtlq, cd.rfl, -k.q0);
         }
       }
+      float rpb[RB];
+#pragma unroll
+      for (int b = 0; b < RB; b++) rpb[b] = rj.rp[b];
       // ---- (PA+1) x (PB+1) joint table by exact integer complement, MI accumulated term by term
       float acc = 0.f;
       int colH[PB], colL[PB];
@@ -167,28 +218,28 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
           int h = (int)H[a][b][jj], l = (int)L[a][b][jj];
           rH += h; rL += l;
           colH[b] += h; colL[b] += l;
-          acc = mi_term<QC>(acc, h, l, rpad[a], rj.rp[b], dq, kH, kL);
+          acc = mi_term<QC>(acc, h, l, rpad[a], rpb[b], dq, k);
         }
-        acc = mi_term<QC>(acc, PiH[a] - rH, PiL[a] - rL, rpad[a], rj.rp[PB], dq, kH, kL);
+        acc = mi_term<QC>(acc, PiH[a] - rH, PiL[a] - rL, rpad[a], rpb[PB], dq, k);
         totH += rH; totL += rL;
       }
 #pragma unroll
       for (int b = 0; b < PB; b++)
-        acc = mi_term<QC>(acc, rj.PH[b] - colH[b], rj.PL[b] - colL[b], rpad[PA], rj.rp[b], dq, kH, kL);
+        acc = mi_term<QC>(acc, rj.PH[b] - colH[b], rj.PL[b] - colL[b], rpad[PA], rpb[b], dq, k);
       {
-        int sjH = p.neffH - rj.PH[PB], sjL = p.neffL - rj.PL[PB];
-        acc = mi_term<QC>(acc, PiH[PA] - sjH + totH, PiL[PA] - sjL + totL, rpad[PA], rj.rp[PB], dq, kH, kL);
+        int sjH = k.neffH - rj.PH[PB], sjL = k.neffL - rj.PL[PB];
+        acc = mi_term<QC>(acc, PiH[PA] - sjH + totH, PiL[PA] - sjL + totL, rpad[PA], rpb[PB], dq, k);
       }
-      const float mi = acc * scale;
+      const float mi = acc * k.scale;
 
       // ---- classification and emission
-      const bool valid = (il >= 0) && (jl >= 0) && (p.diag ? (il > jl) : (il != jl));
-      if (p.dense) {
-        if (il >= 0 && jl >= 0) p.dense_out[(size_t)il + (size_t)jl * (size_t)p.nf] = mi;
+      if (k.dense) {
+        if (il >= 0 && jl >= 0) p.dense_out[(size_t)il + (size_t)jl * (size_t)k.nf] = mi;
         continue;
       }
+      const bool valid = ((uint32_t)jl < jl_lim) && (jl != il);
       bool sr = false;
-      if (has_sr) {
+      if (k.has_sr) {
         const uint32_t la = (uint32_t)(cd.a1 - cd.a0), lb = (uint32_t)(cd.b1 - cd.b0);
         sr = valid && (((uint32_t)(il - cd.a0) < la) || ((uint32_t)(il - cd.b0) < lb));
         if (sr) {
@@ -201,38 +252,12 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
             int bj = min(max(jl + 1 - cd.a0, 0), (int)la) + min(max(jl + 1 - cd.b0, 0), (int)lb);
             slot = cd.baseL + (uint32_t)(below - bj);
           }
-          p.sr_out[slot] = mi;
+          k.sr_out[slot] = mi;
         }
       }
-      if (do_lr) {
-        const bool em = valid && !sr && (mi >= tcand);
-        const unsigned bal = __ballot_sync(0xffffffffu, em);
-        if (bal) {
-          const int leader = __ffs(bal) - 1;
-          uint32_t base = 0;
-          if (c.lane == leader) base = atomicAdd(p.cand_count, (uint32_t)__popc(bal));
-          base = __shfl_sync(0xffffffffu, base, leader);
-          if (em) {
-            uint32_t idx = base + (uint32_t)__popc(bal & ((1u << c.lane) - 1));
-            if (idx < p.cand_cap) {
-              Cand cc;
-              cc.il = il; cc.jl = jl; cc.mi = mi;
-              p.cand[idx] = cc;
-            } else {
-              *p.overflow = 1;
-            }
-            uint32_t bits = __float_as_uint(mi);
-            uint32_t bin = (bits & 0x80000000u) ? 0u : (bits >> 19);
-            atomicAdd(p.hist + bin, 1u);
-          }
-          if (!p.emit_all) {
-            const uint32_t n_new = (uint32_t)__popc(bal);
-            if ((base / p.delta) != ((base + n_new) / p.delta)) {
-              __threadfence();
-              lr_raise_threshold(p, c.lane);
-            }
-          }
-        }
+      if (k.do_lr) {
+        const bool em = valid && !sr && (mi >= k.tcand);
+        if (__any_sync(0xffffffffu, em)) lr_emit(p, em, il, jl, mi, c.lane);
       }
     }
   }
@@ -292,6 +317,10 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // register budget: the control warpgroup (warps 0-3) gives registers to the two epilogue warpgroups
+  // (pool = 168 x 384 = 64512 registers at launch; 96 x 128 + 200 x 256 = 63488 fits)
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -307,18 +336,27 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (sizeof(Rec) + sizeof(ColDyn)));
         bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
         bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
-        for (int a = 0; a < PA; a++) {
-          const int arow = td.a_row0 + a * td.a_pstride;
+        // A planes go two per stage (X1 and X128 slices of each), then the four digit arrays of all PB column planes
+        for (int a0 = 0; a0 < PA; a0 += 2) {
+          const int na = min(2, PA - a0);
           for (int kb = 0; kb < p.nkb; kb++) {
             mbar_wait(&empty[st], ph ^ 1, 11);
             uint8_t* sb = stage_base + st * MI_STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[st], 2 * MI_ARR_BYTES + (uint32_t)(4 * PB * NJ * 128));
-            tma_load_2d(sb, &tm.a[0], &full[st], kb * 128, arow);
-            tma_load_2d(sb + MI_ARR_BYTES, &tm.a[1], &full[st], kb * 128, arow);
-            for (int d = 0; d < 4; d++)
+            mbar_arrive_expect_tx(&full[st], (uint32_t)(na * 2) * MI_ARR_BYTES + (uint32_t)(4 * PB * NJ * 128));
+            for (int a = 0; a < na; a++) {
+              const int arow = td.a_row0 + (a0 + a) * td.a_pstride;
+              tma_load_2d(sb + (a * 2 + 0) * MI_ARR_BYTES, &tm.a[0], &full[st], kb * 128, arow);
+              tma_load_2d(sb + (a * 2 + 1) * MI_ARR_BYTES, &tm.a[1], &full[st], kb * 128, arow);
+            }
+            // digit arrays in shared-memory order D3, D1, D2, D0: the two arrays multiplied by the same A operand
+            // (X128: D3 | D1, X1: D2 | D0) sit next to each other, so one MMA covers both accumulator halves
+            uint8_t* sbB = sb + na * 2 * MI_ARR_BYTES;
+            for (int sl = 0; sl < 4; sl++) {
+              const int d = (sl == 1) ? 2 : (sl == 2) ? 1 : sl;
               for (int b = 0; b < PB; b++)
-                tma_load_2d(sb + (2 + d) * MI_ARR_BYTES + b * NJ * 128, &tm.b[d][njidx], &full[st], kb * 128,
+                tma_load_2d(sbB + (sl * PB + b) * NJ * 128, &tm.b[d][njidx], &full[st], kb * 128,
                             td.b_row0 + b * td.b_pstride);
+            }
             if (++st == MI_STAGES) { st = 0; ph ^= 1; }
           }
         }
@@ -332,7 +370,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         const TileDesc td = p.tiles[t];
         const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
         const bool big = 2 * PA * PB * NJ > 256;
-        const uint32_t idesc = make_idesc_u8(128, (uint32_t)NJ);
+        const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA
+        const uint32_t idesc = make_idesc_u8(128, ncols);
         uint32_t dbase;
         if (big) {
           for (int s = 0; s < 2; s++) {
@@ -345,27 +384,23 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
           dbase = tmem_base + as * 256;
         }
         tc_fence_after();
-        for (int a = 0; a < PA; a++) {
+        for (int a0 = 0; a0 < PA; a0 += 2) {
+          const int na = min(2, PA - a0);
           for (int kb = 0; kb < p.nkb; kb++) {
             mbar_wait(&full[st], ph, 22);
             tc_fence_after();
             const uint32_t sb = smem_u32(stage_base + st * MI_STAGE_BYTES);
-            const uint64_t dx1 = make_smem_desc_sw128(sb);
-            const uint64_t dx128 = make_smem_desc_sw128(sb + MI_ARR_BYTES);
-            for (int b = 0; b < PB; b++) {
-              const uint64_t d3 = make_smem_desc_sw128(sb + 2 * MI_ARR_BYTES + b * NJ * 128);
-              const uint64_t d2 = make_smem_desc_sw128(sb + 3 * MI_ARR_BYTES + b * NJ * 128);
-              const uint64_t d1 = make_smem_desc_sw128(sb + 4 * MI_ARR_BYTES + b * NJ * 128);
-              const uint64_t d0 = make_smem_desc_sw128(sb + 5 * MI_ARR_BYTES + b * NJ * 128);
-              const uint32_t dH = dbase + ((a * 2 + 0) * PB + b) * NJ;
-              const uint32_t dL = dbase + ((a * 2 + 1) * PB + b) * NJ;
+            const uint32_t sbB = sb + na * 2 * MI_ARR_BYTES;
+            const uint64_t dB128 = make_smem_desc_sw128(sbB);                              // D3 | D1
+            const uint64_t dB1 = make_smem_desc_sw128(sbB + 2 * PB * NJ * 128);              // D2 | D0
+            for (int a = 0; a < na; a++) {
+              const uint64_t dx1 = make_smem_desc_sw128(sb + (a * 2 + 0) * MI_ARR_BYTES);
+              const uint64_t dx128 = make_smem_desc_sw128(sb + (a * 2 + 1) * MI_ARR_BYTES);
+              const uint32_t dHL = dbase + (uint32_t)((a0 + a) * 2 * PB * NJ);
 #pragma unroll
-              for (int k = 0; k < 4; k++) {
-                const uint32_t first = (kb > 0 || k > 0) ? 1u : 0u;
-                umma_i8(dH, dx128 + 2 * k, d3 + 2 * k, idesc, first);
-                umma_i8(dH, dx1 + 2 * k, d2 + 2 * k, idesc, 1u);
-                umma_i8(dL, dx128 + 2 * k, d1 + 2 * k, idesc, first);
-                umma_i8(dL, dx1 + 2 * k, d0 + 2 * k, idesc, 1u);
+              for (int kk = 0; kk < 4; kk++) {
+                umma_i8(dHL, dx128 + 2 * kk, dB128 + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+                umma_i8(dHL, dx1 + 2 * kk, dB1 + 2 * kk, idesc, 1u);
               }
             }
             umma_commit(&empty[st]);

@@ -24,23 +24,6 @@ struct Group {
   int32_t slot0 = 0, nslots = 0, row0 = 0, count = 0;
 };
 
-struct HostLinks {
-  PinnedBuf pos1, pos2, c1, c2, len, blk, mi;
-  int64_t n = 0;
-  int ensure(int64_t m) {
-    size_t b4 = (size_t)(m > 0 ? m : 1) * 4, b8 = (size_t)(m > 0 ? m : 1) * 8;
-    LDW_TRY(pos1.ensure(b4)); LDW_TRY(pos2.ensure(b4)); LDW_TRY(c1.ensure(b4)); LDW_TRY(c2.ensure(b4));
-    LDW_TRY(len.ensure(b4)); LDW_TRY(blk.ensure(b4)); LDW_TRY(mi.ensure(b8));
-    return 0;
-  }
-  void fill(ldw_links* o) const {
-    if (!o) return;
-    o->n = n;
-    o->pos1 = pos1.as<int32_t>(); o->pos2 = pos2.as<int32_t>(); o->clust1 = c1.as<int32_t>(); o->clust2 = c2.as<int32_t>();
-    o->len = len.as<int32_t>(); o->MI = mi.as<double>(); o->block = blk.as<int32_t>();
-  }
-};
-
 struct DevLinks {
   DevBuf pos1, pos2, c1, c2, len, blk, mi;
   int ensure(int64_t m) {
@@ -97,7 +80,6 @@ struct ldw_mi_plan {
   DevBuf d_cand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
   DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
   DevLinks d_sr, d_lr;
-  HostLinks h_sr, h_lr, h_border;
   std::vector<BlockResult> results;
   double t_pack_ms = 0;
   ~ldw_mi_plan() {
@@ -512,8 +494,18 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
   sp.sr_only = (cfg.flags & LDW_SCAN_SR_ONLY) ? 1 : 0;
   sp.rfl_arr = D.rfl.as<uint8_t>();
   sp.rtl_arr = D.rtl.as<uint8_t>();
-  sp.kH = (float)(32768.0 / P->scale);
-  sp.kL = (float)(1.0 / P->scale);
+  {
+    // H < 32768 * S: shift it up as far as 32 bits allow, drop the matching low bits of L (with rounding)
+    uint64_t hmax = 32767ull * (uint64_t)P->S;
+    int bits = 0;
+    while ((hmax >> bits) != 0) bits++;
+    int sa = std::min(15, 32 - bits);
+    if (sa < 0) sa = 0;
+    sp.sa = (uint32_t)sa;
+    sp.sb = (uint32_t)(15 - sa);
+    sp.rb = sp.sb ? (1u << (sp.sb - 1)) : 0u;
+    sp.kT = (float)(std::ldexp(1.0, (int)sp.sb) / P->scale);
+  }
   sp.neffH = P->neffH; sp.neffL = P->neffL;
   for (int a = 0; a < 4; a++)
     for (int b = 0; b < 4; b++) {
@@ -734,7 +726,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
         } else {
           uint64_t kp = K + std::max<uint64_t>(1024, K / 8);
           uint64_t delta = std::max<uint64_t>(2 * kp, 32768);
-          uint64_t cap = std::min<uint64_t>((uint64_t)tmp.n_lr, 16 * kp + 2 * delta + 65536);
+          // room for the first wave of tiles that run before any threshold exists (all resident CTAs x one tile)
+          uint64_t cap = std::min<uint64_t>((uint64_t)tmp.n_lr, 16 * kp + (4u << 20));
           if (cap > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "long-range candidate buffer exceeds 2^32 entries");
           s.kprime = (uint32_t)kp; s.delta = (uint32_t)delta; s.cap = (uint32_t)cap;
         }
@@ -764,11 +757,16 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   uint32_t* d_tcand = d_count + 1;
   uint32_t* d_overflow = d_count + 2;
   uint32_t* d_kept_overflow = d_count + 3;
+  uint32_t* d_chain = d_count + 4;
   LDW_CUDA(cudaMemsetAsync(P->d_state.p, 0, 64, st));
 
   LDW_CUDA(cudaEventRecord(ev0, st));
-  int64_t n_reruns = 0;
-  auto run_block = [&](size_t b, int force_emit_all, uint32_t cap_override) -> int {
+  int64_t n_reruns = 0, n_launches = 0, n_scan_launches = 0, n_tiles = 0;
+  double exec_ops = 0;
+  std::vector<cudaEvent_t> kev;  // pairs of events around every scan-kernel launch
+  auto kev_cleanup = [&]() { for (auto e : kev) cudaEventDestroy(e); kev.clear(); };
+  bool chain_valid = false;  // the device-side chained threshold estimate holds a value from an earlier block
+  auto run_block = [&](size_t b, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
     Sel& s = sel[b];
     if (s.skip) return 0;
     int slot = (int)(b % ldw_mi_plan::RING);
@@ -786,8 +784,10 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     const int emit_all = force_emit_all || s.emit_all;
     uint32_t cap = cap_override ? cap_override : s.cap;
     if (lr) {
-      LDW_CUDA(cudaMemsetAsync(P->d_state.p, 0, 12, st));  // count, tcand, overflow
-      LDW_CUDA(cudaMemsetAsync(P->d_hist.p, 0, MI_HIST_BINS * 4, st));
+      mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, P->d_hist.as<uint32_t>(), d_chain, (use_chain && chain_valid && !emit_all) ? 1 : 0);
+      LDW_CUDA(cudaGetLastError());
+      n_launches++;
+      if (!emit_all) chain_valid = true;
       sp.cand = P->d_cand.as<Cand>();
       sp.cand_cap = cap;
       sp.cand_count = d_count;
@@ -802,12 +802,25 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     }
     int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
     if (grid > 0) {
+      cudaEvent_t k0, k1;
+      LDW_CUDA(cudaEventCreate(&k0));
+      LDW_CUDA(cudaEventCreate(&k1));
+      kev.push_back(k0);
+      kev.push_back(k1);
+      LDW_CUDA(cudaEventRecord(k0, st));
       mi_scan_kernel<<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
       LDW_CUDA(cudaGetLastError());
+      LDW_CUDA(cudaEventRecord(k1, st));
+      n_launches++; n_scan_launches++;
+      n_tiles += sp.n_tiles;
+      for (const TileDesc& td : H.tiles)  // 4 K-passes x 2 ops/MAC x 128 rows x (PA*PB*NJ) columns x Kpad
+        exec_ops += 8.0 * 128.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;
     }
     if (lr) {
+      n_launches += 2;
       RefineParams R = make_refine_params(P, D, H, cfg);
-      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 256, 0, st>>>(R, P->d_cand.as<Cand>(), d_count, cap, P->d_mi64.as<double>());
+      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 256, 0, st>>>(R, P->d_cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
+                                                                 P->d_mi64.as<double>());
       LDW_CUDA(cudaGetLastError());
       SelectParams q;
       memset(&q, 0, sizeof(q));
@@ -820,11 +833,13 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       q.kept_key = P->d_kept_key.as<uint64_t>(); q.kept_gi = P->d_kept_gi.as<int32_t>(); q.kept_gj = P->d_kept_gj.as<int32_t>();
       q.kept_mi = P->d_kept_mi.as<double>(); q.kept_count = P->d_kept_count.as<unsigned long long>(); q.kept_cap = kept_cap;
       q.kept_overflow = d_kept_overflow;
+      q.chain_bits = d_chain;
       q.result = P->d_results.as<BlockResult>() + b;
       mi_select_kernel<<<1, 1024, 0, st>>>(q);
       LDW_CUDA(cudaGetLastError());
     }
     if (s.n_sr > 0 && !(flags & LDW_SCAN_NO_LINKS)) {
+      n_launches++;
       SrMatParams m;
       m.col = D.colinfo.as<ColInfo>(); m.from_idx = D.from_idx.as<int32_t>(); m.to_idx = D.to_idx.as<int32_t>();
       m.pos = P->d_pos.as<int32_t>(); m.paint = P->d_paint.as<int32_t>();
@@ -840,7 +855,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     LDW_CUDA(cudaEventRecord(D.done, st));
     return 0;
   };
-  for (size_t b = 0; b < blocks.size(); b++) LDW_TRY(run_block(b, 0, 0));
+  for (size_t b = 0; b < blocks.size(); b++) LDW_TRY(run_block(b, 0, 0, true));
   LDW_CUDA(cudaEventRecord(ev1, st));
 
   // ---- verify the long-range selection of every block; re-run the (rare) blocks whose candidate set is not
@@ -853,14 +868,21 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     for (size_t b = 0; b < blocks.size(); b++) {
       if (sel[b].skip || sel[b].n_lr == 0) continue;
       if (P->results[b].bad) {
-        n_reruns++;
-        if ((uint64_t)sel[b].n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block %lld needs an exhaustive long-range pass over more than 2^32 links", (long long)blocks[b].index);
-        uint32_t cap = (uint32_t)sel[b].n_lr;
-        LDW_TRY(P->d_cand.ensure((size_t)cap * sizeof(Cand)));
-        LDW_TRY(P->d_mi64.ensure((size_t)cap * 8));
-        LDW_TRY(run_block(b, 1, cap));
-        LDW_CUDA(cudaMemcpyAsync(&P->results[b], P->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
-        LDW_CUDA(cudaStreamSynchronize(st));
+        // second attempt: no chained seed (collect from zero, the histogram places the threshold); last resort:
+        // collect every long-range pair of the block
+        for (int attempt = 0; attempt < 2 && P->results[b].bad; attempt++) {
+          n_reruns++;
+          uint32_t cap = 0;
+          if (attempt == 1) {
+            if ((uint64_t)sel[b].n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block %lld needs an exhaustive long-range pass over more than 2^32 links", (long long)blocks[b].index);
+            cap = (uint32_t)sel[b].n_lr;
+            LDW_TRY(P->d_cand.ensure((size_t)cap * sizeof(Cand)));
+            LDW_TRY(P->d_mi64.ensure((size_t)cap * 8));
+          }
+          LDW_TRY(run_block(b, attempt == 1, cap, false));
+          LDW_CUDA(cudaMemcpyAsync(&P->results[b], P->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
+          LDW_CUDA(cudaStreamSynchronize(st));
+        }
         if (P->results[b].bad) return set_error(LDW_ERR_INTERNAL, "long-range selection failed for block %lld (flags %u)", (long long)blocks[b].index, P->results[b].bad);
       }
     }
@@ -876,6 +898,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   int64_t n_border = 0;
   for (auto& r : P->results) n_border += r.n_border;
   if (n_kept > 0 && !(flags & LDW_SCAN_NO_LINKS)) {
+    n_launches += 2 + 4;  // iota, materialise, radix-sort passes (library)
     LDW_TRY(P->d_keys_sorted.ensure(n_kept * 8));
     LDW_TRY(P->d_order_in.ensure(n_kept * 4));
     LDW_TRY(P->d_order_out.ensure(n_kept * 4));
@@ -897,8 +920,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   LDW_CUDA(cudaEventRecord(ev2, st));
 
   // ---- device -> pinned host
-  P->h_sr.n = 0; P->h_lr.n = 0; P->h_border.n = 0;
-  if (!(flags & LDW_SCAN_NO_LINKS)) {
+  P->ctx->h_sr.n = 0; P->ctx->h_lr.n = 0; P->ctx->h_border.n = 0;
+  if (!(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_NO_D2H))) {
     auto d2h = [&](HostLinks& h, DevLinks& d, int64_t m) -> int {
       LDW_TRY(h.ensure(m));
       h.n = m;
@@ -912,8 +935,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       LDW_CUDA(cudaMemcpyAsync(h.mi.p, d.mi.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
       return 0;
     };
-    LDW_TRY(d2h(P->h_sr, P->d_sr, total_sr));
-    LDW_TRY(d2h(P->h_lr, P->d_lr, (int64_t)n_kept));
+    LDW_TRY(d2h(P->ctx->h_sr, P->d_sr, total_sr));
+    LDW_TRY(d2h(P->ctx->h_lr, P->d_lr, (int64_t)n_kept));
   }
   LDW_CUDA(cudaEventRecord(ev3, st));
   LDW_CUDA(cudaStreamSynchronize(st));
@@ -922,29 +945,34 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   // the explicit rows are the LR rows whose MI is within tol of the block threshold
   if (borderline_out) {
     std::vector<int64_t> idx;
-    const int32_t* blkcol = P->h_lr.blk.as<int32_t>();
-    const double* micol = P->h_lr.mi.as<double>();
+    const int32_t* blkcol = P->ctx->h_lr.blk.as<int32_t>();
+    const double* micol = P->ctx->h_lr.mi.as<double>();
     std::vector<double> thr_by_index(nblk_total, NAN);
     for (size_t b = 0; b < blocks.size(); b++)
       if (!sel[b].skip && sel[b].n_lr > 0 && !sr_only) thr_by_index[blocks[b].index] = P->results[b].thr;
-    for (int64_t i = 0; i < P->h_lr.n; i++)
+    for (int64_t i = 0; i < P->ctx->h_lr.n; i++)
       if (std::fabs(micol[i] - thr_by_index[blkcol[i]]) <= 1e-9) idx.push_back(i);
-    LDW_TRY(P->h_border.ensure((int64_t)idx.size()));
-    P->h_border.n = (int64_t)idx.size();
+    LDW_TRY(P->ctx->h_border.ensure((int64_t)idx.size()));
+    P->ctx->h_border.n = (int64_t)idx.size();
     for (size_t k = 0; k < idx.size(); k++) {
       int64_t i = idx[k];
-      P->h_border.pos1.as<int32_t>()[k] = P->h_lr.pos1.as<int32_t>()[i];
-      P->h_border.pos2.as<int32_t>()[k] = P->h_lr.pos2.as<int32_t>()[i];
-      P->h_border.c1.as<int32_t>()[k] = P->h_lr.c1.as<int32_t>()[i];
-      P->h_border.c2.as<int32_t>()[k] = P->h_lr.c2.as<int32_t>()[i];
-      P->h_border.len.as<int32_t>()[k] = P->h_lr.len.as<int32_t>()[i];
-      P->h_border.blk.as<int32_t>()[k] = blkcol[i];
-      P->h_border.mi.as<double>()[k] = micol[i];
+      P->ctx->h_border.pos1.as<int32_t>()[k] = P->ctx->h_lr.pos1.as<int32_t>()[i];
+      P->ctx->h_border.pos2.as<int32_t>()[k] = P->ctx->h_lr.pos2.as<int32_t>()[i];
+      P->ctx->h_border.c1.as<int32_t>()[k] = P->ctx->h_lr.c1.as<int32_t>()[i];
+      P->ctx->h_border.c2.as<int32_t>()[k] = P->ctx->h_lr.c2.as<int32_t>()[i];
+      P->ctx->h_border.len.as<int32_t>()[k] = P->ctx->h_lr.len.as<int32_t>()[i];
+      P->ctx->h_border.blk.as<int32_t>()[k] = blkcol[i];
+      P->ctx->h_border.mi.as<double>()[k] = micol[i];
     }
-    P->h_border.fill(borderline_out);
+    P->ctx->h_border.fill(borderline_out);
   }
-  P->h_sr.fill(sr_out);
-  P->h_lr.fill(lr_out);
+  if (flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_NO_D2H)) {
+    if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = total_sr; }
+    if (lr_out) { memset(lr_out, 0, sizeof(*lr_out)); lr_out->n = (int64_t)n_kept; }
+  } else {
+    P->ctx->h_sr.fill(sr_out);
+    P->ctx->h_lr.fill(lr_out);
+  }
   for (size_t b = 0; b < blocks.size(); b++) {
     if (sel[b].skip || sel[b].n_lr == 0 || sr_only) continue;
     if (thr_out) thr_out[blocks[b].index] = P->results[b].thr;
@@ -967,7 +995,19 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     stats_out->t_scan_ms = a;
     stats_out->t_select_ms = b;
     stats_out->t_d2h_ms = c;
+    double tk = 0;
+    for (size_t k = 0; k + 1 < kev.size(); k += 2) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, kev[k], kev[k + 1]);
+      tk += ms;
+    }
+    stats_out->t_kernel_ms = tk;
+    stats_out->n_scan_launches = n_scan_launches;
+    stats_out->n_launches = n_launches;
+    stats_out->n_tiles = n_tiles;
+    stats_out->exec_int8_ops = exec_ops;
   }
+  kev_cleanup();
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
   return 0;
 }

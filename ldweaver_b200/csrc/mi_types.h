@@ -67,7 +67,8 @@ struct ScanParams {
   int32_t diag, ragged, qcorr, sr_only, dense, emit_all;
   const uint8_t* rfl_arr;  // r of from-list by local index (ragged Q1 path)
   const uint8_t* rtl_arr;  // r of to-list by local index
-  float kH, kL;
+  float kT;               // joint count = t * kT with t = (H << sa) + ((L + rb) >> sb)
+  uint32_t sa, sb, rb;
   int32_t neffH, neffL;
   float den[4][4];          // neff + 0.5 r_i r_j
   float ln2_over_den[4][4];

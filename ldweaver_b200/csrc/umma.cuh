@@ -58,12 +58,18 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = globaltimer_ns();
+  // try_wait itself suspends the thread for a hardware-bounded time; the clock is only consulted now and then
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (globaltimer_ns() - t0 > LDW_WAIT_TIMEOUT_NS) {
-      printf("ldw: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
-             (int)threadIdx.x, parity);
-      __trap();
+    if ((++spins & 0x3FFu) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > LDW_WAIT_TIMEOUT_NS) {
+        printf("ldw: mbarrier wait timeout tag=%d block=%d thread=%d parity=%u\n", tag, (int)blockIdx.x,
+               (int)threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }
@@ -142,8 +148,9 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, uint32_t* v) {
 }
 template <int N>
 __device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t* v) {
-  static_assert(N == 16 || N == 8 || N == 4 || N == 2, "unsupported tcgen05.ld width");
-  if constexpr (N == 16) tmem_ld16(taddr, v);
+  static_assert(N == 16 || N == 8 || N == 4 || N == 2 || N == 1, "unsupported tcgen05.ld width");
+  if constexpr (N == 1) asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v[0]) : "r"(taddr));
+  else if constexpr (N == 16) tmem_ld16(taddr, v);
   else if constexpr (N == 8) tmem_ld8(taddr, v);
   else if constexpr (N == 4) tmem_ld4(taddr, v);
   else tmem_ld2(taddr, v);
