@@ -21,7 +21,8 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
   if (snp < 0) {
     if (lane < 4) {
       Rec z;
-      for (int q = 0; q < 5; q++) { z.PH[q] = 0; z.PL[q] = 0; z.rp[q] = 0.f; }
+      for (int q = 0; q < 4; q++) { z.PH[q] = 0; z.PL[q] = 0; z.rp[q] = 0.f; }
+      z.PH4 = 0; z.PL4 = 0; z.rp4 = 0.f;
       z.pad = 0;
       rec[lane * vstride + slot] = z;
     }
@@ -55,17 +56,20 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
   if (lane < 4) {
     // variant `lane`: partner SNP has r' = lane + 2 observed alleles
     int m = mask[snp];
-    Rec z;
+    int qh[5] = {0, 0, 0, 0, 0}, ql[5] = {0, 0, 0, 0, 0};
+    float qr[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     int q = 0;
     for (int a = 0; a < 5; a++) {
       if (m & (1 << a)) {
-        z.PH[q] = h[a];
-        z.PL[q] = l[a];
-        z.rp[q] = (float)(1.0 / (p[a] + 0.5 * (double)(lane + 2)));
+        qh[q] = h[a];
+        ql[q] = l[a];
+        qr[q] = (float)(1.0 / (p[a] + 0.5 * (double)(lane + 2)));
         q++;
       }
     }
-    for (; q < 5; q++) { z.PH[q] = 0; z.PL[q] = 0; z.rp[q] = 0.f; }
+    Rec z;
+    for (int t = 0; t < 4; t++) { z.PH[t] = qh[t]; z.PL[t] = ql[t]; z.rp[t] = qr[t]; }
+    z.PH4 = qh[4]; z.PL4 = ql[4]; z.rp4 = qr[4];
     z.pad = 0;
     rec[lane * vstride + slot] = z;
   }

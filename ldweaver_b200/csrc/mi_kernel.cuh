@@ -44,7 +44,7 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 // columns handled per TMEM read batch: keeps the unrolled body near 32-64 MI terms (instruction cache) and the
 // accumulator registers at <= 32
 __host__ __device__ constexpr int mi_jc(int pa, int pb) {
-  return (pa + 1) * (pb + 1) <= 4 ? 16 : (pa + 1) * (pb + 1) <= 6 ? 8 : (pa + 1) * (pb + 1) <= 9 ? 4 : (pa + 1) * (pb + 1) <= 12 ? 2 : 1;
+  return (pa + 1) * (pb + 1) <= 4 ? 8 : (pa + 1) * (pb + 1) <= 6 ? 4 : (pa + 1) * (pb + 1) <= 12 ? 2 : 1;
 }
 __host__ __device__ constexpr int mi_njlog2(int pa, int pb) {
   return pa * pb == 1 ? 7 : pa * pb == 2 ? 6 : pa * pb <= 4 ? 5 : 4;
@@ -81,26 +81,24 @@ __device__ __noinline__ void lr_raise_threshold(const ScanParams& p, int lane) {
 
 struct EpiCtx {
   int q, half, lane;
-  uint32_t tmem_base;  // lane-quarter offset already applied, column of this tile's accumulators
-  const Rec* jrec;     // shared
-  const ColDyn* jdyn;  // shared
+  uint32_t tmem_base;   // lane-quarter offset already applied, column of this tile's accumulators
+  uint32_t jrec_saddr;  // shared-memory byte addresses of this tile's column records
+  uint32_t jdyn_saddr;
 };
 
-// Everything the per-pair code needs, held in registers (copied once per tile): reading it through the kernel
-// parameter struct inside the pair loop costs a generic load per use.
-struct EpiConst {
-  float kT, scale, q0, rtlq, qod, tcand;
-  int32_t neffH, neffL, nf, nt, il;
-  uint32_t sa, sb, rb;        // fixed-point count -> float: t = (H << sa) + ((L + rb) >> sb)
-  int32_t diag, ragged, dense, do_lr, has_sr;
-  float* sr_out;
-};
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+  return v;
+}
 
-// One term of the MI sum.  h,l: exact fixed-point halves of the joint count (both non-negative).
+// One term of the MI sum.  h,l: exact fixed-point halves of the joint count (both non-negative);
+// count = ((h << sa) + ((l + rbias) >> sb)) * kT.
 template <bool QC>
-__device__ __forceinline__ float mi_term(float acc, int h, int l, float ra, float rb, float dq, const EpiConst& k) {
-  uint32_t t = ((uint32_t)h << k.sa) + (((uint32_t)l + k.rb) >> k.sb);
-  float x = fmaf(__uint2float_rn(t), k.kT, 0.5f);
+__device__ __forceinline__ float mi_term(float acc, int h, int l, float ra, float rb, float dq, float kT, uint32_t mul_a,
+                                         uint32_t sb, uint32_t rbias) {
+  uint32_t t = (uint32_t)h * mul_a + (((uint32_t)l + rbias) >> sb);
+  float x = fmaf(__uint2float_rn(t), kT, 0.5f);
   float e = ra * rb;
   float v = lg2_fast(x * e);
   if (QC) v -= lg2_fast(fmaf(dq, e, 1.0f));
@@ -134,40 +132,59 @@ __device__ __noinline__ void lr_emit(const ScanParams& p, bool em, int il, int j
   }
 }
 
+// Short-range link: store MI at the link's final, position-determined slot of the block's output.
+__device__ __noinline__ void sr_store(float* sr_out, uint4 d0, uint4 d1, int il, int jl, float mi) {
+  const int a0 = (int)d0.z, a1 = (int)d0.w, b0 = (int)d1.x, b1 = (int)d1.y;
+  const int la = a1 - a0, lb = b1 - b0;
+  int below = min(max(il - a0, 0), la) + min(max(il - b0, 0), lb);  // short-range rows of this column before `il`
+  uint32_t slot;
+  if (il < jl) {
+    slot = d1.z + (uint32_t)below;
+  } else {
+    int bj = min(max(jl + 1 - a0, 0), la) + min(max(jl + 1 - b0, 0), lb);
+    slot = d1.w + (uint32_t)(below - bj);
+  }
+  sr_out[slot] = mi;
+}
+
 template <int PA, int PB, bool QC>
 __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
   constexpr int RA = PA + 1, RB = PB + 1;
   constexpr int JC = mi_jc(PA, PB);
   constexpr int NJ = 1 << mi_njlog2(PA, PB);
   const int row = c.q * 32 + c.lane;
-  // ---- per-tile constants into registers
-  EpiConst k;
+  // ---- per-tile constants, all in registers
   const float den = p.den[RA - 2][RB - 2];
-  k.kT = p.kT; k.scale = p.ln2_over_den[RA - 2][RB - 2]; k.q0 = p.q0[RA - 2][RB - 2];
-  k.qod = p.quarter_over_den[RA - 2][RB - 2];
-  k.neffH = p.neffH; k.neffL = p.neffL; k.nf = p.nf; k.nt = p.nt;
-  k.sa = p.sa; k.sb = p.sb; k.rb = p.rb;
-  k.diag = p.diag; k.ragged = p.ragged; k.dense = p.dense;
-  k.do_lr = (!p.sr_only && !p.dense) ? 1 : 0;
-  k.has_sr = (td.flags & TILE_HAS_SR) ? 1 : 0;
-  k.sr_out = p.sr_out;
-  k.tcand = (k.do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
+  const float kT = p.kT, scale = p.ln2_over_den[RA - 2][RB - 2], q0 = p.q0[RA - 2][RB - 2];
+  const float qod = p.quarter_over_den[RA - 2][RB - 2];
+  const int neffH = p.neffH, neffL = p.neffL, nf = p.nf, nt = p.nt;
+  const uint32_t mul_a = 1u << p.sa, sb = p.sb, rbias = p.rb;
+  const bool diag = p.diag != 0, ragged = p.ragged != 0, dense = p.dense != 0;
+  const bool do_lr = !p.sr_only && !p.dense;
+  const bool has_sr = (td.flags & TILE_HAS_SR) != 0;
+  float* const sr_out = p.sr_out;
+  const float tcand = (do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
   // ---- this thread's row SNP
   const Rec* ri = p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row;
   int PiH[RA], PiL[RA];
   float rpad[RA];
+  {
+    const uint4* rv = reinterpret_cast<const uint4*>(ri);
+    uint4 v0 = __ldg(rv), v1 = __ldg(rv + 1), v2 = __ldg(rv + 2), v3 = __ldg(rv + 3);
+    const uint32_t ph[5] = {v0.x, v0.y, v0.z, v0.w, v3.x}, pl[5] = {v1.x, v1.y, v1.z, v1.w, v3.y};
+    const uint32_t rp[5] = {v2.x, v2.y, v2.z, v2.w, v3.z};
 #pragma unroll
-  for (int a = 0; a < RA; a++) {
-    PiH[a] = __ldg(&ri->PH[a]);
-    PiL[a] = __ldg(&ri->PL[a]);
-    rpad[a] = __ldg(&ri->rp[a]) * den;
+    for (int a = 0; a < RA; a++) {
+      PiH[a] = (int)ph[a];
+      PiL[a] = (int)pl[a];
+      rpad[a] = __uint_as_float(rp[a]) * den;
+    }
   }
   const RowDyn rd = p.rowdyn[td.i_dyn0 + row];
-  k.il = rd.il;
-  k.rtlq = rd.rtl * k.qod;
-  const int il = k.il;
+  const int il = rd.il;
+  const float rtlq = rd.rtl * qod;
   // validity of a pair: diagonal block -> 0 <= jl < il; otherwise 0 <= jl < nt, jl != il (quirk Q2); il must exist
-  const uint32_t jl_lim = il < 0 ? 0u : (k.diag ? (uint32_t)il : (uint32_t)k.nt);
+  const uint32_t jl_lim = il < 0 ? 0u : (diag ? (uint32_t)il : (uint32_t)nt);
 
   const int jbeg = c.half * (NJ / 2);
 #pragma unroll 1
@@ -183,27 +200,30 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
     tmem_ld_wait();
 #pragma unroll
     for (int jj = 0; jj < JC; jj++) {
-      const Rec& rj = c.jrec[j0 + jj];
-      const ColDyn& cd = c.jdyn[j0 + jj];
-      const int jl = cd.jl;
+      // ---- column SNP record (shared memory, same address for the whole warp)
+      const uint32_t ra_ = c.jrec_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(Rec);
+      const uint4 w0 = lds128(ra_), w1 = lds128(ra_ + 16), w2 = lds128(ra_ + 32);
+      uint4 w3 = make_uint4(0, 0, 0, 0);
+      if (RB == 5) w3 = lds128(ra_ + 48);
+      const uint32_t pjh[5] = {w0.x, w0.y, w0.z, w0.w, w3.x}, pjl[5] = {w1.x, w1.y, w1.z, w1.w, w3.y};
+      const uint32_t rpj[5] = {w2.x, w2.y, w2.z, w2.w, w3.z};
+      const uint4 d0 = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn));
+      const int jl = (int)d0.x;
       float dq = 0.f;
       if (QC) {
-        if (k.ragged) {
+        if (ragged) {
           // quirk Q1, general form: rft (nt x nf) is read by the linear index of the nf x nt matrix
-          float v = k.q0;
+          float v = q0;
           if (il >= 0 && jl >= 0) {
-            uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)k.nf;
-            uint32_t cdiv = (uint32_t)(lin / (uint32_t)k.nt), cmod = (uint32_t)(lin % (uint32_t)k.nt);
-            v = (float)p.rfl_arr[cdiv] * (float)p.rtl_arr[cmod] * k.qod;
+            uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)nf;
+            uint32_t cdiv = (uint32_t)(lin / (uint32_t)nt), cmod = (uint32_t)(lin % (uint32_t)nt);
+            v = (float)p.rfl_arr[cdiv] * (float)p.rtl_arr[cmod] * qod;
           }
-          dq = v - k.q0;
+          dq = v - q0;
         } else {
-          dq = fmaf(k.rtlq, cd.rfl, -k.q0);
+          dq = fmaf(rtlq, __uint_as_float(d0.y), -q0);
         }
       }
-      float rpb[RB];
-#pragma unroll
-      for (int b = 0; b < RB; b++) rpb[b] = rj.rp[b];
       // ---- (PA+1) x (PB+1) joint table by exact integer complement, MI accumulated term by term
       float acc = 0.f;
       int colH[PB], colL[PB];
@@ -218,46 +238,38 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
           int h = (int)H[a][b][jj], l = (int)L[a][b][jj];
           rH += h; rL += l;
           colH[b] += h; colL[b] += l;
-          acc = mi_term<QC>(acc, h, l, rpad[a], rpb[b], dq, k);
+          acc = mi_term<QC>(acc, h, l, rpad[a], __uint_as_float(rpj[b]), dq, kT, mul_a, sb, rbias);
         }
-        acc = mi_term<QC>(acc, PiH[a] - rH, PiL[a] - rL, rpad[a], rpb[PB], dq, k);
+        acc = mi_term<QC>(acc, PiH[a] - rH, PiL[a] - rL, rpad[a], __uint_as_float(rpj[PB]), dq, kT, mul_a, sb, rbias);
         totH += rH; totL += rL;
       }
 #pragma unroll
       for (int b = 0; b < PB; b++)
-        acc = mi_term<QC>(acc, rj.PH[b] - colH[b], rj.PL[b] - colL[b], rpad[PA], rpb[b], dq, k);
+        acc = mi_term<QC>(acc, (int)pjh[b] - colH[b], (int)pjl[b] - colL[b], rpad[PA], __uint_as_float(rpj[b]), dq, kT, mul_a,
+                          sb, rbias);
       {
-        int sjH = k.neffH - rj.PH[PB], sjL = k.neffL - rj.PL[PB];
-        acc = mi_term<QC>(acc, PiH[PA] - sjH + totH, PiL[PA] - sjL + totL, rpad[PA], rpb[PB], dq, k);
+        int sjH = neffH - (int)pjh[PB], sjL = neffL - (int)pjl[PB];
+        acc = mi_term<QC>(acc, PiH[PA] - sjH + totH, PiL[PA] - sjL + totL, rpad[PA], __uint_as_float(rpj[PB]), dq, kT, mul_a,
+                          sb, rbias);
       }
-      const float mi = acc * k.scale;
+      const float mi = acc * scale;
 
       // ---- classification and emission
-      if (k.dense) {
-        if (il >= 0 && jl >= 0) p.dense_out[(size_t)il + (size_t)jl * (size_t)k.nf] = mi;
-        continue;
-      }
-      const bool valid = ((uint32_t)jl < jl_lim) && (jl != il);
-      bool sr = false;
-      if (k.has_sr) {
-        const uint32_t la = (uint32_t)(cd.a1 - cd.a0), lb = (uint32_t)(cd.b1 - cd.b0);
-        sr = valid && (((uint32_t)(il - cd.a0) < la) || ((uint32_t)(il - cd.b0) < lb));
-        if (sr) {
-          // rows of this column that are short-range and precede `il`
-          int below = min(max(il - cd.a0, 0), (int)la) + min(max(il - cd.b0, 0), (int)lb);
-          uint32_t slot;
-          if (il < jl) {
-            slot = cd.baseU + (uint32_t)below;
-          } else {
-            int bj = min(max(jl + 1 - cd.a0, 0), (int)la) + min(max(jl + 1 - cd.b0, 0), (int)lb);
-            slot = cd.baseL + (uint32_t)(below - bj);
-          }
-          k.sr_out[slot] = mi;
+      if (dense) {
+        if (il >= 0 && jl >= 0) p.dense_out[(size_t)il + (size_t)jl * (size_t)nf] = mi;
+      } else {
+        const bool valid = ((uint32_t)jl < jl_lim) && (jl != il);
+        bool sr = false;
+        if (has_sr) {
+          const uint4 d1 = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn) + 16);
+          const uint32_t la = d0.w - d0.z, lb = d1.y - d1.x;
+          sr = valid && (((uint32_t)il - d0.z < la) || ((uint32_t)il - d1.x < lb));
+          if (sr) sr_store(sr_out, d0, d1, il, jl, mi);
         }
-      }
-      if (k.do_lr) {
-        const bool em = valid && !sr && (mi >= k.tcand);
-        if (__any_sync(0xffffffffu, em)) lr_emit(p, em, il, jl, mi, c.lane);
+        if (do_lr) {
+          const bool em = valid && !sr && (mi >= tcand);
+          if (__any_sync(0xffffffffu, em)) lr_emit(p, em, il, jl, mi, c.lane);
+        }
       }
     }
   }
@@ -430,8 +442,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       const bool big = 2 * td.PA * td.PB * NJ > 256;
       const int jb = it & 1;
       mbar_wait(&jfull[jb], (it >> 1) & 1, 30);
-      c.jrec = jrec + jb * 128;
-      c.jdyn = jdyn + jb * 128;
+      c.jrec_saddr = smem_u32(jrec + jb * 128);
+      c.jdyn_saddr = smem_u32(jdyn + jb * 128);
       int s0 = as;
       if (big) {
         // both accumulator halves: wait for the two ring slots in order

@@ -10,10 +10,15 @@ namespace ldw {
 //           30-bit weights), 0 for q >= r.  The last observed allele (slot r-1) is the "complement" slot whose
 //           joint counts are derived by subtraction instead of from the GEMM.
 //   rp    : 1/(p_q + 0.5 r') for r' = variant+2 (r of the partner SNP).
+// Layout: four 16-byte vectors {PH0..3} {PL0..3} {rp0..3} {PH4, PL4, rp4, pad}, so kinds with at most four
+// allele slots touch three vectors.
 struct __align__(16) Rec {
-  int32_t PH[5];
-  int32_t PL[5];
-  float rp[5];
+  int32_t PH[4];
+  int32_t PL[4];
+  float rp[4];
+  int32_t PH4;
+  int32_t PL4;
+  float rp4;
   int32_t pad;
 };
 static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
