@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--nsnp", type=int, default=0, help="override the number of SNPs (debug only; invalidates the metric)")
     ap.add_argument("--cpu-sample", type=int, default=4000, help="block edge of the bounded CPU-baseline sample")
+    ap.add_argument("--nrate", type=float, default=-1.0, help="override the per-cell N rate (debug only; invalidates the metric)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -124,6 +125,8 @@ def main():
 
     S, n_cfg, seed, probs, nrate = synth.CONFIGS[args.config]
     n = args.nsnp or n_cfg
+    if args.nrate >= 0:
+        nrate = args.nrate
     workload = f"{args.config}: synthetic {S} seqs x {n} SNPs (seed {seed}), Hamming-weighted MI, sr_dist {int(SR_DIST)}, " \
                f"lr_retain_links {int(LR_RETAIN)}, max_blk_sz {MAX_BLK}"
     config = {"workload": workload, "nseq": S, "nsnp": n, "sr_dist": SR_DIST, "lr_retain_links": LR_RETAIN,
@@ -295,7 +298,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"],
                        "pairs_per_step": pairs_all / args.steps, "n_sr": stats["n_sr"], "n_lr_kept": stats["n_lr_kept"],
-                       "n_reruns": stats["n_reruns"], "tiles_per_step_rank0": agg["n_tiles"] / args.steps,
+                       "n_reruns": stats["n_reruns"], "n_candidates": stats["n_candidates"], "tiles_per_step_rank0": agg["n_tiles"] / args.steps,
                        "lr_links_approx": lra}}
     print(json.dumps(line))
     if world > 1:

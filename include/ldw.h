@@ -146,6 +146,7 @@ typedef struct ldw_scan_stats {
   int64_t n_lr_kept;
   int64_t n_borderline;  /* LR candidates within borderline_tol of their block threshold (listed in `borderline`) */
   int64_t n_reruns;      /* blocks re-run because the candidate threshold guess was too high */
+  int64_t n_candidates;  /* long-range candidates collected by the scan kernel (before refinement / selection) */
   double t_pack_ms, t_scan_ms, t_select_ms, t_d2h_ms; /* CUDA-event phase timings of the last scan (library stream) */
   double t_kernel_ms;    /* sum of the scan kernel's own launch durations (CUDA events around each launch) */
   int64_t n_scan_launches; /* launches of the scan kernel */

@@ -136,23 +136,28 @@ struct RefineParams {
   double neff;
 };
 
-__device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int jl, int lane) {
+// One warp per pair.  `acc` is this warp's scratch in shared memory: 32 lanes x 25 joint-count cells (doubles,
+// lane-major with a stride of 25 so lanes hit different banks).  Each lane adds the weights of its sequences into
+// its own row, then lanes 0..24 each reduce one cell over the 32 rows in a fixed order.
+constexpr int REFINE_WARPS = 6;
+__device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int jl, int lane, double* acc) {
   const int gi = P.from_idx[il], gj = P.to_idx[jl];
   const uint8_t* ci = P.codes + (int64_t)gi * P.S;
   const uint8_t* cj = P.codes + (int64_t)gj * P.S;
-  double c[25];
+  double* mine = acc + lane * 25;
 #pragma unroll
-  for (int k = 0; k < 25; k++) c[k] = 0.0;
+  for (int k = 0; k < 25; k++) mine[k] = 0.0;
   for (int64_t s = lane; s < P.S; s += 32) {
     int idx = (int)ci[s] * 5 + (int)cj[s];
-    double ws = P.w[s];
-#pragma unroll
-    for (int k = 0; k < 25; k++) c[k] += (idx == k) ? ws : 0.0;
+    mine[idx] += P.w[s];
   }
-#pragma unroll
-  for (int k = 0; k < 25; k++)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+  __syncwarp();
+  double cell = 0.0;
+  if (lane < 25) {
+#pragma unroll 8
+    for (int l = 0; l < 32; l++) cell += acc[l * 25 + lane];
+  }
+  __syncwarp();
   const double ri = (double)P.r[gi], rj = (double)P.r[gj];
   const int mi_ = P.mask[gi], mj_ = P.mask[gj];
   const double den = P.neff + ri * rj * 0.5;
@@ -164,56 +169,68 @@ __device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int
     uint32_t cdiv = (uint32_t)(lin / (uint32_t)P.nt), cmod = (uint32_t)(lin % (uint32_t)P.nt);
     Q = (double)P.rfl_arr[cdiv] * (double)P.rtl_arr[cmod] * 0.25;
   }
+  // lane k < 25 owns term (a, b) = (k / 5, k % 5); the 25 terms are then summed in the reference's order
+  // (a-major, b-minor) by lane 0
+  double term = 0.0;
+  if (lane < 25) {
+    const int a = lane / 5, b = lane % 5;
+    if (((mi_ >> a) & 1) && ((mj_ >> b) & 1)) {
+      double pxy = cell + 0.5;
+      double pa = P.p64[(int64_t)gi * 5 + a], pb = P.p64[(int64_t)gj * 5 + b];
+      double dsum = pa * pb + Q + pa * (0.5 * ri) + pb * (0.5 * rj);
+      term = pxy / den * log(pxy / dsum * den);
+    }
+  }
   double mi = 0.0;
 #pragma unroll
-  for (int a = 0; a < 5; a++)
-#pragma unroll
-    for (int b = 0; b < 5; b++) {
-      if (((mi_ >> a) & 1) && ((mj_ >> b) & 1)) {
-        double pxy = c[a * 5 + b] + 0.5;
-        double pa = P.p64[(int64_t)gi * 5 + a], pb = P.p64[(int64_t)gj * 5 + b];
-        double dsum = pa * pb + Q + pa * (0.5 * ri) + pb * (0.5 * rj);
-        mi += pxy / den * log(pxy / dsum * den);
-      }
-    }
+  for (int k = 0; k < 25; k++) mi += __shfl_sync(0xffffffffu, term, k);
   return mi;
 }
 
 // Candidates below the FINAL candidate threshold are an incomplete sample of their MI range (the threshold rose
-// while they were being collected); they cannot take part in the selection and are not refined.
+// while they were being collected); they cannot take part in the selection.  The others are refined to fp64 and
+// written compactly (vcand / vmi, count in *vcount).
 __global__ void mi_refine_cand_kernel(RefineParams P, const Cand* __restrict__ cand, const uint32_t* __restrict__ count,
-                                      uint32_t cap, const uint32_t* __restrict__ tcand_bits, int emit_all, double* mi64) {
+                                      uint32_t cap, const uint32_t* __restrict__ tcand_bits, int emit_all, Cand* vcand,
+                                      double* vmi, uint32_t* vcount) {
+  __shared__ double acc_s[REFINE_WARPS][32 * 25];
   uint32_t n = *count < cap ? *count : cap;
   const float tc = emit_all ? -3.0e38f : __uint_as_float(*tcand_bits);
   int lane = threadIdx.x & 31;
+  double* acc = acc_s[threadIdx.x >> 5];
   for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
-    if (cand[i].mi < tc) {
-      if (lane == 0) mi64[i] = -1.0e300;
-      continue;
+    Cand c = cand[i];
+    if (c.mi < tc) continue;
+    double v = refine_pair(P, c.il, c.jl, lane, acc);
+    if (lane == 0) {
+      uint32_t o = atomicAdd(vcount, 1u);
+      vcand[o] = c;
+      vmi[o] = v;
     }
-    double v = refine_pair(P, cand[i].il, cand[i].jl, lane);
-    if (lane == 0) mi64[i] = v;
   }
 }
 
 // Start of a block's long-range collection: counters cleared, histogram cleared, candidate threshold seeded from
 // the chained estimate of the previous block (or 0 = collect until the histogram can place a threshold).
-__global__ void mi_block_begin_kernel(uint32_t* state /*count, tcand, overflow*/, uint32_t* hist, const uint32_t* chain_bits,
-                                      int use_chain) {
+__global__ void mi_block_begin_kernel(uint32_t* state /*count, tcand, overflow, -, -, vcount*/, uint32_t* hist,
+                                      const uint32_t* chain_bits, int use_chain) {
   for (int i = threadIdx.x; i < MI_HIST_BINS; i += blockDim.x) hist[i] = 0;
   if (threadIdx.x == 0) {
     state[0] = 0;
     state[1] = use_chain ? *chain_bits : 0u;
     state[2] = 0;
+    state[5] = 0;
   }
 }
 
 __global__ void mi_refine_pairs_kernel(RefineParams P, const int32_t* __restrict__ il, const int32_t* __restrict__ jl,
                                        int64_t n, double* out) {
+  __shared__ double acc_s[REFINE_WARPS][32 * 25];
   int lane = threadIdx.x & 31;
+  double* acc = acc_s[threadIdx.x >> 5];
   for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n;
        i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-    double v = refine_pair(P, il[i], jl[i], lane);
+    double v = refine_pair(P, il[i], jl[i], lane, acc);
     if (lane == 0) out[i] = v;
   }
 }
@@ -231,9 +248,10 @@ struct BlockResult {
 };
 
 struct SelectParams {
-  const Cand* cand;
+  const Cand* cand;       // compact: refined candidates only
   const double* mi64;
-  const uint32_t* count;
+  const uint32_t* vcount; // number of refined candidates
+  const uint32_t* count;  // raw number collected by the scan kernel
   uint32_t cap;
   const uint32_t* overflow;
   const uint32_t* tcand_bits;
@@ -319,7 +337,7 @@ __global__ void __launch_bounds__(1024) mi_select_kernel(SelectParams P) {
   __shared__ uint64_t bcast[2];
   __shared__ uint32_t s_kept, s_border;
   const uint32_t raw = *P.count;
-  const uint32_t n = raw < P.cap ? raw : P.cap;
+  const uint32_t n = *P.vcount;
   uint32_t bad = 0;
   if (*P.overflow || raw > P.cap) bad |= 1;
   if ((uint64_t)n < P.k_lo) bad |= 2;
@@ -328,8 +346,25 @@ __global__ void __launch_bounds__(1024) mi_select_kernel(SelectParams P) {
     v_lo = dkey_inv(select_kth_largest(P.mi64, n, P.k_lo, hist, bcast));
     thr = v_lo;
     if (P.interpolate && P.k_hi >= 1 && P.k_hi != P.k_lo) {
-      double v_hi = dkey_inv(select_kth_largest(P.mi64, n, P.k_hi, hist, bcast));
-      if (v_hi != v_lo) thr = (1.0 - P.h) * v_lo + P.h * v_hi;  // stats::quantile type 7
+      // x[hi] is the next order statistic above x[lo]: if exactly k_lo - 1 values are strictly greater it is the
+      // smallest of them, otherwise (ties at x[lo]) it equals x[lo]
+      __shared__ unsigned long long s_min_above;
+      __shared__ uint32_t s_above;
+      if (threadIdx.x == 0) { s_min_above = ~0ull; s_above = 0; }
+      __syncthreads();
+      uint32_t cnt = 0;
+      unsigned long long mn = ~0ull;
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        double v = P.mi64[i];
+        if (v > v_lo) { cnt++; unsigned long long kx = dkey(v); mn = kx < mn ? kx : mn; }
+      }
+      atomicAdd(&s_above, cnt);
+      atomicMin(&s_min_above, mn);
+      __syncthreads();
+      if ((uint64_t)s_above == P.k_lo - 1 && s_above > 0) {
+        double v_hi = dkey_inv((uint64_t)s_min_above);
+        if (v_hi != v_lo) thr = (1.0 - P.h) * v_lo + P.h * v_hi;  // stats::quantile type 7
+      }
     }
     if (!P.emit_all) {
       double tc = (double)__uint_as_float(*P.tcand_bits);

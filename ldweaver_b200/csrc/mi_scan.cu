@@ -77,7 +77,7 @@ struct ldw_mi_plan {
   static constexpr int RING = 4;
   BlockDev ring[RING];
   BlockHost hring[RING];
-  DevBuf d_cand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
+  DevBuf d_cand, d_vcand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
   DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
   DevLinks d_sr, d_lr;
   std::vector<BlockResult> results;
@@ -654,8 +654,8 @@ int ldw_mi_pairs_exact(ldw_mi_plan* P, int64_t block_index, const int32_t* from_
   LDW_CUDA(cudaMemcpyAsync(di.p, from_local, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
   LDW_CUDA(cudaMemcpyAsync(dj.p, to_local, (size_t)n_pairs * 4, cudaMemcpyHostToDevice, st));
   RefineParams R = make_refine_params(P, D, H, cfg);
-  int grid = (int)std::min<int64_t>((n_pairs + 7) / 8, 148 * 8);
-  mi_refine_pairs_kernel<<<grid, 256, 0, st>>>(R, di.as<int32_t>(), dj.as<int32_t>(), n_pairs, dout.as<double>());
+  int grid = (int)std::min<int64_t>((n_pairs + REFINE_WARPS - 1) / REFINE_WARPS, 148 * 8);
+  mi_refine_pairs_kernel<<<grid, 32 * REFINE_WARPS, 0, st>>>(R, di.as<int32_t>(), dj.as<int32_t>(), n_pairs, dout.as<double>());
   LDW_CUDA(cudaGetLastError());
   LDW_CUDA(cudaMemcpyAsync(mi_out, dout.p, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, st));
   LDW_CUDA(cudaStreamSynchronize(st));
@@ -741,6 +741,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   // ---- device workspace
   LDW_TRY(P->d_cand.ensure(max_cap * sizeof(Cand)));
   LDW_TRY(P->d_mi64.ensure(max_cap * 8));
+  LDW_TRY(P->d_vcand.ensure(max_cap * sizeof(Cand)));
   LDW_TRY(P->d_state.ensure(64));
   LDW_TRY(P->d_hist.ensure(MI_HIST_BINS * 4));
   LDW_TRY(P->d_results.ensure(std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult)));
@@ -819,12 +820,12 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     if (lr) {
       n_launches += 2;
       RefineParams R = make_refine_params(P, D, H, cfg);
-      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 256, 0, st>>>(R, P->d_cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
-                                                                 P->d_mi64.as<double>());
+      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, st>>>(R, P->d_cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
+                                                                 P->d_vcand.as<Cand>(), P->d_mi64.as<double>(), d_count + 5);
       LDW_CUDA(cudaGetLastError());
       SelectParams q;
       memset(&q, 0, sizeof(q));
-      q.cand = P->d_cand.as<Cand>(); q.mi64 = P->d_mi64.as<double>(); q.count = d_count; q.cap = cap;
+      q.cand = P->d_vcand.as<Cand>(); q.mi64 = P->d_mi64.as<double>(); q.vcount = d_count + 5; q.count = d_count; q.cap = cap;
       q.overflow = d_overflow; q.tcand_bits = d_tcand; q.emit_all = emit_all;
       q.k_lo = s.k_lo; q.k_hi = s.k_hi; q.h = s.h; q.interpolate = s.interp;
       q.tol_safe = 4e-6; q.tol_border = 1e-9;
@@ -878,6 +879,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
             cap = (uint32_t)sel[b].n_lr;
             LDW_TRY(P->d_cand.ensure((size_t)cap * sizeof(Cand)));
             LDW_TRY(P->d_mi64.ensure((size_t)cap * 8));
+            LDW_TRY(P->d_vcand.ensure((size_t)cap * sizeof(Cand)));
           }
           LDW_TRY(run_block(b, attempt == 1, cap, false));
           LDW_CUDA(cudaMemcpyAsync(&P->results[b], P->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
@@ -986,6 +988,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     stats_out->n_lr_total = sr_only ? 0 : total_lr;
     stats_out->n_lr_kept = (int64_t)n_kept;
     stats_out->n_borderline = n_border;
+    {
+      int64_t nc = 0;
+      for (auto& r : P->results) nc += r.n_cand;
+      stats_out->n_candidates = nc;
+    }
     stats_out->n_reruns = n_reruns;
     float a = 0, b = 0, c = 0;
     cudaEventElapsedTime(&a, ev0, ev1);
