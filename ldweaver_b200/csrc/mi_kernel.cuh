@@ -317,7 +317,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; i++) tma_prefetch_desc(&tm.a[i]);
-    for (int i = 0; i < MI_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < MI_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.cluster ? 3 : 1); }
     for (int i = 0; i < 2; i++) {
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256);
       mbar_init(&jfull[i], 1); mbar_init(&jempty[i], 256);
@@ -327,8 +327,17 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // 2x2 cluster: rank = ri * 2 + rj; CTAs with equal ri share the row tile (A), CTAs with equal rj share the column
+  // tile (B).  Each CTA fetches half rj of A and half ri of B and multicasts it to the sharing pair.
+  const uint32_t crank = p.cluster ? cluster_ctarank() : 0u;
+  const uint32_t ri = crank >> 1, rj = crank & 1u;
+  const uint16_t maskA = (uint16_t)(0x3u << (ri * 2)), maskB = (uint16_t)((1u << rj) | (1u << (rj + 2)));
+  const uint16_t maskE = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));
+  const int tile0 = p.cluster ? (int)((blockIdx.x >> 2) * 4 + crank) : (int)blockIdx.x;
+  const int tstep = p.cluster ? (int)(gridDim.x) : (int)gridDim.x;
   // register budget: the control warpgroup (warps 0-3) gives registers to the two epilogue warpgroups
   // (pool = 168 x 384 = 64512 registers at launch; 96 x 128 + 200 x 256 = 63488 fits)
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
@@ -336,96 +345,148 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
-      int st = 0; uint32_t ph = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
-        const TileDesc td = p.tiles[t];
-        const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
-        const int njidx = 7 - td.njlog2;  // 128,64,32,16 -> 0..3
-        const int jb = it & 1;
-        mbar_wait(&jempty[jb], ((it >> 1) & 1) ^ 1, 10);
-        mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (sizeof(Rec) + sizeof(ColDyn)));
+    // Whole warp runs the loop (uniform registers), one elected lane issues the copies.
+    int st = 0; uint32_t ph = 0;
+    int it = 0;
+    for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
+      const TileDesc td = p.tiles[t];
+      const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
+      const int njidx = 7 - td.njlog2;  // NJ 128,64,32,16 -> half-tile boxes of 64,32,16,8 rows
+      const int hb = NJ / 2;
+      const int jb = it & 1;
+      mbar_wait(&jempty[jb], ((it >> 1) & 1) ^ 1, 10);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (uint32_t)(sizeof(Rec) + sizeof(ColDyn)));
         bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
         bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
-        // A planes go two per stage (X1 and X128 slices of each), then the four digit arrays of all PB column planes
-        for (int a0 = 0; a0 < PA; a0 += 2) {
-          const int na = min(2, PA - a0);
-          for (int kb = 0; kb < p.nkb; kb++) {
-            mbar_wait(&empty[st], ph ^ 1, 11);
+      }
+      __syncwarp();
+      // A planes go two per stage (X1 and X128 slices of each), then the four digit arrays of all PB column planes
+      for (int a0 = 0; a0 < PA; a0 += 2) {
+        const int na = min(2, PA - a0);
+        const uint32_t stage_tx = (uint32_t)(na * 2) * MI_ARR_BYTES + (uint32_t)(4 * PB * NJ * 128);
+        for (int kb = 0; kb < p.nkb; kb++) {
+          mbar_wait(&empty[st], ph ^ 1, 11);
+          if (elect_one()) {
             uint8_t* sb = stage_base + st * MI_STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[st], (uint32_t)(na * 2) * MI_ARR_BYTES + (uint32_t)(4 * PB * NJ * 128));
-            for (int a = 0; a < na; a++) {
-              const int arow = td.a_row0 + (a0 + a) * td.a_pstride;
-              tma_load_2d(sb + (a * 2 + 0) * MI_ARR_BYTES, &tm.a[0], &full[st], kb * 128, arow);
-              tma_load_2d(sb + (a * 2 + 1) * MI_ARR_BYTES, &tm.a[1], &full[st], kb * 128, arow);
+            mbar_arrive_expect_tx(&full[st], stage_tx);
+            if (p.cluster) {
+              for (int a = 0; a < na; a++) {
+                const int arow = td.a_row0 + (a0 + a) * td.a_pstride + (int)rj * 64;
+                tma_load_2d_mc(sb + (a * 2 + 0) * MI_ARR_BYTES + rj * 8192, &tm.a[0], &full[st], kb * 128, arow, maskA);
+                tma_load_2d_mc(sb + (a * 2 + 1) * MI_ARR_BYTES + rj * 8192, &tm.a[1], &full[st], kb * 128, arow, maskA);
+              }
+            } else {
+              for (int a = 0; a < na; a++)
+                for (int hf = 0; hf < 2; hf++) {
+                  const int arow = td.a_row0 + (a0 + a) * td.a_pstride + hf * 64;
+                  tma_load_2d(sb + (a * 2 + 0) * MI_ARR_BYTES + hf * 8192, &tm.a[0], &full[st], kb * 128, arow);
+                  tma_load_2d(sb + (a * 2 + 1) * MI_ARR_BYTES + hf * 8192, &tm.a[1], &full[st], kb * 128, arow);
+                }
             }
             // digit arrays in shared-memory order D3, D1, D2, D0: the two arrays multiplied by the same A operand
             // (X128: D3 | D1, X1: D2 | D0) sit next to each other, so one MMA covers both accumulator halves
             uint8_t* sbB = sb + na * 2 * MI_ARR_BYTES;
+#pragma unroll
             for (int sl = 0; sl < 4; sl++) {
               const int d = (sl == 1) ? 2 : (sl == 2) ? 1 : sl;
-              for (int b = 0; b < PB; b++)
-                tma_load_2d(sbB + (sl * PB + b) * NJ * 128, &tm.b[d][njidx], &full[st], kb * 128,
-                            td.b_row0 + b * td.b_pstride);
+              for (int b = 0; b < PB; b++) {
+                uint8_t* dst = sbB + (sl * PB + b) * NJ * 128;
+                const int brow = td.b_row0 + b * td.b_pstride;
+                if (p.cluster) {
+                  tma_load_2d_mc(dst + ri * hb * 128, &tm.b[d][njidx], &full[st], kb * 128, brow + (int)ri * hb, maskB);
+                } else {
+                  tma_load_2d(dst, &tm.b[d][njidx], &full[st], kb * 128, brow);
+                  tma_load_2d(dst + hb * 128, &tm.b[d][njidx], &full[st], kb * 128, brow + hb);
+                }
+              }
             }
-            if (++st == MI_STAGES) { st = 0; ph ^= 1; }
           }
+          __syncwarp();
+          if (++st == MI_STAGES) { st = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      int st = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
-      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-        const TileDesc td = p.tiles[t];
-        const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
-        const bool big = 2 * PA * PB * NJ > 256;
-        const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA
-        const uint32_t idesc = make_idesc_u8(128, ncols);
-        uint32_t dbase;
-        if (big) {
-          for (int s = 0; s < 2; s++) {
-            mbar_wait(&tempty[as], aph ^ 1, 20);
-            if (++as == 2) { as = 0; aph ^= 1; }
-          }
-          dbase = tmem_base;
-        } else {
-          mbar_wait(&tempty[as], aph ^ 1, 21);
-          dbase = tmem_base + as * 256;
+    // The whole warp runs the loop (so addresses and descriptors live in uniform registers); one elected lane
+    // issues the tcgen05 instructions.  Per MMA the issue cost must stay at a handful of instructions: a single
+    // thread issues only every few cycles, and a tile needs up to 80 MMAs.
+    int st = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+    const uint32_t desc_hi = (uint32_t)(make_smem_desc_sw128(0) >> 32);
+    for (int t = tile0; t < p.n_tiles; t += tstep) {
+      const TileDesc td = p.tiles[t];
+      const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
+      const bool big = 2 * PA * PB * NJ > 256;
+      const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA
+      const uint32_t idesc = make_idesc_u8(128, ncols);
+      uint32_t dbase;
+      if (big) {
+        for (int s2 = 0; s2 < 2; s2++) {
+          mbar_wait(&tempty[as], aph ^ 1, 20);
+          if (++as == 2) { as = 0; aph ^= 1; }
         }
-        tc_fence_after();
-        for (int a0 = 0; a0 < PA; a0 += 2) {
-          const int na = min(2, PA - a0);
-          for (int kb = 0; kb < p.nkb; kb++) {
-            mbar_wait(&full[st], ph, 22);
-            tc_fence_after();
-            const uint32_t sb = smem_u32(stage_base + st * MI_STAGE_BYTES);
-            const uint32_t sbB = sb + na * 2 * MI_ARR_BYTES;
-            const uint64_t dB128 = make_smem_desc_sw128(sbB);                              // D3 | D1
-            const uint64_t dB1 = make_smem_desc_sw128(sbB + 2 * PB * NJ * 128);              // D2 | D0
-            for (int a = 0; a < na; a++) {
-              const uint64_t dx1 = make_smem_desc_sw128(sb + (a * 2 + 0) * MI_ARR_BYTES);
-              const uint64_t dx128 = make_smem_desc_sw128(sb + (a * 2 + 1) * MI_ARR_BYTES);
-              const uint32_t dHL = dbase + (uint32_t)((a0 + a) * 2 * PB * NJ);
+        dbase = tmem_base;
+      } else {
+        mbar_wait(&tempty[as], aph ^ 1, 21);
+        dbase = tmem_base + as * 256;
+      }
+      tc_fence_after();
+      for (int a0 = 0; a0 < PA; a0 += 2) {
+        const int na = min(2, PA - a0);
+        const uint32_t boff = (uint32_t)(na * 2) * MI_ARR_BYTES;          // B region follows the A planes
+        const uint32_t b2off = boff + (uint32_t)(2 * PB * NJ * 128);      // D2 | D0 follow D3 | D1
+        for (int kb = 0; kb < p.nkb; kb++) {
+          mbar_wait(&full[st], ph, 22);
+          tc_fence_after();
+          // low descriptor word of the stage base: address >> 4 | LBO (1 << 16)
+          const uint32_t lo = ((smem_u32(stage_base + st * MI_STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+          if (elect_one()) {
+            const uint64_t dB128 = ((uint64_t)desc_hi << 32) | (lo + (boff >> 4));
+            const uint64_t dB1 = ((uint64_t)desc_hi << 32) | (lo + (b2off >> 4));
+            const uint32_t acc0 = kb > 0 ? 1u : 0u;
+            {
+              const uint64_t dx1 = ((uint64_t)desc_hi << 32) | lo;
+              const uint64_t dx128 = ((uint64_t)desc_hi << 32) | (lo + (MI_ARR_BYTES >> 4));
+              const uint32_t dHL = dbase + (uint32_t)(a0 * 2 * PB * NJ);
+              umma_i8(dHL, dx128, dB128, idesc, acc0);
+              umma_i8(dHL, dx1, dB1, idesc, 1u);
 #pragma unroll
-              for (int kk = 0; kk < 4; kk++) {
-                umma_i8(dHL, dx128 + 2 * kk, dB128 + 2 * kk, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+              for (int kk = 1; kk < 4; kk++) {
+                umma_i8(dHL, dx128 + 2 * kk, dB128 + 2 * kk, idesc, 1u);
                 umma_i8(dHL, dx1 + 2 * kk, dB1 + 2 * kk, idesc, 1u);
               }
             }
-            umma_commit(&empty[st]);
-            if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+            if (na == 2) {
+              const uint64_t dx1 = ((uint64_t)desc_hi << 32) | (lo + ((2 * MI_ARR_BYTES) >> 4));
+              const uint64_t dx128 = ((uint64_t)desc_hi << 32) | (lo + ((3 * MI_ARR_BYTES) >> 4));
+              const uint32_t dHL = dbase + (uint32_t)((a0 + 1) * 2 * PB * NJ);
+              umma_i8(dHL, dx128, dB128, idesc, acc0);
+              umma_i8(dHL, dx1, dB1, idesc, 1u);
+#pragma unroll
+              for (int kk = 1; kk < 4; kk++) {
+                umma_i8(dHL, dx128 + 2 * kk, dB128 + 2 * kk, idesc, 1u);
+                umma_i8(dHL, dx1 + 2 * kk, dB1 + 2 * kk, idesc, 1u);
+              }
+            }
+            if (p.cluster) umma_commit_mc(&empty[st], maskE);
+            else umma_commit(&empty[st]);
           }
+          __syncwarp();
+          if (++st == MI_STAGES) { st = 0; ph ^= 1; }
         }
+      }
+      if (elect_one()) {
         if (big) {
           umma_commit(&tfull[0]);
           umma_commit(&tfull[1]);
         } else {
           umma_commit(&tfull[as]);
-          if (++as == 2) { as = 0; aph ^= 1; }
         }
+      }
+      __syncwarp();
+      if (!big) {
+        if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -436,7 +497,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     c.lane = lane;
     int as = 0; uint32_t aph = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, it++) {
+    for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
       const int NJ = 1 << td.njlog2;
       const bool big = 2 * td.PA * td.PB * NJ > 256;
@@ -458,8 +519,10 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         c.tmem_base = tmem_base + ((uint32_t)(c.q * 32) << 16) + as * 256;
       }
       tc_fence_after();
-      if (p.qcorr) epi_dispatch<true>(p, td, c);
-      else epi_dispatch<false>(p, td, c);
+      if (!(td.flags & TILE_NULL)) {
+        if (p.qcorr) epi_dispatch<true>(p, td, c);
+        else epi_dispatch<false>(p, td, c);
+      }
       tc_fence_before();
       if (big) {
         mbar_arrive(&tempty[0]);
@@ -476,6 +539,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster) cluster_sync_all();  // no CTA leaves while a partner may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

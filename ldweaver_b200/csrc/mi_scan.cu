@@ -70,6 +70,8 @@ struct ldw_mi_plan {
   double neff = 0, scale = 0;          // weight = W / scale
   int32_t neffH = 0, neffL = 0;
   bool pos_sorted = true;
+  int max_clusters = 0;     // co-resident 4-CTA clusters the device can hold (occupancy query)
+  bool use_cluster = false; // 2x2 thread-block clusters with TMA multicast (LDW_CLUSTER=1 enables)
   // device, static
   DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops[6];
   TmapSet tm;
@@ -236,10 +238,10 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
     }
   }
   uint64_t trows = (uint64_t)std::max<int64_t>(row, 128);
-  for (int k = 0; k < 2; k++) LDW_TRY(make_tmap_u8_sw128(&P->tm.a[k], P->d_ops[k].p, trows, (uint64_t)P->Kpad, 128));
+  for (int k = 0; k < 2; k++) LDW_TRY(make_tmap_u8_sw128(&P->tm.a[k], P->d_ops[k].p, trows, (uint64_t)P->Kpad, 64));
   for (int d = 0; d < 4; d++)
     for (int j = 0; j < 4; j++)
-      LDW_TRY(make_tmap_u8_sw128(&P->tm.b[d][j], P->d_ops[2 + d].p, trows, (uint64_t)P->Kpad, 128u >> j));
+      LDW_TRY(make_tmap_u8_sw128(&P->tm.b[d][j], P->d_ops[2 + d].p, trows, (uint64_t)P->Kpad, 64u >> j));
   for (auto& b : P->ring) LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
   LDW_CUDA(cudaEventRecord(e1, st));
   LDW_CUDA(cudaStreamSynchronize(st));
@@ -249,6 +251,26 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   LDW_CUDA(cudaFuncSetAttribute(mi_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MI_SMEM_BYTES));
+  if (P->use_cluster) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3(4 * (unsigned)ctx->num_sms);
+    cfg.blockDim = dim3(MI_THREADS);
+    cfg.dynamicSmemBytes = MI_SMEM_BYTES;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int ncl = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, mi_scan_kernel, &cfg);
+    if (e != cudaSuccess || ncl < 1) {
+      cudaGetLastError();
+      P->use_cluster = false;  // fall back to single-CTA launches (same kernel, no multicast)
+    } else {
+      P->max_clusters = ncl;
+    }
+  }
   return 0;
 }
 
@@ -406,6 +428,9 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
     for (int c = off0 / 16; c < (off0 + nsl) / 16; c++)
       if (first[c] >= 0) { if (lo < 0) lo = first[c]; hi = last[c]; }
   };
+  // Tiles are emitted as 2x2 "super-tiles" (two row tiles x two column tiles of one kind = the four CTAs of a
+  // cluster, which share operand halves by TMA multicast).  Members that do not exist or hold no wanted pair are
+  // flagged TILE_NULL: they still take part in the cooperative loads but emit nothing.
   H.tiles.clear();
   for (int pa = 1; pa <= 4; pa++) {
     const Group& Gi = P->groups[(size_t)bf * 4 + pa - 1];
@@ -414,39 +439,72 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
       const Group& Gj = P->groups[(size_t)bt * 4 + pb - 1];
       if (Gj.count == 0) continue;
       const int njl = mi_njlog2(pa, pb), NJ = 1 << njl;
-      for (int ti = 0; ti * 128 < Gi.count; ti++) {
-        int ilo, ihi;
-        extent(f_first, f_last, Gi.slot0 - fs0 + ti * 128, 128, ilo, ihi);
-        if (ilo < 0) continue;
-        const int il_min = H.rowdyn[ilo].il, il_max = H.rowdyn[ihi].il;
-        const double pi0 = P->pos[P->slot_snp[fs0 + ilo]], pi1 = P->pos[P->slot_snp[fs0 + ihi]];
-        for (int tj = 0; tj * NJ < Gj.count; tj++) {
-          int jlo, jhi;
-          extent(t_first, t_last, Gj.slot0 - ts0 + tj * NJ, NJ, jlo, jhi);
-          if (jlo < 0) continue;
-          const int jl_min = H.coldyn[jlo].jl, jl_max = H.coldyn[jhi].jl;
-          (void)jl_max; (void)il_min;
-          if (H.diag && !cfg.dense && il_max <= jl_min) continue;  // no pair with row > col
-          const double pj0 = P->pos[P->slot_snp[ts0 + jlo]], pj1 = P->pos[P->slot_snp[ts0 + jhi]];
-          const double gap = std::max(0.0, std::max(pi0, pj0) - std::min(pi1, pj1));
-          const double span = std::max(pi1, pj1) - std::min(pi0, pj0);
-          const bool has_sr = all_sr || gap <= sr || (g - span) <= sr;
-          if (sr_only && !has_sr) continue;
-          TileDesc td;
-          memset(&td, 0, sizeof(td));
-          td.a_row0 = Gi.row0 + ti * 128;
-          td.a_pstride = Gi.nslots;
-          td.b_row0 = Gj.row0 + tj * NJ;
-          td.b_pstride = Gj.nslots;
-          td.i_slot0 = Gi.slot0 + ti * 128;
-          td.j_slot0 = Gj.slot0 + tj * NJ;
-          td.i_dyn0 = td.i_slot0 - fs0;
-          td.j_dyn0 = td.j_slot0 - ts0;
-          td.PA = (uint8_t)pa; td.PB = (uint8_t)pb; td.njlog2 = (uint8_t)njl;
-          td.flags = has_sr ? TILE_HAS_SR : 0;
-          H.tiles.push_back(td);
+      const int n_ti = (Gi.count + 127) / 128, n_tj = (Gj.count + NJ - 1) / NJ;
+      // per row tile / column tile extents
+      struct Ext { int lo, hi, lmin, lmax; double p0, p1; };
+      std::vector<Ext> ei(n_ti), ej(n_tj);
+      for (int ti = 0; ti < n_ti; ti++) {
+        Ext& e = ei[ti];
+        extent(f_first, f_last, Gi.slot0 - fs0 + ti * 128, 128, e.lo, e.hi);
+        if (e.lo >= 0) {
+          e.lmin = H.rowdyn[e.lo].il; e.lmax = H.rowdyn[e.hi].il;
+          e.p0 = P->pos[P->slot_snp[fs0 + e.lo]]; e.p1 = P->pos[P->slot_snp[fs0 + e.hi]];
         }
       }
+      for (int tj = 0; tj < n_tj; tj++) {
+        Ext& e = ej[tj];
+        extent(t_first, t_last, Gj.slot0 - ts0 + tj * NJ, NJ, e.lo, e.hi);
+        if (e.lo >= 0) {
+          e.lmin = H.coldyn[e.lo].jl; e.lmax = H.coldyn[e.hi].jl;
+          e.p0 = P->pos[P->slot_snp[ts0 + e.lo]]; e.p1 = P->pos[P->slot_snp[ts0 + e.hi]];
+        }
+      }
+      auto make_tile = [&](int ti, int tj, uint32_t flags) {
+        TileDesc td;
+        memset(&td, 0, sizeof(td));
+        td.a_row0 = Gi.row0 + ti * 128;
+        td.a_pstride = Gi.nslots;
+        td.b_row0 = Gj.row0 + tj * NJ;
+        td.b_pstride = Gj.nslots;
+        td.i_slot0 = Gi.slot0 + ti * 128;
+        td.j_slot0 = Gj.slot0 + tj * NJ;
+        td.i_dyn0 = td.i_slot0 - fs0;
+        td.j_dyn0 = td.j_slot0 - ts0;
+        td.PA = (uint8_t)pa; td.PB = (uint8_t)pb; td.njlog2 = (uint8_t)njl;
+        td.flags = (uint8_t)flags;
+        return td;
+      };
+      // 0: not wanted, else TILE flags | 0x80 marker
+      auto wanted = [&](int ti, int tj, uint32_t& flags) -> bool {
+        if (ti >= n_ti || tj >= n_tj) return false;
+        const Ext &a = ei[ti], &b = ej[tj];
+        if (a.lo < 0 || b.lo < 0) return false;
+        if (H.diag && !cfg.dense && a.lmax <= b.lmin) return false;  // no pair with row > col
+        const double gap = std::max(0.0, std::max(a.p0, b.p0) - std::min(a.p1, b.p1));
+        const double span = std::max(a.p1, b.p1) - std::min(a.p0, b.p0);
+        const bool has_sr = all_sr || gap <= sr || (g - span) <= sr;
+        if (sr_only && !has_sr) return false;
+        flags = has_sr ? TILE_HAS_SR : 0;
+        return true;
+      };
+      for (int ti = 0; ti < n_ti; ti += 2)
+        for (int tj = 0; tj < n_tj; tj += 2) {
+          uint32_t fl[4] = {0, 0, 0, 0};
+          bool w[4];
+          bool any = false;
+          for (int m = 0; m < 4; m++) {
+            w[m] = wanted(ti + (m >> 1), tj + (m & 1), fl[m]);
+            any = any || w[m];
+          }
+          if (!any) continue;
+          for (int m = 0; m < 4; m++) {
+            int a = ti + (m >> 1), b = tj + (m & 1);
+            // a missing member reuses an existing tile's coordinates so that the shared loads stay in bounds
+            if (a >= n_ti) a = ti;
+            if (b >= n_tj) b = tj;
+            H.tiles.push_back(make_tile(a, b, w[m] ? fl[m] : (uint32_t)TILE_NULL));
+          }
+        }
     }
   }
   return 0;
@@ -492,6 +550,7 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
   sp.diag = H.diag; sp.ragged = H.ragged;
   sp.qcorr = (!H.diag && !(cfg.flags & LDW_SCAN_IDEAL_Q)) ? 1 : 0;
   sp.sr_only = (cfg.flags & LDW_SCAN_SR_ONLY) ? 1 : 0;
+  sp.cluster = P->use_cluster ? 1 : 0;
   sp.rfl_arr = D.rfl.as<uint8_t>();
   sp.rtl_arr = D.rtl.as<uint8_t>();
   {
@@ -516,6 +575,34 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
       sp.q0[a][b] = (float)(0.25 * ri * rj / den);
       sp.quarter_over_den[a][b] = (float)(0.25 / den);
     }
+}
+
+// Launch the scan kernel: persistent, one CTA per SM; in cluster mode the grid is a whole number of 2x2 clusters.
+int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st) {
+  if (sp.n_tiles <= 0) return 0;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cudaLaunchAttribute attr[1];
+  int grid;
+  if (sp.cluster) {
+    int n_super = sp.n_tiles / 4;
+    int n_clusters = std::min(n_super, std::max(1, P->max_clusters));
+    grid = n_clusters * 4;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else {
+    grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
+  }
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(MI_THREADS);
+  cfg.dynamicSmemBytes = MI_SMEM_BYTES;
+  cfg.stream = st;
+  LDW_CUDA(cudaLaunchKernelEx(&cfg, mi_scan_kernel, P->tm, sp));
+  return 0;
 }
 
 RefineParams make_refine_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& H, const ScanCfg& cfg) {
@@ -563,6 +650,12 @@ int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_
   ldw_mi_plan* P = new ldw_mi_plan();
   P->ctx = ctx;
   P->n = n_snp; P->S = nseq; P->blk = blk;
+  {
+    // 2x2 thread-block clusters with TMA multicast halve the L2 -> SM operand traffic, but cluster launches cannot
+    // use every SM of the part and couple four CTAs per stage; measured slower at the headline shape, so opt-in.
+    const char* e = getenv("LDW_CLUSTER");
+    P->use_cluster = (e && e[0] == '1');
+  }
   int rc = build_plan(P, codes, hdw, pos, paint);
   if (rc != 0) { delete P; return rc; }
   *out = P;
@@ -608,11 +701,7 @@ int ldw_mi_block_dense(ldw_mi_plan* P, int64_t block_index, double* mi_out, int6
   fill_scan_params(P, D, H, cfg, sp);
   sp.dense = 1;
   sp.dense_out = P->d_dense.as<float>();
-  int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
-  if (grid > 0) {
-    mi_scan_kernel<<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
-    LDW_CUDA(cudaGetLastError());
-  }
+  LDW_TRY(launch_scan(P, sp, st));
   DevBuf d64;
   LDW_TRY(d64.alloc(cells * 8));
   f32_to_f64_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(P->d_dense.as<float>(), (int64_t)cells, d64.as<double>());
@@ -801,16 +890,14 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     } else {
       sp.sr_only = 1;  // nothing long-range to collect in this block
     }
-    int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
-    if (grid > 0) {
+    if (sp.n_tiles > 0) {
       cudaEvent_t k0, k1;
       LDW_CUDA(cudaEventCreate(&k0));
       LDW_CUDA(cudaEventCreate(&k1));
       kev.push_back(k0);
       kev.push_back(k1);
       LDW_CUDA(cudaEventRecord(k0, st));
-      mi_scan_kernel<<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
-      LDW_CUDA(cudaGetLastError());
+      LDW_TRY(launch_scan(P, sp, st));
       LDW_CUDA(cudaEventRecord(k1, st));
       n_launches++; n_scan_launches++;
       n_tiles += sp.n_tiles;

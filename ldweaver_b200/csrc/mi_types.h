@@ -40,7 +40,7 @@ struct __align__(16) ColDyn {
 };
 static_assert(sizeof(ColDyn) == 32, "ColDyn must be 32 bytes");
 
-enum : uint32_t { TILE_HAS_SR = 1u };
+enum : uint32_t { TILE_HAS_SR = 1u, TILE_NULL = 2u };
 
 // One unit of work: 128 row SNPs (PA planes each) x NJ column SNPs (PB planes each).
 struct __align__(16) TileDesc {
@@ -88,11 +88,14 @@ struct ScanParams {
   uint32_t* hist;
   uint32_t kprime, delta;
   uint32_t* overflow;
+  int32_t cluster;          // 1: launched as 2x2 clusters (4 CTAs share operand halves by TMA multicast); 0: single CTAs
 };
 
+// Operand tiles are fetched in halves (the two CTAs that share a tile inside a 2x2 cluster each fetch one half and
+// multicast it), so the boxes are half tiles.
 struct TmapSet {
-  CUtensorMap a[2];      // X1, X128  (box 128 rows)
-  CUtensorMap b[4][4];   // [digit array D3,D2,D1,D0][box rows 128,64,32,16]
+  CUtensorMap a[2];      // X1, X128  (box 64 rows)
+  CUtensorMap b[4][4];   // [digit array D3,D2,D1,D0][box rows 64,32,16,8]
 };
 
 }  // namespace ldw
