@@ -76,21 +76,15 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
 }
 
 // Operand rows.  row_info[R] = snp | allele << 28, or 0xFFFFFFFF for padding rows.  Each thread writes one 16-byte
-// chunk (16 sequences) of the six arrays: X1 (0/1), X128 (0/128), D3..D0 (digit where the allele matches).
+// chunk (16 sequences) of the 0/1 one-hot plane matrix X [rows][Kpad].
 __global__ void mi_pack_operands_kernel(const uint8_t* __restrict__ codes, int64_t S, int64_t Kpad,
-                                        const uint32_t* __restrict__ row_info, int64_t nrows,
-                                        const uint8_t* __restrict__ dig /*[4][Kpad]*/, uint8_t* X1, uint8_t* X128,
-                                        uint8_t* D3, uint8_t* D2, uint8_t* D1, uint8_t* D0) {
+                                        const uint32_t* __restrict__ row_info, int64_t nrows, uint8_t* X) {
   int64_t chunks = Kpad / 16;
   int64_t id = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= nrows * chunks) return;
   int64_t R = id / chunks, ch = id % chunks;
   uint32_t info = row_info[R];
-  uint32_t x1[4] = {0, 0, 0, 0}, x128[4] = {0, 0, 0, 0}, d[4][4];
-#pragma unroll
-  for (int t = 0; t < 4; t++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) d[t][k] = 0;
+  uint32_t x1[4] = {0, 0, 0, 0};
   if (info != 0xFFFFFFFFu) {
     const uint8_t* row = codes + (int64_t)(info & 0x0FFFFFFF) * S;
     int al = info >> 28;
@@ -99,22 +93,10 @@ __global__ void mi_pack_operands_kernel(const uint8_t* __restrict__ codes, int64
     for (int k = 0; k < 16; k++) {
       int64_t s = s0 + k;
       uint32_t bit = (s < S && row[s] == al) ? 1u : 0u;
-      int sh = 8 * (k & 3);
-      x1[k >> 2] |= bit << sh;
-      x128[k >> 2] |= (bit << 7) << sh;
-      if (bit) {
-#pragma unroll
-        for (int t = 0; t < 4; t++) d[t][k >> 2] |= (uint32_t)dig[t * Kpad + s] << sh;
-      }
+      x1[k >> 2] |= bit << (8 * (k & 3));
     }
   }
-  int64_t off = R * Kpad + ch * 16;
-  *reinterpret_cast<uint4*>(X1 + off) = make_uint4(x1[0], x1[1], x1[2], x1[3]);
-  *reinterpret_cast<uint4*>(X128 + off) = make_uint4(x128[0], x128[1], x128[2], x128[3]);
-  *reinterpret_cast<uint4*>(D3 + off) = make_uint4(d[0][0], d[0][1], d[0][2], d[0][3]);
-  *reinterpret_cast<uint4*>(D2 + off) = make_uint4(d[1][0], d[1][1], d[1][2], d[1][3]);
-  *reinterpret_cast<uint4*>(D1 + off) = make_uint4(d[2][0], d[2][1], d[2][2], d[2][3]);
-  *reinterpret_cast<uint4*>(D0 + off) = make_uint4(d[3][0], d[3][1], d[3][2], d[3][3]);
+  *reinterpret_cast<uint4*>(X + R * Kpad + ch * 16) = make_uint4(x1[0], x1[1], x1[2], x1[3]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -15,14 +15,20 @@
 //     MI = sum_ab x/den * ln(x den / D),  x = c + 0.5,  D = (p_i^a + r_j/2)(p_j^b + r_i/2) + dQ   (dQ: quirk Q1)
 // in fp32 with one MUFU.LG2 per term (two with the Q1 correction), and emit: short-range links to their final,
 // position-determined output slot; long-range candidates above a monotonically rising candidate threshold.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue.
+// Only the raw 0/1 one-hot planes travel from L2 to shared memory (the SM's inbound bandwidth, ~30 B/clk, is the
+// scarce resource): six expander warps build the x128 copy of the row tile and the four digit-weighted copies of the
+// column tile in place, inside the stage, before the MMA warp consumes it.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..7 = expanders (2 also owns TMEM), 8..15 = epilogue.
 #pragma once
 #include "mi_types.h"
 #include "umma.cuh"
 
 namespace ldw {
 
-constexpr int MI_THREADS = 384;
+constexpr int MI_EXP_WARPS = 6;
+constexpr int MI_EXP_THREADS = 32 * MI_EXP_WARPS;
+constexpr int MI_EPI_WARP0 = 8;
+constexpr int MI_THREADS = 512;
 constexpr int MI_STAGES = 2;
 constexpr uint32_t MI_ARR_BYTES = 128 * 128;              // one operand array slice: 128 rows x 128 K-bytes
 constexpr uint32_t MI_STAGE_BYTES = 6 * MI_ARR_BYTES;     // X1, X128, D3, D2, D1, D0
@@ -90,6 +96,10 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
   return v;
+}
+
+__device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // One term of the MI sum.  h,l: exact fixed-point halves of the joint count (both non-negative);
@@ -306,18 +316,21 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   Rec* jrec = reinterpret_cast<Rec*>(smem + MI_STAGES * MI_STAGE_BYTES);
   ColDyn* jdyn = reinterpret_cast<ColDyn*>(smem + MI_STAGES * MI_STAGE_BYTES + 2 * MI_JREC_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MI_STAGES * MI_STAGE_BYTES + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES));
-  uint64_t* full = bars;            // [MI_STAGES]
-  uint64_t* empty = bars + 2;       // [MI_STAGES]
+  uint64_t* full = bars;            // [MI_STAGES]  raw planes landed (TMA)
+  uint64_t* empty = bars + 2;       // [MI_STAGES]  MMAs that read the stage have completed
   uint64_t* tfull = bars + 4;       // [2]
   uint64_t* tempty = bars + 6;      // [2]
   uint64_t* jfull = bars + 8;       // [2]
   uint64_t* jempty = bars + 10;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* ready = bars + 12;      // [MI_STAGES]  expanded operands written (expander warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < 2; i++) tma_prefetch_desc(&tm.a[i]);
-    for (int i = 0; i < MI_STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], p.cluster ? 3 : 1); }
+    tma_prefetch_desc(&tm.a);
+    for (int i = 0; i < MI_STAGES; i++) {
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], MI_EXP_THREADS);
+    }
     for (int i = 0; i < 2; i++) {
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256);
       mbar_init(&jfull[i], 1); mbar_init(&jempty[i], 256);
@@ -327,92 +340,65 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
-  if (p.cluster) cluster_sync_all();  // every CTA's barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // 2x2 cluster: rank = ri * 2 + rj; CTAs with equal ri share the row tile (A), CTAs with equal rj share the column
-  // tile (B).  Each CTA fetches half rj of A and half ri of B and multicasts it to the sharing pair.
-  const uint32_t crank = p.cluster ? cluster_ctarank() : 0u;
-  const uint32_t ri = crank >> 1, rj = crank & 1u;
-  const uint16_t maskA = (uint16_t)(0x3u << (ri * 2)), maskB = (uint16_t)((1u << rj) | (1u << (rj + 2)));
-  const uint16_t maskE = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));
-  const int tile0 = p.cluster ? (int)((blockIdx.x >> 2) * 4 + crank) : (int)blockIdx.x;
-  const int tstep = p.cluster ? (int)(gridDim.x) : (int)gridDim.x;
-  // register budget: the control warpgroup (warps 0-3) gives registers to the two epilogue warpgroups
-  // (pool = 168 x 384 = 64512 registers at launch; 96 x 128 + 200 x 256 = 63488 fits)
-  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+  // register budget: the two control warpgroups (warps 0-7) give registers to the two epilogue warpgroups
+  // (pool = 128 x 512 = 65536 registers at launch; 96 x 256 + 160 x 256 = 65536)
+  if (warp < MI_EPI_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+
+  const int tile0 = (int)blockIdx.x, tstep = (int)gridDim.x;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     // Whole warp runs the loop (uniform registers), one elected lane issues the copies.
     int st = 0; uint32_t ph = 0;
     int it = 0;
+    long long w_jempty = 0, w_empty = 0, t_begin = clock64();
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
-      const int njidx = 7 - td.njlog2;  // NJ 128,64,32,16 -> half-tile boxes of 64,32,16,8 rows
-      const int hb = NJ / 2;
+      const int njidx = 7 - td.njlog2;  // NJ 128,64,32,16 -> tm.b[0..3]
       const int jb = it & 1;
-      mbar_wait(&jempty[jb], ((it >> 1) & 1) ^ 1, 10);
+      { long long c0 = clock64(); mbar_wait(&jempty[jb], ((it >> 1) & 1) ^ 1, 10); w_jempty += clock64() - c0; }
       if (elect_one()) {
         mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (uint32_t)(sizeof(Rec) + sizeof(ColDyn)));
         bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
         bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
       }
       __syncwarp();
-      // A planes go two per stage (X1 and X128 slices of each), then the four digit arrays of all PB column planes
+      // per stage: the raw planes of up to two row-tile planes (into their X1 slots) and of all PB column planes
+      // (into the D3 slot, expanded in place later)
       for (int a0 = 0; a0 < PA; a0 += 2) {
         const int na = min(2, PA - a0);
-        const uint32_t stage_tx = (uint32_t)(na * 2) * MI_ARR_BYTES + (uint32_t)(4 * PB * NJ * 128);
+        const uint32_t stage_tx = (uint32_t)na * MI_ARR_BYTES + (uint32_t)(PB * NJ * 128);
         for (int kb = 0; kb < p.nkb; kb++) {
-          mbar_wait(&empty[st], ph ^ 1, 11);
+          { long long c0 = clock64(); mbar_wait(&empty[st], ph ^ 1, 11); w_empty += clock64() - c0; }
           if (elect_one()) {
             uint8_t* sb = stage_base + st * MI_STAGE_BYTES;
             mbar_arrive_expect_tx(&full[st], stage_tx);
-            if (p.cluster) {
-              for (int a = 0; a < na; a++) {
-                const int arow = td.a_row0 + (a0 + a) * td.a_pstride + (int)rj * 64;
-                tma_load_2d_mc(sb + (a * 2 + 0) * MI_ARR_BYTES + rj * 8192, &tm.a[0], &full[st], kb * 128, arow, maskA);
-                tma_load_2d_mc(sb + (a * 2 + 1) * MI_ARR_BYTES + rj * 8192, &tm.a[1], &full[st], kb * 128, arow, maskA);
-              }
-            } else {
-              for (int a = 0; a < na; a++)
-                for (int hf = 0; hf < 2; hf++) {
-                  const int arow = td.a_row0 + (a0 + a) * td.a_pstride + hf * 64;
-                  tma_load_2d(sb + (a * 2 + 0) * MI_ARR_BYTES + hf * 8192, &tm.a[0], &full[st], kb * 128, arow);
-                  tma_load_2d(sb + (a * 2 + 1) * MI_ARR_BYTES + hf * 8192, &tm.a[1], &full[st], kb * 128, arow);
-                }
-            }
-            // digit arrays in shared-memory order D3, D1, D2, D0: the two arrays multiplied by the same A operand
-            // (X128: D3 | D1, X1: D2 | D0) sit next to each other, so one MMA covers both accumulator halves
+            for (int a = 0; a < na; a++)
+              tma_load_2d(sb + (a * 2) * MI_ARR_BYTES, &tm.a, &full[st], kb * 128, td.a_row0 + (a0 + a) * td.a_pstride);
             uint8_t* sbB = sb + na * 2 * MI_ARR_BYTES;
-#pragma unroll
-            for (int sl = 0; sl < 4; sl++) {
-              const int d = (sl == 1) ? 2 : (sl == 2) ? 1 : sl;
-              for (int b = 0; b < PB; b++) {
-                uint8_t* dst = sbB + (sl * PB + b) * NJ * 128;
-                const int brow = td.b_row0 + b * td.b_pstride;
-                if (p.cluster) {
-                  tma_load_2d_mc(dst + ri * hb * 128, &tm.b[d][njidx], &full[st], kb * 128, brow + (int)ri * hb, maskB);
-                } else {
-                  tma_load_2d(dst, &tm.b[d][njidx], &full[st], kb * 128, brow);
-                  tma_load_2d(dst + hb * 128, &tm.b[d][njidx], &full[st], kb * 128, brow + hb);
-                }
-              }
-            }
+            for (int b = 0; b < PB; b++)
+              tma_load_2d(sbB + b * NJ * 128, &tm.b[njidx], &full[st], kb * 128, td.b_row0 + b * td.b_pstride);
           }
           __syncwarp();
           if (++st == MI_STAGES) { st = 0; ph ^= 1; }
         }
       }
     }
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_begin);
+      p.dbg[blockIdx.x * 16 + 1] = (unsigned long long)w_jempty;
+      p.dbg[blockIdx.x * 16 + 2] = (unsigned long long)w_empty;
+    }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     // The whole warp runs the loop (so addresses and descriptors live in uniform registers); one elected lane
-    // issues the tcgen05 instructions.  Per MMA the issue cost must stay at a handful of instructions: a single
-    // thread issues only every few cycles, and a tile needs up to 80 MMAs.
+    // issues the tcgen05 instructions.
     int st = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+    long long w_tempty = 0, w_ready = 0, t_begin = clock64();
     const uint32_t desc_hi = (uint32_t)(make_smem_desc_sw128(0) >> 32);
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const TileDesc td = p.tiles[t];
@@ -423,12 +409,16 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       uint32_t dbase;
       if (big) {
         for (int s2 = 0; s2 < 2; s2++) {
+          long long c0 = clock64();
           mbar_wait(&tempty[as], aph ^ 1, 20);
+          w_tempty += clock64() - c0;
           if (++as == 2) { as = 0; aph ^= 1; }
         }
         dbase = tmem_base;
       } else {
+        long long c0 = clock64();
         mbar_wait(&tempty[as], aph ^ 1, 21);
+        w_tempty += clock64() - c0;
         dbase = tmem_base + as * 256;
       }
       tc_fence_after();
@@ -437,7 +427,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         const uint32_t boff = (uint32_t)(na * 2) * MI_ARR_BYTES;          // B region follows the A planes
         const uint32_t b2off = boff + (uint32_t)(2 * PB * NJ * 128);      // D2 | D0 follow D3 | D1
         for (int kb = 0; kb < p.nkb; kb++) {
-          mbar_wait(&full[st], ph, 22);
+          { long long c0 = clock64(); mbar_wait(&ready[st], ph, 22); w_ready += clock64() - c0; }
           tc_fence_after();
           // low descriptor word of the stage base: address >> 4 | LBO (1 << 16)
           const uint32_t lo = ((smem_u32(stage_base + st * MI_STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -469,8 +459,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
                 umma_i8(dHL, dx1 + 2 * kk, dB1 + 2 * kk, idesc, 1u);
               }
             }
-            if (p.cluster) umma_commit_mc(&empty[st], maskE);
-            else umma_commit(&empty[st]);
+            umma_commit(&empty[st]);
           }
           __syncwarp();
           if (++st == MI_STAGES) { st = 0; ph ^= 1; }
@@ -489,23 +478,87 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+    if (p.dbg && lane == 0) {
+      p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_begin);
+      p.dbg[blockIdx.x * 16 + 4] = (unsigned long long)w_tempty;
+      p.dbg[blockIdx.x * 16 + 5] = (unsigned long long)w_ready;
+    }
+  } else if (warp < MI_EPI_WARP0) {
+    // ===================================================================== operand expanders
+    // stage layout: [plane a: X1 (TMA) | X128 (built here)] x na, then D3 | D1 | D2 | D0 of all PB column planes
+    // (raw one-hot Y lands in the D3 slot; D1, D2, D0 are written, D3 = Y & digit3 is formed in place).
+    // Everything is elementwise on the swizzled image; only the digit lookup needs the logical K position,
+    // i.e. the 16-byte chunk index XOR (row & 7).
+    const int h = (warp - 2) * 32 + lane;  // 0..191
+    int st = 0; uint32_t ph = 0;
+    long long w_full = 0, t_begin = clock64();
+    for (int t = tile0; t < p.n_tiles; t += tstep) {
+      const TileDesc td = p.tiles[t];
+      const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
+      const int brows = PB * NJ;
+      for (int a0 = 0; a0 < PA; a0 += 2) {
+        const int na = min(2, PA - a0);
+        for (int kb = 0; kb < p.nkb; kb++) {
+          // this thread's digit chunks: logical chunk cl of K block kb
+          const int cl = h & 7;
+          const uint8_t* dg = p.dig + (int64_t)kb * 128 + cl * 16;
+          const uint4 g3 = __ldg(reinterpret_cast<const uint4*>(dg));
+          const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(dg + p.kpad));
+          const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(dg + 2 * p.kpad));
+          const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dg + 3 * p.kpad));
+          { long long c0 = clock64(); mbar_wait(&full[st], ph, 40); w_full += clock64() - c0; }
+          const uint32_t sb = smem_u32(stage_base + st * MI_STAGE_BYTES);
+          // X128 = X1 << 7 (bytes are 0/1)
+          for (int a = 0; a < na; a++) {
+            const uint32_t x1 = sb + (uint32_t)(a * 2) * MI_ARR_BYTES;
+#pragma unroll 2
+            for (int id = h; id < 1024; id += MI_EXP_THREADS) {
+              uint4 v = lds128(x1 + id * 16);
+              v.x <<= 7; v.y <<= 7; v.z <<= 7; v.w <<= 7;
+              sts128(x1 + MI_ARR_BYTES + id * 16, v);
+            }
+          }
+          // digit-weighted copies of the column planes
+          const uint32_t yb = sb + (uint32_t)(na * 2) * MI_ARR_BYTES;
+          const uint32_t slot = (uint32_t)brows * 128u;
+          for (int r = h >> 3; r < brows; r += MI_EXP_THREADS / 8) {
+            const uint32_t addr = yb + (uint32_t)r * 128u + (uint32_t)((cl ^ (r & 7)) * 16);
+            uint4 y = lds128(addr);
+            // bytes 0/1 -> 0x00/0xFF
+            y.x *= 255u; y.y *= 255u; y.z *= 255u; y.w *= 255u;
+            sts128(addr + slot, make_uint4(y.x & g1.x, y.y & g1.y, y.z & g1.z, y.w & g1.w));          // D1
+            sts128(addr + 2 * slot, make_uint4(y.x & g2.x, y.y & g2.y, y.z & g2.z, y.w & g2.w));      // D2
+            sts128(addr + 3 * slot, make_uint4(y.x & g0.x, y.y & g0.y, y.z & g0.z, y.w & g0.w));      // D0
+            sts128(addr, make_uint4(y.x & g3.x, y.y & g3.y, y.z & g3.z, y.w & g3.w));                 // D3 in place
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+          mbar_arrive(&ready[st]);
+          if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+        }
+      }
+    }
+    if (p.dbg && h == 0) {
+      p.dbg[blockIdx.x * 16 + 12] = (unsigned long long)(clock64() - t_begin);
+      p.dbg[blockIdx.x * 16 + 13] = (unsigned long long)w_full;
+    }
+  } else {
     // ===================================================================== epilogue
     EpiCtx c;
     c.q = warp & 3;
-    c.half = (warp - 4) >> 2;
+    c.half = (warp - MI_EPI_WARP0) >> 2;
     c.lane = lane;
     int as = 0; uint32_t aph = 0;
     int it = 0;
+    long long w_jfull = 0, w_tfull = 0, t_begin = clock64();
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
       const int NJ = 1 << td.njlog2;
       const bool big = 2 * td.PA * td.PB * NJ > 256;
       const int jb = it & 1;
-      mbar_wait(&jfull[jb], (it >> 1) & 1, 30);
+      { long long c0 = clock64(); mbar_wait(&jfull[jb], (it >> 1) & 1, 30); w_jfull += clock64() - c0; }
+      long long c1 = clock64();
       c.jrec_saddr = smem_u32(jrec + jb * 128);
       c.jdyn_saddr = smem_u32(jdyn + jb * 128);
-      int s0 = as;
       if (big) {
         // both accumulator halves: wait for the two ring slots in order
         uint32_t ph0 = aph;
@@ -518,6 +571,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         mbar_wait(&tfull[as], aph, 33);
         c.tmem_base = tmem_base + ((uint32_t)(c.q * 32) << 16) + as * 256;
       }
+      w_tfull += clock64() - c1;
       tc_fence_after();
       if (!(td.flags & TILE_NULL)) {
         if (p.qcorr) epi_dispatch<true>(p, td, c);
@@ -527,19 +581,22 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       if (big) {
         mbar_arrive(&tempty[0]);
         mbar_arrive(&tempty[1]);
-        // two ring slots consumed: phase flips once
-        aph ^= 1;
-        (void)s0;
+        aph ^= 1;  // two ring slots consumed: phase flips once
       } else {
         mbar_arrive(&tempty[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
       mbar_arrive(&jempty[jb]);
     }
+    if (p.dbg && lane == 0 && (warp == MI_EPI_WARP0 || warp == MI_EPI_WARP0 + 7)) {
+      int o = warp == MI_EPI_WARP0 ? 6 : 9;
+      p.dbg[blockIdx.x * 16 + o] = (unsigned long long)(clock64() - t_begin);
+      p.dbg[blockIdx.x * 16 + o + 1] = (unsigned long long)w_jfull;
+      p.dbg[blockIdx.x * 16 + o + 2] = (unsigned long long)w_tfull;
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster) cluster_sync_all();  // no CTA leaves while a partner may still multicast into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

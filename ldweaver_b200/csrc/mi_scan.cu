@@ -70,15 +70,14 @@ struct ldw_mi_plan {
   double neff = 0, scale = 0;          // weight = W / scale
   int32_t neffH = 0, neffL = 0;
   bool pos_sorted = true;
-  int max_clusters = 0;     // co-resident 4-CTA clusters the device can hold (occupancy query)
-  bool use_cluster = false; // 2x2 thread-block clusters with TMA multicast (LDW_CLUSTER=1 enables)
   // device, static
-  DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops[6];
+  DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops, d_dig;
   TmapSet tm;
   // scan workspace
   static constexpr int RING = 4;
   BlockDev ring[RING];
   BlockHost hring[RING];
+  DevBuf d_dbg;
   DevBuf d_cand, d_vcand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
   DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
   DevLinks d_sr, d_lr;
@@ -199,11 +198,10 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
       }
     }
   // ---- device: weights, records, operands
-  DevBuf d_slot_snp, d_wH, d_wL, d_dig, d_row_info;
+  DevBuf d_slot_snp, d_wH, d_wL, d_row_info;
   LDW_TRY(P->d_w.alloc((size_t)S * 8));
   LDW_TRY(d_wH.alloc((size_t)S * 4));
   LDW_TRY(d_wL.alloc((size_t)S * 4));
-  LDW_TRY(d_dig.alloc(dig.size()));
   LDW_TRY(d_slot_snp.alloc((size_t)std::max<int64_t>(slot, 1) * 4));
   LDW_TRY(d_row_info.alloc(row_info.size() * 4));
   LDW_TRY(P->d_p64.alloc((size_t)n * 5 * 8));
@@ -213,7 +211,6 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   LDW_CUDA(cudaMemcpyAsync(P->d_w.p, hdw, (size_t)S * 8, cudaMemcpyHostToDevice, st));
   LDW_CUDA(cudaMemcpyAsync(d_wH.p, wH.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
   LDW_CUDA(cudaMemcpyAsync(d_wL.p, wL.data(), (size_t)S * 4, cudaMemcpyHostToDevice, st));
-  LDW_CUDA(cudaMemcpyAsync(d_dig.p, dig.data(), dig.size(), cudaMemcpyHostToDevice, st));
   LDW_CUDA(cudaMemcpyAsync(d_slot_snp.p, P->slot_snp.data(), (size_t)slot * 4, cudaMemcpyHostToDevice, st));
   LDW_CUDA(cudaMemcpyAsync(d_row_info.p, row_info.data(), row_info.size() * 4, cudaMemcpyHostToDevice, st));
   LDW_CUDA(cudaMemcpyAsync(P->d_pos.p, pos, (size_t)n * 4, cudaMemcpyHostToDevice, st));
@@ -226,22 +223,21 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
     LDW_CUDA(cudaGetLastError());
   }
   size_t op_bytes = (size_t)std::max<int64_t>(row, 128) * P->Kpad;
-  for (int k = 0; k < 6; k++) LDW_TRY(P->d_ops[k].alloc(op_bytes));
+  LDW_TRY(P->d_ops.alloc(op_bytes));
+  LDW_TRY(P->d_dig.alloc(dig.size()));
+  LDW_CUDA(cudaMemcpyAsync(P->d_dig.p, dig.data(), dig.size(), cudaMemcpyHostToDevice, st));
   {
     int64_t total = row * (P->Kpad / 16);
     if (total > 0) {
-      mi_pack_operands_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-          P->d_codes.as<uint8_t>(), S, P->Kpad, d_row_info.as<uint32_t>(), row, d_dig.as<uint8_t>(), P->d_ops[0].as<uint8_t>(),
-          P->d_ops[1].as<uint8_t>(), P->d_ops[2].as<uint8_t>(), P->d_ops[3].as<uint8_t>(), P->d_ops[4].as<uint8_t>(),
-          P->d_ops[5].as<uint8_t>());
+      mi_pack_operands_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P->d_codes.as<uint8_t>(), S, P->Kpad,
+                                                                               d_row_info.as<uint32_t>(), row,
+                                                                               P->d_ops.as<uint8_t>());
       LDW_CUDA(cudaGetLastError());
     }
   }
   uint64_t trows = (uint64_t)std::max<int64_t>(row, 128);
-  for (int k = 0; k < 2; k++) LDW_TRY(make_tmap_u8_sw128(&P->tm.a[k], P->d_ops[k].p, trows, (uint64_t)P->Kpad, 64));
-  for (int d = 0; d < 4; d++)
-    for (int j = 0; j < 4; j++)
-      LDW_TRY(make_tmap_u8_sw128(&P->tm.b[d][j], P->d_ops[2 + d].p, trows, (uint64_t)P->Kpad, 64u >> j));
+  LDW_TRY(make_tmap_u8_sw128(&P->tm.a, P->d_ops.p, trows, (uint64_t)P->Kpad, 128));
+  for (int j = 0; j < 4; j++) LDW_TRY(make_tmap_u8_sw128(&P->tm.b[j], P->d_ops.p, trows, (uint64_t)P->Kpad, 128u >> j));
   for (auto& b : P->ring) LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
   LDW_CUDA(cudaEventRecord(e1, st));
   LDW_CUDA(cudaStreamSynchronize(st));
@@ -251,26 +247,6 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   LDW_CUDA(cudaFuncSetAttribute(mi_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MI_SMEM_BYTES));
-  if (P->use_cluster) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.gridDim = dim3(4 * (unsigned)ctx->num_sms);
-    cfg.blockDim = dim3(MI_THREADS);
-    cfg.dynamicSmemBytes = MI_SMEM_BYTES;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int ncl = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, mi_scan_kernel, &cfg);
-    if (e != cudaSuccess || ncl < 1) {
-      cudaGetLastError();
-      P->use_cluster = false;  // fall back to single-CTA launches (same kernel, no multicast)
-    } else {
-      P->max_clusters = ncl;
-    }
-  }
   return 0;
 }
 
@@ -428,9 +404,7 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
     for (int c = off0 / 16; c < (off0 + nsl) / 16; c++)
       if (first[c] >= 0) { if (lo < 0) lo = first[c]; hi = last[c]; }
   };
-  // Tiles are emitted as 2x2 "super-tiles" (two row tiles x two column tiles of one kind = the four CTAs of a
-  // cluster, which share operand halves by TMA multicast).  Members that do not exist or hold no wanted pair are
-  // flagged TILE_NULL: they still take part in the cooperative loads but emit nothing.
+  // One tile = 128 row SNPs x NJ column SNPs of one (PA, PB) kind; tiles that hold no wanted pair are skipped.
   H.tiles.clear();
   for (int pa = 1; pa <= 4; pa++) {
     const Group& Gi = P->groups[(size_t)bf * 4 + pa - 1];
@@ -487,23 +461,10 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
         flags = has_sr ? TILE_HAS_SR : 0;
         return true;
       };
-      for (int ti = 0; ti < n_ti; ti += 2)
-        for (int tj = 0; tj < n_tj; tj += 2) {
-          uint32_t fl[4] = {0, 0, 0, 0};
-          bool w[4];
-          bool any = false;
-          for (int m = 0; m < 4; m++) {
-            w[m] = wanted(ti + (m >> 1), tj + (m & 1), fl[m]);
-            any = any || w[m];
-          }
-          if (!any) continue;
-          for (int m = 0; m < 4; m++) {
-            int a = ti + (m >> 1), b = tj + (m & 1);
-            // a missing member reuses an existing tile's coordinates so that the shared loads stay in bounds
-            if (a >= n_ti) a = ti;
-            if (b >= n_tj) b = tj;
-            H.tiles.push_back(make_tile(a, b, w[m] ? fl[m] : (uint32_t)TILE_NULL));
-          }
+      for (int ti = 0; ti < n_ti; ti++)
+        for (int tj = 0; tj < n_tj; tj++) {
+          uint32_t fl = 0;
+          if (wanted(ti, tj, fl)) H.tiles.push_back(make_tile(ti, tj, fl));
         }
     }
   }
@@ -550,7 +511,8 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
   sp.diag = H.diag; sp.ragged = H.ragged;
   sp.qcorr = (!H.diag && !(cfg.flags & LDW_SCAN_IDEAL_Q)) ? 1 : 0;
   sp.sr_only = (cfg.flags & LDW_SCAN_SR_ONLY) ? 1 : 0;
-  sp.cluster = P->use_cluster ? 1 : 0;
+  sp.dig = P->d_dig.as<uint8_t>();
+  sp.kpad = P->Kpad;
   sp.rfl_arr = D.rfl.as<uint8_t>();
   sp.rtl_arr = D.rtl.as<uint8_t>();
   {
@@ -577,31 +539,12 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
     }
 }
 
-// Launch the scan kernel: persistent, one CTA per SM; in cluster mode the grid is a whole number of 2x2 clusters.
+// Launch the scan kernel: persistent, one CTA per SM.
 int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st) {
   if (sp.n_tiles <= 0) return 0;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cudaLaunchAttribute attr[1];
-  int grid;
-  if (sp.cluster) {
-    int n_super = sp.n_tiles / 4;
-    int n_clusters = std::min(n_super, std::max(1, P->max_clusters));
-    grid = n_clusters * 4;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 4;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-  } else {
-    grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
-  }
-  cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(MI_THREADS);
-  cfg.dynamicSmemBytes = MI_SMEM_BYTES;
-  cfg.stream = st;
-  LDW_CUDA(cudaLaunchKernelEx(&cfg, mi_scan_kernel, P->tm, sp));
+  int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
+  mi_scan_kernel<<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
+  LDW_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -650,12 +593,6 @@ int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_
   ldw_mi_plan* P = new ldw_mi_plan();
   P->ctx = ctx;
   P->n = n_snp; P->S = nseq; P->blk = blk;
-  {
-    // 2x2 thread-block clusters with TMA multicast halve the L2 -> SM operand traffic, but cluster launches cannot
-    // use every SM of the part and couple four CTAs per stage; measured slower at the headline shape, so opt-in.
-    const char* e = getenv("LDW_CLUSTER");
-    P->use_cluster = (e && e[0] == '1');
-  }
   int rc = build_plan(P, codes, hdw, pos, paint);
   if (rc != 0) { delete P; return rc; }
   *out = P;
@@ -855,6 +792,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   double exec_ops = 0;
   std::vector<cudaEvent_t> kev;  // pairs of events around every scan-kernel launch
   auto kev_cleanup = [&]() { for (auto e : kev) cudaEventDestroy(e); kev.clear(); };
+  int64_t dbg_block = -1;
+  {
+    const char* e = getenv("LDW_DBG_BLOCK");
+    if (e) dbg_block = atoll(e);
+  }
   bool chain_valid = false;  // the device-side chained threshold estimate holds a value from an earlier block
   auto run_block = [&](size_t b, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
     Sel& s = sel[b];
@@ -870,6 +812,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     ScanParams sp;
     fill_scan_params(P, D, H, cfg, sp);
     sp.sr_out = P->d_sr_f32.as<float>() + s.sr_base;
+    if (dbg_block >= 0 && (int64_t)b == dbg_block) {
+      LDW_TRY(P->d_dbg.ensure(4096 * 16 * 8));
+      LDW_CUDA(cudaMemsetAsync(P->d_dbg.p, 0, 4096 * 16 * 8, st));
+      sp.dbg = P->d_dbg.as<unsigned long long>();
+    }
     const bool lr = !sr_only && s.n_lr > 0;
     const int emit_all = force_emit_all || s.emit_all;
     uint32_t cap = cap_override ? cap_override : s.cap;
@@ -1100,6 +1047,21 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     stats_out->n_launches = n_launches;
     stats_out->n_tiles = n_tiles;
     stats_out->exec_int8_ops = exec_ops;
+  }
+  if (dbg_block >= 0 && P->d_dbg.p) {
+    std::vector<unsigned long long> h(4096 * 16);
+    cudaMemcpy(h.data(), P->d_dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
+    double s[16] = {0};
+    int nb = 0;
+    for (int c = 0; c < 4096; c++)
+      if (h[c * 16 + 3]) { nb++; for (int k = 0; k < 16; k++) s[k] += (double)h[c * 16 + k]; }
+    if (nb) {
+      fprintf(stderr, "ldw dbg block %lld (%d CTAs, kilo-cycles avg): producer total %.0f wait_jempty %.0f wait_empty %.0f | "
+              "mma total %.0f wait_tempty %.0f wait_ready %.0f | expander total %.0f wait_full %.0f | epi(first) total %.0f "
+              "wait_jfull %.0f wait_tfull %.0f | epi(last) total %.0f wait_jfull %.0f wait_tfull %.0f\n", (long long)dbg_block, nb,
+              s[0] / nb / 1e3, s[1] / nb / 1e3, s[2] / nb / 1e3, s[3] / nb / 1e3, s[4] / nb / 1e3, s[5] / nb / 1e3, s[12] / nb / 1e3,
+              s[13] / nb / 1e3, s[6] / nb / 1e3, s[7] / nb / 1e3, s[8] / nb / 1e3, s[9] / nb / 1e3, s[10] / nb / 1e3, s[11] / nb / 1e3);
+    }
   }
   kev_cleanup();
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);

@@ -88,14 +88,17 @@ struct ScanParams {
   uint32_t* hist;
   uint32_t kprime, delta;
   uint32_t* overflow;
-  int32_t cluster;          // 1: launched as 2x2 clusters (4 CTAs share operand halves by TMA multicast); 0: single CTAs
+  const uint8_t* dig;       // [4][Kpad] per-sequence weight digits D3, D2, D1, D0
+  int64_t kpad;
+  unsigned long long* dbg;  // optional per-CTA cycle counters (profiling aid; NULL in production)
 };
 
-// Operand tiles are fetched in halves (the two CTAs that share a tile inside a 2x2 cluster each fetch one half and
-// multicast it), so the boxes are half tiles.
+// One global operand array: the 0/1 one-hot planes X [plane rows][Kpad sequences].  Row tiles (A) and column
+// tiles (B) are boxes of the same tensor; the x128 copy of A and the four digit-weighted copies of B are built
+// inside shared memory by the expander warps.
 struct TmapSet {
-  CUtensorMap a[2];      // X1, X128  (box 64 rows)
-  CUtensorMap b[4][4];   // [digit array D3,D2,D1,D0][box rows 64,32,16,8]
+  CUtensorMap a;      // box 128 rows
+  CUtensorMap b[4];   // box rows 128, 64, 32, 16
 };
 
 }  // namespace ldw
