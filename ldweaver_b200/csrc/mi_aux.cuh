@@ -13,7 +13,7 @@ namespace ldw {
 __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S, const int32_t* __restrict__ slot_snp,
                                     int64_t nslots, const uint8_t* __restrict__ mask, const double* __restrict__ w,
                                     const int32_t* __restrict__ wH, const int32_t* __restrict__ wL, Rec* rec,
-                                    int64_t vstride, double* p64 /*[n][5]*/) {
+                                    int64_t vstride, double* p64 /*[n][5]*/, uint32_t sa, uint32_t sb) {
   int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (slot >= nslots) return;
@@ -21,9 +21,8 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
   if (snp < 0) {
     if (lane < 4) {
       Rec z;
-      for (int q = 0; q < 4; q++) { z.PH[q] = 0; z.PL[q] = 0; z.rp[q] = 0.f; }
-      z.PH4 = 0; z.PL4 = 0; z.rp4 = 0.f;
-      z.pad = 0;
+      for (int q = 0; q < 4; q++) { z.T[q] = 0; z.rp[q] = 0.f; }
+      z.T4 = 0; z.rp4 = 0.f; z.pad[0] = z.pad[1] = 0;
       rec[lane * vstride + slot] = z;
     }
     return;
@@ -56,21 +55,19 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
   if (lane < 4) {
     // variant `lane`: partner SNP has r' = lane + 2 observed alleles
     int m = mask[snp];
-    int qh[5] = {0, 0, 0, 0, 0}, ql[5] = {0, 0, 0, 0, 0};
+    uint32_t qt[5] = {0, 0, 0, 0, 0};
     float qr[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     int q = 0;
     for (int a = 0; a < 5; a++) {
       if (m & (1 << a)) {
-        qh[q] = h[a];
-        ql[q] = l[a];
+        qt[q] = ((uint32_t)h[a] << sa) + ((uint32_t)l[a] >> sb);
         qr[q] = (float)(1.0 / (p[a] + 0.5 * (double)(lane + 2)));
         q++;
       }
     }
     Rec z;
-    for (int t = 0; t < 4; t++) { z.PH[t] = qh[t]; z.PL[t] = ql[t]; z.rp[t] = qr[t]; }
-    z.PH4 = qh[4]; z.PL4 = ql[4]; z.rp4 = qr[4];
-    z.pad = 0;
+    for (int t = 0; t < 4; t++) { z.T[t] = qt[t]; z.rp[t] = qr[t]; }
+    z.T4 = qt[4]; z.rp4 = qr[4]; z.pad[0] = z.pad[1] = 0;
     rec[lane * vstride + slot] = z;
   }
 }

@@ -102,12 +102,9 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// One term of the MI sum.  h,l: exact fixed-point halves of the joint count (both non-negative);
-// count = ((h << sa) + ((l + rbias) >> sb)) * kT.
+// One term of the MI sum.  t: joint count in the fixed-point unit (count = t * kT).
 template <bool QC>
-__device__ __forceinline__ float mi_term(float acc, int h, int l, float ra, float rb, float dq, float kT, uint32_t mul_a,
-                                         uint32_t sb, uint32_t rbias) {
-  uint32_t t = (uint32_t)h * mul_a + (((uint32_t)l + rbias) >> sb);
+__device__ __forceinline__ float mi_term(float acc, uint32_t t, float ra, float rb, float dq, float kT) {
   float x = fmaf(__uint2float_rn(t), kT, 0.5f);
   float e = ra * rb;
   float v = lg2_fast(x * e);
@@ -157,131 +154,184 @@ __device__ __noinline__ void sr_store(float* sr_out, uint4 d0, uint4 d1, int il,
   sr_out[slot] = mi;
 }
 
+// Per-tile constants of the pair loop, all in registers (passed by value into the batch routine).
+template <int RA>
+struct TileRegs {
+  uint32_t Ti[RA];
+  float rpad[RA];
+  float kT, scale, q0, qod, rtlq, tcand;
+  uint32_t mul_a, sb, jl_lim;
+  int il, nf, nt;
+  bool ragged, dense, do_lr, has_sr;
+  float* sr_out;
+};
+
+template <int PA, int PB, int JC>
+__device__ __forceinline__ void epi_load(uint32_t tmem_base, int NJ, int j0, uint32_t (&H)[PA][PB][JC],
+                                         uint32_t (&L)[PA][PB][JC]) {
+#pragma unroll
+  for (int a = 0; a < PA; a++)
+#pragma unroll
+    for (int b = 0; b < PB; b++) {
+      tmem_ldn<JC>(tmem_base + ((a * 2 + 0) * PB + b) * NJ + j0, H[a][b]);
+      tmem_ldn<JC>(tmem_base + ((a * 2 + 1) * PB + b) * NJ + j0, L[a][b]);
+    }
+}
+
+// JC pairs (this thread's row SNP x JC column SNPs), evaluated in lock step: term loop outside, pair loop inside, so
+// JC independent dependency chains overlap each other's MUFU / conversion latency.
+template <int PA, int PB, int JC, bool QC>
+__device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, const TileRegs<PA + 1>& k, int j0,
+                                          const uint32_t (&H)[PA][PB][JC], const uint32_t (&L)[PA][PB][JC]) {
+  constexpr int RB = PB + 1;
+  uint32_t tj[JC][RB], rpj[JC][RB];
+  int jl[JC];
+  float dq[JC];
+  uint4 d0v[JC];
+#pragma unroll
+  for (int jj = 0; jj < JC; jj++) {
+    const uint32_t ra_ = c.jrec_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(Rec);
+    const uint4 w0 = lds128(ra_), w1 = lds128(ra_ + 16);
+    uint4 w2 = make_uint4(0, 0, 0, 0);
+    if (RB == 5) w2 = lds128(ra_ + 32);
+    const uint32_t tt[5] = {w0.x, w0.y, w0.z, w0.w, w2.x}, tr[5] = {w1.x, w1.y, w1.z, w1.w, w2.y};
+#pragma unroll
+    for (int b = 0; b < RB; b++) { tj[jj][b] = tt[b]; rpj[jj][b] = tr[b]; }
+    d0v[jj] = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn));
+    jl[jj] = (int)d0v[jj].x;
+    dq[jj] = 0.f;
+    if (QC) {
+      if (k.ragged) {
+        // quirk Q1, general form: rft (nt x nf) is read by the linear index of the nf x nt matrix
+        float v = k.q0;
+        if (k.il >= 0 && jl[jj] >= 0) {
+          uint64_t lin = (uint64_t)k.il + (uint64_t)jl[jj] * (uint64_t)k.nf;
+          uint32_t cdiv = (uint32_t)(lin / (uint32_t)k.nt), cmod = (uint32_t)(lin % (uint32_t)k.nt);
+          v = (float)p.rfl_arr[cdiv] * (float)p.rtl_arr[cmod] * k.qod;
+        }
+        dq[jj] = v - k.q0;
+      } else {
+        dq[jj] = fmaf(k.rtlq, __uint_as_float(d0v[jj].y), -k.q0);
+      }
+    }
+  }
+  // (PA+1) x (PB+1) joint table: PA x PB cells from the accumulators, the rest by complement in the count unit
+  // (floor semantics keep every row / column complement non-negative; only the corner needs a clamp)
+  float acc[JC];
+  uint32_t col[JC][PB], tot[JC];
+#pragma unroll
+  for (int jj = 0; jj < JC; jj++) {
+    acc[jj] = 0.f; tot[jj] = 0;
+#pragma unroll
+    for (int b = 0; b < PB; b++) col[jj][b] = 0;
+  }
+#pragma unroll
+  for (int a = 0; a < PA; a++) {
+    uint32_t rsum[JC];
+#pragma unroll
+    for (int jj = 0; jj < JC; jj++) rsum[jj] = 0;
+#pragma unroll
+    for (int b = 0; b < PB; b++) {
+#pragma unroll
+      for (int jj = 0; jj < JC; jj++) {
+        const uint32_t t = H[a][b][jj] * k.mul_a + (L[a][b][jj] >> k.sb);
+        rsum[jj] += t;
+        col[jj][b] += t;
+        acc[jj] = mi_term<QC>(acc[jj], t, k.rpad[a], __uint_as_float(rpj[jj][b]), dq[jj], k.kT);
+      }
+    }
+#pragma unroll
+    for (int jj = 0; jj < JC; jj++) {
+      acc[jj] = mi_term<QC>(acc[jj], k.Ti[a] - rsum[jj], k.rpad[a], __uint_as_float(rpj[jj][PB]), dq[jj], k.kT);
+      tot[jj] += rsum[jj];
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < PB; b++)
+#pragma unroll
+    for (int jj = 0; jj < JC; jj++)
+      acc[jj] = mi_term<QC>(acc[jj], tj[jj][b] - col[jj][b], k.rpad[PA], __uint_as_float(rpj[jj][b]), dq[jj], k.kT);
+#pragma unroll
+  for (int jj = 0; jj < JC; jj++) {
+    uint32_t sj = 0;
+#pragma unroll
+    for (int b = 0; b < PB; b++) sj += tj[jj][b];
+    const int corner = (int)(k.Ti[PA] + tot[jj] - sj);
+    acc[jj] = mi_term<QC>(acc[jj], (uint32_t)max(corner, 0), k.rpad[PA], __uint_as_float(rpj[jj][PB]), dq[jj], k.kT);
+  }
+  // ---- classification and emission
+#pragma unroll
+  for (int jj = 0; jj < JC; jj++) {
+    const float mi = acc[jj] * k.scale;
+    const int jlv = jl[jj];
+    if (k.dense) {
+      if (k.il >= 0 && jlv >= 0) p.dense_out[(size_t)k.il + (size_t)jlv * (size_t)k.nf] = mi;
+    } else {
+      const bool valid = ((uint32_t)jlv < k.jl_lim) && (jlv != k.il);
+      bool sr = false;
+      if (k.has_sr) {
+        const uint4 d0 = d0v[jj];
+        const uint4 d1 = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn) + 16);
+        const uint32_t la = d0.w - d0.z, lb = d1.y - d1.x;
+        sr = valid && (((uint32_t)k.il - d0.z < la) || ((uint32_t)k.il - d1.x < lb));
+        if (sr) sr_store(k.sr_out, d0, d1, k.il, jlv, mi);
+      }
+      if (k.do_lr) {
+        const bool em = valid && !sr && (mi >= k.tcand);
+        if (__any_sync(0xffffffffu, em)) lr_emit(p, em, k.il, jlv, mi, c.lane);
+      }
+    }
+  }
+}
+
 template <int PA, int PB, bool QC>
 __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
   constexpr int RA = PA + 1, RB = PB + 1;
   constexpr int JC = mi_jc(PA, PB);
   constexpr int NJ = 1 << mi_njlog2(PA, PB);
+  constexpr int NB = (NJ / 2) / JC;  // batches per warp
+  static_assert(NB >= 2 && NB % 2 == 0, "the batch loop is unrolled by two");
   const int row = c.q * 32 + c.lane;
-  // ---- per-tile constants, all in registers
+  TileRegs<RA> k;
   const float den = p.den[RA - 2][RB - 2];
-  const float kT = p.kT, scale = p.ln2_over_den[RA - 2][RB - 2], q0 = p.q0[RA - 2][RB - 2];
-  const float qod = p.quarter_over_den[RA - 2][RB - 2];
-  const int neffH = p.neffH, neffL = p.neffL, nf = p.nf, nt = p.nt;
-  const uint32_t mul_a = 1u << p.sa, sb = p.sb, rbias = p.rb;
-  const bool diag = p.diag != 0, ragged = p.ragged != 0, dense = p.dense != 0;
-  const bool do_lr = !p.sr_only && !p.dense;
-  const bool has_sr = (td.flags & TILE_HAS_SR) != 0;
-  float* const sr_out = p.sr_out;
-  const float tcand = (do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
-  // ---- this thread's row SNP
-  const Rec* ri = p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row;
-  int PiH[RA], PiL[RA];
-  float rpad[RA];
+  k.kT = p.kT; k.scale = p.ln2_over_den[RA - 2][RB - 2]; k.q0 = p.q0[RA - 2][RB - 2];
+  k.qod = p.quarter_over_den[RA - 2][RB - 2];
+  k.nf = p.nf; k.nt = p.nt;
+  k.mul_a = 1u << p.sa; k.sb = p.sb;
+  k.ragged = p.ragged != 0; k.dense = p.dense != 0;
+  k.do_lr = !p.sr_only && !p.dense;
+  k.has_sr = (td.flags & TILE_HAS_SR) != 0;
+  k.sr_out = p.sr_out;
+  k.tcand = (k.do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
   {
-    const uint4* rv = reinterpret_cast<const uint4*>(ri);
-    uint4 v0 = __ldg(rv), v1 = __ldg(rv + 1), v2 = __ldg(rv + 2), v3 = __ldg(rv + 3);
-    const uint32_t ph[5] = {v0.x, v0.y, v0.z, v0.w, v3.x}, pl[5] = {v1.x, v1.y, v1.z, v1.w, v3.y};
-    const uint32_t rp[5] = {v2.x, v2.y, v2.z, v2.w, v3.z};
+    const uint4* rv = reinterpret_cast<const uint4*>(p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row);
+    const uint4 v0 = __ldg(rv), v1 = __ldg(rv + 1), v2 = __ldg(rv + 2);
+    const uint32_t tt[5] = {v0.x, v0.y, v0.z, v0.w, v2.x}, tr[5] = {v1.x, v1.y, v1.z, v1.w, v2.y};
 #pragma unroll
     for (int a = 0; a < RA; a++) {
-      PiH[a] = (int)ph[a];
-      PiL[a] = (int)pl[a];
-      rpad[a] = __uint_as_float(rp[a]) * den;
+      k.Ti[a] = tt[a];
+      k.rpad[a] = __uint_as_float(tr[a]) * den;
     }
   }
   const RowDyn rd = p.rowdyn[td.i_dyn0 + row];
-  const int il = rd.il;
-  const float rtlq = rd.rtl * qod;
+  k.il = rd.il;
+  k.rtlq = rd.rtl * k.qod;
   // validity of a pair: diagonal block -> 0 <= jl < il; otherwise 0 <= jl < nt, jl != il (quirk Q2); il must exist
-  const uint32_t jl_lim = il < 0 ? 0u : (diag ? (uint32_t)il : (uint32_t)nt);
+  k.jl_lim = k.il < 0 ? 0u : (p.diag ? (uint32_t)k.il : (uint32_t)p.nt);
 
+  // ---- batches of JC columns; the TMEM reads of the next batch are in flight while this one is evaluated
   const int jbeg = c.half * (NJ / 2);
+  uint32_t Ha[PA][PB][JC], La[PA][PB][JC], Hb[PA][PB][JC], Lb[PA][PB][JC];
+  epi_load<PA, PB, JC>(c.tmem_base, NJ, jbeg, Ha, La);
 #pragma unroll 1
-  for (int j0 = jbeg; j0 < jbeg + NJ / 2; j0 += JC) {
-    uint32_t H[PA][PB][JC], L[PA][PB][JC];
-#pragma unroll
-    for (int a = 0; a < PA; a++)
-#pragma unroll
-      for (int b = 0; b < PB; b++) {
-        tmem_ldn<JC>(c.tmem_base + ((a * 2 + 0) * PB + b) * NJ + j0, H[a][b]);
-        tmem_ldn<JC>(c.tmem_base + ((a * 2 + 1) * PB + b) * NJ + j0, L[a][b]);
-      }
+  for (int bi = 0; bi < NB; bi += 2) {
+    const int j0 = jbeg + bi * JC;
     tmem_ld_wait();
-#pragma unroll
-    for (int jj = 0; jj < JC; jj++) {
-      // ---- column SNP record (shared memory, same address for the whole warp)
-      const uint32_t ra_ = c.jrec_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(Rec);
-      const uint4 w0 = lds128(ra_), w1 = lds128(ra_ + 16), w2 = lds128(ra_ + 32);
-      uint4 w3 = make_uint4(0, 0, 0, 0);
-      if (RB == 5) w3 = lds128(ra_ + 48);
-      const uint32_t pjh[5] = {w0.x, w0.y, w0.z, w0.w, w3.x}, pjl[5] = {w1.x, w1.y, w1.z, w1.w, w3.y};
-      const uint32_t rpj[5] = {w2.x, w2.y, w2.z, w2.w, w3.z};
-      const uint4 d0 = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn));
-      const int jl = (int)d0.x;
-      float dq = 0.f;
-      if (QC) {
-        if (ragged) {
-          // quirk Q1, general form: rft (nt x nf) is read by the linear index of the nf x nt matrix
-          float v = q0;
-          if (il >= 0 && jl >= 0) {
-            uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)nf;
-            uint32_t cdiv = (uint32_t)(lin / (uint32_t)nt), cmod = (uint32_t)(lin % (uint32_t)nt);
-            v = (float)p.rfl_arr[cdiv] * (float)p.rtl_arr[cmod] * qod;
-          }
-          dq = v - q0;
-        } else {
-          dq = fmaf(rtlq, __uint_as_float(d0.y), -q0);
-        }
-      }
-      // ---- (PA+1) x (PB+1) joint table by exact integer complement, MI accumulated term by term
-      float acc = 0.f;
-      int colH[PB], colL[PB];
-#pragma unroll
-      for (int b = 0; b < PB; b++) colH[b] = colL[b] = 0;
-      int totH = 0, totL = 0;
-#pragma unroll
-      for (int a = 0; a < PA; a++) {
-        int rH = 0, rL = 0;
-#pragma unroll
-        for (int b = 0; b < PB; b++) {
-          int h = (int)H[a][b][jj], l = (int)L[a][b][jj];
-          rH += h; rL += l;
-          colH[b] += h; colL[b] += l;
-          acc = mi_term<QC>(acc, h, l, rpad[a], __uint_as_float(rpj[b]), dq, kT, mul_a, sb, rbias);
-        }
-        acc = mi_term<QC>(acc, PiH[a] - rH, PiL[a] - rL, rpad[a], __uint_as_float(rpj[PB]), dq, kT, mul_a, sb, rbias);
-        totH += rH; totL += rL;
-      }
-#pragma unroll
-      for (int b = 0; b < PB; b++)
-        acc = mi_term<QC>(acc, (int)pjh[b] - colH[b], (int)pjl[b] - colL[b], rpad[PA], __uint_as_float(rpj[b]), dq, kT, mul_a,
-                          sb, rbias);
-      {
-        int sjH = neffH - (int)pjh[PB], sjL = neffL - (int)pjl[PB];
-        acc = mi_term<QC>(acc, PiH[PA] - sjH + totH, PiL[PA] - sjL + totL, rpad[PA], __uint_as_float(rpj[PB]), dq, kT, mul_a,
-                          sb, rbias);
-      }
-      const float mi = acc * scale;
-
-      // ---- classification and emission
-      if (dense) {
-        if (il >= 0 && jl >= 0) p.dense_out[(size_t)il + (size_t)jl * (size_t)nf] = mi;
-      } else {
-        const bool valid = ((uint32_t)jl < jl_lim) && (jl != il);
-        bool sr = false;
-        if (has_sr) {
-          const uint4 d1 = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn) + 16);
-          const uint32_t la = d0.w - d0.z, lb = d1.y - d1.x;
-          sr = valid && (((uint32_t)il - d0.z < la) || ((uint32_t)il - d1.x < lb));
-          if (sr) sr_store(sr_out, d0, d1, il, jl, mi);
-        }
-        if (do_lr) {
-          const bool em = valid && !sr && (mi >= tcand);
-          if (__any_sync(0xffffffffu, em)) lr_emit(p, em, il, jl, mi, c.lane);
-        }
-      }
-    }
+    epi_load<PA, PB, JC>(c.tmem_base, NJ, j0 + JC, Hb, Lb);
+    epi_batch<PA, PB, JC, QC>(p, c, k, j0, Ha, La);
+    tmem_ld_wait();
+    if (bi + 2 < NB) epi_load<PA, PB, JC>(c.tmem_base, NJ, j0 + 2 * JC, Ha, La);
+    epi_batch<PA, PB, JC, QC>(p, c, k, j0 + JC, Hb, Lb);
   }
 }
 

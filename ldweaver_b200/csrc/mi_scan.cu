@@ -69,6 +69,7 @@ struct ldw_mi_plan {
   int64_t nslots = 0, nrows = 0;
   double neff = 0, scale = 0;          // weight = W / scale
   int32_t neffH = 0, neffL = 0;
+  uint32_t sa = 0, sb = 0;             // epilogue count unit: t = (H << sa) + (L >> sb)
   bool pos_sorted = true;
   // device, static
   DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops, d_dig;
@@ -134,6 +135,16 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   if (sumH > 0x7fffffffLL || sumL > 0x7fffffffLL) return set_error(LDW_ERR_UNSUPPORTED, "too many sequences for int32 accumulation (nseq=%lld)", (long long)S);
   P->neffH = (int32_t)sumH;
   P->neffL = (int32_t)sumL;
+  {
+    // H < 32768 * S: shift it up as far as 32 bits allow and drop the matching low bits of L
+    uint64_t hmax = 32767ull * (uint64_t)S;
+    int bits = 0;
+    while ((hmax >> bits) != 0) bits++;
+    int sa_ = std::min(15, 32 - bits);
+    if (sa_ < 0) sa_ = 0;
+    P->sa = (uint32_t)sa_;
+    P->sb = (uint32_t)(15 - sa_);
+  }
 
   // ---- upload codes, per-SNP allele statistics
   LDW_TRY(P->d_codes.alloc((size_t)n * S));
@@ -219,7 +230,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
     int wpb = 8;
     mi_build_rec_kernel<<<(unsigned)((slot + wpb - 1) / wpb), wpb * 32, 0, st>>>(
         P->d_codes.as<uint8_t>(), S, d_slot_snp.as<int32_t>(), slot, P->d_mask.as<uint8_t>(), P->d_w.as<double>(),
-        d_wH.as<int32_t>(), d_wL.as<int32_t>(), P->d_rec.as<Rec>(), slot, P->d_p64.as<double>());
+        d_wH.as<int32_t>(), d_wL.as<int32_t>(), P->d_rec.as<Rec>(), slot, P->d_p64.as<double>(), P->sa, P->sb);
     LDW_CUDA(cudaGetLastError());
   }
   size_t op_bytes = (size_t)std::max<int64_t>(row, 128) * P->Kpad;
@@ -515,19 +526,9 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
   sp.kpad = P->Kpad;
   sp.rfl_arr = D.rfl.as<uint8_t>();
   sp.rtl_arr = D.rtl.as<uint8_t>();
-  {
-    // H < 32768 * S: shift it up as far as 32 bits allow, drop the matching low bits of L (with rounding)
-    uint64_t hmax = 32767ull * (uint64_t)P->S;
-    int bits = 0;
-    while ((hmax >> bits) != 0) bits++;
-    int sa = std::min(15, 32 - bits);
-    if (sa < 0) sa = 0;
-    sp.sa = (uint32_t)sa;
-    sp.sb = (uint32_t)(15 - sa);
-    sp.rb = sp.sb ? (1u << (sp.sb - 1)) : 0u;
-    sp.kT = (float)(std::ldexp(1.0, (int)sp.sb) / P->scale);
-  }
-  sp.neffH = P->neffH; sp.neffL = P->neffL;
+  sp.sa = P->sa;
+  sp.sb = P->sb;
+  sp.kT = (float)(std::ldexp(1.0, (int)P->sb) / P->scale);
   for (int a = 0; a < 4; a++)
     for (int b = 0; b < 4; b++) {
       double ri = a + 2, rj = b + 2;

@@ -6,22 +6,19 @@
 namespace ldw {
 
 // One record per (slot, variant): everything the epilogue needs to know about one SNP.
-//   PH/PL : fixed-point weighted marginals of the SNP's allele slots q = 0..r-1 (15-bit hi / lo digits of the
-//           30-bit weights), 0 for q >= r.  The last observed allele (slot r-1) is the "complement" slot whose
-//           joint counts are derived by subtraction instead of from the GEMM.
-//   rp    : 1/(p_q + 0.5 r') for r' = variant+2 (r of the partner SNP).
-// Layout: four 16-byte vectors {PH0..3} {PL0..3} {rp0..3} {PH4, PL4, rp4, pad}, so kinds with at most four
-// allele slots touch three vectors.
+//   T   : fixed-point weighted marginals of the SNP's allele slots q = 0..r-1 in the epilogue's count unit
+//         (floor(V / 2^sb), V = the exact 30-bit fixed-point sum), 0 for q >= r.  The last observed allele (slot r-1)
+//         is the "complement" slot whose joint counts are derived by subtraction instead of from the GEMM.
+//   rp  : 1/(p_q + 0.5 r') for r' = variant+2 (r of the partner SNP).
+// Layout: three 16-byte vectors {T0..T3} {rp0..rp3} {T4, rp4, -, -}; kinds with at most four allele slots read two.
 struct __align__(16) Rec {
-  int32_t PH[4];
-  int32_t PL[4];
+  uint32_t T[4];
   float rp[4];
-  int32_t PH4;
-  int32_t PL4;
+  uint32_t T4;
   float rp4;
-  int32_t pad;
+  uint32_t pad[2];
 };
-static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
+static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
 
 // Per-block, per from-slot: local row index (or -1) and r of the TO-list SNP that sits at that local index
 // (quirk Q1: the reference reads the transposed rft by linear index).
@@ -72,9 +69,8 @@ struct ScanParams {
   int32_t diag, ragged, qcorr, sr_only, dense, emit_all;
   const uint8_t* rfl_arr;  // r of from-list by local index (ragged Q1 path)
   const uint8_t* rtl_arr;  // r of to-list by local index
-  float kT;               // joint count = t * kT with t = (H << sa) + ((L + rb) >> sb)
-  uint32_t sa, sb, rb;
-  int32_t neffH, neffL;
+  float kT;               // joint count = t * kT with t = (H << sa) + (L >> sb) = floor(V / 2^sb)
+  uint32_t sa, sb;
   float den[4][4];          // neff + 0.5 r_i r_j
   float ln2_over_den[4][4];
   float q0[4][4];           // 0.25 r_i r_j / den
