@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 // columns handled per TMEM read batch: keeps the unrolled body near 32-64 MI terms (instruction cache) and the
 // accumulator registers at <= 32
 __host__ __device__ constexpr int mi_jc(int pa, int pb) {
-  return (pa + 1) * (pb + 1) <= 4 ? 8 : (pa + 1) * (pb + 1) <= 6 ? 4 : (pa + 1) * (pb + 1) <= 12 ? 2 : 1;
+  return (pa + 1) * (pb + 1) <= 4 ? 8 : (pa + 1) * (pb + 1) <= 9 ? 4 : (pa + 1) * (pb + 1) <= 12 ? 2 : 1;
 }
 __host__ __device__ constexpr int mi_njlog2(int pa, int pb) {
   return pa * pb == 1 ? 7 : pa * pb == 2 ? 6 : pa * pb <= 4 ? 5 : 4;
@@ -290,7 +290,7 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   constexpr int JC = mi_jc(PA, PB);
   constexpr int NJ = 1 << mi_njlog2(PA, PB);
   constexpr int NB = (NJ / 2) / JC;  // batches per warp
-  static_assert(NB >= 2 && NB % 2 == 0, "the batch loop is unrolled by two");
+  static_assert(NB >= 1, "at least one batch per warp");
   const int row = c.q * 32 + c.lane;
   TileRegs<RA> k;
   const float den = p.den[RA - 2][RB - 2];
@@ -319,19 +319,15 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   // validity of a pair: diagonal block -> 0 <= jl < il; otherwise 0 <= jl < nt, jl != il (quirk Q2); il must exist
   k.jl_lim = k.il < 0 ? 0u : (p.diag ? (uint32_t)k.il : (uint32_t)p.nt);
 
-  // ---- batches of JC columns; the TMEM reads of the next batch are in flight while this one is evaluated
+  // ---- batches of JC columns, evaluated in lock step
   const int jbeg = c.half * (NJ / 2);
-  uint32_t Ha[PA][PB][JC], La[PA][PB][JC], Hb[PA][PB][JC], Lb[PA][PB][JC];
-  epi_load<PA, PB, JC>(c.tmem_base, NJ, jbeg, Ha, La);
+  uint32_t Ha[PA][PB][JC], La[PA][PB][JC];
 #pragma unroll 1
-  for (int bi = 0; bi < NB; bi += 2) {
+  for (int bi = 0; bi < NB; bi++) {
     const int j0 = jbeg + bi * JC;
+    epi_load<PA, PB, JC>(c.tmem_base, NJ, j0, Ha, La);
     tmem_ld_wait();
-    epi_load<PA, PB, JC>(c.tmem_base, NJ, j0 + JC, Hb, Lb);
     epi_batch<PA, PB, JC, QC>(p, c, k, j0, Ha, La);
-    tmem_ld_wait();
-    if (bi + 2 < NB) epi_load<PA, PB, JC>(c.tmem_base, NJ, j0 + 2 * JC, Ha, La);
-    epi_batch<PA, PB, JC, QC>(p, c, k, j0 + JC, Hb, Lb);
   }
 }
 
