@@ -6,18 +6,18 @@
 // enumeration / len / sr-lr split (:306-344).
 //
 // How.  The weighted joint allele counts  c_ij^ab = sum_s w_s [code(i,s)=a][code(j,s)=b]  are an integer GEMM:
-// weights are fixed-point (30 bits below the largest weight) split into two 15-bit halves, each half accumulated
-// exactly in an int32 TMEM accumulator by two K-passes of kind::i8 UMMA (A = one-hot plane x {128, 1}, B = one-hot
-// plane x {8-bit, 7-bit digit}).  Only the r-1 non-complement allele planes of a site enter the GEMM; the remaining
+// weights are fixed-point (28 bits below the largest weight) split into two 14-bit halves h = 129 a - 127 b with byte
+// digits a, b; each half is accumulated exactly in an int32 TMEM accumulator by two K-passes of kind::i8 UMMA over
+// the SAME one-hot operand (bytes 0x81): an unsigned pass (x129, digit a) and a signed pass (x-127, digit b).  Only the r-1 non-complement allele planes of a site enter the GEMM; the remaining
 // counts follow from the exact integer marginals (sum_b c^ab = p^a).  SNPs are grouped by plane count so a tile is
 // 128 row SNPs x NJ column SNPs with uniform (PA, PB).  Eight epilogue warps read the accumulators straight out of
 // TMEM (thread = row SNP), rebuild the (PA+1)x(PB+1) table, evaluate
 //     MI = sum_ab x/den * ln(x den / D),  x = c + 0.5,  D = (p_i^a + r_j/2)(p_j^b + r_i/2) + dQ   (dQ: quirk Q1)
 // in fp32 with one MUFU.LG2 per term (two with the Q1 correction), and emit: short-range links to their final,
 // position-determined output slot; long-range candidates above a monotonically rising candidate threshold.
-// Only the raw 0/1 one-hot planes travel from L2 to shared memory (the SM's inbound bandwidth, ~30 B/clk, is the
-// scarce resource): six expander warps build the x128 copy of the row tile and the four digit-weighted copies of the
-// column tile in place, inside the stage, before the MMA warp consumes it.
+// Only the raw one-hot planes travel from L2 to shared memory (the SM's inbound bandwidth, ~30 B/clk, is the scarce
+// resource): the expander warps build the four digit-weighted copies of the column tile in place, inside the stage,
+// before the MMA warp consumes it.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..7 = expanders (2 also owns TMEM), 8..15 = epilogue.
 #pragma once
 #include "mi_types.h"
@@ -31,7 +31,7 @@ constexpr int MI_EPI_WARP0 = 8;
 constexpr int MI_THREADS = 512;
 constexpr int MI_STAGES = 2;
 constexpr uint32_t MI_ARR_BYTES = 128 * 128;              // one operand array slice: 128 rows x 128 K-bytes
-constexpr uint32_t MI_STAGE_BYTES = 6 * MI_ARR_BYTES;     // X1, X128, D3, D2, D1, D0
+constexpr uint32_t MI_STAGE_BYTES = 6 * MI_ARR_BYTES;     // up to 4 row planes + the 4 digit copies of the column planes
 constexpr uint32_t MI_JREC_BYTES = 128 * sizeof(Rec);     // per j-buffer
 constexpr uint32_t MI_JDYN_BYTES = 128 * sizeof(ColDyn);
 constexpr uint32_t MI_SMEM_BYTES = MI_STAGES * MI_STAGE_BYTES + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + 256 + 1024;
@@ -413,19 +413,18 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
       }
       __syncwarp();
-      // per stage: the raw planes of up to two row-tile planes (into their X1 slots) and of all PB column planes
-      // (into the D3 slot, expanded in place later)
-      for (int a0 = 0; a0 < PA; a0 += 2) {
-        const int na = min(2, PA - a0);
-        const uint32_t stage_tx = (uint32_t)na * MI_ARR_BYTES + (uint32_t)(PB * NJ * 128);
+      // per stage: the raw planes of all PA row-tile planes and of all PB column planes (the latter into the first
+      // digit slot, expanded in place by the expander warps)
+      {
+        const uint32_t stage_tx = (uint32_t)PA * MI_ARR_BYTES + (uint32_t)(PB * NJ * 128);
         for (int kb = 0; kb < p.nkb; kb++) {
           { long long c0 = clock64(); mbar_wait(&empty[st], ph ^ 1, 11); w_empty += clock64() - c0; }
           if (elect_one()) {
             uint8_t* sb = stage_base + st * MI_STAGE_BYTES;
             mbar_arrive_expect_tx(&full[st], stage_tx);
-            for (int a = 0; a < na; a++)
-              tma_load_2d(sb + (a * 2) * MI_ARR_BYTES, &tm.a, &full[st], kb * 128, td.a_row0 + (a0 + a) * td.a_pstride);
-            uint8_t* sbB = sb + na * 2 * MI_ARR_BYTES;
+            for (int a = 0; a < PA; a++)
+              tma_load_2d(sb + a * MI_ARR_BYTES, &tm.a, &full[st], kb * 128, td.a_row0 + a * td.a_pstride);
+            uint8_t* sbB = sb + PA * MI_ARR_BYTES;
             for (int b = 0; b < PB; b++)
               tma_load_2d(sbB + b * NJ * 128, &tm.b[njidx], &full[st], kb * 128, td.b_row0 + b * td.b_pstride);
           }
@@ -451,7 +450,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
       const bool big = 2 * PA * PB * NJ > 256;
       const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA
-      const uint32_t idesc = make_idesc_u8(128, ncols);
+      const uint32_t idesc_u = make_idesc_u8(128, ncols);     // A bytes 0x81 read as +129
+      const uint32_t idesc_s = make_idesc_s8u8(128, ncols);   // A bytes 0x81 read as -127
       uint32_t dbase;
       if (big) {
         for (int s2 = 0; s2 < 2; s2++) {
@@ -468,41 +468,27 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         dbase = tmem_base + as * 256;
       }
       tc_fence_after();
-      for (int a0 = 0; a0 < PA; a0 += 2) {
-        const int na = min(2, PA - a0);
-        const uint32_t boff = (uint32_t)(na * 2) * MI_ARR_BYTES;          // B region follows the A planes
-        const uint32_t b2off = boff + (uint32_t)(2 * PB * NJ * 128);      // D2 | D0 follow D3 | D1
+      {
+        const uint32_t boff = (uint32_t)PA * MI_ARR_BYTES;                // B region follows the A planes
+        const uint32_t b2off = boff + (uint32_t)(2 * PB * NJ * 128);      // bH | bL follow aH | aL
         for (int kb = 0; kb < p.nkb; kb++) {
           { long long c0 = clock64(); mbar_wait(&ready[st], ph, 22); w_ready += clock64() - c0; }
           tc_fence_after();
           // low descriptor word of the stage base: address >> 4 | LBO (1 << 16)
           const uint32_t lo = ((smem_u32(stage_base + st * MI_STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
           if (elect_one()) {
-            const uint64_t dB128 = ((uint64_t)desc_hi << 32) | (lo + (boff >> 4));
-            const uint64_t dB1 = ((uint64_t)desc_hi << 32) | (lo + (b2off >> 4));
+            const uint64_t dBa = ((uint64_t)desc_hi << 32) | (lo + (boff >> 4));
+            const uint64_t dBb = ((uint64_t)desc_hi << 32) | (lo + (b2off >> 4));
             const uint32_t acc0 = kb > 0 ? 1u : 0u;
-            {
-              const uint64_t dx1 = ((uint64_t)desc_hi << 32) | lo;
-              const uint64_t dx128 = ((uint64_t)desc_hi << 32) | (lo + (MI_ARR_BYTES >> 4));
-              const uint32_t dHL = dbase + (uint32_t)(a0 * 2 * PB * NJ);
-              umma_i8(dHL, dx128, dB128, idesc, acc0);
-              umma_i8(dHL, dx1, dB1, idesc, 1u);
+            for (int a = 0; a < PA; a++) {
+              const uint64_t dx = ((uint64_t)desc_hi << 32) | (lo + (uint32_t)((a * MI_ARR_BYTES) >> 4));
+              const uint32_t dHL = dbase + (uint32_t)(a * 2 * PB * NJ);
+              umma_i8(dHL, dx, dBa, idesc_u, acc0);
+              umma_i8(dHL, dx, dBb, idesc_s, 1u);
 #pragma unroll
               for (int kk = 1; kk < 4; kk++) {
-                umma_i8(dHL, dx128 + 2 * kk, dB128 + 2 * kk, idesc, 1u);
-                umma_i8(dHL, dx1 + 2 * kk, dB1 + 2 * kk, idesc, 1u);
-              }
-            }
-            if (na == 2) {
-              const uint64_t dx1 = ((uint64_t)desc_hi << 32) | (lo + ((2 * MI_ARR_BYTES) >> 4));
-              const uint64_t dx128 = ((uint64_t)desc_hi << 32) | (lo + ((3 * MI_ARR_BYTES) >> 4));
-              const uint32_t dHL = dbase + (uint32_t)((a0 + 1) * 2 * PB * NJ);
-              umma_i8(dHL, dx128, dB128, idesc, acc0);
-              umma_i8(dHL, dx1, dB1, idesc, 1u);
-#pragma unroll
-              for (int kk = 1; kk < 4; kk++) {
-                umma_i8(dHL, dx128 + 2 * kk, dB128 + 2 * kk, idesc, 1u);
-                umma_i8(dHL, dx1 + 2 * kk, dB1 + 2 * kk, idesc, 1u);
+                umma_i8(dHL, dx + 2 * kk, dBa + 2 * kk, idesc_u, 1u);
+                umma_i8(dHL, dx + 2 * kk, dBb + 2 * kk, idesc_s, 1u);
               }
             }
             umma_commit(&empty[st]);
@@ -531,10 +517,10 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     }
   } else if (warp < MI_EPI_WARP0) {
     // ===================================================================== operand expanders
-    // stage layout: [plane a: X1 (TMA) | X128 (built here)] x na, then D3 | D1 | D2 | D0 of all PB column planes
-    // (raw one-hot Y lands in the D3 slot; D1, D2, D0 are written, D3 = Y & digit3 is formed in place).
-    // Everything is elementwise on the swizzled image; only the digit lookup needs the logical K position,
-    // i.e. the 16-byte chunk index XOR (row & 7).
+    // stage layout: PA row planes (raw, used as they are), then aH | aL | bH | bL digit copies of all PB column
+    // planes (the raw one-hot Y lands in the aH slot; aL, bH, bL are written, aH = Y & digit is formed in place).
+    // Elementwise on the swizzled image; only the digit lookup needs the logical K position, i.e. the 16-byte
+    // chunk index XOR (row & 7).
     const int h = (warp - 2) * 32 + lane;  // 0..191
     int st = 0; uint32_t ph = 0;
     long long w_full = 0, t_begin = clock64();
@@ -542,45 +528,31 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
       const int brows = PB * NJ;
-      for (int a0 = 0; a0 < PA; a0 += 2) {
-        const int na = min(2, PA - a0);
-        for (int kb = 0; kb < p.nkb; kb++) {
-          // this thread's digit chunks: logical chunk cl of K block kb
-          const int cl = h & 7;
-          const uint8_t* dg = p.dig + (int64_t)kb * 128 + cl * 16;
-          const uint4 g3 = __ldg(reinterpret_cast<const uint4*>(dg));
-          const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(dg + p.kpad));
-          const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(dg + 2 * p.kpad));
-          const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dg + 3 * p.kpad));
-          { long long c0 = clock64(); mbar_wait(&full[st], ph, 40); w_full += clock64() - c0; }
-          const uint32_t sb = smem_u32(stage_base + st * MI_STAGE_BYTES);
-          // X128 = X1 << 7 (bytes are 0/1)
-          for (int a = 0; a < na; a++) {
-            const uint32_t x1 = sb + (uint32_t)(a * 2) * MI_ARR_BYTES;
-#pragma unroll 2
-            for (int id = h; id < 1024; id += MI_EXP_THREADS) {
-              uint4 v = lds128(x1 + id * 16);
-              v.x <<= 7; v.y <<= 7; v.z <<= 7; v.w <<= 7;
-              sts128(x1 + MI_ARR_BYTES + id * 16, v);
-            }
-          }
-          // digit-weighted copies of the column planes
-          const uint32_t yb = sb + (uint32_t)(na * 2) * MI_ARR_BYTES;
-          const uint32_t slot = (uint32_t)brows * 128u;
-          for (int r = h >> 3; r < brows; r += MI_EXP_THREADS / 8) {
-            const uint32_t addr = yb + (uint32_t)r * 128u + (uint32_t)((cl ^ (r & 7)) * 16);
-            uint4 y = lds128(addr);
-            // bytes 0/1 -> 0x00/0xFF
-            y.x *= 255u; y.y *= 255u; y.z *= 255u; y.w *= 255u;
-            sts128(addr + slot, make_uint4(y.x & g1.x, y.y & g1.y, y.z & g1.z, y.w & g1.w));          // D1
-            sts128(addr + 2 * slot, make_uint4(y.x & g2.x, y.y & g2.y, y.z & g2.z, y.w & g2.w));      // D2
-            sts128(addr + 3 * slot, make_uint4(y.x & g0.x, y.y & g0.y, y.z & g0.z, y.w & g0.w));      // D0
-            sts128(addr, make_uint4(y.x & g3.x, y.y & g3.y, y.z & g3.z, y.w & g3.w));                 // D3 in place
-          }
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-          mbar_arrive(&ready[st]);
-          if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+      for (int kb = 0; kb < p.nkb; kb++) {
+        // this thread's digit chunks: logical chunk cl of K block kb
+        const int cl = h & 7;
+        const uint8_t* dg = p.dig + (int64_t)kb * 128 + cl * 16;
+        const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(dg));                 // aH
+        const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(dg + p.kpad));        // aL
+        const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(dg + 2 * p.kpad));    // bH
+        const uint4 g3 = __ldg(reinterpret_cast<const uint4*>(dg + 3 * p.kpad));    // bL
+        { long long c0 = clock64(); mbar_wait(&full[st], ph, 40); w_full += clock64() - c0; }
+        const uint32_t yb = smem_u32(stage_base + st * MI_STAGE_BYTES) + (uint32_t)PA * MI_ARR_BYTES;
+        const uint32_t slot = (uint32_t)brows * 128u;
+        for (int r = h >> 3; r < brows; r += MI_EXP_THREADS / 8) {
+          const uint32_t addr = yb + (uint32_t)r * 128u + (uint32_t)((cl ^ (r & 7)) * 16);
+          uint4 y = lds128(addr);
+          // bytes 0x00 / 0x81 -> 0x00 / 0xFF
+          y.x = (y.x & 0x01010101u) * 255u; y.y = (y.y & 0x01010101u) * 255u;
+          y.z = (y.z & 0x01010101u) * 255u; y.w = (y.w & 0x01010101u) * 255u;
+          sts128(addr + slot, make_uint4(y.x & g1.x, y.y & g1.y, y.z & g1.z, y.w & g1.w));          // aL
+          sts128(addr + 2 * slot, make_uint4(y.x & g2.x, y.y & g2.y, y.z & g2.z, y.w & g2.w));      // bH
+          sts128(addr + 3 * slot, make_uint4(y.x & g3.x, y.y & g3.y, y.z & g3.z, y.w & g3.w));      // bL
+          sts128(addr, make_uint4(y.x & g0.x, y.y & g0.y, y.z & g0.z, y.w & g0.w));                 // aH in place
         }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&ready[st]);
+        if (++st == MI_STAGES) { st = 0; ph ^= 1; }
       }
     }
     if (p.dbg && h == 0) {

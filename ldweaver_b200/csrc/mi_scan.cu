@@ -106,8 +106,10 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   P->w.assign(hdw, hdw + S);
   for (int64_t i = 1; i < n; i++)
     if (pos[i] < pos[i - 1]) P->pos_sorted = false;
-  // ---- fixed-point weights: W_s = round(w_s * scale), scale = (2^30 - 1) / max(w); 15-bit halves H, L;
-  //      digits D3 (8 bit) D2 (7 bit) of H and D1, D0 of L
+  // ---- fixed-point weights: W_s = round(w_s * scale), scale = (2^28 - 1) / max(w), two 14-bit halves H, L.
+  //      Each half h is written as 129 a - 127 b with byte digits a, b (every h <= 16767 has such a pair): the
+  //      one-hot operand stores 0x81 where the allele matches, which the tensor core reads as +129 (unsigned pass,
+  //      digit a) or -127 (signed pass, digit b) -- one operand array, no shifted copy.
   double wmax = 0, neff = 0;
   for (int64_t s = 0; s < S; s++) {
     if (!(hdw[s] > 0) || !std::isfinite(hdw[s])) return set_error(LDW_ERR_ARG, "hdw[%lld] = %g is not a positive finite weight", (long long)s, hdw[s]);
@@ -115,35 +117,46 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
     neff += hdw[s];
   }
   P->neff = neff;
-  P->scale = 1073741823.0 / wmax;
+  P->scale = 268435455.0 / wmax;
   P->Kpad = round_up(S, 128);
-  std::vector<uint8_t> dig((size_t)4 * P->Kpad, 0);
+  std::vector<uint8_t> da(16384), db(16384);
+  {
+    std::vector<uint8_t> found(16384, 0);
+    for (int a = 0; a < 256; a++)
+      for (int b = 0; b < 256; b++) {
+        int h = 129 * a - 127 * b;
+        if (h >= 0 && h < 16384 && !found[h]) { found[h] = 1; da[h] = (uint8_t)a; db[h] = (uint8_t)b; }
+      }
+    for (int h = 0; h < 16384; h++)
+      if (!found[h]) return set_error(LDW_ERR_INTERNAL, "digit table incomplete at %d", h);
+  }
+  std::vector<uint8_t> dig((size_t)4 * P->Kpad, 0);  // rows: aH, aL, bH, bL (shared-memory slot order)
   std::vector<int32_t> wH(S), wL(S);
   int64_t sumH = 0, sumL = 0;
   for (int64_t s = 0; s < S; s++) {
     int64_t W = (int64_t)std::llround(hdw[s] * P->scale);
     if (W < 0) W = 0;
-    if (W > 1073741823) W = 1073741823;
-    int32_t H = (int32_t)(W >> 15), L = (int32_t)(W & 32767);
+    if (W > 268435455) W = 268435455;
+    int32_t H = (int32_t)(W >> 14), L = (int32_t)(W & 16383);
     wH[s] = H; wL[s] = L;
     sumH += H; sumL += L;
-    dig[0 * P->Kpad + s] = (uint8_t)(H >> 7);
-    dig[1 * P->Kpad + s] = (uint8_t)(H & 127);
-    dig[2 * P->Kpad + s] = (uint8_t)(L >> 7);
-    dig[3 * P->Kpad + s] = (uint8_t)(L & 127);
+    dig[0 * P->Kpad + s] = da[H];
+    dig[1 * P->Kpad + s] = da[L];
+    dig[2 * P->Kpad + s] = db[H];
+    dig[3 * P->Kpad + s] = db[L];
   }
   if (sumH > 0x7fffffffLL || sumL > 0x7fffffffLL) return set_error(LDW_ERR_UNSUPPORTED, "too many sequences for int32 accumulation (nseq=%lld)", (long long)S);
   P->neffH = (int32_t)sumH;
   P->neffL = (int32_t)sumL;
   {
-    // H < 32768 * S: shift it up as far as 32 bits allow and drop the matching low bits of L
-    uint64_t hmax = 32767ull * (uint64_t)S;
+    // H < 16384 * S: shift it up as far as 32 bits allow and drop the matching low bits of L
+    uint64_t hmax = 16383ull * (uint64_t)S;
     int bits = 0;
     while ((hmax >> bits) != 0) bits++;
-    int sa_ = std::min(15, 32 - bits);
+    int sa_ = std::min(14, 32 - bits);
     if (sa_ < 0) sa_ = 0;
     P->sa = (uint32_t)sa_;
-    P->sb = (uint32_t)(15 - sa_);
+    P->sb = (uint32_t)(14 - sa_);
   }
 
   // ---- upload codes, per-SNP allele statistics
@@ -850,7 +863,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       n_launches++; n_scan_launches++;
       n_tiles += sp.n_tiles;
       for (const TileDesc& td : H.tiles)  // 4 K-passes x 2 ops/MAC x 128 rows x (PA*PB*NJ) columns x Kpad
-        exec_ops += 8.0 * 128.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;
+        exec_ops += 8.0 * 128.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;  // 2 passes x 2 halves
     }
     if (lr) {
       n_launches += 2;

@@ -202,5 +202,9 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_u8(uint32_t M, uint32_t N) {
   return (2u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// Same with a SIGNED 8-bit A operand (a_format = 1) and unsigned B.
+__host__ __device__ constexpr uint32_t make_idesc_s8u8(uint32_t M, uint32_t N) {
+  return (2u << 4) | (1u << 7) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 }  // namespace ldw
