@@ -228,6 +228,15 @@ def make_blocks(nsnp: int, max_blk_sz: int):
     return [(fs[i], fe[i], fs[j], fe[j]) for i in range(p) for j in range(i, p)]
 
 
+def partition_blocks(n_blocks: int, n_parts: int, part: int) -> List[int]:
+    """Blocks (0-based make_blocks rows) that ``ldw_mi_scan(..., n_parts, part)`` processes: dealt round-robin, the
+    same rule as the library (csrc/mi_scan.cu).  Blocks are independent (the LR threshold is per block, quirk Q3),
+    so ranks need no data-path collective."""
+    if n_parts < 1 or not (0 <= part < n_parts):
+        raise ValueError("bad partition")
+    return [b for b in range(n_blocks) if b % n_parts == part]
+
+
 class MIPlan:
     """Device-resident operands for one (snp.dat, hdw): ldw_mi_plan_create / ldw_mi_scan."""
 

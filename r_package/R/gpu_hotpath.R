@@ -1,0 +1,101 @@
+# Drop-in bodies for the three hot functions of LDWeaver (signatures and return values unchanged).
+# They replace R/extractSNPs.R:23-142,168-281, R/performPopulationStuctureCorrection.R:20-81 and the block loop of
+# R/computePairwiseMI.R:69-116; everything after the scan (mergeNsort_sr_links, runARACNE, write.table,
+# R/computePairwiseMI.R:118-143) is the reference's own code and stays on the CPU.
+
+.codes_to_snpdat <- function(enc, pos = NULL) {
+  if (enc$seq.length == -1) stop("Error! sequences are of different lengths!")
+  if (enc$num.seqs == 0) stop("File does not contain any sequences!")
+  if (enc$num.snps == 0) stop("File does not contain any SNPs")
+  nsnp <- enc$num.snps; nseq <- enc$num.seqs
+  codes <- matrix(as.integer(enc$codes), nrow = nseq, ncol = nsnp)   # codes[k*nseq + s] -> [s, k]
+  seq.names <- gsub("^>", "", enc$seq.names)
+  uqe <- apply(enc$ACGTN_table > 0, 1, function(x) as.numeric(x > 0))
+  POS <- if (is.null(pos)) enc$pos else as.integer(pos[enc$pos])
+  mk <- function(a) Matrix::t(Matrix::sparseMatrix(i = row(codes)[codes == a], j = col(codes)[codes == a], x = TRUE,
+                                                   dims = c(nseq, nsnp), dimnames = list(seq.names, POS)))
+  out <- list(snp.matrix_A = mk(0L), snp.matrix_C = mk(1L), snp.matrix_G = mk(2L), snp.matrix_T = mk(3L),
+              snp.matrix_N = mk(4L), g = if (is.null(pos)) enc$seq.length else NULL, nsnp = nsnp, nseq = nseq,
+              seq.names = seq.names, r = rowSums(uqe), uqe = uqe, POS = POS)
+  attr(out, "codes") <- enc$codes   # raw nsnp x nseq class matrix: lets the next two stages skip the rebuild
+  out
+}
+
+.snpdat_codes <- function(snp.dat) {
+  cd <- attr(snp.dat, "codes")
+  if (!is.null(cd)) return(cd)
+  # snp.dat restored from RDS (R/BacGWES.R:281,301-302): rebuild the class matrix from the five lgCMatrix slots
+  m <- matrix(4L, nrow = snp.dat$nseq, ncol = snp.dat$nsnp)
+  for (a in 0:3) {
+    M <- snp.dat[[paste0("snp.matrix_", c("A", "C", "G", "T")[a + 1])]]
+    idx <- Matrix::which(M, arr.ind = TRUE)          # (snp, seq)
+    m[cbind(idx[, 2], idx[, 1])] <- a
+  }
+  as.raw(m)
+}
+
+parse_fasta_alignment <- function(aln_path, gap_freq = 0.15, maf_freq = 0.01, method = "default", mega_dset = F) {
+  aln_path <- normalizePath(aln_path)
+  if (!file.exists(aln_path)) stop(paste("Can't locate file", aln_path))
+  filter <- if (method == "relaxed") 1L else { if (method != "default") warning("Unkown filtering method, using default..."); 0L }
+  enc <- .Call("_LDWeaver_gpu_encode", aln_path, filter, gap_freq, maf_freq, PACKAGE = "LDWeaver")
+  .codes_to_snpdat(enc)
+}
+
+parse_fasta_SNP_alignment <- function(aln_path, pos, gap_freq = 0.15, maf_freq = 0.01, method = "default", mega_dset = F) {
+  aln_path <- normalizePath(aln_path)
+  if (!file.exists(aln_path)) stop(paste("Can't locate file", aln_path))
+  filter <- if (method == "relaxed") 1L else { if (method != "default") warning("Unkown filtering method, using default..."); 0L }
+  enc <- .Call("_LDWeaver_gpu_encode", aln_path, filter, gap_freq, maf_freq, PACKAGE = "LDWeaver")
+  if (enc$seq.length > 0 && length(pos) != enc$seq.length) stop("Error! Number of positions do not match the fasta sequence length")
+  .codes_to_snpdat(enc, pos)
+}
+
+estimate_Hamming_distance_weights <- function(snp.dat, threshold = 0.1, mega_dset = F) {
+  t0 <- Sys.time()
+  hdw <- .Call("_LDWeaver_gpu_hdw", .snpdat_codes(snp.dat), snp.dat$nsnp, snp.dat$nseq, threshold, PACKAGE = "LDWeaver")
+  names(hdw) <- snp.dat$seq.names
+  cat(paste("Done in", round(difftime(Sys.time(), t0, units = "secs"), 2), "s\n"))
+  hdw
+}
+
+perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path = NULL, sr_save_path = NULL, plt_folder = NULL,
+                                   sr_dist = 20000, lr_retain_links = 1e6, max_blk_sz = 10000, srp_cutoff = 3, runARACNE = TRUE,
+                                   perform_SR_analysis_only = FALSE, order_links = T, mega_dset = F) {
+  t000 <- Sys.time()
+  if (is.null(lr_save_path)) lr_save_path <- file.path(getwd(), "lr_links.tsv")
+  if (is.null(sr_save_path)) sr_save_path <- file.path(getwd(), "sr_links.tsv")
+  if (is.null(plt_folder)) plt_folder <- file.path(getwd(), "PLOTS")
+  if (!file.exists(plt_folder)) dir.create(plt_folder)
+  cat("Begin MI computation... \n")
+  max_blk_sz <- round(max_blk_sz, -3)
+  lr_links_approx <- 1
+  if (!perform_SR_analysis_only) {   # R/computePairwiseMI.R:94-97, kept in R because it uses R's RNG stream
+    snp_subset <- min(snp.dat$nsnp, round(snp.dat$nsnp * 0.1))
+    set.seed(1988)
+    lr_link_count <- sapply(snp.dat$POS[sample(snp.dat$nsnp, snp_subset)], function(x)
+      sum((0.5 * snp.dat$g - abs((x - snp.dat$POS) %% snp.dat$g - 0.5 * snp.dat$g)) > sr_dist))
+    lr_links_approx <- sum(lr_link_count) / snp_subset * snp.dat$nsnp / 2
+  }
+  res <- .Call("_LDWeaver_gpu_mi_scan", .snpdat_codes(snp.dat), snp.dat$nsnp, snp.dat$nseq, as.numeric(hdw),
+               as.integer(snp.dat$POS), as.integer(cds_var$paint), as.numeric(snp.dat$g), sr_dist, lr_retain_links,
+               lr_links_approx, max_blk_sz, perform_SR_analysis_only, PACKAGE = "LDWeaver")
+  if (length(res$lr$MI) > 0)   # same rows, same order as the per-block appends of R/computePairwiseMI.R:362
+    write.table(x = as.data.frame(res$lr[1:6]), file = lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
+  sr_df <- as.data.frame(res$sr[1:6])
+  sr_links <- lapply(1:cds_var$nclust, function(i) sr_df[sr_df$clust1 == i | sr_df$clust2 == i, ])   # :372-376
+  # ---- from here on: the reference's own CPU code, unchanged (R/computePairwiseMI.R:118-143)
+  sr_links_all <- mergeNsort_sr_links(cds_var = cds_var, sr_links = sr_links, sr_dist = sr_dist, plt_path = plt_folder, srp_cutoff = srp_cutoff)
+  sr_links_red <- sr_links_all$sr_links_red
+  sr_links_ARACNE_check <- sr_links_all$sr_links_ARACNE_check
+  if (runARACNE) {
+    sr_links_red$ARACNE <- as.numeric(runARACNE(sr_links_red, sr_links_ARACNE_check))
+  } else {
+    warning('ARACNE not run, all values will be set to 1')
+    sr_links_red$ARACNE <- 1
+  }
+  if (order_links) { sr_links_red <- sr_links_red[order(sr_links_red$srp_max, decreasing = T), ]; rownames(sr_links_red) <- NULL }
+  write.table(x = sr_links_red, file = sr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
+  cat(paste("All done in", round(difftime(Sys.time(), t000, units = "mins"), 2), "mins \n"))
+  sr_links_red
+}

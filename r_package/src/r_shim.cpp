@@ -1,0 +1,187 @@
+// R <-> libldwgpu glue (.Call entry points).  NOT compiled in the build container (no R headers there); kept
+// deliberately thin so that review suffices.  Build inside the LDWeaver package with the Makevars next to it.
+//
+// Replaces, for the hot path only, the Rcpp-generated shims of the reference
+// (src/RcppExports.cpp:16 _LDWeaver_ACGTN2num, :109 _LDWeaver_extractAlnParam, :123 _LDWeaver_extractSNPs)
+// and adds the two entry points that the bodies of estimate_Hamming_distance_weights() and
+// perform_MI_computation() call instead of Matrix/MatrixExtra + .fastHadamard.
+//
+// Conventions: all SEXP work happens on the calling (R main) thread; the library never prints; a nonzero
+// return code becomes Rf_error(ldw_last_error()) after every native resource has been released.
+#include <R.h>
+#include <Rinternals.h>
+#include <R_ext/Rdynload.h>
+
+#include <cstring>
+#include <vector>
+
+#include "ldw.h"
+
+namespace {
+
+ldw_ctx* g_ctx = nullptr;
+
+ldw_ctx* ctx() {
+  if (!g_ctx) {
+    int dev = 0;
+    const char* e = getenv("LDW_DEVICE");
+    if (e) dev = atoi(e);
+    if (ldw_create(dev, &g_ctx) != 0) Rf_error("%s", ldw_last_error());
+  }
+  return g_ctx;
+}
+
+SEXP links_to_list(const ldw_links& L) {
+  // data.frame-ready list of columns: pos1, pos2, clust1, clust2, len, MI (R/computePairwiseMI.R:326-331) + block
+  const char* names[] = {"pos1", "pos2", "clust1", "clust2", "len", "MI", "block"};
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 7));
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 7));
+  const int32_t* icol[] = {L.pos1, L.pos2, L.clust1, L.clust2, L.len, nullptr, L.block};
+  for (int k = 0; k < 7; k++) {
+    SET_STRING_ELT(nm, k, Rf_mkChar(names[k]));
+    SEXP col;
+    if (k == 5) {
+      col = PROTECT(Rf_allocVector(REALSXP, L.n));
+      if (L.n) memcpy(REAL(col), L.MI, sizeof(double) * (size_t)L.n);
+    } else if (k == 2 || k == 3 || k == 6) {
+      col = PROTECT(Rf_allocVector(INTSXP, L.n));
+      if (L.n) memcpy(INTEGER(col), icol[k], sizeof(int) * (size_t)L.n);
+    } else {  // pos1, pos2, len are numeric in the reference's data.frame
+      col = PROTECT(Rf_allocVector(REALSXP, L.n));
+      double* d = REAL(col);
+      for (int64_t i = 0; i < L.n; i++) d[i] = (double)icol[k][i];
+    }
+    SET_VECTOR_ELT(out, k, col);
+    UNPROTECT(1);
+  }
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(2);
+  return out;
+}
+
+}  // namespace
+
+extern "C" {
+
+// .Call("_LDWeaver_gpu_encode", path, filter, gap, maf) -> list(num.seqs, num.snps, seq.length, seq.names, pos,
+//                                                              codes (raw nsnp x nseq), ACGTN_table (5 x nsnp))
+// stands in for .extractAlnParam + .extractSNPs (R/extractSNPs.R:39,45)
+SEXP LDWeaver_gpu_encode(SEXP path_, SEXP filter_, SEXP gap_, SEXP maf_) {
+  const char* path = CHAR(STRING_ELT(path_, 0));
+  int64_t nseq = 0, slen = 0;
+  if (ldw_read_fasta(path, &nseq, &slen, nullptr, 0, nullptr, 0) != 0) Rf_error("%s", ldw_last_error());
+  if (slen == -1 || nseq == 0) {  // sentinel values the R wrapper turns into stop() (R/extractSNPs.R:41-42)
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+    SET_VECTOR_ELT(out, 0, Rf_ScalarInteger((int)nseq));
+    SET_VECTOR_ELT(out, 1, Rf_ScalarInteger((int)slen));
+    UNPROTECT(1);
+    return out;
+  }
+  std::vector<uint8_t> aln((size_t)nseq * slen);
+  std::vector<char> names((size_t)nseq * 256);
+  int64_t l2 = slen, n2 = 0;
+  if (ldw_read_fasta(path, &n2, &l2, aln.data(), (int64_t)aln.size(), names.data(), (int64_t)names.size()) != 0)
+    Rf_error("%s", ldw_last_error());
+  std::vector<int32_t> pos((size_t)slen);
+  int64_t nsnp = 0;
+  if (ldw_aln_param(ctx(), aln.data(), nseq, slen, Rf_asInteger(filter_), Rf_asReal(gap_), Rf_asReal(maf_), pos.data(), &nsnp,
+                    nullptr) != 0)
+    Rf_error("%s", ldw_last_error());
+  SEXP codes = PROTECT(Rf_allocVector(RAWSXP, nsnp * nseq));
+  SEXP table = PROTECT(Rf_allocMatrix(REALSXP, 5, (int)nsnp));
+  if (nsnp > 0 &&
+      ldw_extract_snps(ctx(), aln.data(), nseq, slen, pos.data(), nsnp, RAW(codes), REAL(table)) != 0) {
+    UNPROTECT(2);
+    Rf_error("%s", ldw_last_error());
+  }
+  SEXP rpos = PROTECT(Rf_allocVector(INTSXP, nsnp));
+  if (nsnp) memcpy(INTEGER(rpos), pos.data(), sizeof(int) * (size_t)nsnp);
+  SEXP rnames = PROTECT(Rf_allocVector(STRSXP, nseq));
+  const char* q = names.data();
+  for (int64_t i = 0; i < nseq; i++) { SET_STRING_ELT(rnames, i, Rf_mkChar(q)); q += strlen(q) + 1; }
+  const char* nm[] = {"num.seqs", "num.snps", "seq.length", "seq.names", "pos", "codes", "ACGTN_table"};
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 7));
+  SEXP onm = PROTECT(Rf_allocVector(STRSXP, 7));
+  for (int k = 0; k < 7; k++) SET_STRING_ELT(onm, k, Rf_mkChar(nm[k]));
+  SET_VECTOR_ELT(out, 0, Rf_ScalarInteger((int)nseq));
+  SET_VECTOR_ELT(out, 1, Rf_ScalarInteger((int)nsnp));
+  SET_VECTOR_ELT(out, 2, Rf_ScalarInteger((int)slen));
+  SET_VECTOR_ELT(out, 3, rnames);
+  SET_VECTOR_ELT(out, 4, rpos);
+  SET_VECTOR_ELT(out, 5, codes);
+  SET_VECTOR_ELT(out, 6, table);
+  Rf_setAttrib(out, R_NamesSymbol, onm);
+  UNPROTECT(6);
+  return out;
+}
+
+// .Call("_LDWeaver_gpu_hdw", codes(raw nsnp*nseq), nsnp, nseq, threshold) -> numeric(nseq)
+// body of estimate_Hamming_distance_weights (R/performPopulationStuctureCorrection.R:23-76)
+SEXP LDWeaver_gpu_hdw(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP thr_) {
+  int64_t n = (int64_t)Rf_asReal(nsnp_), S = (int64_t)Rf_asReal(nseq_);
+  SEXP w = PROTECT(Rf_allocVector(REALSXP, S));
+  int rc = ldw_hdw(ctx(), RAW(codes_), n, S, Rf_asReal(thr_), nullptr, REAL(w), nullptr);
+  UNPROTECT(1);
+  if (rc != 0) Rf_error("%s", ldw_last_error());
+  return w;
+}
+
+// .Call("_LDWeaver_gpu_mi_scan", codes, nsnp, nseq, hdw, POS, paint, g, sr_dist, lr_retain_links, lr_links_approx, blk, sr_only)
+//   -> list(sr = <columns>, lr = <columns>, borderline = <columns>, thr = numeric(nblocks))
+// scan part of perform_MI_computation (R/computePairwiseMI.R:69-116)
+SEXP LDWeaver_gpu_mi_scan(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP hdw_, SEXP pos_, SEXP paint_, SEXP g_, SEXP srd_, SEXP retain_,
+                          SEXP approx_, SEXP blk_, SEXP sronly_) {
+  int64_t n = (int64_t)Rf_asReal(nsnp_), S = (int64_t)Rf_asReal(nseq_), blk = (int64_t)Rf_asReal(blk_);
+  ldw_mi_plan* plan = nullptr;
+  if (ldw_mi_plan_create(ctx(), RAW(codes_), n, S, REAL(hdw_), INTEGER(pos_), INTEGER(paint_), blk, &plan) != 0)
+    Rf_error("%s", ldw_last_error());
+  int64_t nr = (n + blk - 1) / blk, nblk = nr * (nr + 1) / 2;
+  SEXP thr = PROTECT(Rf_allocVector(REALSXP, nblk));
+  ldw_links sr, lr, bd;
+  ldw_scan_stats st;
+  int flags = Rf_asLogical(sronly_) ? LDW_SCAN_SR_ONLY : 0;
+  int rc = ldw_mi_scan(plan, Rf_asReal(g_), Rf_asReal(srd_), Rf_asReal(retain_), Rf_asReal(approx_), flags, 1, 0, &sr, &lr, &bd,
+                       REAL(thr), nullptr, &st);
+  if (rc != 0) {
+    ldw_mi_plan_destroy(plan);
+    UNPROTECT(1);
+    Rf_error("%s", ldw_last_error());
+  }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
+  SET_VECTOR_ELT(out, 0, links_to_list(sr));
+  SET_VECTOR_ELT(out, 1, links_to_list(lr));
+  SET_VECTOR_ELT(out, 2, links_to_list(bd));
+  SET_VECTOR_ELT(out, 3, thr);
+  const char* nm[] = {"sr", "lr", "borderline", "thr"};
+  SEXP onm = PROTECT(Rf_allocVector(STRSXP, 4));
+  for (int k = 0; k < 4; k++) SET_STRING_ELT(onm, k, Rf_mkChar(nm[k]));
+  Rf_setAttrib(out, R_NamesSymbol, onm);
+  ldw_mi_plan_destroy(plan);  // link columns were copied into R vectors above
+  UNPROTECT(3);
+  return out;
+}
+
+// .Call("_LDWeaver_ACGTN2num", nv, cv, ncores): same symbol and in-place semantics as the reference
+// (src/ACGTN2num_parallel.cpp:10-43, quirk Q11)
+SEXP LDWeaver_gpu_ACGTN2num(SEXP nv_, SEXP cv_, SEXP ncores_) {
+  R_xlen_t n = XLENGTH(cv_);
+  std::vector<char> ref((size_t)n);
+  for (R_xlen_t i = 0; i < n; i++) {
+    const char* s = CHAR(STRING_ELT(cv_, i));
+    ref[i] = s[0];
+  }
+  if (ldw_acgtn2num(ctx(), REAL(nv_), ref.data(), (int64_t)n) != 0) Rf_error("%s", ldw_last_error());
+  return R_NilValue;
+}
+
+static const R_CallMethodDef CallEntries[] = {
+    {"_LDWeaver_gpu_encode", (DL_FUNC)&LDWeaver_gpu_encode, 4},
+    {"_LDWeaver_gpu_hdw", (DL_FUNC)&LDWeaver_gpu_hdw, 4},
+    {"_LDWeaver_gpu_mi_scan", (DL_FUNC)&LDWeaver_gpu_mi_scan, 12},
+    {"_LDWeaver_gpu_ACGTN2num", (DL_FUNC)&LDWeaver_gpu_ACGTN2num, 3},
+    {NULL, NULL, 0}};
+
+// merged into R_init_LDWeaver (src/RcppExports.cpp:169-172) next to the Rcpp-generated table
+void R_init_LDWeaver_gpu(DllInfo* dll) { R_registerRoutines(dll, NULL, CallEntries, NULL, NULL); }
+
+}  // extern "C"

@@ -182,3 +182,60 @@ def test_multiallelic_nrich_vs_oracle():
     print("multi-allelic max abs err:", err, "r histogram", np.unique(osnp.r, return_counts=True))
     assert err < MI_TOL
     plan.close()
+
+
+def test_scan_partition_union_and_determinism(fixture_snp, fixture_expected):
+    """n_parts/part deal make_blocks rows round-robin: the union of the parts equals the full scan, and a repeated
+    scan is bit-identical (SR slots are position-determined; LR rows are sorted into reference order)."""
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    snp = _snp(fixture_snp, 2221315)
+    plan = ldw.MIPlan(snp, e["hdw"], e["paint"], 1000)
+    full = plan.scan(2221315, 20000, 2e4, 1e5)
+    again = plan.scan(2221315, 20000, 2e4, 1e5)
+    for k in ("pos1", "pos2", "MI", "len", "block"):
+        np.testing.assert_array_equal(full[0][k], again[0][k])
+        np.testing.assert_array_equal(full[1][k], again[1][k])
+    parts = [plan.scan(2221315, 20000, 2e4, 1e5, 0, 3, r) for r in range(3)]
+    for tbl in (0, 1):
+        order = np.argsort(np.concatenate([p[tbl]["block"] for p in parts]), kind="stable")
+        for k in ("pos1", "pos2", "MI", "len", "block", "clust1", "clust2"):
+            np.testing.assert_array_equal(np.concatenate([p[tbl][k] for p in parts])[order], full[tbl][k])
+    assert sum(p[5]["n_pairs"] for p in parts) == full[5]["n_pairs"] == 803010
+    plan.close()
+
+
+def test_scan_synthetic_medium_vs_oracle():
+    """Synthetic alignment shaped like the benchmark workload (N at 1 % per cell, so r = 3 dominates), six blocks
+    incl. ragged ones: every SR link and every block threshold against the C oracle."""
+    import c_oracle as CO
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import synth
+    sy = synth.generate(nseq=300, nsnp=2700, seed=11)
+    hdw = CO.hdw(sy.codes, 0.1)[0]
+    osnp = O.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
+    snp = ldw.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
+    lra = synth.exact_lr_links_approx(sy.POS, sy.g, 20000)
+    res = ldw.perform_MI_computation(snp, hdw, ldw.CdsVar(sy.paint, 3), sr_dist=20000, lr_retain_links=5e4, max_blk_sz=1000,
+                                     lr_links_approx=lra, write_tsv=False)
+    POS = osnp.POS.astype(np.float64)
+    worst = 0.0
+    for bi, (fs, fe, ts, te) in enumerate(O.make_blocks(osnp.nsnp, 1000)):
+        f, t = np.arange(fs - 1, fe), np.arange(ts - 1, te)
+        MI = CO.block_mi(sy.codes, hdw, osnp.r, osnp.uqe, f, t)
+        L = CO.block_links(MI, POS, f, t, float(sy.g), 20000.0, 5e4, lra)
+        k = res.sr["block"] == bi
+        np.testing.assert_array_equal(res.sr["pos1"][k], POS[t[L["col"]]][L["is_sr"]].astype(np.int32))
+        np.testing.assert_array_equal(res.sr["pos2"][k], POS[f[L["row"]]][L["is_sr"]].astype(np.int32))
+        if k.any():
+            worst = max(worst, float(np.abs(res.sr["MI"][k] - L["MI"][L["is_sr"]]).max()))
+        if np.isnan(L["thr"]):
+            assert np.isnan(res.thr[bi])
+        else:
+            assert abs(res.thr[bi] - L["thr"]) < 1e-12
+            kk = res.lr["block"] == bi
+            compare_lr_sets(POS[t[L["col"]]][L["lr_keep"]], POS[f[L["row"]]][L["lr_keep"]], L["MI"][L["lr_keep"]],
+                            res.lr["pos1"][kk], res.lr["pos2"][kk], res.lr["MI"][kk], L["thr"])
+    print("synthetic medium: max |dMI| over SR links", worst, res.stats)
+    assert worst < MI_TOL
