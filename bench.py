@@ -248,18 +248,27 @@ def main():
         t0 = time.perf_counter()
         d2h = 0
         pe = 0
+        t_plan = t_scan = t_close = 0.0
         for _ in range(e_steps):
+            ta = time.perf_counter()
             p2 = ldw.MIPlan(snp_pin, hdw, sy.paint, blk, device=local_rank)
+            tb = time.perf_counter()
             sr, lr, bd, thr, prob, st2 = p2.scan(sy.g, SR_DIST, LR_RETAIN, lra, 0, world, rank, copy=False)
+            tc = time.perf_counter()
             d2h += (int(sr.n) + int(lr.n)) * 32
             pe += st2["n_pairs"]
             p2.close()
+            td = time.perf_counter()
+            t_plan += tb - ta; t_scan += tc - tb; t_close += td - tc
         barrier()
         te = allmax(time.perf_counter() - t0)
         pe_all = allsum(float(pe))
         h2d = codes_pin.nbytes + hdw.nbytes + sy.POS.nbytes + sy.paint.nbytes
         e2e = {"value": pe_all / te, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // e_steps),
                "ms_per_step": 1e3 * te / e_steps, "steps": e_steps,
+               "breakdown_ms": {"plan_create": 1e3 * t_plan / e_steps, "scan_call": 1e3 * t_scan / e_steps,
+                                "plan_destroy": 1e3 * t_close / e_steps, "scan_device": st2["t_scan_ms"] + st2["t_select_ms"],
+                                "d2h": st2["t_d2h_ms"]},
                "includes": "host->device upload, operand packing, scan, link materialisation, device->host copy of all link columns"}
 
     if rank != 0:

@@ -63,6 +63,7 @@ int ldw_create(int device, ldw_ctx** out) {
 void ldw_destroy(ldw_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->scan_ws && ctx->scan_ws_free) ctx->scan_ws_free(ctx->scan_ws);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

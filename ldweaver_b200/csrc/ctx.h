@@ -26,6 +26,10 @@ struct ldw_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   HostLinks h_sr, h_lr, h_border;
+  // scan workspace (device scratch, per-block ring, link columns): allocated on first use by mi_scan.cu, reused by
+  // every plan on this context, released by ldw_destroy
+  void* scan_ws = nullptr;
+  void (*scan_ws_free)(void*) = nullptr;
 };
 
 namespace ldw {

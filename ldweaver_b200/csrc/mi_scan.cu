@@ -56,6 +56,32 @@ struct BlockHost {  // pageable staging reused per ring entry (kept alive until 
 
 }  // namespace
 
+// Scratch shared by all plans of one context (see ctx.h).
+struct ScanWS {
+  static constexpr int RING = 4;
+  BlockDev ring[RING];
+  BlockHost hring[RING];
+  DevBuf d_dbg;
+  DevBuf d_cand, d_vcand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
+  DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
+  DevLinks d_sr, d_lr;
+  bool events_ready = false;
+  ~ScanWS() {
+    for (auto& b : ring)
+      if (b.done) cudaEventDestroy(b.done);
+  }
+};
+
+static void scan_ws_free(void* p) { delete static_cast<ScanWS*>(p); }
+
+static ScanWS* get_ws(ldw_ctx* ctx) {
+  if (!ctx->scan_ws) {
+    ctx->scan_ws = new ScanWS();
+    ctx->scan_ws_free = scan_ws_free;
+  }
+  return static_cast<ScanWS*>(ctx->scan_ws);
+}
+
 struct ldw_mi_plan {
   ldw_ctx* ctx = nullptr;
   int64_t n = 0, S = 0, blk = 0, Kpad = 0;
@@ -74,20 +100,8 @@ struct ldw_mi_plan {
   // device, static
   DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops, d_dig;
   TmapSet tm;
-  // scan workspace
-  static constexpr int RING = 4;
-  BlockDev ring[RING];
-  BlockHost hring[RING];
-  DevBuf d_dbg;
-  DevBuf d_cand, d_vcand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
-  DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
-  DevLinks d_sr, d_lr;
   std::vector<BlockResult> results;
   double t_pack_ms = 0;
-  ~ldw_mi_plan() {
-    for (auto& b : ring)
-      if (b.done) cudaEventDestroy(b.done);
-  }
 };
 
 namespace {
@@ -262,7 +276,13 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   uint64_t trows = (uint64_t)std::max<int64_t>(row, 128);
   LDW_TRY(make_tmap_u8_sw128(&P->tm.a, P->d_ops.p, trows, (uint64_t)P->Kpad, 128));
   for (int j = 0; j < 4; j++) LDW_TRY(make_tmap_u8_sw128(&P->tm.b[j], P->d_ops.p, trows, (uint64_t)P->Kpad, 128u >> j));
-  for (auto& b : P->ring) LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+  {
+    ScanWS* W = get_ws(ctx);
+    if (!W->events_ready) {
+      for (auto& b : W->ring) LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+      W->events_ready = true;
+    }
+  }
   LDW_CUDA(cudaEventRecord(e1, st));
   LDW_CUDA(cudaStreamSynchronize(st));
   float ms = 0;
@@ -623,6 +643,7 @@ int ldw_mi_block_dense(ldw_mi_plan* P, int64_t block_index, double* mi_out, int6
   if (!P) return set_error(LDW_ERR_ARG, "null plan");
   LDW_TRY(ctx_bind(P->ctx));
   cudaStream_t st = P->ctx->stream;
+  ScanWS* W = get_ws(P->ctx);
   // block_index -> (bf, bt) in make_blocks order
   int bf = 0, bt = 0;
   {
@@ -637,8 +658,8 @@ int ldw_mi_block_dense(ldw_mi_plan* P, int64_t block_index, double* mi_out, int6
   }
   ScanCfg cfg{1e15, 0.0, 0, 0, 0};
   cfg.dense = 1;
-  BlockHost& H = P->hring[0];
-  BlockDev& D = P->ring[0];
+  BlockHost& H = W->hring[0];
+  BlockDev& D = W->ring[0];
   int e = prepare_block(P, bf, bt, cfg, H);
   if (e > 1) return e;
   if (nf_out) *nf_out = H.nf;
@@ -646,16 +667,16 @@ int ldw_mi_block_dense(ldw_mi_plan* P, int64_t block_index, double* mi_out, int6
   if (!mi_out) return 0;
   LDW_TRY(upload_block(st, D, H));
   size_t cells = (size_t)H.nf * H.nt;
-  LDW_TRY(P->d_dense.ensure(cells * 4));
-  LDW_CUDA(cudaMemsetAsync(P->d_dense.p, 0, cells * 4, st));
+  LDW_TRY(W->d_dense.ensure(cells * 4));
+  LDW_CUDA(cudaMemsetAsync(W->d_dense.p, 0, cells * 4, st));
   ScanParams sp;
   fill_scan_params(P, D, H, cfg, sp);
   sp.dense = 1;
-  sp.dense_out = P->d_dense.as<float>();
+  sp.dense_out = W->d_dense.as<float>();
   LDW_TRY(launch_scan(P, sp, st));
   DevBuf d64;
   LDW_TRY(d64.alloc(cells * 8));
-  f32_to_f64_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(P->d_dense.as<float>(), (int64_t)cells, d64.as<double>());
+  f32_to_f64_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, st>>>(W->d_dense.as<float>(), (int64_t)cells, d64.as<double>());
   LDW_CUDA(cudaMemcpyAsync(mi_out, d64.p, cells * 8, cudaMemcpyDeviceToHost, st));
   LDW_CUDA(cudaStreamSynchronize(st));
   return 0;
@@ -666,6 +687,7 @@ int ldw_mi_pairs_exact(ldw_mi_plan* P, int64_t block_index, const int32_t* from_
   if (!P) return set_error(LDW_ERR_ARG, "null plan");
   LDW_TRY(ctx_bind(P->ctx));
   cudaStream_t st = P->ctx->stream;
+  ScanWS* W = get_ws(P->ctx);
   int bf = 0, bt = 0;
   {
     int64_t k = block_index;
@@ -679,8 +701,8 @@ int ldw_mi_pairs_exact(ldw_mi_plan* P, int64_t block_index, const int32_t* from_
   }
   if (n_pairs <= 0) return 0;
   ScanCfg cfg{1e15, 0.0, 0, 0, 0};
-  BlockHost& H = P->hring[0];
-  BlockDev& D = P->ring[0];
+  BlockHost& H = W->hring[0];
+  BlockDev& D = W->ring[0];
   int e = prepare_block(P, bf, bt, cfg, H);
   if (e != 0) return e == 1 ? set_error(LDW_ERR_ARG, "empty block") : e;
   for (int64_t k = 0; k < n_pairs; k++)
@@ -708,6 +730,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   if (!P) return set_error(LDW_ERR_ARG, "null plan");
   LDW_TRY(ctx_bind(P->ctx));
   cudaStream_t st = P->ctx->stream;
+  ScanWS* W = get_ws(P->ctx);
   ScanCfg cfg{g, sr_dist, lr_retain_links, lr_links_approx, flags};
   LDW_TRY(validate_scan(P, cfg));
   const bool sr_only = (flags & LDW_SCAN_SR_ONLY) != 0;
@@ -779,27 +802,27 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   const uint64_t kept_cap = 2 * sum_keep + (1u << 20);
 
   // ---- device workspace
-  LDW_TRY(P->d_cand.ensure(max_cap * sizeof(Cand)));
-  LDW_TRY(P->d_mi64.ensure(max_cap * 8));
-  LDW_TRY(P->d_vcand.ensure(max_cap * sizeof(Cand)));
-  LDW_TRY(P->d_state.ensure(64));
-  LDW_TRY(P->d_hist.ensure(MI_HIST_BINS * 4));
-  LDW_TRY(P->d_results.ensure(std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult)));
-  LDW_TRY(P->d_sr_f32.ensure((size_t)std::max<int64_t>(total_sr, 1) * 4));
-  LDW_TRY(P->d_kept_key.ensure(kept_cap * 8));
-  LDW_TRY(P->d_kept_gi.ensure(kept_cap * 4));
-  LDW_TRY(P->d_kept_gj.ensure(kept_cap * 4));
-  LDW_TRY(P->d_kept_mi.ensure(kept_cap * 8));
-  LDW_TRY(P->d_kept_count.ensure(16));
-  LDW_TRY(P->d_sr.ensure(total_sr));
-  LDW_CUDA(cudaMemsetAsync(P->d_kept_count.p, 0, 16, st));
-  LDW_CUDA(cudaMemsetAsync(P->d_results.p, 0, std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult), st));
-  uint32_t* d_count = P->d_state.as<uint32_t>();
+  LDW_TRY(W->d_cand.ensure(max_cap * sizeof(Cand)));
+  LDW_TRY(W->d_mi64.ensure(max_cap * 8));
+  LDW_TRY(W->d_vcand.ensure(max_cap * sizeof(Cand)));
+  LDW_TRY(W->d_state.ensure(64));
+  LDW_TRY(W->d_hist.ensure(MI_HIST_BINS * 4));
+  LDW_TRY(W->d_results.ensure(std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult)));
+  LDW_TRY(W->d_sr_f32.ensure((size_t)std::max<int64_t>(total_sr, 1) * 4));
+  LDW_TRY(W->d_kept_key.ensure(kept_cap * 8));
+  LDW_TRY(W->d_kept_gi.ensure(kept_cap * 4));
+  LDW_TRY(W->d_kept_gj.ensure(kept_cap * 4));
+  LDW_TRY(W->d_kept_mi.ensure(kept_cap * 8));
+  LDW_TRY(W->d_kept_count.ensure(16));
+  LDW_TRY(W->d_sr.ensure(total_sr));
+  LDW_CUDA(cudaMemsetAsync(W->d_kept_count.p, 0, 16, st));
+  LDW_CUDA(cudaMemsetAsync(W->d_results.p, 0, std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult), st));
+  uint32_t* d_count = W->d_state.as<uint32_t>();
   uint32_t* d_tcand = d_count + 1;
   uint32_t* d_overflow = d_count + 2;
   uint32_t* d_kept_overflow = d_count + 3;
   uint32_t* d_chain = d_count + 4;
-  LDW_CUDA(cudaMemsetAsync(P->d_state.p, 0, 64, st));
+  LDW_CUDA(cudaMemsetAsync(W->d_state.p, 0, 64, st));
 
   LDW_CUDA(cudaEventRecord(ev0, st));
   int64_t n_reruns = 0, n_launches = 0, n_scan_launches = 0, n_tiles = 0;
@@ -815,9 +838,9 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   auto run_block = [&](size_t b, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
     Sel& s = sel[b];
     if (s.skip) return 0;
-    int slot = (int)(b % ldw_mi_plan::RING);
-    BlockDev& D = P->ring[slot];
-    BlockHost& H = P->hring[slot];
+    int slot = (int)(b % ScanWS::RING);
+    BlockDev& D = W->ring[slot];
+    BlockHost& H = W->hring[slot];
     if (D.used) LDW_CUDA(cudaEventSynchronize(D.done));  // host staging + device arrays of this ring entry are free again
     int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, H);
     if (e > 1) return e;
@@ -825,25 +848,25 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     D.used = true;
     ScanParams sp;
     fill_scan_params(P, D, H, cfg, sp);
-    sp.sr_out = P->d_sr_f32.as<float>() + s.sr_base;
+    sp.sr_out = W->d_sr_f32.as<float>() + s.sr_base;
     if (dbg_block >= 0 && (int64_t)b == dbg_block) {
-      LDW_TRY(P->d_dbg.ensure(4096 * 16 * 8));
-      LDW_CUDA(cudaMemsetAsync(P->d_dbg.p, 0, 4096 * 16 * 8, st));
-      sp.dbg = P->d_dbg.as<unsigned long long>();
+      LDW_TRY(W->d_dbg.ensure(4096 * 16 * 8));
+      LDW_CUDA(cudaMemsetAsync(W->d_dbg.p, 0, 4096 * 16 * 8, st));
+      sp.dbg = W->d_dbg.as<unsigned long long>();
     }
     const bool lr = !sr_only && s.n_lr > 0;
     const int emit_all = force_emit_all || s.emit_all;
     uint32_t cap = cap_override ? cap_override : s.cap;
     if (lr) {
-      mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, P->d_hist.as<uint32_t>(), d_chain, (use_chain && chain_valid && !emit_all) ? 1 : 0);
+      mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, W->d_hist.as<uint32_t>(), d_chain, (use_chain && chain_valid && !emit_all) ? 1 : 0);
       LDW_CUDA(cudaGetLastError());
       n_launches++;
       if (!emit_all) chain_valid = true;
-      sp.cand = P->d_cand.as<Cand>();
+      sp.cand = W->d_cand.as<Cand>();
       sp.cand_cap = cap;
       sp.cand_count = d_count;
       sp.tcand_bits = d_tcand;
-      sp.hist = P->d_hist.as<uint32_t>();
+      sp.hist = W->d_hist.as<uint32_t>();
       sp.kprime = s.kprime;
       sp.delta = s.delta ? s.delta : 1;
       sp.overflow = d_overflow;
@@ -868,22 +891,22 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     if (lr) {
       n_launches += 2;
       RefineParams R = make_refine_params(P, D, H, cfg);
-      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, st>>>(R, P->d_cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
-                                                                 P->d_vcand.as<Cand>(), P->d_mi64.as<double>(), d_count + 5);
+      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, st>>>(R, W->d_cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
+                                                                 W->d_vcand.as<Cand>(), W->d_mi64.as<double>(), d_count + 5);
       LDW_CUDA(cudaGetLastError());
       SelectParams q;
       memset(&q, 0, sizeof(q));
-      q.cand = P->d_vcand.as<Cand>(); q.mi64 = P->d_mi64.as<double>(); q.vcount = d_count + 5; q.count = d_count; q.cap = cap;
+      q.cand = W->d_vcand.as<Cand>(); q.mi64 = W->d_mi64.as<double>(); q.vcount = d_count + 5; q.count = d_count; q.cap = cap;
       q.overflow = d_overflow; q.tcand_bits = d_tcand; q.emit_all = emit_all;
       q.k_lo = s.k_lo; q.k_hi = s.k_hi; q.h = s.h; q.interpolate = s.interp;
       q.tol_safe = 4e-6; q.tol_border = 1e-9;
       q.from_idx = D.from_idx.as<int32_t>(); q.to_idx = D.to_idx.as<int32_t>();
       q.nf = H.nf; q.nt = H.nt; q.diag = H.diag; q.block = (int32_t)blocks[b].index;
-      q.kept_key = P->d_kept_key.as<uint64_t>(); q.kept_gi = P->d_kept_gi.as<int32_t>(); q.kept_gj = P->d_kept_gj.as<int32_t>();
-      q.kept_mi = P->d_kept_mi.as<double>(); q.kept_count = P->d_kept_count.as<unsigned long long>(); q.kept_cap = kept_cap;
+      q.kept_key = W->d_kept_key.as<uint64_t>(); q.kept_gi = W->d_kept_gi.as<int32_t>(); q.kept_gj = W->d_kept_gj.as<int32_t>();
+      q.kept_mi = W->d_kept_mi.as<double>(); q.kept_count = W->d_kept_count.as<unsigned long long>(); q.kept_cap = kept_cap;
       q.kept_overflow = d_kept_overflow;
       q.chain_bits = d_chain;
-      q.result = P->d_results.as<BlockResult>() + b;
+      q.result = W->d_results.as<BlockResult>() + b;
       mi_select_kernel<<<1, 1024, 0, st>>>(q);
       LDW_CUDA(cudaGetLastError());
     }
@@ -892,12 +915,12 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       SrMatParams m;
       m.col = D.colinfo.as<ColInfo>(); m.from_idx = D.from_idx.as<int32_t>(); m.to_idx = D.to_idx.as<int32_t>();
       m.pos = P->d_pos.as<int32_t>(); m.paint = P->d_paint.as<int32_t>();
-      m.sr_mi = P->d_sr_f32.as<float>() + s.sr_base;
+      m.sr_mi = W->d_sr_f32.as<float>() + s.sr_base;
       m.nf = H.nf; m.nt = H.nt; m.diag = H.diag; m.block = (int32_t)blocks[b].index; m.g = (int64_t)g;
-      m.o_pos1 = P->d_sr.pos1.as<int32_t>() + s.sr_base; m.o_pos2 = P->d_sr.pos2.as<int32_t>() + s.sr_base;
-      m.o_c1 = P->d_sr.c1.as<int32_t>() + s.sr_base; m.o_c2 = P->d_sr.c2.as<int32_t>() + s.sr_base;
-      m.o_len = P->d_sr.len.as<int32_t>() + s.sr_base; m.o_blk = P->d_sr.blk.as<int32_t>() + s.sr_base;
-      m.o_mi = P->d_sr.mi.as<double>() + s.sr_base;
+      m.o_pos1 = W->d_sr.pos1.as<int32_t>() + s.sr_base; m.o_pos2 = W->d_sr.pos2.as<int32_t>() + s.sr_base;
+      m.o_c1 = W->d_sr.c1.as<int32_t>() + s.sr_base; m.o_c2 = W->d_sr.c2.as<int32_t>() + s.sr_base;
+      m.o_len = W->d_sr.len.as<int32_t>() + s.sr_base; m.o_blk = W->d_sr.blk.as<int32_t>() + s.sr_base;
+      m.o_mi = W->d_sr.mi.as<double>() + s.sr_base;
       mi_sr_materialize_kernel<<<H.nt, 128, 0, st>>>(m);
       LDW_CUDA(cudaGetLastError());
     }
@@ -911,7 +934,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   //      provably complete with a plain "collect everything" pass
   P->results.assign(blocks.size(), BlockResult());
   if (!blocks.empty())
-    LDW_CUDA(cudaMemcpyAsync(P->results.data(), P->d_results.p, blocks.size() * sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
+    LDW_CUDA(cudaMemcpyAsync(P->results.data(), W->d_results.p, blocks.size() * sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
   LDW_CUDA(cudaStreamSynchronize(st));
   if (!sr_only) {
     for (size_t b = 0; b < blocks.size(); b++) {
@@ -925,12 +948,12 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
           if (attempt == 1) {
             if ((uint64_t)sel[b].n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block %lld needs an exhaustive long-range pass over more than 2^32 links", (long long)blocks[b].index);
             cap = (uint32_t)sel[b].n_lr;
-            LDW_TRY(P->d_cand.ensure((size_t)cap * sizeof(Cand)));
-            LDW_TRY(P->d_mi64.ensure((size_t)cap * 8));
-            LDW_TRY(P->d_vcand.ensure((size_t)cap * sizeof(Cand)));
+            LDW_TRY(W->d_cand.ensure((size_t)cap * sizeof(Cand)));
+            LDW_TRY(W->d_mi64.ensure((size_t)cap * 8));
+            LDW_TRY(W->d_vcand.ensure((size_t)cap * sizeof(Cand)));
           }
           LDW_TRY(run_block(b, attempt == 1, cap, false));
-          LDW_CUDA(cudaMemcpyAsync(&P->results[b], P->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
+          LDW_CUDA(cudaMemcpyAsync(&P->results[b], W->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
           LDW_CUDA(cudaStreamSynchronize(st));
         }
         if (P->results[b].bad) return set_error(LDW_ERR_INTERNAL, "long-range selection failed for block %lld (flags %u)", (long long)blocks[b].index, P->results[b].bad);
@@ -939,8 +962,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   }
   unsigned long long n_kept = 0;
   uint32_t state[4];
-  LDW_CUDA(cudaMemcpyAsync(&n_kept, P->d_kept_count.p, 8, cudaMemcpyDeviceToHost, st));
-  LDW_CUDA(cudaMemcpyAsync(state, P->d_state.p, 16, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaMemcpyAsync(&n_kept, W->d_kept_count.p, 8, cudaMemcpyDeviceToHost, st));
+  LDW_CUDA(cudaMemcpyAsync(state, W->d_state.p, 16, cudaMemcpyDeviceToHost, st));
   LDW_CUDA(cudaStreamSynchronize(st));
   if (state[3] || n_kept > kept_cap) return set_error(LDW_ERR_UNSUPPORTED, "more long-range links pass their block thresholds (%llu) than the output buffer holds (%llu): massive ties at the threshold", n_kept, (unsigned long long)kept_cap);
 
@@ -949,22 +972,22 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   for (auto& r : P->results) n_border += r.n_border;
   if (n_kept > 0 && !(flags & LDW_SCAN_NO_LINKS)) {
     n_launches += 2 + 4;  // iota, materialise, radix-sort passes (library)
-    LDW_TRY(P->d_keys_sorted.ensure(n_kept * 8));
-    LDW_TRY(P->d_order_in.ensure(n_kept * 4));
-    LDW_TRY(P->d_order_out.ensure(n_kept * 4));
-    iota_u32_kernel<<<(unsigned)((n_kept + 255) / 256), 256, 0, st>>>(P->d_order_in.as<uint32_t>(), (int64_t)n_kept);
+    LDW_TRY(W->d_keys_sorted.ensure(n_kept * 8));
+    LDW_TRY(W->d_order_in.ensure(n_kept * 4));
+    LDW_TRY(W->d_order_out.ensure(n_kept * 4));
+    iota_u32_kernel<<<(unsigned)((n_kept + 255) / 256), 256, 0, st>>>(W->d_order_in.as<uint32_t>(), (int64_t)n_kept);
     size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, P->d_kept_key.as<uint64_t>(), P->d_keys_sorted.as<uint64_t>(),
-                                    P->d_order_in.as<uint32_t>(), P->d_order_out.as<uint32_t>(), (int)n_kept, 0, 64, st);
-    LDW_TRY(P->d_sort_tmp.ensure(tmp_bytes));
-    LDW_CUDA(cub::DeviceRadixSort::SortPairs(P->d_sort_tmp.p, tmp_bytes, P->d_kept_key.as<uint64_t>(), P->d_keys_sorted.as<uint64_t>(),
-                                             P->d_order_in.as<uint32_t>(), P->d_order_out.as<uint32_t>(), (int)n_kept, 0, 64, st));
-    LDW_TRY(P->d_lr.ensure((int64_t)n_kept));
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, W->d_kept_key.as<uint64_t>(), W->d_keys_sorted.as<uint64_t>(),
+                                    W->d_order_in.as<uint32_t>(), W->d_order_out.as<uint32_t>(), (int)n_kept, 0, 64, st);
+    LDW_TRY(W->d_sort_tmp.ensure(tmp_bytes));
+    LDW_CUDA(cub::DeviceRadixSort::SortPairs(W->d_sort_tmp.p, tmp_bytes, W->d_kept_key.as<uint64_t>(), W->d_keys_sorted.as<uint64_t>(),
+                                             W->d_order_in.as<uint32_t>(), W->d_order_out.as<uint32_t>(), (int)n_kept, 0, 64, st));
+    LDW_TRY(W->d_lr.ensure((int64_t)n_kept));
     mi_lr_materialize_kernel<<<(unsigned)((n_kept + 255) / 256), 256, 0, st>>>(
-        P->d_order_out.as<uint32_t>(), P->d_keys_sorted.as<uint64_t>(), P->d_kept_gi.as<int32_t>(), P->d_kept_gj.as<int32_t>(),
-        P->d_kept_mi.as<double>(), P->d_pos.as<int32_t>(), P->d_paint.as<int32_t>(), (int64_t)n_kept, (int64_t)g,
-        P->d_lr.pos1.as<int32_t>(), P->d_lr.pos2.as<int32_t>(), P->d_lr.c1.as<int32_t>(), P->d_lr.c2.as<int32_t>(),
-        P->d_lr.len.as<int32_t>(), P->d_lr.mi.as<double>(), P->d_lr.blk.as<int32_t>());
+        W->d_order_out.as<uint32_t>(), W->d_keys_sorted.as<uint64_t>(), W->d_kept_gi.as<int32_t>(), W->d_kept_gj.as<int32_t>(),
+        W->d_kept_mi.as<double>(), P->d_pos.as<int32_t>(), P->d_paint.as<int32_t>(), (int64_t)n_kept, (int64_t)g,
+        W->d_lr.pos1.as<int32_t>(), W->d_lr.pos2.as<int32_t>(), W->d_lr.c1.as<int32_t>(), W->d_lr.c2.as<int32_t>(),
+        W->d_lr.len.as<int32_t>(), W->d_lr.mi.as<double>(), W->d_lr.blk.as<int32_t>());
     LDW_CUDA(cudaGetLastError());
   }
   LDW_CUDA(cudaEventRecord(ev2, st));
@@ -985,8 +1008,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       LDW_CUDA(cudaMemcpyAsync(h.mi.p, d.mi.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
       return 0;
     };
-    LDW_TRY(d2h(P->ctx->h_sr, P->d_sr, total_sr));
-    LDW_TRY(d2h(P->ctx->h_lr, P->d_lr, (int64_t)n_kept));
+    LDW_TRY(d2h(P->ctx->h_sr, W->d_sr, total_sr));
+    LDW_TRY(d2h(P->ctx->h_lr, W->d_lr, (int64_t)n_kept));
   }
   LDW_CUDA(cudaEventRecord(ev3, st));
   LDW_CUDA(cudaStreamSynchronize(st));
@@ -1062,9 +1085,9 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     stats_out->n_tiles = n_tiles;
     stats_out->exec_int8_ops = exec_ops;
   }
-  if (dbg_block >= 0 && P->d_dbg.p) {
+  if (dbg_block >= 0 && W->d_dbg.p) {
     std::vector<unsigned long long> h(4096 * 16);
-    cudaMemcpy(h.data(), P->d_dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h.data(), W->d_dbg.p, h.size() * 8, cudaMemcpyDeviceToHost);
     double s[16] = {0};
     int nb = 0;
     for (int c = 0; c < 4096; c++)
