@@ -56,6 +56,12 @@ int ldw_create(int device, ldw_ctx** out) {
     delete c;
     return set_error(LDW_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
   }
+  e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return set_error(LDW_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+  }
   *out = c;
   return 0;
 }
@@ -64,6 +70,7 @@ void ldw_destroy(ldw_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->scan_ws && ctx->scan_ws_free) ctx->scan_ws_free(ctx->scan_ws);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

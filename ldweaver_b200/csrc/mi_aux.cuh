@@ -21,8 +21,8 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
   if (snp < 0) {
     if (lane < 4) {
       Rec z;
-      for (int q = 0; q < 4; q++) { z.T[q] = 0; z.rp[q] = 0.f; }
-      z.T4 = 0; z.rp4 = 0.f; z.pad[0] = z.pad[1] = 0;
+      for (int q = 0; q < 4; q++) { z.T[q] = 0; z.rp[q] = 0.f; z.q[q] = 1.f; }
+      z.T4 = 0; z.rp4 = 0.f; z.q4 = 1.f; z.pad = 0;
       rec[lane * vstride + slot] = z;
     }
     return;
@@ -56,18 +56,20 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
     // variant `lane`: partner SNP has r' = lane + 2 observed alleles
     int m = mask[snp];
     uint32_t qt[5] = {0, 0, 0, 0, 0};
-    float qr[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    float qr[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, qq[5] = {1.f, 1.f, 1.f, 1.f, 1.f};
     int q = 0;
     for (int a = 0; a < 5; a++) {
       if (m & (1 << a)) {
         qt[q] = ((uint32_t)h[a] << sa) + ((uint32_t)l[a] >> sb);
-        qr[q] = (float)(1.0 / (p[a] + 0.5 * (double)(lane + 2)));
+        const double v = p[a] + 0.5 * (double)(lane + 2);
+        qr[q] = (float)(1.0 / v);
+        qq[q] = (float)v;
         q++;
       }
     }
     Rec z;
-    for (int t = 0; t < 4; t++) { z.T[t] = qt[t]; z.rp[t] = qr[t]; }
-    z.T4 = qt[4]; z.rp4 = qr[4]; z.pad[0] = z.pad[1] = 0;
+    for (int t = 0; t < 4; t++) { z.T[t] = qt[t]; z.rp[t] = qr[t]; z.q[t] = qq[t]; }
+    z.T4 = qt[4]; z.rp4 = qr[4]; z.q4 = qq[4]; z.pad = 0;
     rec[lane * vstride + slot] = z;
   }
 }

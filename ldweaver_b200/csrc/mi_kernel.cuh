@@ -102,14 +102,21 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // One term of the MI sum.  t: joint count in the fixed-point unit (count = t * kT).
+//   QC = false: ra = den / (p_i^a + r_j/2), rb = 1 / (p_j^b + r_i/2)           -> ratio = x * ra * rb
+//   QC = true : ra = (p_i^a + r_j/2) / den, rb = p_j^b + r_i/2, dq = dQ / den   -> ratio = x / (ra * rb + dq)
+// (quirk Q1: dQ is what the reference's transposed rft adds to the denominator on off-diagonal blocks)
 template <bool QC>
 __device__ __forceinline__ float mi_term(float acc, uint32_t t, float ra, float rb, float dq, float kT) {
   float x = fmaf(__uint2float_rn(t), kT, 0.5f);
-  float e = ra * rb;
-  float v = lg2_fast(x * e);
-  if (QC) v -= lg2_fast(fmaf(dq, e, 1.0f));
-  return fmaf(x, v, acc);
+  float ratio = QC ? x * rcp_fast(fmaf(ra, rb, dq)) : x * (ra * rb);
+  return fmaf(x, lg2_fast(ratio), acc);
 }
 
 // Rare path (a long-range candidate somewhere in the warp): reads its parameters straight from the kernel parameters.
@@ -191,10 +198,10 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
 #pragma unroll
   for (int jj = 0; jj < JC; jj++) {
     const uint32_t ra_ = c.jrec_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(Rec);
-    const uint4 w0 = lds128(ra_), w1 = lds128(ra_ + 16);
-    uint4 w2 = make_uint4(0, 0, 0, 0);
-    if (RB == 5) w2 = lds128(ra_ + 32);
-    const uint32_t tt[5] = {w0.x, w0.y, w0.z, w0.w, w2.x}, tr[5] = {w1.x, w1.y, w1.z, w1.w, w2.y};
+    const uint4 w0 = lds128(ra_), w1 = lds128(ra_ + (QC ? 32 : 16));  // T, then q (Q1 form) or rp (plain form)
+    uint4 w3 = make_uint4(0, 0, 0, 0);
+    if (RB == 5) w3 = lds128(ra_ + 48);
+    const uint32_t tt[5] = {w0.x, w0.y, w0.z, w0.w, w3.x}, tr[5] = {w1.x, w1.y, w1.z, w1.w, QC ? w3.z : w3.y};
 #pragma unroll
     for (int b = 0; b < RB; b++) { tj[jj][b] = tt[b]; rpj[jj][b] = tr[b]; }
     d0v[jj] = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn));
@@ -305,12 +312,14 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   k.tcand = (k.do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
   {
     const uint4* rv = reinterpret_cast<const uint4*>(p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row);
-    const uint4 v0 = __ldg(rv), v1 = __ldg(rv + 1), v2 = __ldg(rv + 2);
-    const uint32_t tt[5] = {v0.x, v0.y, v0.z, v0.w, v2.x}, tr[5] = {v1.x, v1.y, v1.z, v1.w, v2.y};
+    const uint4 v0 = __ldg(rv), v1 = __ldg(rv + (QC ? 2 : 1)), v3 = __ldg(rv + 3);
+    const uint32_t tt[5] = {v0.x, v0.y, v0.z, v0.w, v3.x}, tr[5] = {v1.x, v1.y, v1.z, v1.w, QC ? v3.z : v3.y};
+    const float rden = 1.0f / den;
 #pragma unroll
     for (int a = 0; a < RA; a++) {
       k.Ti[a] = tt[a];
-      k.rpad[a] = __uint_as_float(tr[a]) * den;
+      // Q1 form: (p + r'/2) / den; plain form: den / (p + r'/2)
+      k.rpad[a] = QC ? __uint_as_float(tr[a]) * rden : __uint_as_float(tr[a]) * den;
     }
   }
   const RowDyn rd = p.rowdyn[td.i_dyn0 + row];

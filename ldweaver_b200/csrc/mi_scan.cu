@@ -824,6 +824,13 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   uint32_t* d_chain = d_count + 4;
   LDW_CUDA(cudaMemsetAsync(W->d_state.p, 0, 64, st));
 
+  const bool want_host = !(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_NO_D2H));
+  cudaStream_t cst = P->ctx->copy_stream;
+  cudaEvent_t ev_blk = nullptr;  // "this block's SR columns are materialised"
+  if (want_host) {
+    LDW_TRY(P->ctx->h_sr.ensure(total_sr));
+    LDW_CUDA(cudaEventCreateWithFlags(&ev_blk, cudaEventDisableTiming));
+  }
   LDW_CUDA(cudaEventRecord(ev0, st));
   int64_t n_reruns = 0, n_launches = 0, n_scan_launches = 0, n_tiles = 0;
   double exec_ops = 0;
@@ -923,6 +930,20 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       m.o_mi = W->d_sr.mi.as<double>() + s.sr_base;
       mi_sr_materialize_kernel<<<H.nt, 128, 0, st>>>(m);
       LDW_CUDA(cudaGetLastError());
+      if (want_host) {
+        // copy this block's finished rows to the host while the next blocks are being scanned
+        LDW_CUDA(cudaEventRecord(ev_blk, st));
+        LDW_CUDA(cudaStreamWaitEvent(cst, ev_blk, 0));
+        HostLinks& h = P->ctx->h_sr;
+        const size_t o = (size_t)s.sr_base, nb4 = (size_t)s.n_sr * 4, nb8 = (size_t)s.n_sr * 8;
+        LDW_CUDA(cudaMemcpyAsync(h.pos1.as<int32_t>() + o, m.o_pos1, nb4, cudaMemcpyDeviceToHost, cst));
+        LDW_CUDA(cudaMemcpyAsync(h.pos2.as<int32_t>() + o, m.o_pos2, nb4, cudaMemcpyDeviceToHost, cst));
+        LDW_CUDA(cudaMemcpyAsync(h.c1.as<int32_t>() + o, m.o_c1, nb4, cudaMemcpyDeviceToHost, cst));
+        LDW_CUDA(cudaMemcpyAsync(h.c2.as<int32_t>() + o, m.o_c2, nb4, cudaMemcpyDeviceToHost, cst));
+        LDW_CUDA(cudaMemcpyAsync(h.len.as<int32_t>() + o, m.o_len, nb4, cudaMemcpyDeviceToHost, cst));
+        LDW_CUDA(cudaMemcpyAsync(h.blk.as<int32_t>() + o, m.o_blk, nb4, cudaMemcpyDeviceToHost, cst));
+        LDW_CUDA(cudaMemcpyAsync(h.mi.as<double>() + o, m.o_mi, nb8, cudaMemcpyDeviceToHost, cst));
+      }
     }
     LDW_CUDA(cudaEventRecord(D.done, st));
     return 0;
@@ -1008,11 +1029,13 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       LDW_CUDA(cudaMemcpyAsync(h.mi.p, d.mi.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
       return 0;
     };
-    LDW_TRY(d2h(P->ctx->h_sr, W->d_sr, total_sr));
+    P->ctx->h_sr.n = total_sr;  // short-range rows were streamed out block by block on the copy stream
     LDW_TRY(d2h(P->ctx->h_lr, W->d_lr, (int64_t)n_kept));
   }
   LDW_CUDA(cudaEventRecord(ev3, st));
   LDW_CUDA(cudaStreamSynchronize(st));
+  if (want_host) LDW_CUDA(cudaStreamSynchronize(cst));
+  if (ev_blk) cudaEventDestroy(ev_blk);
 
   // borderline list: kept-or-not candidates within tol of their block threshold are reported by count per block;
   // the explicit rows are the LR rows whose MI is within tol of the block threshold

@@ -9,16 +9,19 @@ namespace ldw {
 //   T   : fixed-point weighted marginals of the SNP's allele slots q = 0..r-1 in the epilogue's count unit
 //         (floor(V / 2^sb), V = the exact 30-bit fixed-point sum), 0 for q >= r.  The last observed allele (slot r-1)
 //         is the "complement" slot whose joint counts are derived by subtraction instead of from the GEMM.
-//   rp  : 1/(p_q + 0.5 r') for r' = variant+2 (r of the partner SNP).
-// Layout: three 16-byte vectors {T0..T3} {rp0..rp3} {T4, rp4, -, -}; kinds with at most four allele slots read two.
+//   q   : p_q + 0.5 r' for r' = variant+2 (r of the partner SNP); rp = 1/q.
+// Layout: four 16-byte vectors {T0..T3} {rp0..rp3} {q0..q3} {T4, rp4, q4, -}; kinds with at most four allele slots
+// read two of the first three (the Q1-corrected form uses q, the plain form rp).
 struct __align__(16) Rec {
   uint32_t T[4];
   float rp[4];
+  float q[4];
   uint32_t T4;
   float rp4;
-  uint32_t pad[2];
+  float q4;
+  uint32_t pad;
 };
-static_assert(sizeof(Rec) == 48, "Rec must be 48 bytes");
+static_assert(sizeof(Rec) == 64, "Rec must be 64 bytes");
 
 // Per-block, per from-slot: local row index (or -1) and r of the TO-list SNP that sits at that local index
 // (quirk Q1: the reference reads the transposed rft by linear index).
