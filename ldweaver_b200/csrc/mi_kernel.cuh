@@ -28,7 +28,17 @@ namespace ldw {
 constexpr int MI_EXP_WARPS = 6;
 constexpr int MI_EXP_THREADS = 32 * MI_EXP_WARPS;
 constexpr int MI_EPI_WARP0 = 8;
-constexpr int MI_THREADS = 512;
+constexpr int MI_EPI_GROUPS = 4;                          // column groups; each is 4 warps (one per TMEM lane quarter)
+constexpr int MI_EPI_WARPS = 4 * MI_EPI_GROUPS;
+constexpr int MI_EPI_THREADS = 32 * MI_EPI_WARPS;
+constexpr int MI_THREADS = 32 * (MI_EPI_WARP0 + MI_EPI_WARPS);
+#define LDW_STR2(x) #x
+#define LDW_STR(x) LDW_STR2(x)
+// register budget (65536 per SM): control warps shrink, epilogue warps grow
+#define MI_REGS_CTRL 48
+#define MI_REGS_EPI 96
+// the CTA's pool is what the launch allocated: MI_THREADS x (65536 / MI_THREADS rounded down to a multiple of 8)
+static_assert(MI_EPI_WARP0 * 32 * MI_REGS_CTRL + MI_EPI_THREADS * MI_REGS_EPI <= MI_THREADS * ((65536 / MI_THREADS) & ~7), "register budget");
 constexpr int MI_STAGES = 2;
 constexpr uint32_t MI_ARR_BYTES = 128 * 128;              // one operand array slice: 128 rows x 128 K-bytes
 constexpr uint32_t MI_STAGE_BYTES = 6 * MI_ARR_BYTES;     // up to 4 row planes + the 4 digit copies of the column planes
@@ -86,7 +96,7 @@ __device__ __noinline__ void lr_raise_threshold(const ScanParams& p, int lane) {
 }
 
 struct EpiCtx {
-  int q, half, lane;
+  int q, cg, lane;
   uint32_t tmem_base;   // lane-quarter offset already applied, column of this tile's accumulators
   uint32_t jrec_saddr;  // shared-memory byte addresses of this tile's column records
   uint32_t jdyn_saddr;
@@ -296,8 +306,8 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   constexpr int RA = PA + 1, RB = PB + 1;
   constexpr int JC = mi_jc(PA, PB);
   constexpr int NJ = 1 << mi_njlog2(PA, PB);
-  constexpr int NB = (NJ / 2) / JC;  // batches per warp
-  static_assert(NB >= 1, "at least one batch per warp");
+  constexpr int NB = (NJ / MI_EPI_GROUPS) / JC;  // batches per warp
+  static_assert(NB >= 1 && NB * JC * MI_EPI_GROUPS == NJ, "column split must be exact");
   const int row = c.q * 32 + c.lane;
   TileRegs<RA> k;
   const float den = p.den[RA - 2][RB - 2];
@@ -329,7 +339,7 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   k.jl_lim = k.il < 0 ? 0u : (p.diag ? (uint32_t)k.il : (uint32_t)p.nt);
 
   // ---- batches of JC columns, evaluated in lock step
-  const int jbeg = c.half * (NJ / 2);
+  const int jbeg = c.cg * (NJ / MI_EPI_GROUPS);
   uint32_t Ha[PA][PB][JC], La[PA][PB][JC];
 #pragma unroll 1
   for (int bi = 0; bi < NB; bi++) {
@@ -387,8 +397,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], MI_EXP_THREADS);
     }
     for (int i = 0; i < 2; i++) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 256);
-      mbar_init(&jfull[i], 1); mbar_init(&jempty[i], 256);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], MI_EPI_THREADS);
+      mbar_init(&jfull[i], 1); mbar_init(&jempty[i], MI_EPI_THREADS);
     }
     fence_barrier_init();
   }
@@ -397,13 +407,12 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // register budget: the two control warpgroups (warps 0-7) give registers to the two epilogue warpgroups
-  // (pool = 128 x 512 = 65536 registers at launch; 96 x 256 + 160 x 256 = 65536)
-  if (warp < MI_EPI_WARP0) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
-
+  // register budget: the control warps (0-7) give registers to the epilogue warps; setmaxnreg sits at the top of
+  // each role's own branch so that ptxas allocates every role against its own budget
   const int tile0 = (int)blockIdx.x, tstep = (int)gridDim.x;
 
+  if (warp < MI_EPI_WARP0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 " LDW_STR(MI_REGS_CTRL) ";");
   if (warp == 0) {
     // ===================================================================== TMA producer
     // Whole warp runs the loop (uniform registers), one elected lane issues the copies.
@@ -524,7 +533,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       p.dbg[blockIdx.x * 16 + 4] = (unsigned long long)w_tempty;
       p.dbg[blockIdx.x * 16 + 5] = (unsigned long long)w_ready;
     }
-  } else if (warp < MI_EPI_WARP0) {
+  } else {
     // ===================================================================== operand expanders
     // stage layout: PA row planes (raw, used as they are), then aH | aL | bH | bL digit copies of all PB column
     // planes (the raw one-hot Y lands in the aH slot; aL, bH, bL are written, aH = Y & digit is formed in place).
@@ -568,11 +577,13 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       p.dbg[blockIdx.x * 16 + 12] = (unsigned long long)(clock64() - t_begin);
       p.dbg[blockIdx.x * 16 + 13] = (unsigned long long)w_full;
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " LDW_STR(MI_REGS_EPI) ";");
     // ===================================================================== epilogue
     EpiCtx c;
     c.q = warp & 3;
-    c.half = (warp - MI_EPI_WARP0) >> 2;
+    c.cg = (warp - MI_EPI_WARP0) >> 2;
     c.lane = lane;
     int as = 0; uint32_t aph = 0;
     int it = 0;
@@ -615,7 +626,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       }
       mbar_arrive(&jempty[jb]);
     }
-    if (p.dbg && lane == 0 && (warp == MI_EPI_WARP0 || warp == MI_EPI_WARP0 + 7)) {
+    if (p.dbg && lane == 0 && (warp == MI_EPI_WARP0 || warp == MI_EPI_WARP0 + MI_EPI_WARPS - 1)) {
       int o = warp == MI_EPI_WARP0 ? 6 : 9;
       p.dbg[blockIdx.x * 16 + o] = (unsigned long long)(clock64() - t_begin);
       p.dbg[blockIdx.x * 16 + o + 1] = (unsigned long long)w_jfull;
