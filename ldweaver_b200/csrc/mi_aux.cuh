@@ -75,8 +75,8 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
 }
 
 // Operand rows.  row_info[R] = snp | allele << 28, or 0xFFFFFFFF for padding rows.  Each thread writes one 16-byte
-// chunk (16 sequences) of the one-hot plane matrix X [rows][Kpad]; a match is stored as 0x81 (+129 unsigned /
-// -127 signed, see the weight digits in build_plan).
+// chunk (16 sequences) of the one-hot plane matrix X [rows][Kpad]; a match is stored as 0xFF (+255 unsigned /
+// -1 signed, see the weight digits in build_plan).
 __global__ void mi_pack_operands_kernel(const uint8_t* __restrict__ codes, int64_t S, int64_t Kpad,
                                         const uint32_t* __restrict__ row_info, int64_t nrows, uint8_t* X) {
   int64_t chunks = Kpad / 16;
@@ -92,7 +92,7 @@ __global__ void mi_pack_operands_kernel(const uint8_t* __restrict__ codes, int64
 #pragma unroll
     for (int k = 0; k < 16; k++) {
       int64_t s = s0 + k;
-      uint32_t bit = (s < S && row[s] == al) ? 0x81u : 0u;
+      uint32_t bit = (s < S && row[s] == al) ? 0xFFu : 0u;
       x1[k >> 2] |= bit << (8 * (k & 3));
     }
   }

@@ -6,9 +6,9 @@
 // enumeration / len / sr-lr split (:306-344).
 //
 // How.  The weighted joint allele counts  c_ij^ab = sum_s w_s [code(i,s)=a][code(j,s)=b]  are an integer GEMM:
-// weights are fixed-point (28 bits below the largest weight) split into two 14-bit halves h = 129 a - 127 b with byte
+// weights are fixed-point (28 bits below the largest weight) split into two 14-bit halves h = 255 a - b with byte
 // digits a, b; each half is accumulated exactly in an int32 TMEM accumulator by two K-passes of kind::i8 UMMA over
-// the SAME one-hot operand (bytes 0x81): an unsigned pass (x129, digit a) and a signed pass (x-127, digit b).  Only the r-1 non-complement allele planes of a site enter the GEMM; the remaining
+// the SAME one-hot operand (bytes 0xFF): an unsigned pass (x255, digit a) and a signed pass (x-1, digit b).  Only the r-1 non-complement allele planes of a site enter the GEMM; the remaining
 // counts follow from the exact integer marginals (sum_b c^ab = p^a).  SNPs are grouped by plane count so a tile is
 // 128 row SNPs x NJ column SNPs with uniform (PA, PB).  Eight epilogue warps read the accumulators straight out of
 // TMEM (thread = row SNP), rebuild the (PA+1)x(PB+1) table, evaluate
@@ -92,6 +92,17 @@ __device__ __noinline__ void lr_raise_threshold(const ScanParams& p, int lane) {
         break;
       }
     }
+  }
+}
+
+template <bool DBG>
+__device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, int tag, long long& acc) {
+  if constexpr (DBG) {
+    long long c0 = clock64();
+    mbar_wait(bar, parity, tag);
+    acc += clock64() - c0;
+  } else {
+    mbar_wait(bar, parity, tag);
   }
 }
 
@@ -197,7 +208,7 @@ __device__ __forceinline__ void epi_load(uint32_t tmem_base, int NJ, int j0, uin
 
 // JC pairs (this thread's row SNP x JC column SNPs), evaluated in lock step: term loop outside, pair loop inside, so
 // JC independent dependency chains overlap each other's MUFU / conversion latency.
-template <int PA, int PB, int JC, bool QC>
+template <int PA, int PB, int JC, bool QC, bool RG>
 __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, const TileRegs<PA + 1>& k, int j0,
                                           const uint32_t (&H)[PA][PB][JC], const uint32_t (&L)[PA][PB][JC]) {
   constexpr int RB = PB + 1;
@@ -218,7 +229,7 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
     jl[jj] = (int)d0v[jj].x;
     dq[jj] = 0.f;
     if (QC) {
-      if (k.ragged) {
+      if (RG) {
         // quirk Q1, general form: rft (nt x nf) is read by the linear index of the nf x nt matrix
         float v = k.q0;
         if (k.il >= 0 && jl[jj] >= 0) {
@@ -276,32 +287,45 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
     const int corner = (int)(k.Ti[PA] + tot[jj] - sj);
     acc[jj] = mi_term<QC>(acc[jj], (uint32_t)max(corner, 0), k.rpad[PA], __uint_as_float(rpj[jj][PB]), dq[jj], k.kT);
   }
-  // ---- classification and emission
+  // ---- classification and emission: tile-uniform branches only; the per-lane work is predicated
+  float mi[JC];
 #pragma unroll
-  for (int jj = 0; jj < JC; jj++) {
-    const float mi = acc[jj] * k.scale;
-    const int jlv = jl[jj];
-    if (k.dense) {
-      if (k.il >= 0 && jlv >= 0) p.dense_out[(size_t)k.il + (size_t)jlv * (size_t)k.nf] = mi;
-    } else {
-      const bool valid = ((uint32_t)jlv < k.jl_lim) && (jlv != k.il);
-      bool sr = false;
-      if (k.has_sr) {
-        const uint4 d0 = d0v[jj];
-        const uint4 d1 = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn) + 16);
-        const uint32_t la = d0.w - d0.z, lb = d1.y - d1.x;
-        sr = valid && (((uint32_t)k.il - d0.z < la) || ((uint32_t)k.il - d1.x < lb));
-        if (sr) sr_store(k.sr_out, d0, d1, k.il, jlv, mi);
-      }
-      if (k.do_lr) {
-        const bool em = valid && !sr && (mi >= k.tcand);
-        if (__any_sync(0xffffffffu, em)) lr_emit(p, em, k.il, jlv, mi, c.lane);
-      }
+  for (int jj = 0; jj < JC; jj++) mi[jj] = acc[jj] * k.scale;
+  if (k.dense) {
+#pragma unroll
+    for (int jj = 0; jj < JC; jj++)
+      if (k.il >= 0 && jl[jj] >= 0) p.dense_out[(size_t)k.il + (size_t)jl[jj] * (size_t)k.nf] = mi[jj];
+    return;
+  }
+  bool live[JC];  // a wanted pair that is not (yet) classified short-range
+#pragma unroll
+  for (int jj = 0; jj < JC; jj++) live[jj] = ((uint32_t)jl[jj] < k.jl_lim) && (jl[jj] != k.il);
+  if (k.has_sr) {
+#pragma unroll
+    for (int jj = 0; jj < JC; jj++) {
+      const uint4 d0 = d0v[jj];
+      const uint4 d1 = lds128(c.jdyn_saddr + (uint32_t)(j0 + jj) * (uint32_t)sizeof(ColDyn) + 16);
+      const uint32_t la = d0.w - d0.z, lb = d1.y - d1.x;
+      const bool sr = live[jj] && (((uint32_t)k.il - d0.z < la) || ((uint32_t)k.il - d1.x < lb));
+      if (sr) sr_store(k.sr_out, d0, d1, k.il, jl[jj], mi[jj]);
+      live[jj] = live[jj] && !sr;
+    }
+  }
+  if (k.do_lr) {
+    bool any = false;
+#pragma unroll
+    for (int jj = 0; jj < JC; jj++) {
+      live[jj] = live[jj] && (mi[jj] >= k.tcand);
+      any = any || live[jj];
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+      for (int jj = 0; jj < JC; jj++) lr_emit(p, live[jj], k.il, jl[jj], mi[jj], c.lane);
     }
   }
 }
 
-template <int PA, int PB, bool QC>
+template <int PA, int PB, bool QC, bool RG>
 __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
   constexpr int RA = PA + 1, RB = PB + 1;
   constexpr int JC = mi_jc(PA, PB);
@@ -346,33 +370,34 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
     const int j0 = jbeg + bi * JC;
     epi_load<PA, PB, JC>(c.tmem_base, NJ, j0, Ha, La);
     tmem_ld_wait();
-    epi_batch<PA, PB, JC, QC>(p, c, k, j0, Ha, La);
+    epi_batch<PA, PB, JC, QC, RG>(p, c, k, j0, Ha, La);
   }
 }
 
-template <bool QC>
+template <bool QC, bool RG>
 __device__ __forceinline__ void epi_dispatch(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
   switch (td.PA * 4 + td.PB - 5) {
-    case 0: epi_tile<1, 1, QC>(p, td, c); break;
-    case 1: epi_tile<1, 2, QC>(p, td, c); break;
-    case 2: epi_tile<1, 3, QC>(p, td, c); break;
-    case 3: epi_tile<1, 4, QC>(p, td, c); break;
-    case 4: epi_tile<2, 1, QC>(p, td, c); break;
-    case 5: epi_tile<2, 2, QC>(p, td, c); break;
-    case 6: epi_tile<2, 3, QC>(p, td, c); break;
-    case 7: epi_tile<2, 4, QC>(p, td, c); break;
-    case 8: epi_tile<3, 1, QC>(p, td, c); break;
-    case 9: epi_tile<3, 2, QC>(p, td, c); break;
-    case 10: epi_tile<3, 3, QC>(p, td, c); break;
-    case 11: epi_tile<3, 4, QC>(p, td, c); break;
-    case 12: epi_tile<4, 1, QC>(p, td, c); break;
-    case 13: epi_tile<4, 2, QC>(p, td, c); break;
-    case 14: epi_tile<4, 3, QC>(p, td, c); break;
-    case 15: epi_tile<4, 4, QC>(p, td, c); break;
+    case 0: epi_tile<1, 1, QC, RG>(p, td, c); break;
+    case 1: epi_tile<1, 2, QC, RG>(p, td, c); break;
+    case 2: epi_tile<1, 3, QC, RG>(p, td, c); break;
+    case 3: epi_tile<1, 4, QC, RG>(p, td, c); break;
+    case 4: epi_tile<2, 1, QC, RG>(p, td, c); break;
+    case 5: epi_tile<2, 2, QC, RG>(p, td, c); break;
+    case 6: epi_tile<2, 3, QC, RG>(p, td, c); break;
+    case 7: epi_tile<2, 4, QC, RG>(p, td, c); break;
+    case 8: epi_tile<3, 1, QC, RG>(p, td, c); break;
+    case 9: epi_tile<3, 2, QC, RG>(p, td, c); break;
+    case 10: epi_tile<3, 3, QC, RG>(p, td, c); break;
+    case 11: epi_tile<3, 4, QC, RG>(p, td, c); break;
+    case 12: epi_tile<4, 1, QC, RG>(p, td, c); break;
+    case 13: epi_tile<4, 2, QC, RG>(p, td, c); break;
+    case 14: epi_tile<4, 3, QC, RG>(p, td, c); break;
+    case 15: epi_tile<4, 4, QC, RG>(p, td, c); break;
     default: break;
   }
 }
 
+template <bool DBG>
 __global__ void __launch_bounds__(MI_THREADS, 1)
 mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -418,13 +443,13 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     // Whole warp runs the loop (uniform registers), one elected lane issues the copies.
     int st = 0; uint32_t ph = 0;
     int it = 0;
-    long long w_jempty = 0, w_empty = 0, t_begin = clock64();
+    long long w_jempty = 0, w_empty = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
       const int njidx = 7 - td.njlog2;  // NJ 128,64,32,16 -> tm.b[0..3]
       const int jb = it & 1;
-      { long long c0 = clock64(); mbar_wait(&jempty[jb], ((it >> 1) & 1) ^ 1, 10); w_jempty += clock64() - c0; }
+      timed_wait<DBG>(&jempty[jb], ((it >> 1) & 1) ^ 1, 10, w_jempty);
       if (elect_one()) {
         mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (uint32_t)(sizeof(Rec) + sizeof(ColDyn)));
         bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
@@ -436,7 +461,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       {
         const uint32_t stage_tx = (uint32_t)PA * MI_ARR_BYTES + (uint32_t)(PB * NJ * 128);
         for (int kb = 0; kb < p.nkb; kb++) {
-          { long long c0 = clock64(); mbar_wait(&empty[st], ph ^ 1, 11); w_empty += clock64() - c0; }
+          timed_wait<DBG>(&empty[st], ph ^ 1, 11, w_empty);
           if (elect_one()) {
             uint8_t* sb = stage_base + st * MI_STAGE_BYTES;
             mbar_arrive_expect_tx(&full[st], stage_tx);
@@ -451,7 +476,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         }
       }
     }
-    if (p.dbg && lane == 0) {
+    if (DBG && p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_begin);
       p.dbg[blockIdx.x * 16 + 1] = (unsigned long long)w_jempty;
       p.dbg[blockIdx.x * 16 + 2] = (unsigned long long)w_empty;
@@ -461,28 +486,24 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     // The whole warp runs the loop (so addresses and descriptors live in uniform registers); one elected lane
     // issues the tcgen05 instructions.
     int st = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
-    long long w_tempty = 0, w_ready = 0, t_begin = clock64();
+    long long w_tempty = 0, w_ready = 0, t_begin = DBG ? clock64() : 0;
     const uint32_t desc_hi = (uint32_t)(make_smem_desc_sw128(0) >> 32);
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
       const bool big = 2 * PA * PB * NJ > 256;
       const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA
-      const uint32_t idesc_u = make_idesc_u8(128, ncols);     // A bytes 0x81 read as +129
-      const uint32_t idesc_s = make_idesc_s8u8(128, ncols);   // A bytes 0x81 read as -127
+      const uint32_t idesc_u = make_idesc_u8(128, ncols);     // A bytes 0xFF read as +255
+      const uint32_t idesc_s = make_idesc_s8u8(128, ncols);   // A bytes 0xFF read as -1
       uint32_t dbase;
       if (big) {
         for (int s2 = 0; s2 < 2; s2++) {
-          long long c0 = clock64();
-          mbar_wait(&tempty[as], aph ^ 1, 20);
-          w_tempty += clock64() - c0;
+          timed_wait<DBG>(&tempty[as], aph ^ 1, 20, w_tempty);
           if (++as == 2) { as = 0; aph ^= 1; }
         }
         dbase = tmem_base;
       } else {
-        long long c0 = clock64();
-        mbar_wait(&tempty[as], aph ^ 1, 21);
-        w_tempty += clock64() - c0;
+        timed_wait<DBG>(&tempty[as], aph ^ 1, 21, w_tempty);
         dbase = tmem_base + as * 256;
       }
       tc_fence_after();
@@ -490,7 +511,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         const uint32_t boff = (uint32_t)PA * MI_ARR_BYTES;                // B region follows the A planes
         const uint32_t b2off = boff + (uint32_t)(2 * PB * NJ * 128);      // bH | bL follow aH | aL
         for (int kb = 0; kb < p.nkb; kb++) {
-          { long long c0 = clock64(); mbar_wait(&ready[st], ph, 22); w_ready += clock64() - c0; }
+          timed_wait<DBG>(&ready[st], ph, 22, w_ready);
           tc_fence_after();
           // low descriptor word of the stage base: address >> 4 | LBO (1 << 16)
           const uint32_t lo = ((smem_u32(stage_base + st * MI_STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -528,7 +549,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         if (++as == 2) { as = 0; aph ^= 1; }
       }
     }
-    if (p.dbg && lane == 0) {
+    if (DBG && p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 16 + 3] = (unsigned long long)(clock64() - t_begin);
       p.dbg[blockIdx.x * 16 + 4] = (unsigned long long)w_tempty;
       p.dbg[blockIdx.x * 16 + 5] = (unsigned long long)w_ready;
@@ -541,7 +562,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     // chunk index XOR (row & 7).
     const int h = (warp - 2) * 32 + lane;  // 0..191
     int st = 0; uint32_t ph = 0;
-    long long w_full = 0, t_begin = clock64();
+    long long w_full = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
@@ -554,15 +575,12 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(dg + p.kpad));        // aL
         const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(dg + 2 * p.kpad));    // bH
         const uint4 g3 = __ldg(reinterpret_cast<const uint4*>(dg + 3 * p.kpad));    // bL
-        { long long c0 = clock64(); mbar_wait(&full[st], ph, 40); w_full += clock64() - c0; }
+        timed_wait<DBG>(&full[st], ph, 40, w_full);
         const uint32_t yb = smem_u32(stage_base + st * MI_STAGE_BYTES) + (uint32_t)PA * MI_ARR_BYTES;
         const uint32_t slot = (uint32_t)brows * 128u;
         for (int r = h >> 3; r < brows; r += MI_EXP_THREADS / 8) {
           const uint32_t addr = yb + (uint32_t)r * 128u + (uint32_t)((cl ^ (r & 7)) * 16);
-          uint4 y = lds128(addr);
-          // bytes 0x00 / 0x81 -> 0x00 / 0xFF
-          y.x = (y.x & 0x01010101u) * 255u; y.y = (y.y & 0x01010101u) * 255u;
-          y.z = (y.z & 0x01010101u) * 255u; y.w = (y.w & 0x01010101u) * 255u;
+          const uint4 y = lds128(addr);  // bytes 0x00 / 0xFF: the one-hot plane is its own select mask
           sts128(addr + slot, make_uint4(y.x & g1.x, y.y & g1.y, y.z & g1.z, y.w & g1.w));          // aL
           sts128(addr + 2 * slot, make_uint4(y.x & g2.x, y.y & g2.y, y.z & g2.z, y.w & g2.w));      // bH
           sts128(addr + 3 * slot, make_uint4(y.x & g3.x, y.y & g3.y, y.z & g3.z, y.w & g3.w));      // bL
@@ -573,7 +591,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         if (++st == MI_STAGES) { st = 0; ph ^= 1; }
       }
     }
-    if (p.dbg && h == 0) {
+    if (DBG && p.dbg && h == 0) {
       p.dbg[blockIdx.x * 16 + 12] = (unsigned long long)(clock64() - t_begin);
       p.dbg[blockIdx.x * 16 + 13] = (unsigned long long)w_full;
     }
@@ -587,14 +605,14 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     c.lane = lane;
     int as = 0; uint32_t aph = 0;
     int it = 0;
-    long long w_jfull = 0, w_tfull = 0, t_begin = clock64();
+    long long w_jfull = 0, w_tfull = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
       const int NJ = 1 << td.njlog2;
       const bool big = 2 * td.PA * td.PB * NJ > 256;
       const int jb = it & 1;
-      { long long c0 = clock64(); mbar_wait(&jfull[jb], (it >> 1) & 1, 30); w_jfull += clock64() - c0; }
-      long long c1 = clock64();
+      timed_wait<DBG>(&jfull[jb], (it >> 1) & 1, 30, w_jfull);
+      long long c1 = DBG ? clock64() : 0;
       c.jrec_saddr = smem_u32(jrec + jb * 128);
       c.jdyn_saddr = smem_u32(jdyn + jb * 128);
       if (big) {
@@ -609,11 +627,12 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         mbar_wait(&tfull[as], aph, 33);
         c.tmem_base = tmem_base + ((uint32_t)(c.q * 32) << 16) + as * 256;
       }
-      w_tfull += clock64() - c1;
+      if constexpr (DBG) w_tfull += clock64() - c1;
       tc_fence_after();
       if (!(td.flags & TILE_NULL)) {
-        if (p.qcorr) epi_dispatch<true>(p, td, c);
-        else epi_dispatch<false>(p, td, c);
+        if (!p.qcorr) epi_dispatch<false, false>(p, td, c);
+        else if (p.ragged) epi_dispatch<true, true>(p, td, c);
+        else epi_dispatch<true, false>(p, td, c);
       }
       tc_fence_before();
       if (big) {
@@ -626,7 +645,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       }
       mbar_arrive(&jempty[jb]);
     }
-    if (p.dbg && lane == 0 && (warp == MI_EPI_WARP0 || warp == MI_EPI_WARP0 + MI_EPI_WARPS - 1)) {
+    if (DBG && p.dbg && lane == 0 && (warp == MI_EPI_WARP0 || warp == MI_EPI_WARP0 + MI_EPI_WARPS - 1)) {
       int o = warp == MI_EPI_WARP0 ? 6 : 9;
       p.dbg[blockIdx.x * 16 + o] = (unsigned long long)(clock64() - t_begin);
       p.dbg[blockIdx.x * 16 + o + 1] = (unsigned long long)w_jfull;

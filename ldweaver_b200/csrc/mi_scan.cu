@@ -121,9 +121,10 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   for (int64_t i = 1; i < n; i++)
     if (pos[i] < pos[i - 1]) P->pos_sorted = false;
   // ---- fixed-point weights: W_s = round(w_s * scale), scale = (2^28 - 1) / max(w), two 14-bit halves H, L.
-  //      Each half h is written as 129 a - 127 b with byte digits a, b (every h <= 16767 has such a pair): the
-  //      one-hot operand stores 0x81 where the allele matches, which the tensor core reads as +129 (unsigned pass,
-  //      digit a) or -127 (signed pass, digit b) -- one operand array, no shifted copy.
+  //      Each half h is written as 255 a - b with byte digits a = ceil(h / 255) <= 65, b = 255 a - h <= 254: the
+  //      one-hot operand stores 0xFF where the allele matches, which the tensor core reads as +255 (unsigned pass,
+  //      digit a) or -1 (signed pass, digit b) -- one operand array, no shifted copy, and the byte doubles as the
+  //      select mask of the expander warps.  Partial sums stay below 65 * 255 * nseq < 2^31.
   double wmax = 0, neff = 0;
   for (int64_t s = 0; s < S; s++) {
     if (!(hdw[s] > 0) || !std::isfinite(hdw[s])) return set_error(LDW_ERR_ARG, "hdw[%lld] = %g is not a positive finite weight", (long long)s, hdw[s]);
@@ -135,14 +136,11 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   P->Kpad = round_up(S, 128);
   std::vector<uint8_t> da(16384), db(16384);
   {
-    std::vector<uint8_t> found(16384, 0);
-    for (int a = 0; a < 256; a++)
-      for (int b = 0; b < 256; b++) {
-        int h = 129 * a - 127 * b;
-        if (h >= 0 && h < 16384 && !found[h]) { found[h] = 1; da[h] = (uint8_t)a; db[h] = (uint8_t)b; }
-      }
-    for (int h = 0; h < 16384; h++)
-      if (!found[h]) return set_error(LDW_ERR_INTERNAL, "digit table incomplete at %d", h);
+    for (int h = 0; h < 16384; h++) {
+      int a = (h + 254) / 255, b = 255 * a - h;
+      da[h] = (uint8_t)a;
+      db[h] = (uint8_t)b;
+    }
   }
   std::vector<uint8_t> dig((size_t)4 * P->Kpad, 0);  // rows: aH, aL, bH, bL (shared-memory slot order)
   std::vector<int32_t> wH(S), wL(S);
@@ -290,7 +288,8 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   P->t_pack_ms = ms;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  LDW_CUDA(cudaFuncSetAttribute(mi_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MI_SMEM_BYTES));
+  LDW_CUDA(cudaFuncSetAttribute(mi_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MI_SMEM_BYTES));
+  LDW_CUDA(cudaFuncSetAttribute(mi_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MI_SMEM_BYTES));
   return 0;
 }
 
@@ -577,7 +576,8 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
 int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st) {
   if (sp.n_tiles <= 0) return 0;
   int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
-  mi_scan_kernel<<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
+  if (sp.dbg) mi_scan_kernel<true><<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
+  else mi_scan_kernel<false><<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
   LDW_CUDA(cudaGetLastError());
   return 0;
 }
