@@ -268,7 +268,7 @@ def main():
                "ms_per_step": 1e3 * te / e_steps, "steps": e_steps,
                "breakdown_ms": {"plan_create": 1e3 * t_plan / e_steps, "scan_call": 1e3 * t_scan / e_steps,
                                 "plan_destroy": 1e3 * t_close / e_steps, "scan_device": st2["t_scan_ms"] + st2["t_select_ms"],
-                                "d2h": st2["t_d2h_ms"]},
+                                "scan_kernels": st2["t_kernel_ms"], "select_tail": st2["t_select_ms"], "d2h_tail": st2["t_d2h_ms"]},
                "includes": "host->device upload, operand packing, scan, link materialisation, device->host copy of all link columns"}
 
     if rank != 0:

@@ -57,6 +57,7 @@ int ldw_create(int device, ldw_ctx** out) {
     return set_error(LDW_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
   }
   e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->select_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     cudaStreamDestroy(c->stream);
     delete c;
@@ -70,7 +71,10 @@ void ldw_destroy(ldw_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->scan_ws && ctx->scan_ws_free) ctx->scan_ws_free(ctx->scan_ws);
+  cudaDeviceSynchronize();
+  ldw::dev_cache_trim();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->select_stream) cudaStreamDestroy(ctx->select_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

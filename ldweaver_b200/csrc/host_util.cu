@@ -1,5 +1,8 @@
 #include "host_util.h"
 
+#include <map>
+#include <mutex>
+
 namespace ldw {
 
 std::string& last_error_ref() {
@@ -15,6 +18,80 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   last_error_ref() = buf;
   return code;
+}
+
+// ------------------------------------------------------------------ cached device allocations
+namespace {
+struct DevCache {
+  std::mutex mu;
+  std::map<int, std::multimap<size_t, void*>> free_blocks;  // device -> size -> block
+  std::map<int, size_t> cached_bytes;
+};
+DevCache& dev_cache() {
+  static DevCache c;
+  return c;
+}
+constexpr size_t kCacheLimit = (size_t)48 << 30;  // per device
+size_t round_block(size_t n) {
+  const size_t g = n >= ((size_t)1 << 20) ? ((size_t)2 << 20) : 512;  // 2 MiB granules for large blocks
+  return (n + g - 1) / g * g;
+}
+}  // namespace
+
+cudaError_t dev_alloc(void** p, size_t bytes, size_t* granted) {
+  const size_t want = round_block(bytes);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevCache& c = dev_cache();
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    auto& fb = c.free_blocks[dev];
+    auto it = fb.lower_bound(want);
+    if (it != fb.end() && it->first <= want + want / 4 + 4096) {  // best fit, at most 25 % slack
+      *p = it->second;
+      *granted = it->first;
+      c.cached_bytes[dev] -= it->first;
+      fb.erase(it);
+      return cudaSuccess;
+    }
+  }
+  cudaError_t e = cudaMalloc(p, want);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    dev_cache_trim();
+    e = cudaMalloc(p, want);
+  }
+  if (e == cudaSuccess) *granted = want;
+  return e;
+}
+
+void dev_free(void* p, size_t granted) {
+  if (!p) return;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevCache& c = dev_cache();
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (c.cached_bytes[dev] + granted <= kCacheLimit) {
+      c.free_blocks[dev].emplace(granted, p);
+      c.cached_bytes[dev] += granted;
+      return;
+    }
+  }
+  cudaFree(p);
+}
+
+void dev_cache_trim() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  DevCache& c = dev_cache();
+  std::multimap<size_t, void*> blocks;
+  {
+    std::lock_guard<std::mutex> lk(c.mu);
+    blocks.swap(c.free_blocks[dev]);
+    c.cached_bytes[dev] = 0;
+  }
+  for (auto& kv : blocks) cudaFree(kv.second);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

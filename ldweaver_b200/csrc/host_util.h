@@ -32,6 +32,15 @@ int set_error(int code, const char* fmt, ...);
     if (rc__ != 0) return rc__; \
   } while (0)
 
+// Device memory comes from a per-device cache of freed blocks: cudaMalloc / cudaFree of the gigabyte-sized operand
+// and link arrays cost tens of milliseconds and cudaFree synchronises the device, which would otherwise dominate a
+// plan-create / scan / plan-destroy cycle.  Blocks are only handed back after the owning stream has been
+// synchronised (all DevBuf owners release after their last use completed).  dev_cache_trim() returns the cached
+// blocks of the current device to the driver (called by ldw_destroy and on allocation failure).
+cudaError_t dev_alloc(void** p, size_t bytes, size_t* granted);
+void dev_free(void* p, size_t granted);
+void dev_cache_trim();
+
 // Simple owning device buffer.
 struct DevBuf {
   void* p = nullptr;
@@ -41,19 +50,20 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p, bytes);
     p = nullptr;
     bytes = 0;
   }
   int alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    cudaError_t e = cudaMalloc(&p, n);
+    size_t granted = 0;
+    cudaError_t e = dev_alloc(&p, n, &granted);
     if (e != cudaSuccess) {
       p = nullptr;
       return set_error(LDW_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
     }
-    bytes = n;
+    bytes = granted;
     return 0;
   }
   int ensure(size_t n) { return (n <= bytes && p) ? 0 : alloc(n); }

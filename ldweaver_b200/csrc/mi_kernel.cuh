@@ -39,12 +39,18 @@ constexpr int MI_THREADS = 32 * (MI_EPI_WARP0 + MI_EPI_WARPS);
 #define MI_REGS_EPI 96
 // the CTA's pool is what the launch allocated: MI_THREADS x (65536 / MI_THREADS rounded down to a multiple of 8)
 static_assert(MI_EPI_WARP0 * 32 * MI_REGS_CTRL + MI_EPI_THREADS * MI_REGS_EPI <= MI_THREADS * ((65536 / MI_THREADS) & ~7), "register budget");
-constexpr int MI_STAGES = 2;
+constexpr int MI_MAX_STAGES = 3;
 constexpr uint32_t MI_ARR_BYTES = 128 * 128;              // one operand array slice: 128 rows x 128 K-bytes
-constexpr uint32_t MI_STAGE_BYTES = 6 * MI_ARR_BYTES;     // up to 4 row planes + the 4 digit copies of the column planes
+// The stage region is cut per tile kind: three 64 KB stages when the kind's planes fit (PA row planes + the 4 digit
+// copies of the PB column planes), otherwise two 96 KB stages (the largest kind needs 4 + 2 array slices).
+constexpr uint32_t MI_STAGE_REGION = 12 * MI_ARR_BYTES;
+constexpr uint32_t MI_STAGE_SMALL = 4 * MI_ARR_BYTES, MI_STAGE_LARGE = 6 * MI_ARR_BYTES;
+__host__ __device__ constexpr uint32_t mi_stage_need(int pa, int pb, int njlog2) {
+  return (uint32_t)pa * MI_ARR_BYTES + 4u * (uint32_t)pb * (128u << njlog2);
+}
 constexpr uint32_t MI_JREC_BYTES = 128 * sizeof(Rec);     // per j-buffer
 constexpr uint32_t MI_JDYN_BYTES = 128 * sizeof(ColDyn);
-constexpr uint32_t MI_SMEM_BYTES = MI_STAGES * MI_STAGE_BYTES + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + 256 + 1024;
+constexpr uint32_t MI_SMEM_BYTES = MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + 256 + 1024;
 
 __device__ __forceinline__ float lg2_fast(float x) {
   float y;
@@ -403,24 +409,26 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
-  Rec* jrec = reinterpret_cast<Rec*>(smem + MI_STAGES * MI_STAGE_BYTES);
-  ColDyn* jdyn = reinterpret_cast<ColDyn*>(smem + MI_STAGES * MI_STAGE_BYTES + 2 * MI_JREC_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MI_STAGES * MI_STAGE_BYTES + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES));
-  uint64_t* full = bars;            // [MI_STAGES]  raw planes landed (TMA)
-  uint64_t* empty = bars + 2;       // [MI_STAGES]  MMAs that read the stage have completed
-  uint64_t* tfull = bars + 4;       // [2]
-  uint64_t* tempty = bars + 6;      // [2]
-  uint64_t* jfull = bars + 8;       // [2]
-  uint64_t* jempty = bars + 10;     // [2]
-  uint64_t* ready = bars + 12;      // [MI_STAGES]  expanded operands written (expander warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  Rec* jrec = reinterpret_cast<Rec*>(smem + MI_STAGE_REGION);
+  ColDyn* jdyn = reinterpret_cast<ColDyn*>(smem + MI_STAGE_REGION + 2 * MI_JREC_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES));
+  uint64_t* full = bars;            // [MI_MAX_STAGES]  raw planes landed (TMA)
+  uint64_t* empty = bars + 3;       // [MI_MAX_STAGES]  MMAs that read the stage have completed
+  uint64_t* ready = bars + 6;       // [MI_MAX_STAGES]  expanded operands written (expander warps)
+  uint64_t* tfull = bars + 9;       // [2]
+  uint64_t* tempty = bars + 11;     // [2]
+  uint64_t* jfull = bars + 13;      // [2]
+  uint64_t* jempty = bars + 15;     // [2]
+  uint64_t* drained = bars + 17;    // all MMAs of the tiles issued so far have completed (stage-geometry switch)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.a);
-    for (int i = 0; i < MI_STAGES; i++) {
+    for (int i = 0; i < MI_MAX_STAGES; i++) {
       mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], MI_EXP_THREADS);
     }
+    mbar_init(drained, 1);
     for (int i = 0; i < 2; i++) {
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], MI_EPI_THREADS);
       mbar_init(&jfull[i], 1); mbar_init(&jempty[i], MI_EPI_THREADS);
@@ -441,29 +449,31 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   if (warp == 0) {
     // ===================================================================== TMA producer
     // Whole warp runs the loop (uniform registers), one elected lane issues the copies.
-    int st = 0; uint32_t ph = 0;
+    // Stage ring: `st` walks the stages of the current geometry, bit i of `phb` is the parity of stage i's barriers
+    // (every role walks the same sequence, so the bits agree without communication).
+    int st = 0; uint32_t phb = 0; int geo = -1; uint32_t dph = 0;
     int it = 0;
     long long w_jempty = 0, w_empty = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
       const int njidx = 7 - td.njlog2;  // NJ 128,64,32,16 -> tm.b[0..3]
-      const int jb = it & 1;
-      timed_wait<DBG>(&jempty[jb], ((it >> 1) & 1) ^ 1, 10, w_jempty);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (uint32_t)(sizeof(Rec) + sizeof(ColDyn)));
-        bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
-        bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
+      const int g3 = mi_stage_need(PA, PB, td.njlog2) <= MI_STAGE_SMALL ? 1 : 0;
+      const int nst = g3 ? 3 : 2;
+      const uint32_t sbytes = g3 ? MI_STAGE_SMALL : MI_STAGE_LARGE;
+      if (g3 != geo) {
+        // the stage region is re-cut: every stage of the old geometry must have been consumed
+        if (geo >= 0) { mbar_wait(drained, dph, 12); dph ^= 1; }
+        geo = g3; st = 0;
       }
-      __syncwarp();
       // per stage: the raw planes of all PA row-tile planes and of all PB column planes (the latter into the first
       // digit slot, expanded in place by the expander warps)
       {
         const uint32_t stage_tx = (uint32_t)PA * MI_ARR_BYTES + (uint32_t)(PB * NJ * 128);
         for (int kb = 0; kb < p.nkb; kb++) {
-          timed_wait<DBG>(&empty[st], ph ^ 1, 11, w_empty);
+          timed_wait<DBG>(&empty[st], ((phb >> st) & 1) ^ 1, 11, w_empty);
           if (elect_one()) {
-            uint8_t* sb = stage_base + st * MI_STAGE_BYTES;
+            uint8_t* sb = stage_base + st * sbytes;
             mbar_arrive_expect_tx(&full[st], stage_tx);
             for (int a = 0; a < PA; a++)
               tma_load_2d(sb + a * MI_ARR_BYTES, &tm.a, &full[st], kb * 128, td.a_row0 + a * td.a_pstride);
@@ -472,9 +482,20 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
               tma_load_2d(sbB + b * NJ * 128, &tm.b[njidx], &full[st], kb * 128, td.b_row0 + b * td.b_pstride);
           }
           __syncwarp();
-          if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+          phb ^= 1u << st;
+          if (++st == nst) st = 0;
         }
       }
+      // column records last: only the epilogue reads them, and waiting for their buffer here (instead of before the
+      // operand loads) lets the operands of this tile stream in while the epilogue is still two tiles behind
+      const int jb = it & 1;
+      timed_wait<DBG>(&jempty[jb], ((it >> 1) & 1) ^ 1, 10, w_jempty);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (uint32_t)(sizeof(Rec) + sizeof(ColDyn)));
+        bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
+        bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
+      }
+      __syncwarp();
     }
     if (DBG && p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_begin);
@@ -485,12 +506,22 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     // ===================================================================== MMA issuer
     // The whole warp runs the loop (so addresses and descriptors live in uniform registers); one elected lane
     // issues the tcgen05 instructions.
-    int st = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+    int st = 0; uint32_t phb = 0; int geo = -1; int as = 0; uint32_t aph = 0;
     long long w_tempty = 0, w_ready = 0, t_begin = DBG ? clock64() : 0;
     const uint32_t desc_hi = (uint32_t)(make_smem_desc_sw128(0) >> 32);
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
+      const int g3 = mi_stage_need(PA, PB, td.njlog2) <= MI_STAGE_SMALL ? 1 : 0;
+      const int nst = g3 ? 3 : 2;
+      const uint32_t sbytes = g3 ? MI_STAGE_SMALL : MI_STAGE_LARGE;
+      if (g3 != geo) { geo = g3; st = 0; }
+      // does this CTA's next tile use the other stage geometry?  Then the producer waits for `drained`.
+      bool sw = false;
+      if (t + tstep < p.n_tiles) {
+        const TileDesc tn = p.tiles[t + tstep];
+        sw = (mi_stage_need(tn.PA, tn.PB, tn.njlog2) <= MI_STAGE_SMALL ? 1 : 0) != g3;
+      }
       const bool big = 2 * PA * PB * NJ > 256;
       const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA
       const uint32_t idesc_u = make_idesc_u8(128, ncols);     // A bytes 0xFF read as +255
@@ -511,10 +542,10 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         const uint32_t boff = (uint32_t)PA * MI_ARR_BYTES;                // B region follows the A planes
         const uint32_t b2off = boff + (uint32_t)(2 * PB * NJ * 128);      // bH | bL follow aH | aL
         for (int kb = 0; kb < p.nkb; kb++) {
-          timed_wait<DBG>(&ready[st], ph, 22, w_ready);
+          timed_wait<DBG>(&ready[st], (phb >> st) & 1, 22, w_ready);
           tc_fence_after();
           // low descriptor word of the stage base: address >> 4 | LBO (1 << 16)
-          const uint32_t lo = ((smem_u32(stage_base + st * MI_STAGE_BYTES) & 0x3FFFFu) >> 4) | (1u << 16);
+          const uint32_t lo = ((smem_u32(stage_base + st * sbytes) & 0x3FFFFu) >> 4) | (1u << 16);
           if (elect_one()) {
             const uint64_t dBa = ((uint64_t)desc_hi << 32) | (lo + (boff >> 4));
             const uint64_t dBb = ((uint64_t)desc_hi << 32) | (lo + (b2off >> 4));
@@ -533,10 +564,12 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
             umma_commit(&empty[st]);
           }
           __syncwarp();
-          if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+          phb ^= 1u << st;
+          if (++st == nst) st = 0;
         }
       }
       if (elect_one()) {
+        if (sw) umma_commit(drained);
         if (big) {
           umma_commit(&tfull[0]);
           umma_commit(&tfull[1]);
@@ -561,12 +594,16 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     // Elementwise on the swizzled image; only the digit lookup needs the logical K position, i.e. the 16-byte
     // chunk index XOR (row & 7).
     const int h = (warp - 2) * 32 + lane;  // 0..191
-    int st = 0; uint32_t ph = 0;
+    int st = 0; uint32_t phb = 0; int geo = -1;
     long long w_full = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
       const int brows = PB * NJ;
+      const int g3 = mi_stage_need(PA, PB, td.njlog2) <= MI_STAGE_SMALL ? 1 : 0;
+      const int nst = g3 ? 3 : 2;
+      const uint32_t sbytes = g3 ? MI_STAGE_SMALL : MI_STAGE_LARGE;
+      if (g3 != geo) { geo = g3; st = 0; }
       for (int kb = 0; kb < p.nkb; kb++) {
         // this thread's digit chunks: logical chunk cl of K block kb
         const int cl = h & 7;
@@ -575,8 +612,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(dg + p.kpad));        // aL
         const uint4 g2 = __ldg(reinterpret_cast<const uint4*>(dg + 2 * p.kpad));    // bH
         const uint4 g3 = __ldg(reinterpret_cast<const uint4*>(dg + 3 * p.kpad));    // bL
-        timed_wait<DBG>(&full[st], ph, 40, w_full);
-        const uint32_t yb = smem_u32(stage_base + st * MI_STAGE_BYTES) + (uint32_t)PA * MI_ARR_BYTES;
+        timed_wait<DBG>(&full[st], (phb >> st) & 1, 40, w_full);
+        const uint32_t yb = smem_u32(stage_base + st * sbytes) + (uint32_t)PA * MI_ARR_BYTES;
         const uint32_t slot = (uint32_t)brows * 128u;
         for (int r = h >> 3; r < brows; r += MI_EXP_THREADS / 8) {
           const uint32_t addr = yb + (uint32_t)r * 128u + (uint32_t)((cl ^ (r & 7)) * 16);
@@ -588,7 +625,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(&ready[st]);
-        if (++st == MI_STAGES) { st = 0; ph ^= 1; }
+        phb ^= 1u << st;
+        if (++st == nst) st = 0;
       }
     }
     if (DBG && p.dbg && h == 0) {

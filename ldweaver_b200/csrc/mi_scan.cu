@@ -38,8 +38,8 @@ struct DevLinks {
 struct BlockDev {
   DevBuf rowdyn, coldyn, colinfo, tiles, from_idx, to_idx, rfl, rtl;
   PinnedBuf stage;
-  cudaEvent_t done = nullptr;
-  bool used = false;
+  cudaEvent_t done = nullptr, done2 = nullptr;  // last use on the scan stream / on the select stream
+  bool used = false, used2 = false;
 };
 
 struct BlockHost {  // pageable staging reused per ring entry (kept alive until the async copies are issued)
@@ -62,13 +62,26 @@ struct ScanWS {
   BlockDev ring[RING];
   BlockHost hring[RING];
   DevBuf d_dbg;
-  DevBuf d_cand, d_vcand, d_mi64, d_state /*count, tcand, overflow, kept_overflow*/, d_hist, d_results, d_sr_f32, d_dense;
+  // long-range collection state, double-buffered: block b's candidates are refined and selected on the select
+  // stream while block b+1 is being scanned into the other buffer
+  struct LrBuf {
+    DevBuf cand, vcand, mi64, state /*count, tcand, overflow, -, -, vcount*/, hist;
+    cudaEvent_t scan_done = nullptr, sel_done = nullptr;
+    bool used = false, chain_valid = false;
+  } lr[2];
+  DevBuf d_state /*-, -, -, kept_overflow, -, -, -, -, chain[2]*/, d_results, d_sr_f32, d_dense;
   DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
   DevLinks d_sr, d_lr;
   bool events_ready = false;
   ~ScanWS() {
-    for (auto& b : ring)
+    for (auto& b : ring) {
       if (b.done) cudaEventDestroy(b.done);
+      if (b.done2) cudaEventDestroy(b.done2);
+    }
+    for (auto& l : lr) {
+      if (l.scan_done) cudaEventDestroy(l.scan_done);
+      if (l.sel_done) cudaEventDestroy(l.sel_done);
+    }
   }
 };
 
@@ -277,7 +290,14 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   {
     ScanWS* W = get_ws(ctx);
     if (!W->events_ready) {
-      for (auto& b : W->ring) LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+      for (auto& b : W->ring) {
+        LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        LDW_CUDA(cudaEventCreateWithFlags(&b.done2, cudaEventDisableTiming));
+      }
+      for (auto& l : W->lr) {
+        LDW_CUDA(cudaEventCreateWithFlags(&l.scan_done, cudaEventDisableTiming));
+        LDW_CUDA(cudaEventCreateWithFlags(&l.sel_done, cudaEventDisableTiming));
+      }
       W->events_ready = true;
     }
   }
@@ -622,8 +642,19 @@ int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_
   if (n_snp < 2 || nseq < 1) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: need at least 2 SNPs and 1 sequence");
   if (nseq > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: nseq > 65535 not supported by the 15-bit digit accumulation");
   if (blk < 128 || blk > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: block size %lld outside [128, 65535]", (long long)blk);
-  for (int64_t i = 0; i < n_snp * nseq; i++)
-    if (codes[i] > 4) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: codes[%lld] = %d outside 0..4", (long long)i, (int)codes[i]);
+  {
+    // every code must be 0..4; eight bytes per step (a byte > 4 sets bit 7 of byte + 0x7B, or has it set already)
+    const int64_t total = n_snp * nseq;
+    int64_t i = 0, bad = -1;
+    for (; i + 8 <= total; i += 8) {
+      uint64_t x;
+      memcpy(&x, codes + i, 8);
+      if ((((x & 0x7F7F7F7F7F7F7F7Full) + 0x7B7B7B7B7B7B7B7Bull) | x) & 0x8080808080808080ull) break;
+    }
+    for (; i < total; i++)
+      if (codes[i] > 4) { bad = i; break; }
+    if (bad >= 0) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: codes[%lld] = %d outside 0..4", (long long)bad, (int)codes[bad]);
+  }
   ldw_mi_plan* P = new ldw_mi_plan();
   P->ctx = ctx;
   P->n = n_snp; P->S = nseq; P->blk = blk;
@@ -802,11 +833,15 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   const uint64_t kept_cap = 2 * sum_keep + (1u << 20);
 
   // ---- device workspace
-  LDW_TRY(W->d_cand.ensure(max_cap * sizeof(Cand)));
-  LDW_TRY(W->d_mi64.ensure(max_cap * 8));
-  LDW_TRY(W->d_vcand.ensure(max_cap * sizeof(Cand)));
+  for (auto& l : W->lr) {
+    LDW_TRY(l.cand.ensure(max_cap * sizeof(Cand)));
+    LDW_TRY(l.mi64.ensure(max_cap * 8));
+    LDW_TRY(l.vcand.ensure(max_cap * sizeof(Cand)));
+    LDW_TRY(l.state.ensure(64));
+    LDW_TRY(l.hist.ensure(MI_HIST_BINS * 4));
+    l.used = false; l.chain_valid = false;
+  }
   LDW_TRY(W->d_state.ensure(64));
-  LDW_TRY(W->d_hist.ensure(MI_HIST_BINS * 4));
   LDW_TRY(W->d_results.ensure(std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult)));
   LDW_TRY(W->d_sr_f32.ensure((size_t)std::max<int64_t>(total_sr, 1) * 4));
   LDW_TRY(W->d_kept_key.ensure(kept_cap * 8));
@@ -817,12 +852,10 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   LDW_TRY(W->d_sr.ensure(total_sr));
   LDW_CUDA(cudaMemsetAsync(W->d_kept_count.p, 0, 16, st));
   LDW_CUDA(cudaMemsetAsync(W->d_results.p, 0, std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult), st));
-  uint32_t* d_count = W->d_state.as<uint32_t>();
-  uint32_t* d_tcand = d_count + 1;
-  uint32_t* d_overflow = d_count + 2;
-  uint32_t* d_kept_overflow = d_count + 3;
-  uint32_t* d_chain = d_count + 4;
+  uint32_t* d_kept_overflow = W->d_state.as<uint32_t>() + 3;
+  uint32_t* d_chain2 = W->d_state.as<uint32_t>() + 8;  // [2]: threshold seeds, one per buffer parity
   LDW_CUDA(cudaMemsetAsync(W->d_state.p, 0, 64, st));
+  cudaStream_t sst = P->ctx->select_stream;
 
   const bool want_host = !(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_NO_D2H));
   cudaStream_t cst = P->ctx->copy_stream;
@@ -841,14 +874,20 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     const char* e = getenv("LDW_DBG_BLOCK");
     if (e) dbg_block = atoll(e);
   }
-  bool chain_valid = false;  // the device-side chained threshold estimate holds a value from an earlier block
   auto run_block = [&](size_t b, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
     Sel& s = sel[b];
     if (s.skip) return 0;
     int slot = (int)(b % ScanWS::RING);
     BlockDev& D = W->ring[slot];
     BlockHost& H = W->hring[slot];
-    if (D.used) LDW_CUDA(cudaEventSynchronize(D.done));  // host staging + device arrays of this ring entry are free again
+    // host staging + device arrays of this ring entry are free again
+    if (D.used) LDW_CUDA(cudaEventSynchronize(D.done));
+    if (D.used2) { LDW_CUDA(cudaEventSynchronize(D.done2)); D.used2 = false; }
+    ScanWS::LrBuf& L = W->lr[b & 1];
+    uint32_t* d_count = L.state.as<uint32_t>();
+    uint32_t* d_tcand = d_count + 1;
+    uint32_t* d_overflow = d_count + 2;
+    uint32_t* d_chain = d_chain2 + (b & 1);  // written by the selection of block b - 2 (same buffer parity)
     int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, H);
     if (e > 1) return e;
     LDW_TRY(upload_block(st, D, H));
@@ -865,15 +904,17 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     const int emit_all = force_emit_all || s.emit_all;
     uint32_t cap = cap_override ? cap_override : s.cap;
     if (lr) {
-      mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, W->d_hist.as<uint32_t>(), d_chain, (use_chain && chain_valid && !emit_all) ? 1 : 0);
+      // this buffer's previous selection (block b - 2) must be done before its counters are cleared
+      if (L.used) LDW_CUDA(cudaStreamWaitEvent(st, L.sel_done, 0));
+      mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, L.hist.as<uint32_t>(), d_chain, (use_chain && L.chain_valid && !emit_all) ? 1 : 0);
       LDW_CUDA(cudaGetLastError());
       n_launches++;
-      if (!emit_all) chain_valid = true;
-      sp.cand = W->d_cand.as<Cand>();
+      if (!emit_all) L.chain_valid = true;
+      sp.cand = L.cand.as<Cand>();
       sp.cand_cap = cap;
       sp.cand_count = d_count;
       sp.tcand_bits = d_tcand;
-      sp.hist = W->d_hist.as<uint32_t>();
+      sp.hist = L.hist.as<uint32_t>();
       sp.kprime = s.kprime;
       sp.delta = s.delta ? s.delta : 1;
       sp.overflow = d_overflow;
@@ -896,14 +937,17 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
         exec_ops += 8.0 * 128.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;  // 2 passes x 2 halves
     }
     if (lr) {
+      // fp64 refinement + exact selection on the select stream, overlapping the next block's scan
       n_launches += 2;
+      LDW_CUDA(cudaEventRecord(L.scan_done, st));
+      LDW_CUDA(cudaStreamWaitEvent(sst, L.scan_done, 0));
       RefineParams R = make_refine_params(P, D, H, cfg);
-      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, st>>>(R, W->d_cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
-                                                                 W->d_vcand.as<Cand>(), W->d_mi64.as<double>(), d_count + 5);
+      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, sst>>>(R, L.cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
+                                                                  L.vcand.as<Cand>(), L.mi64.as<double>(), d_count + 5);
       LDW_CUDA(cudaGetLastError());
       SelectParams q;
       memset(&q, 0, sizeof(q));
-      q.cand = W->d_vcand.as<Cand>(); q.mi64 = W->d_mi64.as<double>(); q.vcount = d_count + 5; q.count = d_count; q.cap = cap;
+      q.cand = L.vcand.as<Cand>(); q.mi64 = L.mi64.as<double>(); q.vcount = d_count + 5; q.count = d_count; q.cap = cap;
       q.overflow = d_overflow; q.tcand_bits = d_tcand; q.emit_all = emit_all;
       q.k_lo = s.k_lo; q.k_hi = s.k_hi; q.h = s.h; q.interpolate = s.interp;
       q.tol_safe = 4e-6; q.tol_border = 1e-9;
@@ -914,8 +958,12 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       q.kept_overflow = d_kept_overflow;
       q.chain_bits = d_chain;
       q.result = W->d_results.as<BlockResult>() + b;
-      mi_select_kernel<<<1, 1024, 0, st>>>(q);
+      mi_select_kernel<<<1, 1024, 0, sst>>>(q);
       LDW_CUDA(cudaGetLastError());
+      LDW_CUDA(cudaEventRecord(L.sel_done, sst));
+      LDW_CUDA(cudaEventRecord(D.done2, sst));
+      L.used = true;
+      D.used2 = true;
     }
     if (s.n_sr > 0 && !(flags & LDW_SCAN_NO_LINKS)) {
       n_launches++;
@@ -949,6 +997,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     return 0;
   };
   for (size_t b = 0; b < blocks.size(); b++) LDW_TRY(run_block(b, 0, 0, true));
+  for (auto& l : W->lr)
+    if (l.used) LDW_CUDA(cudaStreamWaitEvent(st, l.sel_done, 0));  // join the select stream
   LDW_CUDA(cudaEventRecord(ev1, st));
 
   // ---- verify the long-range selection of every block; re-run the (rare) blocks whose candidate set is not
@@ -969,11 +1019,13 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
           if (attempt == 1) {
             if ((uint64_t)sel[b].n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block %lld needs an exhaustive long-range pass over more than 2^32 links", (long long)blocks[b].index);
             cap = (uint32_t)sel[b].n_lr;
-            LDW_TRY(W->d_cand.ensure((size_t)cap * sizeof(Cand)));
-            LDW_TRY(W->d_mi64.ensure((size_t)cap * 8));
-            LDW_TRY(W->d_vcand.ensure((size_t)cap * sizeof(Cand)));
+            ScanWS::LrBuf& L = W->lr[b & 1];
+            LDW_TRY(L.cand.ensure((size_t)cap * sizeof(Cand)));
+            LDW_TRY(L.mi64.ensure((size_t)cap * 8));
+            LDW_TRY(L.vcand.ensure((size_t)cap * sizeof(Cand)));
           }
           LDW_TRY(run_block(b, attempt == 1, cap, false));
+          LDW_CUDA(cudaStreamWaitEvent(st, W->lr[b & 1].sel_done, 0));
           LDW_CUDA(cudaMemcpyAsync(&P->results[b], W->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
           LDW_CUDA(cudaStreamSynchronize(st));
         }
