@@ -268,7 +268,7 @@ def main():
                "ms_per_step": 1e3 * te / e_steps, "steps": e_steps,
                "breakdown_ms": {"plan_create": 1e3 * t_plan / e_steps, "scan_call": 1e3 * t_scan / e_steps,
                                 "plan_destroy": 1e3 * t_close / e_steps, "scan_device": st2["t_scan_ms"] + st2["t_select_ms"],
-                                "scan_kernels": st2["t_kernel_ms"], "select_tail": st2["t_select_ms"], "d2h_tail": st2["t_d2h_ms"]},
+                                "scan_kernels": st2["t_kernel_ms"], "select_tail": st2["t_select_ms"], "host_prep": st2["t_host_prep_ms"], "d2h_tail": st2["t_d2h_ms"]},
                "includes": "host->device upload, operand packing, scan, link materialisation, device->host copy of all link columns"}
 
     if rank != 0:
@@ -305,7 +305,7 @@ def main():
             "vs_baseline": None, "dtype": "int8 x int8 -> int32 (30-bit fixed-point weights), fp32 epilogue, fp64 LR refinement",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all),
             "roofline": roofline, "cpu_baseline": cpu,
-            "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"],
+            "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"], "host_prep_ms": stats["t_host_prep_ms"],
                        "pairs_per_step": pairs_all / args.steps, "n_sr": stats["n_sr"], "n_lr_kept": stats["n_lr_kept"],
                        "n_reruns": stats["n_reruns"], "n_candidates": stats["n_candidates"], "tiles_per_step_rank0": agg["n_tiles"] / args.steps,
                        "lr_links_approx": lra}}

@@ -153,6 +153,7 @@ typedef struct ldw_scan_stats {
   int64_t n_launches;    /* all kernels this library launched during the scan */
   int64_t n_tiles;       /* tiles processed */
   double exec_int8_ops;  /* int8 tensor operations actually issued (2 * MACs) */
+  double t_host_prep_ms; /* host time spent building and staging the per-block tables (overlaps the device work) */
 } ldw_scan_stats;
 
 LDW_API int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, const double* hdw,

@@ -58,6 +58,7 @@ int ldw_create(int device, ldw_ctx** out) {
   }
   e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->select_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     cudaStreamDestroy(c->stream);
     delete c;
@@ -75,6 +76,7 @@ void ldw_destroy(ldw_ctx* ctx) {
   ldw::dev_cache_trim();
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->select_stream) cudaStreamDestroy(ctx->select_stream);
+  if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

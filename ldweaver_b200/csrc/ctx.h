@@ -26,6 +26,7 @@ struct ldw_ctx {
   int num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // device -> host copies of finished link columns overlap the scan
+  cudaStream_t upload_stream = nullptr;  // per-block tables host -> device, ahead of the block's scan
   cudaStream_t select_stream = nullptr;  // fp64 refinement + long-range selection of block b overlap the scan of block b+1
   HostLinks h_sr, h_lr, h_border;
   // scan workspace (device scratch, per-block ring, link columns): allocated on first use by mi_scan.cu, reused by

@@ -376,10 +376,10 @@ __global__ void __launch_bounds__(1024) mi_select_kernel(SelectParams P) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    // chain: the next block starts collecting at 0.8 x this block's threshold; after a failure fall back hard
+    // chain: a later block starts collecting at 0.9 x this block's threshold; after a failure fall back hard
     if (!P.emit_all) {
       float tc = __uint_as_float(*P.tcand_bits);
-      float nxt = bad ? 0.25f * tc : 0.8f * (float)v_lo;
+      float nxt = bad ? 0.25f * tc : 0.9f * (float)v_lo;
       if (!(nxt > 0.f)) nxt = 0.f;
       *P.chain_bits = __float_as_uint(nxt);
     }
@@ -469,6 +469,12 @@ __global__ void mi_lr_materialize_kernel(const uint32_t* __restrict__ order, con
   o_len[i] = circ_len_i32(p1, p2, g);
   o_mi[i] = mi[src];
   o_blk[i] = (int32_t)(keys_sorted[i] >> 36);
+}
+
+// counters the host needs after the last block -> pinned host memory
+__global__ void publish_kernel(const unsigned long long* kept_count, const uint32_t* state, unsigned long long* out) {
+  out[0] = *kept_count;
+  out[1] = state[3];
 }
 
 __global__ void iota_u32_kernel(uint32_t* p, int64_t n) {

@@ -6,6 +6,7 @@
 //                                                                     per-block type-7 quantile Q3, SR-only drop Q12)
 //   computeMI_Sprase/.fastHadamard  R/computePairwiseMI.R:390-398, src/computeMI.cpp:11-21 (incl. quirk Q1)
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cub/cub.cuh>
 #include <vector>
@@ -38,6 +39,7 @@ struct DevLinks {
 struct BlockDev {
   DevBuf rowdyn, coldyn, colinfo, tiles, from_idx, to_idx, rfl, rtl;
   PinnedBuf stage;
+  cudaEvent_t uploaded = nullptr;               // the block's tables have arrived (upload stream)
   cudaEvent_t done = nullptr, done2 = nullptr;  // last use on the scan stream / on the select stream
   bool used = false, used2 = false;
 };
@@ -69,7 +71,10 @@ struct ScanWS {
     cudaEvent_t scan_done = nullptr, sel_done = nullptr;
     bool used = false, chain_valid = false;
   } lr[2];
-  DevBuf d_state /*-, -, -, kept_overflow, -, -, -, -, chain[2]*/, d_results, d_sr_f32, d_dense;
+  DevBuf d_state /*-, -, -, kept_overflow, -, -, -, -, chain[2]*/, d_sr_f32, d_dense;
+  // written by the selection kernels / the publish kernel straight into host memory (pinned memory is device-
+  // accessible under unified addressing): no small device->host copy has to queue behind the link columns
+  PinnedBuf h_results, h_pub;
   DevBuf d_kept_key, d_kept_gi, d_kept_gj, d_kept_mi, d_kept_count, d_sort_tmp, d_keys_sorted, d_order_in, d_order_out;
   DevLinks d_sr, d_lr;
   bool events_ready = false;
@@ -77,6 +82,7 @@ struct ScanWS {
     for (auto& b : ring) {
       if (b.done) cudaEventDestroy(b.done);
       if (b.done2) cudaEventDestroy(b.done2);
+      if (b.uploaded) cudaEventDestroy(b.uploaded);
     }
     for (auto& l : lr) {
       if (l.scan_done) cudaEventDestroy(l.scan_done);
@@ -293,6 +299,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
       for (auto& b : W->ring) {
         LDW_CUDA(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
         LDW_CUDA(cudaEventCreateWithFlags(&b.done2, cudaEventDisableTiming));
+        LDW_CUDA(cudaEventCreateWithFlags(&b.uploaded, cudaEventDisableTiming));
       }
       for (auto& l : W->lr) {
         LDW_CUDA(cudaEventCreateWithFlags(&l.scan_done, cudaEventDisableTiming));
@@ -536,7 +543,7 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
 
 // All per-block arrays go through one pinned staging buffer per ring entry, so the copies are truly
 // asynchronous and the host can prepare the next block while the device works on this one.
-int upload_block(cudaStream_t st, BlockDev& D, const BlockHost& H) {
+int upload_block(cudaStream_t st, BlockDev& D, const BlockHost& H) {  // st: the stream the copies are issued on
   struct Part { DevBuf* d; const void* src; size_t bytes; };
   Part parts[8] = {{&D.rowdyn, H.rowdyn.data(), H.rowdyn.size() * sizeof(RowDyn)},
                    {&D.coldyn, H.coldyn.data(), H.coldyn.size() * sizeof(ColDyn)},
@@ -842,7 +849,9 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     l.used = false; l.chain_valid = false;
   }
   LDW_TRY(W->d_state.ensure(64));
-  LDW_TRY(W->d_results.ensure(std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult)));
+  LDW_TRY(W->h_results.ensure(std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult)));
+  LDW_TRY(W->h_pub.ensure(64));
+  memset(W->h_results.p, 0, std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult));
   LDW_TRY(W->d_sr_f32.ensure((size_t)std::max<int64_t>(total_sr, 1) * 4));
   LDW_TRY(W->d_kept_key.ensure(kept_cap * 8));
   LDW_TRY(W->d_kept_gi.ensure(kept_cap * 4));
@@ -851,7 +860,6 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   LDW_TRY(W->d_kept_count.ensure(16));
   LDW_TRY(W->d_sr.ensure(total_sr));
   LDW_CUDA(cudaMemsetAsync(W->d_kept_count.p, 0, 16, st));
-  LDW_CUDA(cudaMemsetAsync(W->d_results.p, 0, std::max<size_t>(blocks.size(), 1) * sizeof(BlockResult), st));
   uint32_t* d_kept_overflow = W->d_state.as<uint32_t>() + 3;
   uint32_t* d_chain2 = W->d_state.as<uint32_t>() + 8;  // [2]: threshold seeds, one per buffer parity
   LDW_CUDA(cudaMemsetAsync(W->d_state.p, 0, 64, st));
@@ -864,6 +872,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     LDW_TRY(P->ctx->h_sr.ensure(total_sr));
     LDW_CUDA(cudaEventCreateWithFlags(&ev_blk, cudaEventDisableTiming));
   }
+  auto tpre = std::chrono::steady_clock::now();
   LDW_CUDA(cudaEventRecord(ev0, st));
   int64_t n_reruns = 0, n_launches = 0, n_scan_launches = 0, n_tiles = 0;
   double exec_ops = 0;
@@ -874,23 +883,30 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     const char* e = getenv("LDW_DBG_BLOCK");
     if (e) dbg_block = atoll(e);
   }
-  auto run_block = [&](size_t b, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
+  double host_prep_ms = 0;
+  // b: index into this rank's block list (output offsets, results); seq: position in the execution order (ring slots)
+  auto run_block = [&](size_t b, size_t seq, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
     Sel& s = sel[b];
     if (s.skip) return 0;
-    int slot = (int)(b % ScanWS::RING);
+    int slot = (int)(seq % ScanWS::RING);
     BlockDev& D = W->ring[slot];
     BlockHost& H = W->hring[slot];
     // host staging + device arrays of this ring entry are free again
     if (D.used) LDW_CUDA(cudaEventSynchronize(D.done));
     if (D.used2) { LDW_CUDA(cudaEventSynchronize(D.done2)); D.used2 = false; }
-    ScanWS::LrBuf& L = W->lr[b & 1];
+    ScanWS::LrBuf& L = W->lr[seq & 1];
     uint32_t* d_count = L.state.as<uint32_t>();
     uint32_t* d_tcand = d_count + 1;
     uint32_t* d_overflow = d_count + 2;
-    uint32_t* d_chain = d_chain2 + (b & 1);  // written by the selection of block b - 2 (same buffer parity)
+    uint32_t* d_chain = d_chain2 + (seq & 1);  // written by the selection two blocks earlier (same buffer parity)
+    auto hp0 = std::chrono::steady_clock::now();
     int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, H);
     if (e > 1) return e;
-    LDW_TRY(upload_block(st, D, H));
+    // the tables travel on the upload stream while earlier blocks are still being scanned
+    LDW_TRY(upload_block(P->ctx->upload_stream, D, H));
+    LDW_CUDA(cudaEventRecord(D.uploaded, P->ctx->upload_stream));
+    LDW_CUDA(cudaStreamWaitEvent(st, D.uploaded, 0));
+    host_prep_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - hp0).count();
     D.used = true;
     ScanParams sp;
     fill_scan_params(P, D, H, cfg, sp);
@@ -957,7 +973,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       q.kept_mi = W->d_kept_mi.as<double>(); q.kept_count = W->d_kept_count.as<unsigned long long>(); q.kept_cap = kept_cap;
       q.kept_overflow = d_kept_overflow;
       q.chain_bits = d_chain;
-      q.result = W->d_results.as<BlockResult>() + b;
+      q.result = W->h_results.as<BlockResult>() + b;
       mi_select_kernel<<<1, 1024, 0, sst>>>(q);
       LDW_CUDA(cudaGetLastError());
       LDW_CUDA(cudaEventRecord(L.sel_done, sst));
@@ -996,17 +1012,32 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     LDW_CUDA(cudaEventRecord(D.done, st));
     return 0;
   };
-  for (size_t b = 0; b < blocks.size(); b++) LDW_TRY(run_block(b, 0, 0, true));
+  // Execution order: blocks that hold short-range links first, so their (large) link columns cross PCIe while the
+  // long-range-only blocks are still being scanned.  Output order is unaffected: short-range rows have fixed
+  // offsets and the kept long-range rows are sorted by (block, row rank) afterwards.
+  std::vector<size_t> order;
+  for (size_t b = 0; b < blocks.size(); b++) if (sel[b].n_sr > 0) order.push_back(b);
+  for (size_t b = 0; b < blocks.size(); b++) if (!(sel[b].n_sr > 0)) order.push_back(b);
+  for (size_t k = 0; k < order.size(); k++) LDW_TRY(run_block(order[k], k, 0, 0, true));
   for (auto& l : W->lr)
     if (l.used) LDW_CUDA(cudaStreamWaitEvent(st, l.sel_done, 0));  // join the select stream
   LDW_CUDA(cudaEventRecord(ev1, st));
+  const bool dbg_timing = getenv("LDW_DBG_TIMING") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg_timing) return;
+    cudaStreamSynchronize(st);
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "ldw timing: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+    tp0 = t;
+  };
+  if (dbg_timing) fprintf(stderr, "ldw timing: %-28s %8.3f ms\n", "submit blocks (host)", std::chrono::duration<double, std::milli>(tp0 - tpre).count());
+  lap("drain blocks");
 
   // ---- verify the long-range selection of every block; re-run the (rare) blocks whose candidate set is not
   //      provably complete with a plain "collect everything" pass
-  P->results.assign(blocks.size(), BlockResult());
-  if (!blocks.empty())
-    LDW_CUDA(cudaMemcpyAsync(P->results.data(), W->d_results.p, blocks.size() * sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
   LDW_CUDA(cudaStreamSynchronize(st));
+  P->results.assign(W->h_results.as<BlockResult>(), W->h_results.as<BlockResult>() + blocks.size());
   if (!sr_only) {
     for (size_t b = 0; b < blocks.size(); b++) {
       if (sel[b].skip || sel[b].n_lr == 0) continue;
@@ -1019,25 +1050,28 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
           if (attempt == 1) {
             if ((uint64_t)sel[b].n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block %lld needs an exhaustive long-range pass over more than 2^32 links", (long long)blocks[b].index);
             cap = (uint32_t)sel[b].n_lr;
-            ScanWS::LrBuf& L = W->lr[b & 1];
+            ScanWS::LrBuf& L = W->lr[0];
             LDW_TRY(L.cand.ensure((size_t)cap * sizeof(Cand)));
             LDW_TRY(L.mi64.ensure((size_t)cap * 8));
             LDW_TRY(L.vcand.ensure((size_t)cap * sizeof(Cand)));
           }
-          LDW_TRY(run_block(b, attempt == 1, cap, false));
-          LDW_CUDA(cudaStreamWaitEvent(st, W->lr[b & 1].sel_done, 0));
-          LDW_CUDA(cudaMemcpyAsync(&P->results[b], W->d_results.as<BlockResult>() + b, sizeof(BlockResult), cudaMemcpyDeviceToHost, st));
+          LDW_TRY(run_block(b, 0, attempt == 1, cap, false));
+          LDW_CUDA(cudaStreamWaitEvent(st, W->lr[0].sel_done, 0));
           LDW_CUDA(cudaStreamSynchronize(st));
+          P->results[b] = W->h_results.as<BlockResult>()[b];
         }
         if (P->results[b].bad) return set_error(LDW_ERR_INTERNAL, "long-range selection failed for block %lld (flags %u)", (long long)blocks[b].index, P->results[b].bad);
       }
     }
   }
+  lap("results + reruns");
   unsigned long long n_kept = 0;
-  uint32_t state[4];
-  LDW_CUDA(cudaMemcpyAsync(&n_kept, W->d_kept_count.p, 8, cudaMemcpyDeviceToHost, st));
-  LDW_CUDA(cudaMemcpyAsync(state, W->d_state.p, 16, cudaMemcpyDeviceToHost, st));
+  uint32_t state[4] = {0, 0, 0, 0};
+  publish_kernel<<<1, 1, 0, st>>>(W->d_kept_count.as<unsigned long long>(), W->d_state.as<uint32_t>(), W->h_pub.as<unsigned long long>());
+  LDW_CUDA(cudaGetLastError());
   LDW_CUDA(cudaStreamSynchronize(st));
+  n_kept = W->h_pub.as<unsigned long long>()[0];
+  state[3] = (uint32_t)W->h_pub.as<unsigned long long>()[1];
   if (state[3] || n_kept > kept_cap) return set_error(LDW_ERR_UNSUPPORTED, "more long-range links pass their block thresholds (%llu) than the output buffer holds (%llu): massive ties at the threshold", n_kept, (unsigned long long)kept_cap);
 
   // ---- long-range rows into reference order (block, then row order inside the block)
@@ -1064,6 +1098,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     LDW_CUDA(cudaGetLastError());
   }
   LDW_CUDA(cudaEventRecord(ev2, st));
+  lap("lr sort + materialise");
 
   // ---- device -> pinned host
   P->ctx->h_sr.n = 0; P->ctx->h_lr.n = 0; P->ctx->h_border.n = 0;
@@ -1086,7 +1121,9 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   }
   LDW_CUDA(cudaEventRecord(ev3, st));
   LDW_CUDA(cudaStreamSynchronize(st));
+  lap("lr d2h");
   if (want_host) LDW_CUDA(cudaStreamSynchronize(cst));
+  lap("copy stream drain");
   if (ev_blk) cudaEventDestroy(ev_blk);
 
   // borderline list: kept-or-not candidates within tol of their block threshold are reported by count per block;
@@ -1159,6 +1196,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     stats_out->n_launches = n_launches;
     stats_out->n_tiles = n_tiles;
     stats_out->exec_int8_ops = exec_ops;
+    stats_out->t_host_prep_ms = host_prep_ms;
   }
   if (dbg_block >= 0 && W->d_dbg.p) {
     std::vector<unsigned long long> h(4096 * 16);
