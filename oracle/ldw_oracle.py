@@ -623,6 +623,43 @@ def block_mi_closed_form(snp: SnpDat, hdw: np.ndarray, from_idx: np.ndarray, to_
     return MI
 
 
+def pair_mi_closed_form(snp: SnpDat, hdw: np.ndarray, from_idx: np.ndarray, to_idx: np.ndarray, il: np.ndarray,
+                        jl: np.ndarray) -> np.ndarray:
+    """MI of selected cells (il[k], jl[k]) of the block (from_idx, to_idx): the same closed form as
+    block_mi_closed_form (R/computePairwiseMI.R:238-298, src/computeMI.cpp:19, quirk Q1 by
+    the linear index il + jl*nf), evaluated per pair so that full-size blocks can be spot-checked without forming
+    the nf x nt matrices."""
+    w = hdw.astype(np.float64)
+    neff = w.sum()
+    from_idx = np.asarray(from_idx); to_idx = np.asarray(to_idx)
+    il = np.asarray(il, dtype=np.int64); jl = np.asarray(jl, dtype=np.int64)
+    nf, nt = len(from_idx), len(to_idx)
+    fromISto = nf == nt and bool(np.all(from_idx == to_idx))
+    gi, gj = from_idx[il], to_idx[jl]
+    ci, cj = snp.codes[gi], snp.codes[gj]                 # [m, S]
+    rf = snp.r[from_idx].astype(np.float64)
+    rt = snp.r[to_idx].astype(np.float64)
+    ri, rj = rf[il], rt[jl]
+    den = neff + 0.5 * ri * rj
+    if fromISto:
+        Q = 0.25 * ri * rj
+    else:
+        c = il + jl * nf
+        Q = 0.25 * rf[c // nt] * rt[c % nt]
+    out = np.zeros(len(il))
+    for a in range(5):
+        xa = (ci == a)
+        pa = xa @ w
+        for b in range(5):
+            yb = (cj == b)
+            pb = yb @ w
+            cab = (xa & yb) @ w + 0.5
+            D = pa * pb + 0.5 * pa * ri + 0.5 * pb * rj + Q
+            u = snp.uqe[gi, a] * snp.uqe[gj, b]
+            out += u * cab / den * np.log(cab * den / D)
+    return out
+
+
 def format_r_numeric(x: float) -> str:
     """``write.table`` number formatting: up to 15 significant digits, shortest
     representation that round-trips at that precision (R/computePairwiseMI.R:140,362)."""

@@ -116,6 +116,19 @@ def test_block_mi_c_vs_numpy_vs_closed_form(fixture_snp, fixture_expected):
         assert np.abs(lit - cc).max() < 1e-12
 
 
+def test_pair_closed_form_matches_block_form(fixture_snp, fixture_expected):
+    # the per-pair evaluator used by the full-size GPU spot checks is the block closed form cell by cell
+    snp, hdw = fixture_snp, fixture_expected["hdw"]
+    rng = np.random.default_rng(5)
+    for f, t in [(np.arange(0, 300), np.arange(0, 300)), (np.arange(100, 400), np.arange(900, 1077)),
+                 (np.arange(0, 300), np.arange(300, 600))]:
+        blk = O.block_mi_closed_form(snp, hdw, f, t)
+        il = rng.integers(0, len(f), 500)
+        jl = rng.integers(0, len(t), 500)
+        got = O.pair_mi_closed_form(snp, hdw, f, t, il, jl)
+        assert np.abs(got - blk[il, jl]).max() < 1e-13
+
+
 def test_golden_single_block_mi(fixture_snp, fixture_expected):
     e = fixture_expected
     idx = np.arange(fixture_snp.nsnp)
