@@ -35,7 +35,7 @@ MAX_BLK = 10000
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
@@ -166,6 +166,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: ldweaver_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; rank 0's stdout must hold the JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import ldweaver_b200 as ldw
     from ldweaver_b200 import api
