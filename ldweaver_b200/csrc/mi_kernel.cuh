@@ -426,12 +426,12 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.a);
     for (int i = 0; i < MI_MAX_STAGES; i++) {
-      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], MI_EXP_THREADS);
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], MI_EXP_WARPS);
     }
     mbar_init(drained, 1);
     for (int i = 0; i < 2; i++) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], MI_EPI_THREADS);
-      mbar_init(&jfull[i], 1); mbar_init(&jempty[i], MI_EPI_THREADS);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], MI_EPI_WARPS);
+      mbar_init(&jfull[i], 1); mbar_init(&jempty[i], MI_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -624,7 +624,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
           sts128(addr, make_uint4(y.x & g0.x, y.y & g0.y, y.z & g0.z, y.w & g0.w));                 // aH in place
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&ready[st]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ready[st]);  // one arrival per warp: every arrival wakes the sleeping waiters
         phb ^= 1u << st;
         if (++st == nst) st = 0;
       }
@@ -673,15 +674,15 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         else epi_dispatch<true, false>(p, td, c);
       }
       tc_fence_before();
+      __syncwarp();
       if (big) {
-        mbar_arrive(&tempty[0]);
-        mbar_arrive(&tempty[1]);
+        if (lane == 0) { mbar_arrive(&tempty[0]); mbar_arrive(&tempty[1]); }
         aph ^= 1;  // two ring slots consumed: phase flips once
       } else {
-        mbar_arrive(&tempty[as]);
+        if (lane == 0) mbar_arrive(&tempty[as]);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
-      mbar_arrive(&jempty[jb]);
+      if (lane == 0) mbar_arrive(&jempty[jb]);
     }
     if (DBG && p.dbg && lane == 0 && (warp == MI_EPI_WARP0 || warp == MI_EPI_WARP0 + MI_EPI_WARPS - 1)) {
       int o = warp == MI_EPI_WARP0 ? 6 : 9;
