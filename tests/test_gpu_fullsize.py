@@ -144,28 +144,7 @@ def test_c2_partition_union_is_bitwise_single_run(c2):
     plan.close()
 
 
-def _cheap_codes(S, n, seed, n_rate, multi):
-    """uint8-only generator for the big shapes: founders + 3 % re-draws + N; every site has >= 2 alleles."""
-    rng = np.random.default_rng(seed)
-    F = max(8, S // 16)
-    wts = 1.0 / np.arange(1, F + 1)
-    fos = rng.choice(F, size=S, p=wts / wts.sum())
-    out = np.empty((n, S), dtype=np.uint8)
-    for lo in range(0, n, 4096):
-        m = min(4096, n - lo)
-        k = rng.choice([2, 3, 4], size=m, p=multi)
-        fa = (rng.integers(0, 256, (m, F), dtype=np.uint8) % 8)
-        fa = np.where(fa < 5, 0, np.minimum(fa - 4, (k - 1)[:, None])).astype(np.uint8)   # major allele ~ 62 %
-        fa[:, 0] = 0
-        fa[:, 1] = 1
-        c = fa[:, fos]
-        mut = rng.integers(0, 256, (m, S), dtype=np.uint8) < 8
-        c = np.where(mut, (rng.integers(0, 256, (m, S), dtype=np.uint8) % k[:, None]).astype(np.uint8), c)
-        perm = np.argsort(rng.random((m, 4)), axis=1).astype(np.uint8)
-        c = np.take_along_axis(perm, c.astype(np.int64), axis=1).astype(np.uint8)
-        c[rng.integers(0, 65536, (m, S), dtype=np.uint16) < int(n_rate * 65536)] = 4
-        out[lo:lo + m] = c
-    return out
+from ldweaver_b200.synth import cheap_codes as _cheap_codes  # noqa: E402
 
 
 def test_c4_shaped_5000_sequences_spot_check():
