@@ -9,7 +9,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ldw.h"
@@ -31,6 +34,22 @@ int set_error(int code, const char* fmt, ...);
     int rc__ = (call);       \
     if (rc__ != 0) return rc__; \
   } while (0)
+
+// Runs fn(i) for i in [0, n) on up to `max_threads` host threads (static interleaved split).  fn must not throw.
+template <class F>
+inline void parallel_for(int64_t n, int max_threads, F fn) {
+  int nt = (int)std::min<int64_t>(std::min<int64_t>(n, max_threads), std::max(1u, std::thread::hardware_concurrency()));
+  if (nt <= 1) {
+    for (int64_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; t++)
+    th.emplace_back([=]() {
+      for (int64_t i = t; i < n; i += nt) fn(i);
+    });
+  for (auto& x : th) x.join();
+}
 
 // Device memory comes from a per-device cache of freed blocks: cudaMalloc / cudaFree of the gigabyte-sized operand
 // and link arrays cost tens of milliseconds and cudaFree synchronises the device, which would otherwise dominate a

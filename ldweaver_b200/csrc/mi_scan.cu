@@ -650,17 +650,26 @@ int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_
   if (nseq > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: nseq > 65535 not supported by the 15-bit digit accumulation");
   if (blk < 128 || blk > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: block size %lld outside [128, 65535]", (long long)blk);
   {
-    // every code must be 0..4; eight bytes per step (a byte > 4 sets bit 7 of byte + 0x7B, or has it set already)
+    // every code must be 0..4; eight bytes per step (a byte > 4 sets bit 7 of byte + 0x7B, or has it set already),
+    // chunks spread over a few host threads
     const int64_t total = n_snp * nseq;
-    int64_t i = 0, bad = -1;
-    for (; i + 8 <= total; i += 8) {
-      uint64_t x;
-      memcpy(&x, codes + i, 8);
-      if ((((x & 0x7F7F7F7F7F7F7F7Full) + 0x7B7B7B7B7B7B7B7Bull) | x) & 0x8080808080808080ull) break;
-    }
-    for (; i < total; i++)
-      if (codes[i] > 4) { bad = i; break; }
-    if (bad >= 0) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: codes[%lld] = %d outside 0..4", (long long)bad, (int)codes[bad]);
+    const int64_t chunk = (int64_t)1 << 22;
+    const int64_t nchunks = (total + chunk - 1) / chunk;
+    std::vector<int64_t> bad_at(nchunks, -1);
+    parallel_for(nchunks, 8, [&](int64_t c) {
+      int64_t i = c * chunk;
+      const int64_t end = std::min<int64_t>(total, i + chunk);
+      for (; i + 8 <= end; i += 8) {
+        uint64_t x;
+        memcpy(&x, codes + i, 8);
+        if ((((x & 0x7F7F7F7F7F7F7F7Full) + 0x7B7B7B7B7B7B7B7Bull) | x) & 0x8080808080808080ull) break;
+      }
+      for (; i < end; i++)
+        if (codes[i] > 4) { bad_at[c] = i; break; }
+    });
+    for (int64_t c = 0; c < nchunks; c++)
+      if (bad_at[c] >= 0)
+        return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: codes[%lld] = %d outside 0..4", (long long)bad_at[c], (int)codes[bad_at[c]]);
   }
   ldw_mi_plan* P = new ldw_mi_plan();
   P->ctx = ctx;
@@ -766,6 +775,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
                 int n_parts, int part, ldw_links* sr_out, ldw_links* lr_out, ldw_links* borderline_out, double* thr_out,
                 double* prob_out, ldw_scan_stats* stats_out) {
   if (!P) return set_error(LDW_ERR_ARG, "null plan");
+  const auto t_entry = std::chrono::steady_clock::now();
   LDW_TRY(ctx_bind(P->ctx));
   cudaStream_t st = P->ctx->stream;
   ScanWS* W = get_ws(P->ctx);
@@ -798,13 +808,24 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   int64_t total_sr = 0, total_pairs = 0, total_lr = 0;
   uint64_t max_cap = 1, sum_keep = 0;
   {
-    BlockHost tmp;
-    for (size_t b = 0; b < blocks.size(); b++) {
+    // block sizes on a few host threads (they gate the first launch), then the serial prefix / rank arithmetic
+    std::vector<int> perr(blocks.size(), 0);
+    parallel_for((int64_t)blocks.size(), 8, [&](int64_t b) {
+      BlockHost tmp;
       int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, tmp, true);
-      if (e > 1) return e;
+      perr[b] = e;
+      Sel& s = sel[b];
+      s.n_lr = tmp.n_lr; s.n_sr = tmp.n_sr; s.n_pairs = tmp.n_pairs;
+    });
+    for (size_t b = 0; b < blocks.size(); b++) {
+      const int e = perr[b];
+      if (e > 1) {  // re-run on this thread so that the (thread-local) error message is the caller's
+        BlockHost t2;
+        return prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, t2, true);
+      }
       Sel& s = sel[b];
       s.skip = (e == 1);
-      s.n_lr = tmp.n_lr; s.n_sr = tmp.n_sr; s.n_pairs = tmp.n_pairs;
+      struct { int64_t n_lr, n_sr, n_pairs; } tmp{s.n_lr, s.n_sr, s.n_pairs};
       s.sr_base = total_sr;
       total_sr += tmp.n_sr; total_pairs += tmp.n_pairs; total_lr += tmp.n_lr;
       if (!sr_only && tmp.n_lr > 0) {
@@ -1031,6 +1052,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     fprintf(stderr, "ldw timing: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
     tp0 = t;
   };
+  if (dbg_timing) fprintf(stderr, "ldw timing: %-28s %8.3f ms\n", "sizes + workspace (host)", std::chrono::duration<double, std::milli>(tpre - t_entry).count());
   if (dbg_timing) fprintf(stderr, "ldw timing: %-28s %8.3f ms\n", "submit blocks (host)", std::chrono::duration<double, std::milli>(tp0 - tpre).count());
   lap("drain blocks");
 
@@ -1215,6 +1237,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   }
   kev_cleanup();
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
+  lap("borderline + stats (host)");
   return 0;
 }
 
