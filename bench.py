@@ -131,7 +131,7 @@ def main():
                f"lr_retain_links {int(LR_RETAIN)}, max_blk_sz {MAX_BLK}"
     config = {"workload": workload, "nseq": S, "nsnp": n, "sr_dist": SR_DIST, "lr_retain_links": LR_RETAIN,
               "max_blk_sz": MAX_BLK, "partition": f"make_blocks blocks round-robin over {world} rank(s)",
-              "l2": "operand arrays (6 x rows x Kpad bytes) exceed the 126 MB L2; no explicit flush"}
+              "l2": "inputs larger than L2: operand planes + records are 170 MB (> 126 MB L2) and every step writes 2.9 GB of link columns, so no input survives in L2 between timed steps; no explicit flush"}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
