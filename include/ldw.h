@@ -174,6 +174,15 @@ LDW_API int ldw_mi_scan(ldw_mi_plan* plan, double g, double sr_dist, double lr_r
                 int flags, int n_parts, int part, ldw_links* sr_out, ldw_links* lr_out, ldw_links* borderline_out,
                 double* thr_out, double* prob_out, ldw_scan_stats* stats_out);
 
+/* ldw_write_lr_tsv writes the long-range rows exactly as perform_MI_computation_ACGTN appends them with
+ *   write.table(MI_df_lr, lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
+ * (R/computePairwiseMI.R:362): tab-separated pos1 pos2 clust1 clust2 len MI, integers as digits, doubles the way
+ * write.table encodes a single cell (15 significant digits, scientific notation only when strictly narrower, so a
+ * len of 100000 is "1e+05").  Host only, no device needed.  ldw_format_r_real exposes the cell encoder (tests).
+ */
+LDW_API int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int append);
+LDW_API int ldw_format_r_real(double x, char* out, int cap);
+
 /* Dense MI matrix of one block (debug / parity aid; nf x nt doubles, column-major, fp32-accurate values).
  * from/to are 0-based ascending global SNP ids, as `from`/`to` of perform_MI_computation_ACGTN. */
 LDW_API int ldw_mi_block_dense(ldw_mi_plan* plan, int64_t block_index, double* mi_out, int64_t* nf_out, int64_t* nt_out);

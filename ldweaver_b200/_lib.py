@@ -28,6 +28,21 @@ class Links(C.Structure):
     _fields_ = [("n", i64), ("pos1", P(C.c_int32)), ("pos2", P(C.c_int32)), ("clust1", P(C.c_int32)),
                 ("clust2", P(C.c_int32)), ("len", P(C.c_int32)), ("MI", P(f64)), ("block", P(C.c_int32))]
 
+    @classmethod
+    def from_dict(cls, d: dict):
+        """Borrow the columns of a link table held as NumPy arrays (kept alive on the returned object)."""
+        self = cls()
+        keep = {}
+        for name, dt, ct in (("pos1", np.int32, C.c_int32), ("pos2", np.int32, C.c_int32), ("clust1", np.int32, C.c_int32),
+                             ("clust2", np.int32, C.c_int32), ("len", np.int32, C.c_int32), ("MI", np.float64, f64),
+                             ("block", np.int32, C.c_int32)):
+            a = np.ascontiguousarray(d[name] if name in d else np.zeros(len(d["MI"]), dtype=dt), dtype=dt)
+            keep[name] = a
+            setattr(self, name, a.ctypes.data_as(P(ct)))
+        self.n = len(keep["MI"])
+        self._keep = keep
+        return self
+
     def to_dict(self) -> dict:
         n = int(self.n)
         out = {}
@@ -81,6 +96,8 @@ def lib():
     L.ldw_mi_scan.argtypes = [C.c_void_p, f64, f64, f64, f64, C.c_int, C.c_int, C.c_int, P(Links), P(Links), P(Links),
                               C.c_void_p, C.c_void_p, P(ScanStats)]
     L.ldw_mi_block_dense.argtypes = [C.c_void_p, i64, C.c_void_p, P(i64), P(i64)]
+    L.ldw_write_lr_tsv.argtypes = [C.c_char_p, P(Links), C.c_int]
+    L.ldw_format_r_real.argtypes = [f64, C.c_char_p, C.c_int]
     L.ldw_mi_pairs_exact.argtypes = [C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]
     _lib = L
     return L

@@ -296,19 +296,40 @@ class MIPlan:
 
 
 def _format_r(x) -> str:
-    """write.table's number formatting (15 significant digits)."""
-    if float(x) == int(x) and abs(x) < 1e15:
-        return str(int(x))
-    return repr(float(f"{float(x):.15g}")) if "e" not in f"{float(x):.15g}" else f"{float(x):.15g}"
+    """One double the way ``write.table`` encodes a cell (utils:::writetable -> formatReal with 15 significant digits,
+    scipen 0): the fewest significant digits (<= 15) that reproduce the 15-digit rounding, fixed notation unless
+    scientific notation is strictly narrower.  Python mirror of csrc/tsv_host.cpp (used by the tests)."""
+    x = float(x)
+    if x != x:
+        return "NA"
+    if x in (float("inf"), float("-inf")):
+        return "Inf" if x > 0 else "-Inf"
+    if x == 0:
+        return "0"
+    m, e = f"{x:.14e}".split("e")
+    neg = m.startswith("-")
+    digits = m.lstrip("-").replace(".", "").rstrip("0") or "0"
+    nsig, k = len(digits), int(e)
+    left, rgt = (k + 1, max(0, nsig - k - 1)) if k >= 0 else (1, nsig - k - 1)
+    if 0 < k <= 22 and abs(x) < 10.0 ** k:  # formatReal's `roundingwidens`
+        left -= 1
+    w_fixed = neg + left + (rgt + 1 if rgt else 0)
+    w_sci = neg + (nsig + 1 if nsig > 1 else 1) + (5 if abs(k) >= 100 else 4)
+    return f"{x:.{rgt}f}" if w_fixed <= w_sci else f"{x:.{nsig - 1}e}"
 
 
-def write_lr_tsv(path: str, lr: dict, append: bool = True) -> None:
+def format_r_real_native(x: float) -> str:
+    buf = C.create_string_buffer(512)
+    check(_lib.lib().ldw_format_r_real(float(x), buf, 512))
+    return buf.value.decode()
+
+
+def write_lr_tsv(path: str, lr, append: bool = True) -> None:
     """lr_links.tsv rows ``pos1 pos2 clust1 clust2 len MI`` (R/computePairwiseMI.R:362; no header, tab separated,
-    appended per block in the reference -- here once, in the same row order)."""
-    with open(path, "a" if append else "w") as fh:
-        for i in range(len(lr["MI"])):
-            fh.write(f"{lr['pos1'][i]}\t{lr['pos2'][i]}\t{lr['clust1'][i]}\t{lr['clust2'][i]}\t{lr['len'][i]}\t"
-                     f"{_format_r(lr['MI'][i])}\n")
+    appended per block in the reference -- here once, in the same row order), written by the native writer
+    (``ldw_write_lr_tsv``) with write.table's cell encoding.  ``lr``: a dict of columns or a ``_lib.Links``."""
+    links = lr if isinstance(lr, _lib.Links) else _lib.Links.from_dict(lr)
+    check(_lib.lib().ldw_write_lr_tsv(os.fsencode(path), C.byref(links), 1 if append else 0))
 
 
 def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: int = 1, lr_save_path: Optional[str] = None,

@@ -1,0 +1,97 @@
+// Host-side writer of lr_links.tsv: the rows perform_MI_computation_ACGTN appends per block with
+//   write.table(x = MI_df_lr, file = lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
+// (R/computePairwiseMI.R:362; columns pos1 pos2 clust1 clust2 len MI, :326-331; reader R/io_functions.R:34-35).
+// write.table encodes every cell on its own (utils:::writetable -> EncodeElement0): integers as plain digits, doubles
+// with up to 15 significant digits, in fixed notation unless scientific notation is strictly narrower (formatReal with
+// R_print.digits = DBL_DIG, scipen = 0).  pos1 / pos2 are integer columns (POS is an IntegerVector,
+// src/getACGTNsites.cpp:97,173), clust1 / clust2 / len / MI are doubles (paint is built by rep(0, n),
+// R/estimateCDSDiversity.R:152) -- so len = 100000 is written "1e+05", exactly as R does.
+// Rows are formatted on a few host threads and written in order.
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "host_util.h"
+#include "../../include/ldw.h"
+
+namespace {
+
+// One double the way write.table prints it.  Returns the number of characters written (no terminator needed).
+int format_r_real(double x, char* out) {
+  if (isnan(x)) { memcpy(out, "NA", 2); return 2; }
+  if (isinf(x)) { if (x > 0) { memcpy(out, "Inf", 3); return 3; } memcpy(out, "-Inf", 4); return 4; }
+  if (x == 0.0) { out[0] = '0'; return 1; }
+  // 15 significant digits, correctly rounded: d.dddddddddddddde[+-]XX
+  char e15[40];
+  snprintf(e15, sizeof(e15), "%.14e", x);
+  const char* p = e15;
+  const int neg = (*p == '-');
+  if (neg) p++;
+  // mantissa digits: p[0], p[2..15]
+  int nsig = 15;
+  while (nsig > 1 && p[nsig == 1 ? 0 : nsig] == '0') nsig--;  // digit k (k >= 2) sits at p[k]; stop at the first non-zero
+  const char* ep = strchr(p, 'e');
+  const int kpower = atoi(ep + 1);
+  int left, rgt;
+  if (kpower >= 0) {
+    left = kpower + 1;
+    rgt = nsig - kpower - 1;
+    if (rgt < 0) rgt = 0;
+    if (kpower > 0 && kpower <= 22 && fabs(x) < pow(10.0, kpower)) left--;  // formatReal's `roundingwidens`
+  }
+  else { left = 1; rgt = nsig - kpower - 1; }
+  const int wF = neg + left + (rgt ? rgt + 1 : 0);
+  const int wE = neg + (nsig > 1 ? nsig + 1 : 1) + ((kpower >= 100 || kpower <= -100) ? 5 : 4);
+  if (wF <= wE) return snprintf(out, 400, "%.*f", rgt, x);
+  return snprintf(out, 64, "%.*e", nsig - 1, x);
+}
+
+int format_int(int32_t v, char* out) { return snprintf(out, 16, "%d", (int)v); }
+
+}  // namespace
+
+extern "C" int ldw_format_r_real(double x, char* out, int cap) {
+  char buf[512];
+  int n = format_r_real(x, buf);
+  if (!out || cap <= n) return ldw::set_error(LDW_ERR_ARG, "ldw_format_r_real: buffer too small");
+  memcpy(out, buf, n);
+  out[n] = 0;
+  return 0;
+}
+
+extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int append) {
+  if (!path || !lr) return ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: null argument");
+  FILE* f = fopen(path, append ? "ab" : "wb");
+  if (!f) return ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: can't open %s", path);
+  const int64_t n = lr->n;
+  const int64_t chunk = 1 << 16;
+  const int64_t nchunks = (n + chunk - 1) / chunk;
+  const int64_t wave = 32;  // chunks formatted concurrently, then written in order
+  int rc = 0;
+  for (int64_t c0 = 0; c0 < nchunks && rc == 0; c0 += wave) {
+    const int64_t nc = std::min<int64_t>(wave, nchunks - c0);
+    std::vector<std::string> bufs(nc);
+    ldw::parallel_for(nc, 8, [&](int64_t k) {
+      std::string& s = bufs[k];
+      const int64_t lo = (c0 + k) * chunk, hi = std::min<int64_t>(n, lo + chunk);
+      s.reserve((size_t)(hi - lo) * 64);
+      char tmp[512];
+      for (int64_t i = lo; i < hi; i++) {
+        s.append(tmp, format_int(lr->pos1[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_int(lr->pos2[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_r_real((double)lr->clust1[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_r_real((double)lr->clust2[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_r_real((double)lr->len[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_r_real(lr->MI[i], tmp)); s.push_back('\n');
+      }
+    });
+    for (int64_t k = 0; k < nc; k++)
+      if (fwrite(bufs[k].data(), 1, bufs[k].size(), f) != bufs[k].size()) { rc = ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: write to %s failed", path); break; }
+  }
+  if (fclose(f) != 0 && rc == 0) rc = ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: closing %s failed", path);
+  return rc;
+}

@@ -661,17 +661,28 @@ def pair_mi_closed_form(snp: SnpDat, hdw: np.ndarray, from_idx: np.ndarray, to_i
 
 
 def format_r_numeric(x: float) -> str:
-    """``write.table`` number formatting: up to 15 significant digits, shortest
-    representation that round-trips at that precision (R/computePairwiseMI.R:140,362)."""
-    if x == int(x) and abs(x) < 1e15:
-        return str(int(x))
-    for p in range(1, 16):
-        s = f"{x:.{p}g}"
-        if float(s) == float(f"{x:.15g}"):
-            break
-    if "e" in s:
-        mant, ex = s.split("e")
-        sign = ex[0] if ex[0] in "+-" else "+"
-        digits = ex.lstrip("+-").lstrip("0") or "0"
-        s = f"{mant}e{sign}{int(digits):02d}"
-    return s
+    """One double as ``write.table`` encodes a cell (R/computePairwiseMI.R:140,362 -> utils:::writetable ->
+    EncodeElement0 -> formatReal with R_print.digits = DBL_DIG = 15, scipen = 0; base R, not in the reference tree):
+    the fewest significant digits (<= 15) that reproduce the 15-digit rounding; fixed notation unless scientific
+    notation is strictly narrower -- so 20000 stays "20000" but 100000 becomes "1e+05", and MI values below 1e-4 with
+    many digits come out as d.ddde-05.  Restated from the published algorithm; not checked against a live R here."""
+    x = float(x)
+    if x != x:
+        return "NA"
+    if x in (float("inf"), float("-inf")):
+        return "Inf" if x > 0 else "-Inf"
+    if x == 0:
+        return "0"
+    mant, ex = f"{x:.14e}".split("e")
+    neg = 1 if mant.startswith("-") else 0
+    digits = mant.lstrip("-").replace(".", "").rstrip("0") or "0"
+    nsig, kp = len(digits), int(ex)
+    if kp >= 0:
+        left, rgt = kp + 1, max(0, nsig - kp - 1)
+        if 0 < kp <= 22 and abs(x) < 10.0 ** kp:   # formatReal's `roundingwidens`
+            left -= 1
+    else:
+        left, rgt = 1, nsig - kp - 1
+    w_fixed = neg + left + (rgt + 1 if rgt else 0)
+    w_sci = neg + (nsig + 1 if nsig > 1 else 1) + (5 if abs(kp) >= 100 else 4)
+    return f"{x:.{rgt}f}" if w_fixed <= w_sci else f"{x:.{nsig - 1}e}"
