@@ -50,7 +50,35 @@ int format_r_real(double x, char* out) {
   return snprintf(out, 64, "%.*e", nsig - 1, x);
 }
 
-int format_int(int32_t v, char* out) { return snprintf(out, 16, "%d", (int)v); }
+int format_int(int64_t v, char* out) {
+  char tmp[24];
+  int n = 0, o = 0;
+  uint64_t u = v < 0 ? (uint64_t)(-v) : (uint64_t)v;
+  do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+  if (v < 0) out[o++] = '-';
+  while (n) out[o++] = tmp[--n];
+  return o;
+}
+
+// Whole-valued doubles below 10^15 (clust, len): same rule as format_r_real without going through printf.
+int format_r_whole(int64_t v, char* out) {
+  if (v == 0) { out[0] = '0'; return 1; }
+  char dig[24];
+  const int neg = v < 0;
+  const int nd = format_int(neg ? -v : v, dig);
+  int nsig = nd;
+  while (nsig > 1 && dig[nsig - 1] == '0') nsig--;
+  const int kpower = nd - 1;
+  const int wF = neg + nd, wE = neg + (nsig > 1 ? nsig + 1 : 1) + 4;
+  int o = 0;
+  if (neg) out[o++] = '-';
+  if (wF <= wE) { memcpy(out + o, dig, nd); return o + nd; }
+  out[o++] = dig[0];
+  if (nsig > 1) { out[o++] = '.'; memcpy(out + o, dig + 1, nsig - 1); o += nsig - 1; }
+  out[o++] = 'e'; out[o++] = '+';
+  out[o++] = (char)('0' + kpower / 10); out[o++] = (char)('0' + kpower % 10);
+  return o;
+}
 
 }  // namespace
 
@@ -83,9 +111,9 @@ extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int appen
       for (int64_t i = lo; i < hi; i++) {
         s.append(tmp, format_int(lr->pos1[i], tmp)); s.push_back('\t');
         s.append(tmp, format_int(lr->pos2[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_r_real((double)lr->clust1[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_r_real((double)lr->clust2[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_r_real((double)lr->len[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_r_whole(lr->clust1[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_r_whole(lr->clust2[i], tmp)); s.push_back('\t');
+        s.append(tmp, format_r_whole(lr->len[i], tmp)); s.push_back('\t');
         s.append(tmp, format_r_real(lr->MI[i], tmp)); s.push_back('\n');
       }
     });
