@@ -6,7 +6,7 @@
 
 A "step" is one full weighted pairwise-MI scan (all make_blocks blocks: GEMM + fused MI epilogue + sr/lr link
 filter + per-block exact LR selection + link-column materialisation) of the synthetic 616 x 100k alignment
-(SURVEY.md 8d, config C2), blocks dealt round-robin over the ranks.  `value` is pairs/s with the packed operands
+(SURVEY.md 8d, config C2), blocks dealt by cost over the ranks.  `value` is pairs/s with the packed operands
 already resident in HBM (device time from CUDA events on the library's stream, max over ranks); `e2e` is the same
 metric through the C ABI from host buffers: host->device upload + operand packing + scan + device->host copy of
 every link column, inside the timed region.
@@ -130,7 +130,7 @@ def main():
     workload = f"{args.config}: synthetic {S} seqs x {n} SNPs (seed {seed}), Hamming-weighted MI, sr_dist {int(SR_DIST)}, " \
                f"lr_retain_links {int(LR_RETAIN)}, max_blk_sz {MAX_BLK}"
     config = {"workload": workload, "nseq": S, "nsnp": n, "sr_dist": SR_DIST, "lr_retain_links": LR_RETAIN,
-              "max_blk_sz": MAX_BLK, "partition": f"make_blocks blocks round-robin over {world} rank(s)",
+              "max_blk_sz": MAX_BLK, "partition": f"make_blocks blocks dealt by cost (pairs, largest first, least-loaded rank) over {world} rank(s)",
               "l2": "inputs larger than L2: operand planes + records are 170 MB (> 126 MB L2) and every step writes 2.9 GB of link columns, so no input survives in L2 between timed steps; no explicit flush"}
 
     # ------------------------------------------------------------------ reference arm (CPU)

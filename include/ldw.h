@@ -160,8 +160,9 @@ LDW_API int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp
                        const int32_t* pos, const int32_t* paint, int64_t blk, ldw_mi_plan** out);
 LDW_API void ldw_mi_plan_destroy(ldw_mi_plan* plan);
 
-/* Run the scan over all make_blocks() blocks whose index b satisfies b % n_parts == part
- * (multi-GPU: one plan per device, blocks dealt round-robin; n_parts = 1, part = 0 for everything).
+/* Run the scan over this part's share of the make_blocks() blocks (multi-GPU: one plan per device; n_parts = 1,
+ * part = 0 for everything).  Blocks are dealt by cost -- pairs, largest first, each to the least-loaded part,
+ * lowest part on ties -- so every rank derives the same assignment (ldweaver_b200/api.py:partition_blocks mirrors it).
  *   g               : genome length (snp.dat$g)
  *   sr_dist         : short-range cut-off (len <= sr_dist is SR, R/computePairwiseMI.R:333)
  *   lr_retain_links, lr_links_approx : as R/computePairwiseMI.R:352 (lr_links_approx computed by the

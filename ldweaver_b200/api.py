@@ -228,13 +228,25 @@ def make_blocks(nsnp: int, max_blk_sz: int):
     return [(fs[i], fe[i], fs[j], fe[j]) for i in range(p) for j in range(i, p)]
 
 
-def partition_blocks(n_blocks: int, n_parts: int, part: int) -> List[int]:
-    """Blocks (0-based make_blocks rows) that ``ldw_mi_scan(..., n_parts, part)`` processes: dealt round-robin, the
-    same rule as the library (csrc/mi_scan.cu).  Blocks are independent (the LR threshold is per block, quirk Q3),
-    so ranks need no data-path collective."""
+def partition_blocks(nsnp: int, blk: int, n_parts: int, part: int) -> List[int]:
+    """Blocks (0-based make_blocks rows) that ``ldw_mi_scan(..., n_parts, part)`` processes -- the same rule as the
+    library (csrc/mi_scan.cu): blocks are dealt by cost (number of pairs), largest first, each to the least-loaded
+    part (lowest part on ties; make_blocks order among equal costs).  Diagonal blocks cost half of the others, so this
+    balances better than round-robin.  Blocks are independent (the LR threshold is per block, quirk Q3), so ranks
+    need no data-path collective."""
     if n_parts < 1 or not (0 <= part < n_parts):
         raise ValueError("bad partition")
-    return [b for b in range(n_blocks) if b % n_parts == part]
+    items = []
+    for idx, (fs, fe, ts, te) in enumerate(make_blocks(nsnp, blk)):
+        ni, nj = fe - fs + 1, te - ts + 1
+        items.append((ni * (ni - 1) // 2 if fs == ts else ni * nj, idx))
+    load = [0] * n_parts
+    owner = {}
+    for cost, idx in sorted(items, key=lambda t: (-t[0], t[1])):
+        best = min(range(n_parts), key=lambda p: (load[p], p))
+        owner[idx] = best
+        load[best] += cost
+    return [idx for _, idx in items if owner[idx] == part]
 
 
 class MIPlan:

@@ -785,14 +785,34 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   if (!sr_only && !(lr_links_approx > 0)) return set_error(LDW_ERR_ARG, "lr_links_approx must be > 0");
   if (n_parts < 1 || part < 0 || part >= n_parts) return set_error(LDW_ERR_ARG, "bad partition %d of %d", part, n_parts);
 
-  // ---- block list (make_blocks order), this part's share
+  // ---- block list (make_blocks order), this part's share.  Blocks are dealt by cost (pairs), largest first, each to
+  //      the least-loaded part (lowest part on ties): diagonal blocks cost half of the others, so plain round-robin
+  //      would leave up to 12 % imbalance at 8 parts.  Deterministic: every rank derives the same assignment.
   struct Blk { int bf, bt; int64_t index; };
   std::vector<Blk> blocks;
   {
+    struct Item { int64_t cost, idx; int bf, bt; };
+    std::vector<Item> items;
     int64_t idx = 0;
     for (int i = 0; i < P->nranges; i++)
-      for (int j = i; j < P->nranges; j++, idx++)
-        if (idx % n_parts == part) blocks.push_back({i, j, idx});
+      for (int j = i; j < P->nranges; j++, idx++) {
+        const int64_t ni = std::min<int64_t>(P->n, (int64_t)(i + 1) * P->blk) - (int64_t)i * P->blk;
+        const int64_t nj = std::min<int64_t>(P->n, (int64_t)(j + 1) * P->blk) - (int64_t)j * P->blk;
+        items.push_back({i == j ? ni * (ni - 1) / 2 : ni * nj, idx, i, j});
+      }
+    std::vector<Item> order = items;
+    std::stable_sort(order.begin(), order.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+    std::vector<int64_t> load(n_parts, 0);
+    std::vector<int> owner(items.size(), 0);
+    for (const Item& it : order) {
+      int best = 0;
+      for (int p = 1; p < n_parts; p++)
+        if (load[p] < load[best]) best = p;
+      owner[it.idx] = best;
+      load[best] += it.cost;
+    }
+    for (const Item& it : items)
+      if (owner[it.idx] == part) blocks.push_back({it.bf, it.bt, it.idx});
   }
   const int64_t nblk_total = (int64_t)P->nranges * (P->nranges + 1) / 2;
   if (thr_out) for (int64_t b = 0; b < nblk_total; b++) thr_out[b] = NAN;

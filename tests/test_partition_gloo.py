@@ -42,7 +42,7 @@ def _worker(rank, world, port, out_dir):
     assert np.array_equal(hdw, e["hdw"])
     blocks = O.make_blocks(snp.nsnp, 1000)
     assert blocks == api.make_blocks(snp.nsnp, 1000)
-    mine = api.partition_blocks(len(blocks), world, rank)
+    mine = api.partition_blocks(snp.nsnp, 1000, world, rank)
     POS = snp.POS.astype(np.float64)
     rows = []
     for b in mine:
@@ -81,8 +81,17 @@ def test_two_rank_partition_reproduces_single_rank(tmp_path, fixture_expected):
 
 def test_partition_rule():
     from ldweaver_b200 import api
-    for n in (1, 3, 55, 465):
+    for nsnp, blk in ((900, 1000), (2500, 1000), (100000, 10000), (300000, 10000), (31234, 10000)):
+        blocks = api.make_blocks(nsnp, blk)
+        cost = [(fe - fs + 1) * (fe - fs) // 2 if fs == ts else (fe - fs + 1) * (te - ts + 1) for fs, fe, ts, te in blocks]
         for w in (1, 2, 4, 8):
-            parts = [api.partition_blocks(n, w, r) for r in range(w)]
-            assert sorted(b for p in parts for b in p) == list(range(n))
-            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            parts = [api.partition_blocks(nsnp, blk, w, r) for r in range(w)]
+            assert sorted(b for p in parts for b in p) == list(range(len(blocks)))     # every block exactly once
+            assert all(p == sorted(p) for p in parts)                                   # make_blocks order within a part
+            loads = [sum(cost[b] for b in p) for p in parts]
+            if len(blocks) >= 4 * w:                                                    # enough blocks to balance
+                assert max(loads) <= 1.08 * sum(loads) / w
+    # C2 on 8 GPUs: 45 full + 10 half blocks -> at most 6.5 block units per rank (round-robin: 7)
+    loads = [sum(1.0 if blocks_[0] != blocks_[2] else 0.5 for blocks_ in [api.make_blocks(100000, 10000)[b] for b in
+             api.partition_blocks(100000, 10000, 8, r)]) for r in range(8)]
+    assert max(loads) <= 6.5
