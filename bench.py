@@ -166,9 +166,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: ldweaver_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; rank 0's stdout must hold the JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner / debug lines to stdout; rank 0's stdout must hold the JSON line only
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import ldweaver_b200 as ldw
     from ldweaver_b200 import api
