@@ -57,45 +57,66 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  The sampler is
+    started before the warm-up (nvidia-smi needs a few hundred ms to produce its first line) and only the samples whose
+    timestamps fall inside the timed window are used; if the window is shorter than the sampling period the nearest
+    samples (within 0.5 s, i.e. still under the same back-to-back load) are reported and flagged."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index: int):
         self.idx = device_index
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def window_begin(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)  # let the sample that covers the end of the window land
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.tmp.flush()
-        rows = [r.strip().split(",") for r in open(self.tmp.name) if r.strip()]
+        rows = [r.strip().split(", ") for r in open(self.tmp.name) if r.strip()]
         os.unlink(self.tmp.name)
-        sm, mx, reasons = [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        samples = []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if "Active" in r[5 + k] and "Not" not in r[5 + k]:
-                        reasons.add(nm)
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rs = [nm for k, nm in enumerate(names) if "Active" in r[4 + k] and "Not" not in r[4 + k]]
+                samples.append((ts, float(r[1]), float(r[2]), rs))
             except Exception:
                 pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        t0, t1 = self.t0 or 0.0, self.t1 or 1e18
+        inside = [s for s in samples if t0 <= s[0] <= t1]
+        note = None
+        if not inside:
+            inside = [s for s in samples if t0 - 0.5 <= s[0] <= t1 + 0.5]
+            note = f"timed window of {1e3 * (t1 - t0):.0f} ms is shorter than the sampling period: nearest samples (+-0.5 s, same back-to-back load)"
+        out = {"sm_mhz": float(np.median([s[1] for s in inside])) if inside else None,
+               "sm_max_mhz": max(s[2] for s in inside) if inside else None,
+               "reasons": sorted({r for s in inside for r in s[3]}), "samples": len(inside)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def cpu_reference_sample(sy, hdw, edge: int):
@@ -197,11 +218,12 @@ def main():
     codes_pin = torch.from_numpy(sy.codes).pin_memory().numpy()
     plan = ldw.MIPlan(ldw.snp_dat_from_codes(codes_pin, sy.POS, sy.g), hdw, sy.paint, blk, device=local_rank)
     flags_dev = api.SCAN_NO_D2H
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         plan.scan(sy.g, SR_DIST, LR_RETAIN, lra, flags_dev, world, rank, copy=False)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.window_begin()
     t_wall0 = time.perf_counter()
     dev_ms = 0.0
     kern_ms = 0.0
@@ -215,6 +237,7 @@ def main():
             agg[k] += stats[k]
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    sampler.window_end()
     clocks = sampler.stop()
 
     def allmax(x):
