@@ -309,8 +309,13 @@ def main():
     alg_flop_per_launch = 50.0 * S * (agg["n_pairs"] / n_launch)  # 50*S flop per SNP pair
     achieved_tf = alg_flop_per_launch / avg_launch_s / 1e12
     exec_tops = agg["exec_int8_ops"] / (kern_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "mi_scan_traffic.json")
+    if os.path.exists(tpath) and args.config == "C2" and not args.nsnp:
+        tj = json.load(open(tpath))
+        traffic = tj["dram_bytes_read_per_launch"] + tj["dram_bytes_write_per_launch"]  # from one ncu --set full capture
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                "traffic": traffic, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                 "kernel": "mi_scan_kernel", "avg_launch_ms": 1e3 * avg_launch_s, "launches": n_launch,
                 "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
                 "executed_int8_tops": exec_tops,
@@ -327,7 +332,7 @@ def main():
 
     line = {"metric": "weighted SNP-pair MI/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "int8 x int8 -> int32 (30-bit fixed-point weights), fp32 epilogue, fp64 LR refinement",
+            "vs_baseline": None, "dtype": "int8 (tcgen05 kind::i8 with int32 accumulation of 28-bit fixed-point weights; fp32 MI epilogue, fp64 refinement of long-range links)",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all),
             "roofline": roofline, "cpu_baseline": cpu,
             "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"], "host_prep_ms": stats["t_host_prep_ms"],
