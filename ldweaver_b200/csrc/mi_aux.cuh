@@ -9,11 +9,11 @@ namespace ldw {
 // ------------------------------------------------------------------------------------------------
 // Per-slot records.  One warp per slot: class-wise exact fp64 marginals p^a = sum_s w_s [code = a] (kept per SNP for
 // the fp64 refinement) and the fixed-point marginals in the SAME digits the GEMM uses, so that
-// sum_b C^ab == P^a holds exactly in integers.
+// sum_b C^ab == P^a holds exactly in integers.  T carries the pseudocounts of its row of the joint table (see M below).
 __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S, const int32_t* __restrict__ slot_snp,
                                     int64_t nslots, const uint8_t* __restrict__ mask, const double* __restrict__ w,
                                     const int32_t* __restrict__ wH, const int32_t* __restrict__ wL, Rec* rec,
-                                    int64_t vstride, double* p64 /*[n][5]*/, uint32_t sa, uint32_t sb) {
+                                    int64_t vstride, double* p64 /*[n][5]*/, uint32_t sa, uint32_t sb, uint32_t M) {
   int64_t slot = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (slot >= nslots) return;
@@ -60,7 +60,8 @@ __global__ void mi_build_rec_kernel(const uint8_t* __restrict__ codes, int64_t S
     int q = 0;
     for (int a = 0; a < 5; a++) {
       if (m & (1 << a)) {
-        qt[q] = ((uint32_t)h[a] << sa) + ((uint32_t)l[a] >> sb);
+        // the pseudocount 0.5 is M count units; a row of the joint table holds r' cells, so the marginal carries r' * M
+        qt[q] = ((uint32_t)h[a] << sa) + ((uint32_t)l[a] >> sb) + M * (uint32_t)(lane + 2);
         const double v = p[a] + 0.5 * (double)(lane + 2);
         qr[q] = (float)(1.0 / v);
         qq[q] = (float)v;

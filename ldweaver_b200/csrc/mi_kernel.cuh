@@ -135,14 +135,15 @@ __device__ __forceinline__ float rcp_fast(float x) {
   return y;
 }
 
-// One term of the MI sum.  t: joint count in the fixed-point unit (count = t * kT).
-//   QC = false: ra = den / (p_i^a + r_j/2), rb = 1 / (p_j^b + r_i/2)           -> ratio = x * ra * rb
-//   QC = true : ra = (p_i^a + r_j/2) / den, rb = p_j^b + r_i/2, dq = dQ / den   -> ratio = x / (ra * rb + dq)
+// One term of the MI sum.  t: joint count PLUS the pseudocount in the fixed-point unit (x = c + 1/2 = t * kT); the
+// factor kT is folded into the per-tile constants and into the final scale, so a term is I2FP + the ratio + LG2 + FMA.
+//   QC = false: ra = kT den / (p_i^a + r_j/2), rb = 1 / (p_j^b + r_i/2)              -> ratio = t * ra * rb
+//   QC = true : ra = (p_i^a + r_j/2) / (kT den), rb = p_j^b + r_i/2, dq = dQ / (kT den) -> ratio = t / (ra * rb + dq)
 // (quirk Q1: dQ is what the reference's transposed rft adds to the denominator on off-diagonal blocks)
 template <bool QC>
-__device__ __forceinline__ float mi_term(float acc, uint32_t t, float ra, float rb, float dq, float kT) {
-  float x = fmaf(__uint2float_rn(t), kT, 0.5f);
-  float ratio = QC ? x * rcp_fast(fmaf(ra, rb, dq)) : x * (ra * rb);
+__device__ __forceinline__ float mi_term(float acc, uint32_t t, float ra, float rb, float dq) {
+  const float x = __uint2float_rn(t);
+  const float ratio = QC ? x * rcp_fast(fmaf(ra, rb, dq)) : x * (ra * rb);
   return fmaf(x, lg2_fast(ratio), acc);
 }
 
@@ -193,8 +194,8 @@ template <int RA>
 struct TileRegs {
   uint32_t Ti[RA];
   float rpad[RA];
-  float kT, scale, q0, qod, rtlq, tcand;
-  uint32_t mul_a, sb, jl_lim;
+  float scale, q0, qod, rtlq, tcand;  // q0, qod, rtlq carry 1 / kT
+  uint32_t mul_a, sb, jl_lim, M;
   int il, nf, nt;
   bool ragged, dense, do_lr, has_sr;
   float* sr_out;
@@ -250,7 +251,8 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
     }
   }
   // (PA+1) x (PB+1) joint table: PA x PB cells from the accumulators, the rest by complement in the count unit
-  // (floor semantics keep every row / column complement non-negative; only the corner needs a clamp)
+  // (floor semantics keep every row / column complement non-negative; only the corner needs a clamp).  Every cell
+  // is carried as count + M (M = the pseudocount 1/2 in count units); the marginals in Rec hold their row's M's.
   float acc[JC];
   uint32_t col[JC][PB], tot[JC];
 #pragma unroll
@@ -268,15 +270,15 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
     for (int b = 0; b < PB; b++) {
 #pragma unroll
       for (int jj = 0; jj < JC; jj++) {
-        const uint32_t t = H[a][b][jj] * k.mul_a + (L[a][b][jj] >> k.sb);
+        const uint32_t t = H[a][b][jj] * k.mul_a + ((L[a][b][jj] >> k.sb) + k.M);  // count + pseudocount
         rsum[jj] += t;
         col[jj][b] += t;
-        acc[jj] = mi_term<QC>(acc[jj], t, k.rpad[a], __uint_as_float(rpj[jj][b]), dq[jj], k.kT);
+        acc[jj] = mi_term<QC>(acc[jj], t, k.rpad[a], __uint_as_float(rpj[jj][b]), dq[jj]);
       }
     }
 #pragma unroll
     for (int jj = 0; jj < JC; jj++) {
-      acc[jj] = mi_term<QC>(acc[jj], k.Ti[a] - rsum[jj], k.rpad[a], __uint_as_float(rpj[jj][PB]), dq[jj], k.kT);
+      acc[jj] = mi_term<QC>(acc[jj], k.Ti[a] - rsum[jj], k.rpad[a], __uint_as_float(rpj[jj][PB]), dq[jj]);
       tot[jj] += rsum[jj];
     }
   }
@@ -284,14 +286,16 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
   for (int b = 0; b < PB; b++)
 #pragma unroll
     for (int jj = 0; jj < JC; jj++)
-      acc[jj] = mi_term<QC>(acc[jj], tj[jj][b] - col[jj][b], k.rpad[PA], __uint_as_float(rpj[jj][b]), dq[jj], k.kT);
+      acc[jj] = mi_term<QC>(acc[jj], tj[jj][b] - col[jj][b], k.rpad[PA], __uint_as_float(rpj[jj][b]), dq[jj]);
 #pragma unroll
   for (int jj = 0; jj < JC; jj++) {
     uint32_t sj = 0;
 #pragma unroll
     for (int b = 0; b < PB; b++) sj += tj[jj][b];
+    // every marginal carries the pseudocounts of its row / column, so the corner comes out as count + M; the count
+    // itself can be slightly negative (floor semantics of the other cells): clamp it at zero
     const int corner = (int)(k.Ti[PA] + tot[jj] - sj);
-    acc[jj] = mi_term<QC>(acc[jj], (uint32_t)max(corner, 0), k.rpad[PA], __uint_as_float(rpj[jj][PB]), dq[jj], k.kT);
+    acc[jj] = mi_term<QC>(acc[jj], (uint32_t)max(corner, (int)k.M), k.rpad[PA], __uint_as_float(rpj[jj][PB]), dq[jj]);
   }
   // ---- classification and emission: tile-uniform branches only; the per-lane work is predicated
   float mi[JC];
@@ -341,8 +345,10 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   const int row = c.q * 32 + c.lane;
   TileRegs<RA> k;
   const float den = p.den[RA - 2][RB - 2];
-  k.kT = p.kT; k.scale = p.ln2_over_den[RA - 2][RB - 2]; k.q0 = p.q0[RA - 2][RB - 2];
-  k.qod = p.quarter_over_den[RA - 2][RB - 2];
+  const float rkT = 1.0f / p.kT;
+  k.scale = p.ln2_over_den[RA - 2][RB - 2] * p.kT; k.q0 = p.q0[RA - 2][RB - 2] * rkT;
+  k.qod = p.quarter_over_den[RA - 2][RB - 2] * rkT;
+  k.M = p.M;
   k.nf = p.nf; k.nt = p.nt;
   k.mul_a = 1u << p.sa; k.sb = p.sb;
   k.ragged = p.ragged != 0; k.dense = p.dense != 0;
@@ -358,8 +364,8 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
 #pragma unroll
     for (int a = 0; a < RA; a++) {
       k.Ti[a] = tt[a];
-      // Q1 form: (p + r'/2) / den; plain form: den / (p + r'/2)
-      k.rpad[a] = QC ? __uint_as_float(tr[a]) * rden : __uint_as_float(tr[a]) * den;
+      // Q1 form: (p + r'/2) / (kT den); plain form: kT den / (p + r'/2)
+      k.rpad[a] = QC ? __uint_as_float(tr[a]) * (rden * rkT) : __uint_as_float(tr[a]) * (den * p.kT);
     }
   }
   const RowDyn rd = p.rowdyn[td.i_dyn0 + row];

@@ -115,6 +115,7 @@ struct ldw_mi_plan {
   double neff = 0, scale = 0;          // weight = W / scale
   int32_t neffH = 0, neffL = 0;
   uint32_t sa = 0, sb = 0;             // epilogue count unit: t = (H << sa) + (L >> sb)
+  uint32_t M = 0;                      // pseudocount 0.5 in count units
   bool pos_sorted = true;
   // device, static
   DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops, d_dig;
@@ -151,7 +152,34 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
     neff += hdw[s];
   }
   P->neff = neff;
-  P->scale = 268435455.0 / wmax;
+  {
+    // count unit of the epilogue: t = (H << sa) + (L >> sb).  H < 16384 * S; one spare bit so that t + (pseudocounts)
+    // stays below 2^32 (the pseudocount of a whole table, r r' / 2 <= 12.5, is below the total weight whenever
+    // neff >= 12.5; the spare bit covers that and validate below covers the rest)
+    uint64_t hmax = 2 * 16383ull * (uint64_t)S;
+    int bits = 0;
+    while ((hmax >> bits) != 0) bits++;
+    int sa_ = std::min(14, 32 - bits);
+    if (sa_ < 0) sa_ = 0;
+    P->sa = (uint32_t)sa_;
+    P->sb = (uint32_t)(14 - sa_);
+  }
+  // weights are W_s = round(w_s * scale) <= 2^28 - 1, with the scale chosen such that the pseudocount 0.5 is an
+  // integer number M of count units (2^sb weight units each): scale = M * 2^(sb+1)
+  {
+    const double unit2 = std::ldexp(1.0, (int)P->sb + 1);
+    double M = std::floor(268435455.0 / wmax / unit2);
+    if (M < 1) return set_error(LDW_ERR_UNSUPPORTED, "largest weight %g too large for the fixed-point count unit", wmax);
+    if (M > 1073741823.0) M = 1073741823.0;
+    P->M = (uint32_t)M;
+    P->scale = M * unit2;
+    // all cells of a table plus their pseudocounts must fit 32 bits: (neff + 12.5) * scale / 2^sb < 2^32
+    if ((neff + 12.5) * P->scale / std::ldexp(1.0, (int)P->sb) >= 4294967295.0) {
+      // shrink the unit until it fits (loses weight bits only for pathological weight vectors, e.g. neff << 1)
+      while (P->M > 1 && (neff + 12.5) * (P->M * unit2) / std::ldexp(1.0, (int)P->sb) >= 4294967295.0) P->M >>= 1;
+      P->scale = P->M * unit2;
+    }
+  }
   P->Kpad = round_up(S, 128);
   std::vector<uint8_t> da(16384), db(16384);
   {
@@ -179,17 +207,6 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   if (sumH > 0x7fffffffLL || sumL > 0x7fffffffLL) return set_error(LDW_ERR_UNSUPPORTED, "too many sequences for int32 accumulation (nseq=%lld)", (long long)S);
   P->neffH = (int32_t)sumH;
   P->neffL = (int32_t)sumL;
-  {
-    // H < 16384 * S: shift it up as far as 32 bits allow and drop the matching low bits of L
-    uint64_t hmax = 16383ull * (uint64_t)S;
-    int bits = 0;
-    while ((hmax >> bits) != 0) bits++;
-    int sa_ = std::min(14, 32 - bits);
-    if (sa_ < 0) sa_ = 0;
-    P->sa = (uint32_t)sa_;
-    P->sb = (uint32_t)(14 - sa_);
-  }
-
   // ---- upload codes, per-SNP allele statistics
   LDW_TRY(P->d_codes.alloc((size_t)n * S));
   LDW_TRY(P->d_mask.alloc((size_t)n));
@@ -274,7 +291,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
     int wpb = 8;
     mi_build_rec_kernel<<<(unsigned)((slot + wpb - 1) / wpb), wpb * 32, 0, st>>>(
         P->d_codes.as<uint8_t>(), S, d_slot_snp.as<int32_t>(), slot, P->d_mask.as<uint8_t>(), P->d_w.as<double>(),
-        d_wH.as<int32_t>(), d_wL.as<int32_t>(), P->d_rec.as<Rec>(), slot, P->d_p64.as<double>(), P->sa, P->sb);
+        d_wH.as<int32_t>(), d_wL.as<int32_t>(), P->d_rec.as<Rec>(), slot, P->d_p64.as<double>(), P->sa, P->sb, P->M);
     LDW_CUDA(cudaGetLastError());
   }
   size_t op_bytes = (size_t)std::max<int64_t>(row, 128) * P->Kpad;
@@ -587,7 +604,8 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
   sp.rtl_arr = D.rtl.as<uint8_t>();
   sp.sa = P->sa;
   sp.sb = P->sb;
-  sp.kT = (float)(std::ldexp(1.0, (int)P->sb) / P->scale);
+  sp.kT = (float)(std::ldexp(1.0, (int)P->sb) / P->scale);  // == 0.5 / M
+  sp.M = P->M;
   for (int a = 0; a < 4; a++)
     for (int b = 0; b < 4; b++) {
       double ri = a + 2, rj = b + 2;

@@ -7,7 +7,8 @@ namespace ldw {
 
 // One record per (slot, variant): everything the epilogue needs to know about one SNP.
 //   T   : fixed-point weighted marginals of the SNP's allele slots q = 0..r-1 in the epilogue's count unit
-//         (floor(V / 2^sb), V = the exact 30-bit fixed-point sum), 0 for q >= r.  The last observed allele (slot r-1)
+//         (floor(V / 2^sb), V = the exact fixed-point sum) PLUS r' * M, the pseudocounts of the r' cells of that row of
+//         the joint table (M = 0.5 in count units, r' = variant + 2); 0 for q >= r.  The last observed allele (slot r-1)
 //         is the "complement" slot whose joint counts are derived by subtraction instead of from the GEMM.
 //   q   : p_q + 0.5 r' for r' = variant+2 (r of the partner SNP); rp = 1/q.
 // Layout: four 16-byte vectors {T0..T3} {rp0..rp3} {q0..q3} {T4, rp4, q4, -}; kinds with at most four allele slots
@@ -74,6 +75,7 @@ struct ScanParams {
   const uint8_t* rtl_arr;  // r of to-list by local index
   float kT;               // joint count = t * kT with t = (H << sa) + (L >> sb) = floor(V / 2^sb)
   uint32_t sa, sb;
+  uint32_t M;             // the pseudocount 0.5 in count units (kT = 0.5 / M exactly): cells are evaluated as t + M
   float den[4][4];          // neff + 0.5 r_i r_j
   float ln2_over_den[4][4];
   float q0[4][4];           // 0.25 r_i r_j / den
