@@ -147,6 +147,35 @@ __device__ __forceinline__ float mi_term(float acc, uint32_t t, float ra, float 
   return fmaf(x, lg2_fast(ratio), acc);
 }
 
+// One row of the joint table (NB cells sharing the row constant ra).  In the Q1 form the reciprocals of the NB
+// denominators are taken two at a time -- 1/d0 = d1 / (d0 d1), 1/d1 = d0 / (d0 d1) -- which trades every second
+// MUFU.RCP for three FMULs: the MUFU pipe, not the issue slots, is what the epilogue waits for.
+template <bool QC, int NB>
+__device__ __forceinline__ float mi_row(float acc, const uint32_t (&t)[NB], float ra, const float (&rb)[NB], float dq) {
+  if constexpr (!QC) {
+#pragma unroll
+    for (int b = 0; b < NB; b++) acc = mi_term<false>(acc, t[b], ra, rb[b], dq);
+    return acc;
+  } else {
+    float d[NB], inv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; b++) d[b] = fmaf(ra, rb[b], dq);
+#pragma unroll
+    for (int b = 0; b + 1 < NB; b += 2) {
+      const float r = rcp_fast(d[b] * d[b + 1]);
+      inv[b] = r * d[b + 1];
+      inv[b + 1] = r * d[b];
+    }
+    if (NB & 1) inv[NB - 1] = rcp_fast(d[NB - 1]);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      const float x = __uint2float_rn(t[b]);
+      acc = fmaf(x, lg2_fast(x * inv[b]), acc);
+    }
+    return acc;
+  }
+}
+
 // Rare path (a long-range candidate somewhere in the warp): reads its parameters straight from the kernel parameters.
 __device__ __noinline__ void lr_emit(const ScanParams& p, bool em, int il, int jl, float mi, int lane) {
   const unsigned bal = __ballot_sync(0xffffffffu, em);
@@ -263,39 +292,41 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
   }
 #pragma unroll
   for (int a = 0; a < PA; a++) {
-    uint32_t rsum[JC];
+    uint32_t row[JC][RB];
 #pragma unroll
-    for (int jj = 0; jj < JC; jj++) rsum[jj] = 0;
+    for (int jj = 0; jj < JC; jj++) {
+      uint32_t rsum = 0;
 #pragma unroll
-    for (int b = 0; b < PB; b++) {
-#pragma unroll
-      for (int jj = 0; jj < JC; jj++) {
+      for (int b = 0; b < PB; b++) {
         const uint32_t t = H[a][b][jj] * k.mul_a + ((L[a][b][jj] >> k.sb) + k.M);  // count + pseudocount
-        rsum[jj] += t;
+        rsum += t;
         col[jj][b] += t;
-        acc[jj] = mi_term<QC>(acc[jj], t, k.rpad[a], __uint_as_float(rpj[jj][b]), dq[jj]);
+        row[jj][b] = t;
       }
+      row[jj][PB] = k.Ti[a] - rsum;
+      tot[jj] += rsum;
     }
 #pragma unroll
     for (int jj = 0; jj < JC; jj++) {
-      acc[jj] = mi_term<QC>(acc[jj], k.Ti[a] - rsum[jj], k.rpad[a], __uint_as_float(rpj[jj][PB]), dq[jj]);
-      tot[jj] += rsum[jj];
+      float rbv[RB];
+#pragma unroll
+      for (int b = 0; b < RB; b++) rbv[b] = __uint_as_float(rpj[jj][b]);
+      acc[jj] = mi_row<QC, RB>(acc[jj], row[jj], k.rpad[a], rbv, dq[jj]);
     }
   }
 #pragma unroll
-  for (int b = 0; b < PB; b++)
-#pragma unroll
-    for (int jj = 0; jj < JC; jj++)
-      acc[jj] = mi_term<QC>(acc[jj], tj[jj][b] - col[jj][b], k.rpad[PA], __uint_as_float(rpj[jj][b]), dq[jj]);
-#pragma unroll
   for (int jj = 0; jj < JC; jj++) {
-    uint32_t sj = 0;
+    uint32_t row[RB], sj = 0;
+    float rbv[RB];
 #pragma unroll
-    for (int b = 0; b < PB; b++) sj += tj[jj][b];
+    for (int b = 0; b < PB; b++) { row[b] = tj[jj][b] - col[jj][b]; sj += tj[jj][b]; }
+#pragma unroll
+    for (int b = 0; b < RB; b++) rbv[b] = __uint_as_float(rpj[jj][b]);
     // every marginal carries the pseudocounts of its row / column, so the corner comes out as count + M; the count
     // itself can be slightly negative (floor semantics of the other cells): clamp it at zero
     const int corner = (int)(k.Ti[PA] + tot[jj] - sj);
-    acc[jj] = mi_term<QC>(acc[jj], (uint32_t)max(corner, (int)k.M), k.rpad[PA], __uint_as_float(rpj[jj][PB]), dq[jj]);
+    row[PB] = (uint32_t)max(corner, (int)k.M);
+    acc[jj] = mi_row<QC, RB>(acc[jj], row, k.rpad[PA], rbv, dq[jj]);
   }
   // ---- classification and emission: tile-uniform branches only; the per-lane work is predicated
   float mi[JC];
