@@ -193,6 +193,100 @@ __global__ void mi_refine_cand_kernel(RefineParams P, const Cand* __restrict__ c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pre-selection on the fp32 values the scan kernel produced.  The exact (fp64) K-th largest MI of a block lies within
+// eps (the fp32 epilogue's error, < 5e-7 measured) of the K-th largest fp32 value v32, and every candidate whose exact
+// value reaches it has an fp32 value >= v32 - 2 eps.  So only the candidates with mi32 >= v32 - delta (delta = 4e-6)
+// have to be refined and ranked exactly: about K of them instead of every collected candidate (4-30 x K).  Candidates
+// below the FINAL candidate threshold are an incomplete sample of their MI range (the threshold rose while they were
+// being collected) and never take part.  Single CTA; MSB-first radix select on order-preserving 32-bit keys.
+__device__ __forceinline__ uint32_t fkey(float v) {
+  uint32_t b = __float_as_uint(v);
+  return (b >> 31) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+__global__ void __launch_bounds__(1024) mi_presel_kernel(const Cand* __restrict__ cand, const uint32_t* __restrict__ count,
+                                                         uint32_t cap, const uint32_t* __restrict__ tcand_bits, int emit_all,
+                                                         unsigned long long k_lo, float delta, Cand* vcand, uint32_t* vcount) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bc[2];
+  __shared__ uint32_t s_nvalid;
+  const uint32_t n = *count < cap ? *count : cap;
+  const float tc = emit_all ? -3.0e38f : __uint_as_float(*tcand_bits);
+  if (threadIdx.x == 0) s_nvalid = 0;
+  __syncthreads();
+  {
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) c += (cand[i].mi >= tc) ? 1u : 0u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_nvalid, c);
+  }
+  __syncthreads();
+  float lim = tc;  // fewer valid candidates than the rank asked for: pass them all on, the selection reports it
+  if ((unsigned long long)s_nvalid >= k_lo && k_lo >= 1) {
+    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k_lo;
+    for (int byte = 3; byte >= 0; byte--) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float v = cand[i].mi;
+        if (v >= tc) {
+          const uint32_t k = fkey(v);
+          if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        uint32_t cum = 0;
+        int d = 255;
+        for (; d > 0; d--) {
+          if (cum + hist[d] >= remaining) break;
+          cum += hist[d];
+        }
+        bc[0] = (uint32_t)d;
+        bc[1] = remaining - cum;
+      }
+      __syncthreads();
+      prefix |= bc[0] << (8 * byte);
+      mask |= 0xFFu << (8 * byte);
+      remaining = bc[1];
+      __syncthreads();
+    }
+    const float v32 = fkey_inv(prefix);
+    lim = fmaxf(tc, v32 - delta);
+  }
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+    const uint32_t i = i0 + threadIdx.x;
+    Cand c;
+    bool take = false;
+    if (i < n) { c = cand[i]; take = (c.mi >= lim) && (c.mi >= tc); }
+    const unsigned bal = __ballot_sync(0xffffffffu, take);
+    if (bal) {
+      uint32_t base = 0;
+      if (lane == __ffs(bal) - 1) base = atomicAdd(vcount, (uint32_t)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+      if (take) vcand[base + (uint32_t)__popc(bal & ((1u << lane) - 1))] = c;
+    }
+  }
+}
+
+// fp64 refinement of a compact candidate list (one warp per pair).
+__global__ void mi_refine_list_kernel(RefineParams P, const Cand* __restrict__ list, const uint32_t* __restrict__ n_ptr, double* vmi) {
+  __shared__ double acc_s[REFINE_WARPS][32 * 25];
+  const uint32_t n = *n_ptr;
+  const int lane = threadIdx.x & 31;
+  double* acc = acc_s[threadIdx.x >> 5];
+  for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
+    const Cand c = list[i];
+    const double v = refine_pair(P, c.il, c.jl, lane, acc);
+    if (lane == 0) vmi[i] = v;
+  }
+}
+
 // Start of a block's long-range collection: counters cleared, histogram cleared, candidate threshold seeded from
 // the chained estimate of the previous block (or 0 = collect until the histogram can place a threshold).
 __global__ void mi_block_begin_kernel(uint32_t* state /*count, tcand, overflow, -, -, vcount*/, uint32_t* hist,

@@ -1017,8 +1017,12 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       LDW_CUDA(cudaEventRecord(L.scan_done, st));
       LDW_CUDA(cudaStreamWaitEvent(sst, L.scan_done, 0));
       RefineParams R = make_refine_params(P, D, H, cfg);
-      mi_refine_cand_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, sst>>>(R, L.cand.as<Cand>(), d_count, cap, d_tcand, emit_all,
-                                                                  L.vcand.as<Cand>(), L.mi64.as<double>(), d_count + 5);
+      // candidates that can reach the exact K-th largest value (fp32 pre-selection), then their fp64 refinement
+      n_launches++;
+      mi_presel_kernel<<<1, 1024, 0, sst>>>(L.cand.as<Cand>(), d_count, cap, d_tcand, emit_all, (unsigned long long)s.k_lo, 4e-6f,
+                                           L.vcand.as<Cand>(), d_count + 5);
+      LDW_CUDA(cudaGetLastError());
+      mi_refine_list_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, sst>>>(R, L.vcand.as<Cand>(), d_count + 5, L.mi64.as<double>());
       LDW_CUDA(cudaGetLastError());
       SelectParams q;
       memset(&q, 0, sizeof(q));
