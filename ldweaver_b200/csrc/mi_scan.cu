@@ -64,14 +64,15 @@ struct ScanWS {
   BlockDev ring[RING];
   BlockHost hring[RING];
   DevBuf d_dbg;
-  // long-range collection state, double-buffered: block b's candidates are refined and selected on the select
-  // stream while block b+1 is being scanned into the other buffer
+  // long-range collection state, triple-buffered: block b's candidates are pre-selected, refined and ranked on the
+  // select stream while blocks b+1 and b+2 are being scanned into the other buffers
   struct LrBuf {
     DevBuf cand, vcand, mi64, state /*count, tcand, overflow, -, -, vcount*/, hist;
     cudaEvent_t scan_done = nullptr, sel_done = nullptr;
     bool used = false, chain_valid = false;
-  } lr[2];
-  DevBuf d_state /*-, -, -, kept_overflow, -, -, -, -, chain[2]*/, d_sr_f32, d_dense;
+  } lr[3];
+  static constexpr int NLR = 3;
+  DevBuf d_state /*-, -, -, kept_overflow, -, -, -, -, chain[3]*/, d_sr_f32, d_dense;
   // written by the selection kernels / the publish kernel straight into host memory (pinned memory is device-
   // accessible under unified addressing): no small device->host copy has to queue behind the link columns
   PinnedBuf h_results, h_pub;
@@ -618,9 +619,11 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
 }
 
 // Launch the scan kernel: persistent, one CTA per SM.
-int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st) {
+// `reserve`: SMs left free for the single-CTA selection kernels of earlier blocks (the persistent scan CTAs hold every
+// SM they run on for the whole launch, so anything else would otherwise wait for the gap between two scans).
+int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st, int reserve = 0) {
   if (sp.n_tiles <= 0) return 0;
-  int grid = std::min<int>(sp.n_tiles, P->ctx->num_sms);
+  int grid = std::min<int>(sp.n_tiles, std::max(1, P->ctx->num_sms - reserve));
   if (sp.dbg) mi_scan_kernel<true><<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
   else mi_scan_kernel<false><<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
   LDW_CUDA(cudaGetLastError());
@@ -920,7 +923,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   LDW_TRY(W->d_sr.ensure(total_sr));
   LDW_CUDA(cudaMemsetAsync(W->d_kept_count.p, 0, 16, st));
   uint32_t* d_kept_overflow = W->d_state.as<uint32_t>() + 3;
-  uint32_t* d_chain2 = W->d_state.as<uint32_t>() + 8;  // [2]: threshold seeds, one per buffer parity
+  uint32_t* d_chain2 = W->d_state.as<uint32_t>() + 8;  // [3]: threshold seeds, one per candidate buffer
   LDW_CUDA(cudaMemsetAsync(W->d_state.p, 0, 64, st));
   cudaStream_t sst = P->ctx->select_stream;
 
@@ -943,6 +946,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     if (e) dbg_block = atoll(e);
   }
   double host_prep_ms = 0;
+  int scan_reserve = 3;  // SMs left to the selection stream (presel, refine, select of earlier blocks); 3 measured best at C2
+  if (const char* e = getenv("LDW_SCAN_RESERVE")) scan_reserve = atoi(e);
   // b: index into this rank's block list (output offsets, results); seq: position in the execution order (ring slots)
   auto run_block = [&](size_t b, size_t seq, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
     Sel& s = sel[b];
@@ -953,11 +958,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     // host staging + device arrays of this ring entry are free again
     if (D.used) LDW_CUDA(cudaEventSynchronize(D.done));
     if (D.used2) { LDW_CUDA(cudaEventSynchronize(D.done2)); D.used2 = false; }
-    ScanWS::LrBuf& L = W->lr[seq & 1];
+    ScanWS::LrBuf& L = W->lr[seq % ScanWS::NLR];
     uint32_t* d_count = L.state.as<uint32_t>();
     uint32_t* d_tcand = d_count + 1;
     uint32_t* d_overflow = d_count + 2;
-    uint32_t* d_chain = d_chain2 + (seq & 1);  // written by the selection two blocks earlier (same buffer parity)
+    uint32_t* d_chain = d_chain2 + (seq % ScanWS::NLR);  // written by the selection three blocks earlier (same buffer)
     auto hp0 = std::chrono::steady_clock::now();
     int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, H);
     if (e > 1) return e;
@@ -979,7 +984,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     const int emit_all = force_emit_all || s.emit_all;
     uint32_t cap = cap_override ? cap_override : s.cap;
     if (lr) {
-      // this buffer's previous selection (block b - 2) must be done before its counters are cleared
+      // this buffer's previous selection (three blocks earlier) must be done before its counters are cleared
       if (L.used) LDW_CUDA(cudaStreamWaitEvent(st, L.sel_done, 0));
       mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, L.hist.as<uint32_t>(), d_chain, (use_chain && L.chain_valid && !emit_all) ? 1 : 0);
       LDW_CUDA(cudaGetLastError());
@@ -1004,7 +1009,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       kev.push_back(k0);
       kev.push_back(k1);
       LDW_CUDA(cudaEventRecord(k0, st));
-      LDW_TRY(launch_scan(P, sp, st));
+      LDW_TRY(launch_scan(P, sp, st, lr ? scan_reserve : 0));
       LDW_CUDA(cudaEventRecord(k1, st));
       n_launches++; n_scan_launches++;
       n_tiles += sp.n_tiles;
@@ -1256,6 +1261,24 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       tk += ms;
     }
     stats_out->t_kernel_ms = tk;
+    if (dbg_timing && kev.size() >= 4) {
+      double gaps = 0, gmax = 0;
+      std::string detail;
+      for (size_t k = 1; k + 1 < kev.size(); k += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, kev[k], kev[k + 1]);
+        gaps += ms;
+        gmax = std::max<double>(gmax, ms);
+        char b[32];
+        snprintf(b, sizeof(b), " %.0f", 1e3 * ms);
+        detail += b;
+      }
+      float first = 0, last = 0;
+      cudaEventElapsedTime(&first, ev0, kev[0]);
+      cudaEventElapsedTime(&last, kev[kev.size() - 1], ev1);
+      fprintf(stderr, "ldw timing: gaps between scan kernels: sum %.3f ms, max %.3f ms; before first %.3f ms, after last %.3f ms; us:%s\n",
+              gaps, gmax, first, last, detail.c_str());
+    }
     stats_out->n_scan_launches = n_scan_launches;
     stats_out->n_launches = n_launches;
     stats_out->n_tiles = n_tiles;
