@@ -848,10 +848,21 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   std::vector<Sel> sel(blocks.size());
   int64_t total_sr = 0, total_pairs = 0, total_lr = 0;
   uint64_t max_cap = 1, sum_keep = 0;
+  int64_t first_guess = -1;
+  int first_rc = -1;
   {
     // block sizes on a few host threads (they gate the first launch), then the serial prefix / rank arithmetic
     std::vector<int> perr(blocks.size(), 0);
-    parallel_for((int64_t)blocks.size(), 8, [&](int64_t b) {
+    // The block that will run first (the first one holding short-range links: diagonal or next to it) gets its full
+    // tables built alongside, into ring slot 0, so the first launch does not wait for them.
+    for (size_t b = 0; b < blocks.size() && first_guess < 0; b++)
+      if (blocks[b].bt - blocks[b].bf <= 1) first_guess = (int64_t)b;
+    if (first_guess < 0 && !blocks.empty()) first_guess = 0;
+    parallel_for((int64_t)blocks.size() + 1, 8, [&](int64_t b) {
+      if (b == (int64_t)blocks.size()) {
+        if (first_guess >= 0) first_rc = prepare_block(P, blocks[first_guess].bf, blocks[first_guess].bt, cfg, W->hring[0]);
+        return;
+      }
       BlockHost tmp;
       int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, tmp, true);
       perr[b] = e;
@@ -964,7 +975,13 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     uint32_t* d_overflow = d_count + 2;
     uint32_t* d_chain = d_chain2 + (seq % ScanWS::NLR);  // written by the selection three blocks earlier (same buffer)
     auto hp0 = std::chrono::steady_clock::now();
-    int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, H);
+    int e;
+    if (seq == 0 && first_guess == (int64_t)b && first_rc >= 0 && first_rc <= 1 && !force_emit_all && !cap_override) {
+      e = first_rc;  // built during pass 1
+      first_rc = -1;
+    } else {
+      e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, H);
+    }
     if (e > 1) return e;
     // the tables travel on the upload stream while earlier blocks are still being scanned
     LDW_TRY(upload_block(P->ctx->upload_stream, D, H));
