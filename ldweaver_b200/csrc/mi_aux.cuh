@@ -220,7 +220,14 @@ __global__ void __launch_bounds__(1024) mi_presel_kernel(const Cand* __restrict_
   __syncthreads();
   {
     uint32_t c = 0;
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) c += (cand[i].mi >= tc) ? 1u : 0u;
+    // four independent loads in flight per thread: these single-CTA passes are latency-bound
+    for (uint32_t i = threadIdx.x; i < n; i += 4 * blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const uint32_t j = i + u * blockDim.x; v[u] = j < n ? cand[j].mi : -3.0e38f; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) c += (i + u * blockDim.x < n && v[u] >= tc) ? 1u : 0u;
+    }
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_nvalid, c);
   }
@@ -231,11 +238,16 @@ __global__ void __launch_bounds__(1024) mi_presel_kernel(const Cand* __restrict_
     for (int byte = 3; byte >= 0; byte--) {
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
       __syncthreads();
-      for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const float v = cand[i].mi;
-        if (v >= tc) {
-          const uint32_t k = fkey(v);
-          if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
+      for (uint32_t i = threadIdx.x; i < n; i += 4 * blockDim.x) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { const uint32_t j = i + u * blockDim.x; v[u] = j < n ? cand[j].mi : -3.0e38f; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (i + u * blockDim.x < n && v[u] >= tc) {
+            const uint32_t k = fkey(v[u]);
+            if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
+          }
         }
       }
       __syncthreads();
@@ -370,9 +382,17 @@ __device__ uint64_t select_kth_largest(const double* v, uint32_t n, uint64_t K, 
   for (int byte = 7; byte >= 0; byte--) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-      uint64_t k = dkey(v[i]);
-      if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
+    for (uint32_t i = threadIdx.x; i < n; i += 4 * blockDim.x) {
+      double x[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const uint32_t j = i + u * blockDim.x; x[u] = j < n ? v[j] : 0.0; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (i + u * blockDim.x < n) {
+          const uint64_t k = dkey(x[u]);
+          if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
+        }
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
