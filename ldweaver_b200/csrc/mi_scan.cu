@@ -934,7 +934,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   LDW_TRY(W->d_sr.ensure(total_sr));
   LDW_CUDA(cudaMemsetAsync(W->d_kept_count.p, 0, 16, st));
   uint32_t* d_kept_overflow = W->d_state.as<uint32_t>() + 3;
-  uint32_t* d_chain2 = W->d_state.as<uint32_t>() + 8;  // [3]: threshold seeds, one per candidate buffer
+  // Threshold seed for the next blocks: ONE word, overwritten by every selection and read by every block's begin
+  // kernel, whichever selection finished last (usually one or two blocks back).  The value read only steers how many
+  // candidates get collected -- results do not depend on it (the selection verifies completeness and is exact) -- so
+  // the unordered read across the two streams is harmless; zero (nothing selected yet) means "collect from zero".
+  uint32_t* d_chain2 = W->d_state.as<uint32_t>() + 8;
   LDW_CUDA(cudaMemsetAsync(W->d_state.p, 0, 64, st));
   cudaStream_t sst = P->ctx->select_stream;
 
@@ -973,7 +977,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     uint32_t* d_count = L.state.as<uint32_t>();
     uint32_t* d_tcand = d_count + 1;
     uint32_t* d_overflow = d_count + 2;
-    uint32_t* d_chain = d_chain2 + (seq % ScanWS::NLR);  // written by the selection three blocks earlier (same buffer)
+    uint32_t* d_chain = d_chain2;
     auto hp0 = std::chrono::steady_clock::now();
     int e;
     if (seq == 0 && first_guess == (int64_t)b && first_rc >= 0 && first_rc <= 1 && !force_emit_all && !cap_override) {
@@ -1003,10 +1007,9 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     if (lr) {
       // this buffer's previous selection (three blocks earlier) must be done before its counters are cleared
       if (L.used) LDW_CUDA(cudaStreamWaitEvent(st, L.sel_done, 0));
-      mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, L.hist.as<uint32_t>(), d_chain, (use_chain && L.chain_valid && !emit_all) ? 1 : 0);
+      mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, L.hist.as<uint32_t>(), d_chain, (use_chain && !emit_all) ? 1 : 0);
       LDW_CUDA(cudaGetLastError());
       n_launches++;
-      if (!emit_all) L.chain_valid = true;
       sp.cand = L.cand.as<Cand>();
       sp.cand_cap = cap;
       sp.cand_count = d_count;
