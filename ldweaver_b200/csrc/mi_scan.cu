@@ -136,6 +136,14 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   LDW_CUDA(cudaEventCreate(&e0));
   LDW_CUDA(cudaEventCreate(&e1));
   LDW_CUDA(cudaEventRecord(e0, st));
+  const bool dbg_t = getenv("LDW_DBG_TIMING") != nullptr;
+  auto bt0 = std::chrono::steady_clock::now();
+  auto blap = [&](const char* what) {
+    if (!dbg_t) return;
+    auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "ldw timing: plan %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - bt0).count());
+    bt0 = t;
+  };
   P->pos.assign(pos, pos + n);
   P->paint.assign(paint, paint + n);
   P->w.assign(hdw, hdw + S);
@@ -208,6 +216,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   if (sumH > 0x7fffffffLL || sumL > 0x7fffffffLL) return set_error(LDW_ERR_UNSUPPORTED, "too many sequences for int32 accumulation (nseq=%lld)", (long long)S);
   P->neffH = (int32_t)sumH;
   P->neffL = (int32_t)sumL;
+  blap("weights/digits");
   // ---- upload codes, per-SNP allele statistics
   LDW_TRY(P->d_codes.alloc((size_t)n * S));
   LDW_TRY(P->d_mask.alloc((size_t)n));
@@ -221,6 +230,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   LDW_CUDA(cudaMemcpyAsync(P->r.data(), P->d_r.p, (size_t)n, cudaMemcpyDeviceToHost, st));
   LDW_CUDA(cudaMemcpyAsync(P->mask.data(), P->d_mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
   LDW_CUDA(cudaStreamSynchronize(st));
+  blap("upload + allele stats");
   for (int64_t i = 0; i < n; i++)
     if (P->r[i] < 2)
       return set_error(LDW_ERR_UNSUPPORTED, "SNP %lld is monomorphic (r=%d); the reference's filters never retain such sites "
@@ -270,6 +280,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
           }
       }
     }
+  blap("slots + row_info (host)");
   // ---- device: weights, records, operands
   DevBuf d_slot_snp, d_wH, d_wL, d_row_info;
   LDW_TRY(P->d_w.alloc((size_t)S * 8));
@@ -328,6 +339,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   }
   LDW_CUDA(cudaEventRecord(e1, st));
   LDW_CUDA(cudaStreamSynchronize(st));
+  blap("records + pack + tmaps");
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   P->t_pack_ms = ms;
