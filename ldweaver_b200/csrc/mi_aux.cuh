@@ -208,6 +208,62 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
   return __uint_as_float((k >> 31) ? (k & 0x7FFFFFFFu) : ~k);
 }
 
+// k-th largest (1-based) fp32 MI among the candidates with mi >= tc.  Whole CTA (any block size), MSB-first radix select
+// on order-preserving keys; hist: 256 words, bc: 2 words of shared memory.  Four loads in flight per thread: these
+// single-CTA passes are latency-bound.
+__device__ float kth_largest_f32(const Cand* __restrict__ cand, uint32_t n, float tc, uint32_t kth, uint32_t* hist, uint32_t* bc) {
+  uint32_t prefix = 0, mask = 0, remaining = kth;
+  for (int byte = 3; byte >= 0; byte--) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += 4 * blockDim.x) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const uint32_t j = i + u * blockDim.x; v[u] = j < n ? cand[j].mi : -3.0e38f; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (i + u * blockDim.x < n && v[u] >= tc) {
+          const uint32_t k = fkey(v[u]);
+          if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t cum = 0;
+      int d = 255;
+      for (; d > 0; d--) {
+        if (cum + hist[d] >= remaining) break;
+        cum += hist[d];
+      }
+      bc[0] = (uint32_t)d;
+      bc[1] = remaining - cum;
+    }
+    __syncthreads();
+    prefix |= bc[0] << (8 * byte);
+    mask |= 0xFFu << (8 * byte);
+    remaining = bc[1];
+    __syncthreads();
+  }
+  return fkey_inv(prefix);
+}
+
+// Pilot seed for the first block of a scan call.  A few dozen tiles spread over the block were scanned with every
+// long-range pair collected; the rank K of the block scales to K * (pairs collected / long-range pairs of the block)
+// in that sample, and 0.85 x the sample's value at that rank seeds the block's candidate threshold (the MI tail is
+// steep: a 15 % error in the rank moves the value by ~2 %).  Without it every CTA's first tile is collected whole
+// (~6 x 10^5 candidates per block).  Only steers how much is collected; the selection stays exact and self-checking.
+__global__ void __launch_bounds__(1024) mi_pilot_seed_kernel(const Cand* __restrict__ cand, const uint32_t* __restrict__ count,
+                                                             uint32_t cap, unsigned long long k_lo, double n_lr, uint32_t* chain_bits) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t bc[2];
+  const uint32_t n = *count < cap ? *count : cap;
+  const double ks = (double)k_lo * (double)n / n_lr;
+  if (!(ks >= 16.0) || n < 1024) return;  // too small a sample: start from zero as before
+  const float v = kth_largest_f32(cand, n, -3.0e38f, (uint32_t)ks, hist, bc);
+  if (threadIdx.x == 0 && v > 0.f) *chain_bits = __float_as_uint(0.85f * v);
+}
+
 __global__ void __launch_bounds__(1024) mi_presel_kernel(const Cand* __restrict__ cand, const uint32_t* __restrict__ count,
                                                          uint32_t cap, const uint32_t* __restrict__ tcand_bits, int emit_all,
                                                          unsigned long long k_lo, float delta, Cand* vcand, uint32_t* vcount) {
@@ -234,40 +290,7 @@ __global__ void __launch_bounds__(1024) mi_presel_kernel(const Cand* __restrict_
   __syncthreads();
   float lim = tc;  // fewer valid candidates than the rank asked for: pass them all on, the selection reports it
   if ((unsigned long long)s_nvalid >= k_lo && k_lo >= 1) {
-    uint32_t prefix = 0, mask = 0, remaining = (uint32_t)k_lo;
-    for (int byte = 3; byte >= 0; byte--) {
-      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-      __syncthreads();
-      for (uint32_t i = threadIdx.x; i < n; i += 4 * blockDim.x) {
-        float v[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) { const uint32_t j = i + u * blockDim.x; v[u] = j < n ? cand[j].mi : -3.0e38f; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (i + u * blockDim.x < n && v[u] >= tc) {
-            const uint32_t k = fkey(v[u]);
-            if ((k & mask) == prefix) atomicAdd(&hist[(k >> (8 * byte)) & 255], 1u);
-          }
-        }
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        uint32_t cum = 0;
-        int d = 255;
-        for (; d > 0; d--) {
-          if (cum + hist[d] >= remaining) break;
-          cum += hist[d];
-        }
-        bc[0] = (uint32_t)d;
-        bc[1] = remaining - cum;
-      }
-      __syncthreads();
-      prefix |= bc[0] << (8 * byte);
-      mask |= 0xFFu << (8 * byte);
-      remaining = bc[1];
-      __syncthreads();
-    }
-    const float v32 = fkey_inv(prefix);
+    const float v32 = kth_largest_f32(cand, n, tc, (uint32_t)k_lo, hist, bc);
     lim = fmaxf(tc, v32 - delta);
   }
   const int lane = threadIdx.x & 31;

@@ -52,6 +52,7 @@ struct BlockHost {  // pageable staging reused per ring entry (kept alive until 
   std::vector<int32_t> from_idx, to_idx;
   std::vector<uint8_t> rfl, rtl;
   int32_t nf = 0, nt = 0;
+  int32_t n_real_tiles = 0;  // tiles [n_real_tiles, tiles.size()) are the pilot sample (copies of real tiles)
   int diag = 0, ragged = 0;
   int64_t n_pairs = 0, n_sr = 0, n_lr = 0;
 };
@@ -568,6 +569,12 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
         }
     }
   }
+  // pilot sample: up to 64 tiles spread evenly over the list (kinds in proportion), appended as copies
+  H.n_real_tiles = (int32_t)H.tiles.size();
+  if (!cfg.dense && H.n_real_tiles >= 1024) {
+    const int np = 64;
+    for (int k = 0; k < np; k++) H.tiles.push_back(H.tiles[(size_t)((2 * k + 1) * (int64_t)H.n_real_tiles / (2 * np))]);
+  }
   return 0;
 }
 
@@ -601,7 +608,7 @@ int upload_block(cudaStream_t st, BlockDev& D, const BlockHost& H) {  // st: the
 void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& H, const ScanCfg& cfg, ScanParams& sp) {
   memset(&sp, 0, sizeof(sp));
   sp.tiles = D.tiles.as<TileDesc>();
-  sp.n_tiles = (int32_t)H.tiles.size();
+  sp.n_tiles = H.n_real_tiles;
   sp.rec = P->d_rec.as<Rec>();
   sp.rec_vstride = P->nslots;
   sp.rowdyn = D.rowdyn.as<RowDyn>();
@@ -1019,6 +1026,22 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     if (lr) {
       // this buffer's previous selection (three blocks earlier) must be done before its counters are cleared
       if (L.used) LDW_CUDA(cudaStreamWaitEvent(st, L.sel_done, 0));
+      const int n_pilot = (int)H.tiles.size() - H.n_real_tiles;
+      if (seq == 0 && use_chain && !emit_all && n_pilot > 0) {
+        // first block of the call: nothing has been selected yet, so estimate its threshold from a pilot sample
+        mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, L.hist.as<uint32_t>(), d_chain, 0);
+        ScanParams pp = sp;
+        pp.tiles = D.tiles.as<TileDesc>() + H.n_real_tiles;
+        pp.n_tiles = n_pilot;
+        pp.cand = L.cand.as<Cand>(); pp.cand_cap = cap; pp.cand_count = d_count; pp.tcand_bits = d_tcand;
+        pp.hist = L.hist.as<uint32_t>(); pp.kprime = s.kprime; pp.delta = s.delta ? s.delta : 1; pp.overflow = d_overflow;
+        pp.emit_all = 1;
+        pp.dbg = nullptr;
+        LDW_TRY(launch_scan(P, pp, st, 0));
+        mi_pilot_seed_kernel<<<1, 1024, 0, st>>>(L.cand.as<Cand>(), d_count, cap, (unsigned long long)s.k_lo, (double)s.n_lr, d_chain);
+        LDW_CUDA(cudaGetLastError());
+        n_launches += 3;
+      }
       mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, L.hist.as<uint32_t>(), d_chain, (use_chain && !emit_all) ? 1 : 0);
       LDW_CUDA(cudaGetLastError());
       n_launches++;
@@ -1045,8 +1068,10 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       LDW_CUDA(cudaEventRecord(k1, st));
       n_launches++; n_scan_launches++;
       n_tiles += sp.n_tiles;
-      for (const TileDesc& td : H.tiles)  // 4 K-passes x 2 ops/MAC x 128 rows x (PA*PB*NJ) columns x Kpad
+      for (int32_t ti = 0; ti < H.n_real_tiles; ti++) {  // 4 K-passes x 2 ops/MAC x 128 rows x (PA*PB*NJ) columns x Kpad
+        const TileDesc& td = H.tiles[ti];
         exec_ops += 8.0 * 128.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;  // 2 passes x 2 halves
+      }
     }
     if (lr) {
       // fp64 refinement + exact selection on the select stream, overlapping the next block's scan
