@@ -980,8 +980,12 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     if (e) dbg_block = atoll(e);
   }
   double host_prep_ms = 0;
-  int scan_reserve = 3;  // SMs left to the selection stream (presel, refine, select of earlier blocks); 3 measured best at C2
+  int scan_reserve = 2;  // SMs left to the selection stream (presel, refine, select of earlier blocks); 1-3 within 1 % at C2
   if (const char* e = getenv("LDW_SCAN_RESERVE")) scan_reserve = atoi(e);
+  // test hook: force every block's first attempt to start from this candidate threshold (a value above the true
+  // threshold makes the selection fail its completeness check and exercises the re-run path)
+  float force_seed = -1.f;
+  if (const char* e = getenv("LDW_DBG_FORCE_SEED")) force_seed = (float)atof(e);
   // b: index into this rank's block list (output offsets, results); seq: position in the execution order (ring slots)
   auto run_block = [&](size_t b, size_t seq, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
     Sel& s = sel[b];
@@ -1041,6 +1045,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
         mi_pilot_seed_kernel<<<1, 1024, 0, st>>>(L.cand.as<Cand>(), d_count, cap, (unsigned long long)s.k_lo, (double)s.n_lr, d_chain);
         LDW_CUDA(cudaGetLastError());
         n_launches += 3;
+      }
+      if (force_seed >= 0.f && use_chain && !emit_all) {
+        static_assert(sizeof(float) == 4, "float bits");
+        LDW_CUDA(cudaMemcpyAsync(d_chain, &force_seed, 4, cudaMemcpyHostToDevice, st));
+        LDW_CUDA(cudaStreamSynchronize(st));
       }
       mi_block_begin_kernel<<<1, 256, 0, st>>>(d_count, L.hist.as<uint32_t>(), d_chain, (use_chain && !emit_all) ? 1 : 0);
       LDW_CUDA(cudaGetLastError());

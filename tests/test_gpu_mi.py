@@ -239,3 +239,26 @@ def test_scan_synthetic_medium_vs_oracle():
                             res.lr["pos1"][kk], res.lr["pos2"][kk], res.lr["MI"][kk], L["thr"])
     print("synthetic medium: max |dMI| over SR links", worst, res.stats)
     assert worst < MI_TOL
+
+
+def test_rerun_path_after_a_failed_threshold_seed(monkeypatch):
+    """A candidate-threshold seed above the true threshold makes the selection fail its completeness check; the block
+    is then re-run (first from a zero threshold, then with every long-range pair collected) and must give exactly the
+    result of an undisturbed scan."""
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import synth
+    sy = synth.generate(nseq=300, nsnp=6000, seed=21)
+    snp = ldw.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
+    hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    lra = synth.exact_lr_links_approx(sy.POS, sy.g, 20000.0)
+    plan = ldw.MIPlan(snp, hdw, sy.paint, 2000)
+    ref = plan.scan(sy.g, 20000.0, 5e4, lra)   # may itself re-run a block: the seed comes from whichever block was selected last
+    monkeypatch.setenv("LDW_DBG_FORCE_SEED", "0.5")          # far above any block threshold of this data set
+    got = plan.scan(sy.g, 20000.0, 5e4, lra)
+    monkeypatch.delenv("LDW_DBG_FORCE_SEED")
+    assert got[5]["n_reruns"] > 0
+    for which in (0, 1):
+        for col in ("pos1", "pos2", "clust1", "clust2", "len", "MI", "block"):
+            assert np.array_equal(ref[which][col], got[which][col]), (which, col)
+    assert np.array_equal(ref[3], got[3], equal_nan=True)
+    plan.close()
