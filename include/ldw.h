@@ -184,6 +184,74 @@ LDW_API int ldw_mi_scan(ldw_mi_plan* plan, double g, double sr_dist, double lr_r
 LDW_API int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int append);
 LDW_API int ldw_format_r_real(double x, char* out, int cap);
 
+/* ------------------------------------------------------------------------------------------------
+ * After the scan: the rest of perform_MI_computation, host only -- these take the
+ * link columns where R would see them (host memory) and need no device.
+ *
+ * ldw_sr_postprocess replaces mergeNsort_sr_links(cds_var, sr_links, sr_dist, plt_path, srp_cutoff)
+ *   (R/computePairwiseMI.R:400-495): per cluster c = 1..nclust, the short-range links with clust1 == c or
+ *   clust2 == c (:372-376) and 0 < len < sr_dist (:417-419); 95th percentile (quantile type 7) of MI per distinct
+ *   len (:422); log-log least-squares decay fit (RcppArmadillo::fastLm, :428-429); residuals above the fit, the fitted
+ *   values being subscripted BY THE VALUE of len as the reference does (:448); beta maximum-likelihood fit of the
+ *   positive residuals (fitdistrplus::fitdist(., "beta") = moment start + optim Nelder-Mead, :452);
+ *   srp_max = -pbeta(., lower.tail = F, log.p = T) (:453); links between two clusters kept once, from the cluster
+ *   that gives the larger srp_max (:474-483); sr_links_red = srp_max > srp_cutoff (:494);
+ *   sr_links_ARACNE_check = MI >= min(sr_links_red$MI) (:495).
+ *   The plots and the .rds files the reference also writes (:430-442) are not produced; the fitted curves are returned.
+ *   `sr` is the short-range table of ldw_mi_scan (borrowed).  Everything in ldw_sr_post is library-owned and released
+ *   by ldw_sr_post_free.  Errors (message in ldw_last_error) mirror the R failures: a cluster without links,
+ *   residuals outside [0, 1] ("values must be in [0-1] to fit a beta distribution"), a likelihood that cannot be
+ *   evaluated at the start values.
+ */
+typedef struct ldw_sr_post {
+  int64_t n_df;             /* rows of sr_links_df, in the reference's order */
+  const int32_t* clust_c;   /* cluster whose fit scored the link */
+  const int64_t* row;       /* 0-based row of the link in `sr` */
+  const double* srp_max;
+  int64_t n_red;            /* sr_links_red: 0-based indices into the df rows, ascending */
+  const int64_t* red;
+  int64_t n_chk;            /* sr_links_ARACNE_check: 0-based indices into the df rows, ascending */
+  const int64_t* chk;
+  int32_t nclust;
+  const int64_t* fit_off;   /* nclust + 1 offsets into fit_len / fit_q95 / fit_val (maxvls of each cluster) */
+  const int32_t* fit_len;   /* distinct lengths, ascending */
+  const double* fit_q95;    /* maxvls$max */
+  const double* fit_val;    /* maxvls$fit = exp(fitted) */
+  const double* coef;       /* nclust x {slope, intercept} of log(max) ~ log(len) */
+  const double* shape;      /* nclust x {shape1, shape2} */
+  const double* start;      /* nclust x {shape1, shape2} start values */
+  const int64_t* n_pos;     /* links above the fit, per cluster */
+  const int32_t* nm_evals;  /* Nelder-Mead function evaluations (optim's counts[1]) */
+  const int32_t* nm_fail;   /* optim's convergence code (0, 1 = maxit reached, 10 = degenerate simplex) */
+  void* priv;
+} ldw_sr_post;
+LDW_API int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr_dist, double srp_cutoff, ldw_sr_post* out);
+LDW_API void ldw_sr_post_free(ldw_sr_post* p);
+
+/* Building blocks of ldw_sr_postprocess, exposed for parity tests: stats::optim's Nelder-Mead (restated from R's nmmin)
+ * run on Rosenbrock's function, the example of R's ?optim -- from c(-1.2, 1) R prints par 1.000260 1.000506, value
+ * 8.825241e-08, 195 function evaluations --, and out[i] = -pbeta(x[i], shape1, shape2, lower.tail = F, log.p = T). */
+LDW_API int ldw_nm_rosenbrock(const double* start, double* par_out, double* value_out, int* count_out);
+LDW_API int ldw_neg_log_pbeta_upper(const double* x, int64_t n, double shape1, double shape2, double* out);
+
+/* ldw_run_aracne replaces runARACNE(links_to_check, links_full) (R/io_functions.R:101-164, with .compareToRow,
+ *   .vecPosMatch, .compareTriplet of src/computeMI.cpp:25-79 and .fast_intersect of src/fintersect.cpp:6-33):
+ *   aracne_out[i] = 0 when some third position Y is linked to both ends of link i in `full` with
+ *   MI_i < MI(X,Y) and MI_i < MI(Z,Y) (the first row of `full` holding each pair counts), else 1.
+ *   Positions are doubles as in the R matrices.  Used for the short-range links (R/computePairwiseMI.R:124-126) and
+ *   for the long-range ones (R/lr_analyser.R:101-108).
+ */
+LDW_API int ldw_run_aracne(int64_t n_chk, const double* chk_pos1, const double* chk_pos2, const double* chk_MI, int64_t n_full,
+                   const double* full_pos1, const double* full_pos2, const double* full_MI, uint8_t* aracne_out);
+
+/* ldw_write_sr_tsv writes sr_links.tsv as perform_MI_computation does (R/computePairwiseMI.R:140,
+ *   write.table(sr_links_red, sr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t');
+ *   reader R/io_functions.R:62-63): clust_c pos1 pos2 clust1 clust2 len MI srp_max ARACNE.  `rows` (n of them) index
+ *   the short-range table `sr`; clust_c / srp_max / aracne are parallel to `rows`.
+ */
+LDW_API int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n, const int64_t* rows, const int32_t* clust_c,
+                     const double* srp_max, const double* aracne, int append);
+
 /* Dense MI matrix of one block (debug / parity aid; nf x nt doubles, column-major, fp32-accurate values).
  * from/to are 0-based ascending global SNP ids, as `from`/`to` of perform_MI_computation_ACGTN. */
 LDW_API int ldw_mi_block_dense(ldw_mi_plan* plan, int64_t block_index, double* mi_out, int64_t* nf_out, int64_t* nt_out);

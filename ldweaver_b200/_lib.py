@@ -68,6 +68,22 @@ class ScanStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class SrPost(C.Structure):
+    """struct ldw_sr_post (include/ldw.h)."""
+    _fields_ = [("n_df", i64), ("clust_c", P(C.c_int32)), ("row", P(i64)), ("srp_max", P(f64)),
+                ("n_red", i64), ("red", P(i64)), ("n_chk", i64), ("chk", P(i64)), ("nclust", C.c_int32),
+                ("fit_off", P(i64)), ("fit_len", P(C.c_int32)), ("fit_q95", P(f64)), ("fit_val", P(f64)),
+                ("coef", P(f64)), ("shape", P(f64)), ("start", P(f64)), ("n_pos", P(i64)), ("nm_evals", P(C.c_int32)),
+                ("nm_fail", P(C.c_int32)), ("priv", C.c_void_p)]
+
+
+def copy_array(ptr, n: int, dtype) -> np.ndarray:
+    """Copy n elements out of a library-owned buffer."""
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
+
+
 _lib = None
 
 
@@ -98,6 +114,13 @@ def lib():
     L.ldw_mi_block_dense.argtypes = [C.c_void_p, i64, C.c_void_p, P(i64), P(i64)]
     L.ldw_write_lr_tsv.argtypes = [C.c_char_p, P(Links), C.c_int]
     L.ldw_format_r_real.argtypes = [f64, C.c_char_p, C.c_int]
+    L.ldw_sr_postprocess.argtypes = [P(Links), C.c_int32, f64, f64, P(SrPost)]
+    L.ldw_sr_post_free.argtypes = [P(SrPost)]
+    L.ldw_sr_post_free.restype = None
+    L.ldw_run_aracne.argtypes = [i64, C.c_void_p, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ldw_write_sr_tsv.argtypes = [C.c_char_p, P(Links), i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    L.ldw_nm_rosenbrock.argtypes = [C.c_void_p, C.c_void_p, P(f64), P(C.c_int)]
+    L.ldw_neg_log_pbeta_upper.argtypes = [C.c_void_p, i64, f64, f64, C.c_void_p]
     L.ldw_mi_pairs_exact.argtypes = [C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]
     _lib = L
     return L

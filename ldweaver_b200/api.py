@@ -212,6 +212,8 @@ class MIScanResult:
     prob: np.ndarray
     stats: dict
     lr_links_approx: Optional[float]
+    sr_links_red: Optional[dict] = None   # what the reference returns (R/computePairwiseMI.R:143), column-wise
+    sr_post: Optional["SrLinks"] = None
 
 
 def round_half_even_thousands(x: float) -> int:
@@ -344,17 +346,105 @@ def write_lr_tsv(path: str, lr, append: bool = True) -> None:
     check(_lib.lib().ldw_write_lr_tsv(os.fsencode(path), C.byref(links), 1 if append else 0))
 
 
+@dataclass
+class SrLinks:
+    """Result of ``mergeNsort_sr_links``: ``df`` holds sr_links_df column-wise (clust_c, pos1, pos2, clust1, clust2, len,
+    MI, srp_max, plus ``row`` = index into the scan's short-range table); ``red`` / ``chk`` are the row indices of
+    sr_links_red / sr_links_ARACNE_check inside it (R/computePairwiseMI.R:494-495); ``fits`` the per-cluster decay and
+    beta fits (what the reference stores as c<i>_fit_data.rds / plots)."""
+    df: dict
+    red: np.ndarray
+    chk: np.ndarray
+    fits: List[dict]
+
+
+def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[str] = None, srp_cutoff: float = 3) -> SrLinks:
+    """R/computePairwiseMI.R:400-495 through ``ldw_sr_postprocess`` (native host code).  ``sr_links`` is the scan's
+    short-range table (dict of columns, all clusters together -- the per-cluster lists of the reference are the rows
+    with clust1 == c or clust2 == c, :372-376).  ``plt_path`` is accepted for signature compatibility: no plots or .rds
+    files are written, the fitted curves come back in ``fits``."""
+    nclust = int(cds_var.nclust if hasattr(cds_var, "nclust") else cds_var["nclust"])
+    links = sr_links if isinstance(sr_links, _lib.Links) else _lib.Links.from_dict(sr_links)
+    out = _lib.SrPost()
+    check(_lib.lib().ldw_sr_postprocess(C.byref(links), nclust, float(sr_dist), float(srp_cutoff), C.byref(out)))
+    try:
+        cp = _lib.copy_array
+        row = cp(out.row, out.n_df, np.int64)
+        df = {"clust_c": cp(out.clust_c, out.n_df, np.int32), "row": row, "srp_max": cp(out.srp_max, out.n_df, np.float64)}
+        cols = links._keep if hasattr(links, "_keep") else links.to_dict()
+        for k in ("pos1", "pos2", "clust1", "clust2", "len", "MI"):
+            df[k] = np.asarray(cols[k])[row]
+        off = cp(out.fit_off, nclust + 1, np.int64)
+        nfit = int(off[-1])
+        fl, fq, fv = cp(out.fit_len, nfit, np.int32), cp(out.fit_q95, nfit, np.float64), cp(out.fit_val, nfit, np.float64)
+        coef, shape, start = (cp(x, 2 * nclust, np.float64).reshape(nclust, 2) for x in (out.coef, out.shape, out.start))
+        npos, ev, fail = cp(out.n_pos, nclust, np.int64), cp(out.nm_evals, nclust, np.int32), cp(out.nm_fail, nclust, np.int32)
+        fits = [dict(len=fl[off[c]:off[c + 1]], max=fq[off[c]:off[c + 1]], fit=fv[off[c]:off[c + 1]], coef=coef[c],
+                     shape=shape[c], start=start[c], n_pos=int(npos[c]), nm_evals=int(ev[c]), nm_fail=int(fail[c]))
+                for c in range(nclust)]
+        return SrLinks(df=df, red=cp(out.red, out.n_red, np.int64), chk=cp(out.chk, out.n_chk, np.int64), fits=fits)
+    finally:
+        _lib.lib().ldw_sr_post_free(C.byref(out))
+
+
+def runARACNE(links_to_check, links_full) -> np.ndarray:
+    """R/io_functions.R:101-164 through ``ldw_run_aracne``: one logical per row of ``links_to_check`` (dicts / frames
+    with pos1, pos2, MI), FALSE when a third position closes a triangle whose other two links both have larger MI."""
+    f64 = lambda a: np.ascontiguousarray(np.asarray(a), dtype=np.float64)
+    c1, c2, cm = f64(links_to_check["pos1"]), f64(links_to_check["pos2"]), f64(links_to_check["MI"])
+    p1, p2, pm = f64(links_full["pos1"]), f64(links_full["pos2"]), f64(links_full["MI"])
+    out = np.ones(len(c1), dtype=np.uint8)
+    check(_lib.lib().ldw_run_aracne(len(c1), ptr(c1), ptr(c2), ptr(cm), len(p1), ptr(p1), ptr(p2), ptr(pm), ptr(out)))
+    return out.astype(bool)
+
+
+def write_sr_tsv(path: str, sr, rows: np.ndarray, clust_c: np.ndarray, srp_max: np.ndarray, aracne: np.ndarray,
+                 append: bool = True) -> None:
+    """sr_links.tsv rows ``clust_c pos1 pos2 clust1 clust2 len MI srp_max ARACNE`` (R/computePairwiseMI.R:140)."""
+    links = sr if isinstance(sr, _lib.Links) else _lib.Links.from_dict(sr)
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    cc = np.ascontiguousarray(clust_c, dtype=np.int32)
+    sp = np.ascontiguousarray(srp_max, dtype=np.float64)
+    ar = np.ascontiguousarray(aracne, dtype=np.float64)
+    check(_lib.lib().ldw_write_sr_tsv(os.fsencode(path), C.byref(links), len(rows), ptr(rows), ptr(cc), ptr(sp), ptr(ar),
+                                      1 if append else 0))
+
+
+def finish_sr_links(sr: dict, cds_var, sr_dist: float, srp_cutoff: float = 3, run_aracne: bool = True,
+                    order_links: bool = True, sr_save_path: Optional[str] = None, plt_folder: Optional[str] = None):
+    """Lines 118-143 of R/computePairwiseMI.R: mergeNsort_sr_links, ARACNE on sr_links_red against
+    sr_links_ARACNE_check, the optional ordering by srp_max (stable, decreasing) and the append to sr_links.tsv.
+    Returns (sr_links_red as a dict of columns incl. ``ARACNE``, the SrLinks it came from)."""
+    post = mergeNsort_sr_links(cds_var, sr, sr_dist, plt_folder, srp_cutoff)
+    red = {k: v[post.red] for k, v in post.df.items()}
+    if run_aracne:
+        chk = {k: post.df[k][post.chk] for k in ("pos1", "pos2", "MI")}
+        red["ARACNE"] = runARACNE(red, chk).astype(np.float64)  # :125-126
+    else:
+        import warnings
+        warnings.warn("ARACNE not run, all values will be set to 1")  # :128
+        red["ARACNE"] = np.ones(len(post.red))
+    if order_links:
+        o = np.argsort(-red["srp_max"], kind="stable")  # :134 order(decreasing = T): ties keep their order
+        red = {k: v[o] for k, v in red.items()}
+    if sr_save_path is not None:
+        write_sr_tsv(sr_save_path, sr, red["row"], red["clust_c"], red["srp_max"], red["ARACNE"], append=True)
+    return red, post
+
+
 def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: int = 1, lr_save_path: Optional[str] = None,
                            sr_save_path: Optional[str] = None, plt_folder: Optional[str] = None, sr_dist: float = 20000,
                            lr_retain_links: float = 1e6, max_blk_sz: float = 10000, srp_cutoff: float = 3,
                            runARACNE: bool = True, perform_SR_analysis_only: bool = False, order_links: bool = True,
                            mega_dset: bool = False, lr_links_approx: Optional[float] = None, device: int = 0,
-                           write_tsv: bool = True, plan: Optional[MIPlan] = None) -> MIScanResult:
-    """Scan part of R/computePairwiseMI.R:46-116.  Same arguments as the reference (``ncores`` is accepted and
-    ignored by the GPU path; ``srp_cutoff``, ``runARACNE``, ``order_links``, ``plt_folder``, ``sr_save_path``
-    belong to the CPU post-processing that stays in R -- mergeNsort_sr_links / runARACNE, :118-143 -- and are
-    accepted for signature compatibility).  Extra keyword arguments are extensions: ``lr_links_approx`` overrides the
-    R-RNG based estimate of :94-97."""
+                           write_tsv: bool = True, plan: Optional[MIPlan] = None,
+                           postprocess: Optional[bool] = None) -> MIScanResult:
+    """R/computePairwiseMI.R:46-145.  Same arguments as the reference (``ncores`` is accepted and ignored by the GPU
+    path; ``plt_folder`` is accepted, no plots are drawn).  The scan (:46-116) runs on the device; what follows it
+    (:118-143: mergeNsort_sr_links, runARACNE, ordering, sr_links.tsv) runs in native host code and fills
+    ``sr_links_red`` -- the data.frame the reference returns.  Extra keyword arguments are extensions:
+    ``lr_links_approx`` overrides the R-RNG based estimate of :94-97; ``write_tsv=False`` returns the scan's link tables
+    without touching the file system and, unless ``postprocess=True``, without the post-processing."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -377,5 +467,11 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     if write_tsv and len(lr["MI"]):
         write_lr_tsv(lr_save_path, lr, append=True)
     by_cluster = [np.nonzero((sr["clust1"] == c) | (sr["clust2"] == c))[0] for c in range(1, nclust + 1)]  # :372-376
-    return MIScanResult(sr=sr, lr=lr, borderline=bd, sr_links=by_cluster, thr=thr, prob=prob, stats=stats,
-                        lr_links_approx=lr_links_approx)
+    res = MIScanResult(sr=sr, lr=lr, borderline=bd, sr_links=by_cluster, thr=thr, prob=prob, stats=stats,
+                       lr_links_approx=lr_links_approx)
+    if postprocess if postprocess is not None else write_tsv:
+        if write_tsv and sr_save_path is None:
+            sr_save_path = os.path.join(os.getcwd(), "sr_links.tsv")  # :62
+        res.sr_links_red, res.sr_post = finish_sr_links(sr, cds_var, sr_dist, srp_cutoff, runARACNE, order_links,
+                                                        sr_save_path if write_tsv else None, plt_folder)
+    return res

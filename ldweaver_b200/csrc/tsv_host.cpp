@@ -91,11 +91,12 @@ extern "C" int ldw_format_r_real(double x, char* out, int cap) {
   return 0;
 }
 
-extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int append) {
-  if (!path || !lr) return ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: null argument");
+namespace {
+// Rows are formatted chunk by chunk on a few host threads and written in order.
+template <class RowFn>
+int write_rows(const char* who, const char* path, int append, int64_t n, RowFn row) {
   FILE* f = fopen(path, append ? "ab" : "wb");
-  if (!f) return ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: can't open %s", path);
-  const int64_t n = lr->n;
+  if (!f) return ldw::set_error(LDW_ERR_ARG, "%s: can't open %s", who, path);
   const int64_t chunk = 1 << 16;
   const int64_t nchunks = (n + chunk - 1) / chunk;
   const int64_t wave = 32;  // chunks formatted concurrently, then written in order
@@ -106,20 +107,48 @@ extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int appen
     ldw::parallel_for(nc, 8, [&](int64_t k) {
       std::string& s = bufs[k];
       const int64_t lo = (c0 + k) * chunk, hi = std::min<int64_t>(n, lo + chunk);
-      s.reserve((size_t)(hi - lo) * 64);
-      char tmp[512];
-      for (int64_t i = lo; i < hi; i++) {
-        s.append(tmp, format_int(lr->pos1[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_int(lr->pos2[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_r_whole(lr->clust1[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_r_whole(lr->clust2[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_r_whole(lr->len[i], tmp)); s.push_back('\t');
-        s.append(tmp, format_r_real(lr->MI[i], tmp)); s.push_back('\n');
-      }
+      s.reserve((size_t)(hi - lo) * 96);
+      for (int64_t i = lo; i < hi; i++) row(i, s);
     });
     for (int64_t k = 0; k < nc; k++)
-      if (fwrite(bufs[k].data(), 1, bufs[k].size(), f) != bufs[k].size()) { rc = ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: write to %s failed", path); break; }
+      if (fwrite(bufs[k].data(), 1, bufs[k].size(), f) != bufs[k].size()) { rc = ldw::set_error(LDW_ERR_ARG, "%s: write to %s failed", who, path); break; }
   }
-  if (fclose(f) != 0 && rc == 0) rc = ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: closing %s failed", path);
+  if (fclose(f) != 0 && rc == 0) rc = ldw::set_error(LDW_ERR_ARG, "%s: closing %s failed", who, path);
   return rc;
+}
+}  // namespace
+
+extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int append) {
+  if (!path || !lr) return ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: null argument");
+  return write_rows("ldw_write_lr_tsv", path, append, lr->n, [&](int64_t i, std::string& s) {
+    char tmp[512];
+    s.append(tmp, format_int(lr->pos1[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_int(lr->pos2[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(lr->clust1[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(lr->clust2[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(lr->len[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_real(lr->MI[i], tmp)); s.push_back('\n');
+  });
+}
+
+// sr_links.tsv (R/computePairwiseMI.R:140): clust_c is the integer loop index of mergeNsort_sr_links (:411,470), pos1 / pos2
+// integer, clust1 / clust2 / len / MI / srp_max doubles, ARACNE = as.numeric(logical) (:126) or the constant 1 (:129).
+extern "C" int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n, const int64_t* rows, const int32_t* clust_c,
+                                const double* srp_max, const double* aracne, int append) {
+  if (!path || !sr || (n > 0 && (!rows || !clust_c || !srp_max || !aracne))) return ldw::set_error(LDW_ERR_ARG, "ldw_write_sr_tsv: null argument");
+  for (int64_t i = 0; i < n; i++)
+    if (rows[i] < 0 || rows[i] >= sr->n) return ldw::set_error(LDW_ERR_ARG, "ldw_write_sr_tsv: row %lld outside the link table", (long long)rows[i]);
+  return write_rows("ldw_write_sr_tsv", path, append, n, [&](int64_t i, std::string& s) {
+    char tmp[512];
+    const int64_t r = rows[i];
+    s.append(tmp, format_int(clust_c[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_int(sr->pos1[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_int(sr->pos2[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(sr->clust1[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(sr->clust2[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(sr->len[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_real(sr->MI[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_real(srp_max[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_real(aracne[i], tmp)); s.push_back('\n');
+  });
 }

@@ -1,0 +1,208 @@
+"""Post-scan steps of perform_MI_computation, native host code against the oracle:
+mergeNsort_sr_links (R/computePairwiseMI.R:400-495), runARACNE (R/io_functions.R:101-164), sr_links.tsv
+(R/computePairwiseMI.R:140).  No device needed.  What pins the restatements, there being no R here and no expected
+values in the reference: R's own printed output of optim() on Rosenbrock's function (?optim), closed forms of the
+regularised incomplete beta function, and a literal second implementation (oracle/post_oracle.py)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+from scipy import special
+
+import ldw_oracle as O
+import post_oracle as PO
+import ldweaver_b200 as ldw
+from ldweaver_b200 import _lib
+
+
+def _fixture_sr(e):
+    """Short-range table of the bundled fixture (g = 50 000, max_blk_sz = 1000) from the golden scan output."""
+    POS, paint = e["relaxed_POS"], e["paint"]
+    p1, p2, MI = e["g50k_b1000_sr_pos1"], e["g50k_b1000_sr_pos2"], e["g50k_b1000_sr_MI"]
+    lut = np.zeros(int(POS.max()) + 1, dtype=np.int32)
+    lut[POS] = paint
+    ln = O.circ_len(p1.astype(float), p2.astype(float), 50000.0)
+    return dict(pos1=p1, pos2=p2, clust1=lut[p1], clust2=lut[p2], len=ln, MI=MI), paint
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# building blocks
+# ---------------------------------------------------------------------------------------------------------------------
+def test_nelder_mead_reproduces_r_optim_example():
+    """?optim:  fr <- function(x) 100 * (x[2] - x[1]^2)^2 + (1 - x[1])^2;  optim(c(-1.2, 1), fr)  prints
+    $par 1.000260 1.000506, $value 8.825241e-08, $counts function 195."""
+    fr = lambda x: 100 * (x[1] - x[0] * x[0]) ** 2 + (1 - x[0]) ** 2
+    par, val, cnt, fail = PO.nmmin(fr, [-1.2, 1.0])
+    assert cnt == 195 and fail == 0
+    assert f"{par[0]:.6f} {par[1]:.6f}" == "1.000260 1.000506" and f"{val:.6e}" == "8.825241e-08"
+    start = np.array([-1.2, 1.0])
+    out, v, c = np.zeros(2), C.c_double(), C.c_int()
+    _lib.check(_lib.lib().ldw_nm_rosenbrock(_lib.ptr(start), _lib.ptr(out), C.byref(v), C.byref(c)))
+    assert c.value == 195 and np.array_equal(out, par) and v.value == val  # same path, bit for bit
+
+
+def test_log_upper_beta_tail_closed_forms_and_scipy():
+    L = _lib.lib()
+
+    def native(x, a, b):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.zeros_like(x)
+        _lib.check(L.ldw_neg_log_pbeta_upper(_lib.ptr(x), len(x), a, b, _lib.ptr(out)))
+        return out
+    # pbeta(0.5, 2, 3) = 11/16;  shape (1, b): upper tail (1 - x)^b;  shape (a, 1): 1 - x^a
+    assert abs(native([0.5], 2, 3)[0] + math.log(1 - 11 / 16)) < 1e-14
+    x = np.array([1e-12, 1e-6, 0.01, 0.3, 0.5, 0.9, 0.999, 1 - 1e-9])
+    assert np.allclose(native(x, 1.0, 7.5), -7.5 * np.log1p(-x), rtol=1e-13, atol=1e-300)
+    assert np.allclose(native(x, 1.0, 250.0), -250.0 * np.log1p(-x), rtol=1e-13, atol=1e-300)  # up to 5180: far past exp() underflow
+    exact = np.where(x < 0.5, -np.log1p(-x ** 3.25), -np.log(-np.expm1(3.25 * np.log(x))))  # each form where it is well conditioned
+    assert np.allclose(native(x, 3.25, 1.0), exact, rtol=1e-12, atol=0)
+    # shapes of the size the fits produce, deep tails included (srp values of several hundred)
+    rng = np.random.default_rng(5)
+    for a, b in ((0.95, 23.4), (0.98, 32.4), (0.6, 250.0), (2.5, 9.0), (0.4, 0.7)):
+        xs = np.concatenate([rng.uniform(0, 1, 2000), 10.0 ** rng.uniform(-9, 0, 2000), 1 - 10.0 ** rng.uniform(-9, 0, 500)])
+        xs = xs[(xs > 0) & (xs < 1)]
+        with np.errstate(divide="ignore"):
+            ref = -np.log(special.betaincc(a, b, xs))
+        ok = np.isfinite(ref) & (ref > 1e-300) & (ref < 690)   # betaincc itself degrades in the subnormal range
+        got = native(xs, a, b)
+        assert np.allclose(got[ok], ref[ok], rtol=2e-11, atol=1e-15), (a, b, np.abs(got[ok] / ref[ok] - 1).max())
+    assert native([0.0, 1.0], 2, 2).tolist() == [0.0, math.inf]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mergeNsort_sr_links
+# ---------------------------------------------------------------------------------------------------------------------
+def _compare_post(got, ref):
+    assert np.array_equal(got.df["row"], ref.df["row"]) and np.array_equal(got.df["clust_c"], ref.df["clust_c"])
+    for h, f in zip(got.fits, ref.fits):
+        assert np.array_equal(h["len"], f.len)
+        assert np.array_equal(h["max"], f.max)                       # type-7 quantiles: same arithmetic, bit-exact
+        assert np.allclose(h["fit"], f.fit, rtol=1e-11, atol=0)      # least squares: solver-dependent last digits
+        assert np.allclose(h["start"], f.start, rtol=1e-10)
+        assert np.allclose(h["shape"], f.shape, rtol=1e-7)           # Nelder-Mead vertex
+        assert h["n_pos"] == f.n_pos and h["nm_fail"] == f.nm_fail
+    assert np.allclose(got.df["srp_max"], ref.df["srp_max"], rtol=1e-6, atol=1e-10)
+    assert np.array_equal(got.red, ref.red) and np.array_equal(got.chk, ref.chk)
+
+
+def test_merge_n_sort_matches_oracle_on_fixture(fixture_expected):
+    sr, paint = _fixture_sr(fixture_expected)
+    ref = PO.merge_n_sort_sr_links(sr, 3, 20000.0, 3.0)
+    got = ldw.mergeNsort_sr_links(ldw.CdsVar(paint, 3), sr, 20000.0, None, 3.0)
+    _compare_post(got, ref)
+    # the fixture has 19 links with len == sr_dist (quirk Q4): they reach the SR table and are dropped here (:418)
+    assert int((sr["len"] == 20000).sum()) == 19 and not np.any(got.df["len"] == 20000)
+    # links between two clusters are scored by both and kept once (:474-483)
+    cross = got.df["clust1"] != got.df["clust2"]
+    assert cross.any()
+    keys = set(zip(got.df["pos1"][cross].tolist(), got.df["pos2"][cross].tolist()))
+    assert len(keys) == int(cross.sum())
+    assert [f["nm_evals"] for f in got.fits] == [f.nm_evals for f in ref.fits]
+    assert len(got.red) > 0 and np.all(got.df["srp_max"][got.red] > 3.0)
+    assert np.all(got.df["MI"][got.chk] >= got.df["MI"][got.red].min())
+
+
+def test_missing_lengths_shift_the_fit_lookup_like_the_reference():
+    """`mean_dist[sr_links_t$len]` (R/computePairwiseMI.R:448) subscripts the fitted values by the value of len: with
+    lengths missing the lookup lands on another length's fit, and lengths beyond the number of groups give NA and drop
+    out.  Both implementations must reproduce that, not "fix" it."""
+    rng = np.random.default_rng(11)
+    n = 40000
+    ln = rng.choice(np.arange(2, 400, 2), size=n).astype(np.float64)      # even lengths only: 199 groups, values up to 398
+    mi = rng.beta(0.8, 30.0, size=n) * (ln ** -0.3)
+    pos1 = rng.integers(1, 10 ** 6, n)
+    sr = dict(pos1=pos1, pos2=pos1 + ln.astype(np.int64), clust1=np.ones(n, int), clust2=np.ones(n, int), len=ln, MI=mi)
+    ref = PO.merge_n_sort_sr_links(sr, 1, 1000.0, 2.0)
+    got = ldw.mergeNsort_sr_links(ldw.CdsVar(None, 1), sr, 1000.0, None, 2.0)
+    _compare_post(got, ref)
+    assert len(got.fits[0]["len"]) == 199
+    assert got.df["len"].max() <= 199                                      # lengths 200..398 index past the fit: NA
+    assert got.fits[0]["n_pos"] < n
+
+
+def test_postprocess_errors_mirror_r():
+    one = dict(pos1=np.array([1, 2]), pos2=np.array([5, 9]), clust1=np.array([1, 1]), clust2=np.array([1, 1]),
+               len=np.array([4.0, 7.0]), MI=np.array([0.1, 0.2]))
+    with pytest.raises(_lib.LdwError, match="fewer than two"):
+        ldw.mergeNsort_sr_links(ldw.CdsVar(None, 1), one, 100.0)
+    rng = np.random.default_rng(2)
+    n = 5000
+    ln = rng.integers(1, 50, n).astype(float)
+    big = dict(pos1=np.arange(n), pos2=np.arange(n) + ln.astype(int), clust1=np.ones(n, int), clust2=np.ones(n, int), len=ln,
+               MI=np.where(rng.random(n) < 0.01, 3.0, rng.beta(0.9, 20.0, n)))   # a few residuals above 1
+    with pytest.raises(_lib.LdwError, match=r"values must be in \[0-1\] to fit a beta distribution"):
+        ldw.mergeNsort_sr_links(ldw.CdsVar(None, 1), big, 100.0)
+    with pytest.raises(ValueError, match=r"values must be in \[0-1\]"):
+        PO.merge_n_sort_sr_links(big, 1, 100.0, 3.0)
+    big["MI"] = rng.beta(0.9, 20.0, n)
+    ldw.mergeNsort_sr_links(ldw.CdsVar(None, 1), big, 100.0)
+    with pytest.raises(_lib.LdwError, match="cluster 2 holds no short-range link"):   # R: subscript / quantile errors on an empty frame
+        ldw.mergeNsort_sr_links(ldw.CdsVar(None, 2), big, 100.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# runARACNE
+# ---------------------------------------------------------------------------------------------------------------------
+def test_aracne_hand_cases():
+    # triangle 10-20-30: the weakest edge (10,30) is indirect; ties are NOT indirect (strict <, src/computeMI.cpp:69-70)
+    full = dict(pos1=np.array([10, 20, 10, 40, 50.]), pos2=np.array([20, 30, 30, 50, 60.]), MI=np.array([0.9, 0.8, 0.3, 0.5, 0.5]))
+    chk = dict(pos1=np.array([10, 10, 20, 40, 40, 70.]), pos2=np.array([30, 20, 30, 60, 50, 80.]),
+               MI=np.array([0.3, 0.9, 0.8, 0.5, 0.5, 0.1]))
+    want = [False, True, True, True, True, True]  # (40,60): via 50 both 0.5, not strictly larger; (70,80): unknown -> TRUE
+    assert ldw.runARACNE(chk, full).tolist() == want
+    assert PO.run_aracne(chk["pos1"], chk["pos2"], chk["MI"], full["pos1"], full["pos2"], full["MI"]).tolist() == want
+    # a link repeated in `full`: the FIRST row holding the pair is the one compared (.vecPosMatch)
+    full2 = dict(pos1=np.array([1, 1, 2, 1.]), pos2=np.array([2, 2, 3, 3.]), MI=np.array([0.2, 0.9, 0.9, 0.5]))
+    chk2 = dict(pos1=np.array([1.]), pos2=np.array([3.]), MI=np.array([0.5]))
+    assert ldw.runARACNE(chk2, full2).tolist() == [True]     # first (1,2) row has MI 0.2 < 0.5
+    assert PO.run_aracne(chk2["pos1"], chk2["pos2"], chk2["MI"], full2["pos1"], full2["pos2"], full2["MI"]).tolist() == [True]
+    full2["MI"][:2] = [0.9, 0.2]
+    assert ldw.runARACNE(chk2, full2).tolist() == [False]
+    assert PO.run_aracne(chk2["pos1"], chk2["pos2"], chk2["MI"], full2["pos1"], full2["pos2"], full2["MI"]).tolist() == [False]
+    assert ldw.runARACNE(dict(pos1=[], pos2=[], MI=[]), full).tolist() == []
+    assert ldw.runARACNE(chk2, dict(pos1=[], pos2=[], MI=[])).tolist() == [True]
+
+
+def test_aracne_matches_literal_restatement_on_random_graphs():
+    rng = np.random.default_rng(3)
+    for nv, ne, nc in ((30, 200, 150), (200, 3000, 400), (50, 60, 60)):
+        p1 = rng.integers(1, nv, ne)
+        p2 = p1 + rng.integers(1, 8, ne)                      # repeats of the same pair do occur
+        mi = np.round(rng.uniform(0, 1, ne), 2)               # ties do occur
+        k = rng.integers(0, ne, nc)
+        c1, c2, cm = p1[k].astype(float), p2[k].astype(float), mi[k]
+        flip = rng.random(nc) < 0.3                           # orientation of a checked link does not matter
+        c1[flip], c2[flip] = c2[flip].copy(), c1[flip].copy()
+        got = ldw.runARACNE(dict(pos1=c1, pos2=c2, MI=cm), dict(pos1=p1, pos2=p2, MI=mi))
+        ref = PO.run_aracne(c1, c2, cm, p1, p2, mi)
+        assert np.array_equal(got, ref) and 0 < got.sum() < nc
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the whole tail of perform_MI_computation (:118-143) and sr_links.tsv
+# ---------------------------------------------------------------------------------------------------------------------
+def test_finish_sr_links_and_tsv(fixture_expected, tmp_path):
+    sr, paint = _fixture_sr(fixture_expected)
+    path = tmp_path / "sr_links.tsv"
+    red, post = ldw.finish_sr_links(sr, ldw.CdsVar(paint, 3), 20000.0, 3.0, True, True, str(path))
+    ref = PO.merge_n_sort_sr_links(sr, 3, 20000.0, 3.0)
+    d = ref.df
+    ar = PO.run_aracne(d["pos1"][ref.red], d["pos2"][ref.red], d["MI"][ref.red], d["pos1"][ref.chk], d["pos2"][ref.chk], d["MI"][ref.chk])
+    o = PO.order_links_by_srp(post.df["srp_max"][post.red])   # order by the native values (they agree to 1e-6 with the oracle's)
+    assert np.array_equal(red["row"], d["row"][ref.red][o])
+    assert np.array_equal(red["ARACNE"], ar[o].astype(float))
+    assert np.all(np.diff(red["srp_max"]) <= 0)
+    lines = path.read_text().splitlines()
+    assert len(lines) == len(red["row"])
+    for k in list(range(5)) + [len(lines) // 2, len(lines) - 1]:
+        want = "\t".join([str(int(red["clust_c"][k])), str(int(red["pos1"][k])), str(int(red["pos2"][k]))] +
+                         [O.format_r_numeric(float(red[c][k])) for c in ("clust1", "clust2", "len", "MI", "srp_max", "ARACNE")])
+        assert lines[k] == want
+    # appending (the reference's write.table(append = T))
+    ldw.write_sr_tsv(str(path), sr, red["row"][:3], red["clust_c"][:3], red["srp_max"][:3], red["ARACNE"][:3], append=True)
+    assert len(path.read_text().splitlines()) == len(lines) + 3
+    # runARACNE = FALSE: warning, constant 1 (:128-129); order_links = FALSE keeps sr_links_df order
+    with pytest.warns(UserWarning, match="ARACNE not run"):
+        red2, _ = ldw.finish_sr_links(sr, ldw.CdsVar(paint, 3), 20000.0, 3.0, False, False, None)
+    assert np.all(red2["ARACNE"] == 1) and np.array_equal(red2["row"], d["row"][ref.red])
