@@ -2,7 +2,7 @@
 import numpy as np
 import pytest
 
-from util import compare_lr_sets
+from util import compare_lr_sets, compare_sr_post_with_tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -262,3 +262,39 @@ def test_rerun_path_after_a_failed_threshold_seed(monkeypatch):
             assert np.array_equal(ref[which][col], got[which][col]), (which, col)
     assert np.array_equal(ref[3], got[3], equal_nan=True)
     plan.close()
+
+
+def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, tmp_path):
+    """perform_MI_computation as the reference runs it (R/computePairwiseMI.R:46-145): scan on the device, then the
+    native mergeNsort_sr_links / runARACNE / ordering / sr_links.tsv + lr_links.tsv, against the oracle chain on the
+    golden short-range table.  srp_max is a statistic of ALL short-range MI values (per-length percentiles, a decay fit,
+    a beta fit whose likelihood weighs residuals near zero by their logarithm), so the 1e-6 tolerance on MI shows up
+    amplified: +-4e-7 on MI moves srp_max by up to ~2e-2 (tests/test_post_cpu.py covers the exact-input case)."""
+    import ldw_oracle as O
+    import post_oracle as PO
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    tag = "g50k_b1000"
+    snp = _snp(fixture_snp, 50000)
+    lr_path, sr_path = tmp_path / "lr_links.tsv", tmp_path / "sr_links.tsv"
+    res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), ncores=1, lr_save_path=str(lr_path),
+                                     sr_save_path=str(sr_path), plt_folder=str(tmp_path), sr_dist=20000, lr_retain_links=1e4,
+                                     max_blk_sz=1000, srp_cutoff=3, runARACNE=True, lr_links_approx=1e5)
+    red = res.sr_links_red
+    assert red is not None and len(red["row"]) > 0
+    # oracle chain on the golden (fp64) short-range table
+    p1, p2, MI = e[f"{tag}_sr_pos1"], e[f"{tag}_sr_pos2"], e[f"{tag}_sr_MI"]
+    np.testing.assert_array_equal(res.sr["pos1"], p1.astype(np.int32))
+    lut = np.zeros(int(snp.POS.max()) + 1, dtype=np.int32)
+    lut[snp.POS] = e["paint"]
+    sr = dict(pos1=p1, pos2=p2, clust1=lut[p1], clust2=lut[p2], len=O.circ_len(p1.astype(float), p2.astype(float), 50000.0), MI=MI)
+    ref = PO.merge_n_sort_sr_links(sr, 3, 20000.0, 3.0)
+    compare_sr_post_with_tolerance(red, res.sr_post, ref, 3.0, MI_TOL)
+    # files: one row per returned link, 9 columns; lr_links.tsv 6 columns
+    rows = sr_path.read_text().splitlines()
+    assert len(rows) == len(red["row"]) and all(len(r.split("\t")) == 9 for r in rows[:50])
+    first = rows[0].split("\t")
+    assert int(first[1]) == int(red["pos1"][0]) and int(first[2]) == int(red["pos2"][0])
+    assert abs(float(first[6]) - red["MI"][0]) < 1e-14 and abs(float(first[7]) - red["srp_max"][0]) < 1e-12 * red["srp_max"][0] + 1e-14
+    lrows = lr_path.read_text().splitlines()
+    assert len(lrows) == len(res.lr["MI"]) and len(lrows[0].split("\t")) == 6

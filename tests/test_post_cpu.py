@@ -206,3 +206,18 @@ def test_finish_sr_links_and_tsv(fixture_expected, tmp_path):
     with pytest.warns(UserWarning, match="ARACNE not run"):
         red2, _ = ldw.finish_sr_links(sr, ldw.CdsVar(paint, 3), 20000.0, 3.0, False, False, None)
     assert np.all(red2["ARACNE"] == 1) and np.array_equal(red2["row"], d["row"][ref.red])
+
+
+def test_tolerance_of_the_chain_under_scan_sized_mi_errors(fixture_expected):
+    """The device hands over fp32-accurate MI (|error| < 1e-6, 2e-7 measured).  The same comparison the GPU test makes
+    (tests/util.py), here with the golden fp64 values perturbed by that much: shows how far the MI tolerance travels into
+    srp_max and that only links at the srp cut-off can change sides."""
+    from util import compare_sr_post_with_tolerance
+    sr, paint = _fixture_sr(fixture_expected)
+    ref = PO.merge_n_sort_sr_links(sr, 3, 20000.0, 3.0)
+    rng = np.random.default_rng(0)
+    for amp in (2e-7, 8e-7):
+        noisy = dict(sr)
+        noisy["MI"] = (sr["MI"] + rng.uniform(-amp, amp, len(sr["MI"]))).astype(np.float32).astype(np.float64)
+        red, post = ldw.finish_sr_links(noisy, ldw.CdsVar(paint, 3), 20000.0, 3.0, True, True, None)
+        compare_sr_post_with_tolerance(red, post, ref, 3.0, 1e-6)
