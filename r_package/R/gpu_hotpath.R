@@ -1,7 +1,9 @@
 # Drop-in bodies for the three hot functions of LDWeaver (signatures and return values unchanged).
 # They replace R/extractSNPs.R:23-142,168-281, R/performPopulationStuctureCorrection.R:20-81 and the block loop of
-# R/computePairwiseMI.R:69-116; everything after the scan (mergeNsort_sr_links, runARACNE, write.table,
-# R/computePairwiseMI.R:118-143) is the reference's own code and stays on the CPU.
+# R/computePairwiseMI.R:69-116.  What follows the scan (R/computePairwiseMI.R:118-143) runs through the library's host
+# entry points: mergeNsort_sr_links -> ldw_sr_postprocess (no plots / .rds files), runARACNE -> ldw_run_aracne (also a
+# drop-in for the exported runARACNE, used by analyse_long_range_links, R/lr_analyser.R:101-108).  Setting
+# options(LDWeaver.native_post = FALSE) keeps the reference's own R code for those steps.
 
 .codes_to_snpdat <- function(enc, pos = NULL) {
   if (enc$seq.length == -1) stop("Error! sequences are of different lengths!")
@@ -82,12 +84,23 @@ perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path =
                lr_links_approx, max_blk_sz, perform_SR_analysis_only, PACKAGE = "LDWeaver")
   if (length(res$lr$MI) > 0)   # same rows, same order as the per-block appends of R/computePairwiseMI.R:362
     write.table(x = as.data.frame(res$lr[1:6]), file = lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
-  sr_df <- as.data.frame(res$sr[1:6])
-  sr_links <- lapply(1:cds_var$nclust, function(i) sr_df[sr_df$clust1 == i | sr_df$clust2 == i, ])   # :372-376
-  # ---- from here on: the reference's own CPU code, unchanged (R/computePairwiseMI.R:118-143)
-  sr_links_all <- mergeNsort_sr_links(cds_var = cds_var, sr_links = sr_links, sr_dist = sr_dist, plt_path = plt_folder, srp_cutoff = srp_cutoff)
-  sr_links_red <- sr_links_all$sr_links_red
-  sr_links_ARACNE_check <- sr_links_all$sr_links_ARACNE_check
+  if (!isTRUE(getOption("LDWeaver.native_post", TRUE))) {
+    sr_df <- as.data.frame(res$sr[1:6])
+    sr_links <- lapply(1:cds_var$nclust, function(i) sr_df[sr_df$clust1 == i | sr_df$clust2 == i, ])   # :372-376
+    sr_links_all <- mergeNsort_sr_links(cds_var = cds_var, sr_links = sr_links, sr_dist = sr_dist, plt_path = plt_folder, srp_cutoff = srp_cutoff)
+    sr_links_red <- sr_links_all$sr_links_red
+    sr_links_ARACNE_check <- sr_links_all$sr_links_ARACNE_check
+  } else {
+    post <- .Call("_LDWeaver_gpu_sr_post", res$sr$pos1, res$sr$pos2, res$sr$clust1, res$sr$clust2, res$sr$len, res$sr$MI,
+                  as.integer(cds_var$nclust), sr_dist, srp_cutoff, PACKAGE = "LDWeaver")
+    frame <- function(idx) {   # columns of sr_links_df (R/computePairwiseMI.R:470): clust_c + the six link columns + srp_max
+      r <- post$row[idx]
+      data.frame(clust_c = post$clust_c[idx], pos1 = res$sr$pos1[r], pos2 = res$sr$pos2[r], clust1 = as.numeric(res$sr$clust1[r]),
+                 clust2 = as.numeric(res$sr$clust2[r]), len = as.numeric(res$sr$len[r]), MI = res$sr$MI[r], srp_max = post$srp_max[idx])
+    }
+    sr_links_red <- frame(post$red)
+    sr_links_ARACNE_check <- frame(post$chk)
+  }
   if (runARACNE) {
     sr_links_red$ARACNE <- as.numeric(runARACNE(sr_links_red, sr_links_ARACNE_check))
   } else {
@@ -98,4 +111,14 @@ perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path =
   write.table(x = sr_links_red, file = sr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
   cat(paste("All done in", round(difftime(Sys.time(), t000, units = "mins"), 2), "mins \n"))
   sr_links_red
+}
+
+# Drop-in for runARACNE (R/io_functions.R:101-164): same arguments, same logical vector
+runARACNE <- function(links_to_check, links_full) {
+  t0 <- Sys.time()
+  cat(paste("Running ARACNE on", nrow(links_to_check), "links... \n"))
+  out <- .Call("_LDWeaver_gpu_runARACNE", as.numeric(links_to_check$pos1), as.numeric(links_to_check$pos2), as.numeric(links_to_check$MI),
+               as.numeric(links_full$pos1), as.numeric(links_full$pos2), as.numeric(links_full$MI), PACKAGE = "LDWeaver")
+  cat(paste("\nDone in", round(difftime(Sys.time(), t0, units = "secs"), 2), "s\n"))
+  out
 }

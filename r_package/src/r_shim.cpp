@@ -12,6 +12,8 @@
 #include <Rinternals.h>
 #include <R_ext/Rdynload.h>
 
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -174,11 +176,56 @@ SEXP LDWeaver_gpu_ACGTN2num(SEXP nv_, SEXP cv_, SEXP ncores_) {
   return R_NilValue;
 }
 
+// .Call("_LDWeaver_gpu_runARACNE", chk_pos1, chk_pos2, chk_MI, full_pos1, full_pos2, full_MI) -> logical(length(chk_MI))
+// body of runARACNE(links_to_check, links_full) (R/io_functions.R:101-164); all arguments numeric vectors
+SEXP LDWeaver_gpu_runARACNE(SEXP c1_, SEXP c2_, SEXP cm_, SEXP f1_, SEXP f2_, SEXP fm_) {
+  const R_xlen_t nc = XLENGTH(cm_), nf = XLENGTH(fm_);
+  std::vector<uint8_t> keep((size_t)nc, 1);
+  if (ldw_run_aracne((int64_t)nc, REAL(c1_), REAL(c2_), REAL(cm_), (int64_t)nf, REAL(f1_), REAL(f2_), REAL(fm_), keep.data()) != 0)
+    Rf_error("%s", ldw_last_error());
+  SEXP out = PROTECT(Rf_allocVector(LGLSXP, nc));
+  for (R_xlen_t i = 0; i < nc; i++) LOGICAL(out)[i] = keep[i];
+  UNPROTECT(1);
+  return out;
+}
+
+// .Call("_LDWeaver_gpu_sr_post", pos1, pos2, clust1, clust2, len, MI (the scan's short-range columns: integer x5, numeric),
+//       nclust, sr_dist, srp_cutoff) -> list(clust_c, row (1-based), srp_max, red (1-based), chk (1-based), shape, coef)
+// body of mergeNsort_sr_links (R/computePairwiseMI.R:400-495) on the un-split short-range table
+SEXP LDWeaver_gpu_sr_post(SEXP p1_, SEXP p2_, SEXP c1_, SEXP c2_, SEXP len_, SEXP mi_, SEXP nclust_, SEXP srd_, SEXP cut_) {
+  ldw_links sr;
+  memset(&sr, 0, sizeof(sr));
+  sr.n = (int64_t)XLENGTH(mi_);
+  sr.pos1 = INTEGER(p1_); sr.pos2 = INTEGER(p2_); sr.clust1 = INTEGER(c1_); sr.clust2 = INTEGER(c2_); sr.len = INTEGER(len_);
+  sr.MI = REAL(mi_);
+  ldw_sr_post post;
+  const int nclust = Rf_asInteger(nclust_);
+  if (ldw_sr_postprocess(&sr, nclust, Rf_asReal(srd_), Rf_asReal(cut_), &post) != 0) Rf_error("%s", ldw_last_error());
+  SEXP cc = PROTECT(Rf_allocVector(INTSXP, post.n_df)), row = PROTECT(Rf_allocVector(REALSXP, post.n_df));
+  SEXP srp = PROTECT(Rf_allocVector(REALSXP, post.n_df));
+  SEXP red = PROTECT(Rf_allocVector(REALSXP, post.n_red)), chk = PROTECT(Rf_allocVector(REALSXP, post.n_chk));
+  SEXP shape = PROTECT(Rf_allocVector(REALSXP, 2 * nclust)), coef = PROTECT(Rf_allocVector(REALSXP, 2 * nclust));
+  for (int64_t i = 0; i < post.n_df; i++) { INTEGER(cc)[i] = post.clust_c[i]; REAL(row)[i] = (double)(post.row[i] + 1); REAL(srp)[i] = post.srp_max[i]; }
+  for (int64_t i = 0; i < post.n_red; i++) REAL(red)[i] = (double)(post.red[i] + 1);
+  for (int64_t i = 0; i < post.n_chk; i++) REAL(chk)[i] = (double)(post.chk[i] + 1);
+  for (int k = 0; k < 2 * nclust; k++) { REAL(shape)[k] = post.shape[k]; REAL(coef)[k] = post.coef[k]; }
+  ldw_sr_post_free(&post);  // everything needed was copied into R vectors above
+  const char* nm[] = {"clust_c", "row", "srp_max", "red", "chk", "shape", "coef"};
+  SEXP vals[] = {cc, row, srp, red, chk, shape, coef};
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 7)), onm = PROTECT(Rf_allocVector(STRSXP, 7));
+  for (int k = 0; k < 7; k++) { SET_VECTOR_ELT(out, k, vals[k]); SET_STRING_ELT(onm, k, Rf_mkChar(nm[k])); }
+  Rf_setAttrib(out, R_NamesSymbol, onm);
+  UNPROTECT(9);
+  return out;
+}
+
 static const R_CallMethodDef CallEntries[] = {
     {"_LDWeaver_gpu_encode", (DL_FUNC)&LDWeaver_gpu_encode, 4},
     {"_LDWeaver_gpu_hdw", (DL_FUNC)&LDWeaver_gpu_hdw, 4},
     {"_LDWeaver_gpu_mi_scan", (DL_FUNC)&LDWeaver_gpu_mi_scan, 12},
     {"_LDWeaver_gpu_ACGTN2num", (DL_FUNC)&LDWeaver_gpu_ACGTN2num, 3},
+    {"_LDWeaver_gpu_runARACNE", (DL_FUNC)&LDWeaver_gpu_runARACNE, 6},
+    {"_LDWeaver_gpu_sr_post", (DL_FUNC)&LDWeaver_gpu_sr_post, 9},
     {NULL, NULL, 0}};
 
 // merged into R_init_LDWeaver (src/RcppExports.cpp:169-172) next to the Rcpp-generated table

@@ -57,3 +57,18 @@ def test_host_fasta_reader(tmp_path):
     e.write_text("")
     with pytest.raises(ValueError, match="any sequences"):
         api.read_fasta_matrix(str(e))
+
+
+def test_r_shim_type_checks_against_the_abi():
+    """r_package/src/r_shim.cpp (the .Call glue a maintainer adds to the R package) cannot be built here -- no R -- but
+    it must at least type-check against include/ldw.h; tests/mock_r/ declares the handful of R C API functions it uses."""
+    import subprocess
+    cmd = ["g++", "-fsyntax-only", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+           "-I", os.path.join(ROOT, "tests", "mock_r"), os.path.join(ROOT, "r_package", "src", "r_shim.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    shim = open(os.path.join(ROOT, "r_package", "src", "r_shim.cpp")).read()
+    rcode = open(os.path.join(ROOT, "r_package", "R", "gpu_hotpath.R")).read()
+    for name, nargs in re.findall(r'\{"(_LDWeaver_gpu_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim):
+        calls = re.findall(r'\.Call\("%s",(.*?)PACKAGE = "LDWeaver"\)' % name, rcode, flags=re.S)
+        assert calls or name == "_LDWeaver_gpu_ACGTN2num", f"{name} registered but never called from gpu_hotpath.R"
