@@ -35,8 +35,8 @@ MAX_BLK = 10000
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--nsnp", type=int, default=0, help="override the number of SNPs (debug only; invalidates the metric)")
@@ -227,11 +227,13 @@ def main():
     t_wall0 = time.perf_counter()
     dev_ms = 0.0
     kern_ms = 0.0
+    step_ms = []
     stats = None
     agg = {"n_pairs": 0, "n_launches": 0, "n_scan_launches": 0, "exec_int8_ops": 0.0, "n_tiles": 0}
     for _ in range(args.steps):
         *_, stats = plan.scan(sy.g, SR_DIST, LR_RETAIN, lra, flags_dev, world, rank, copy=False)
         dev_ms += stats["t_scan_ms"] + stats["t_select_ms"]
+        step_ms.append(stats["t_scan_ms"] + stats["t_select_ms"])
         kern_ms += stats["t_kernel_ms"]
         for k in agg:
             agg[k] += stats[k]
@@ -335,7 +337,8 @@ def main():
             "vs_baseline": None, "dtype": "int8 (tcgen05 kind::i8 with int32 accumulation of 28-bit fixed-point weights; fp32 MI epilogue, fp64 refinement of long-range links)",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all),
             "roofline": roofline, "cpu_baseline": cpu,
-            "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"], "host_prep_ms": stats["t_host_prep_ms"],
+            "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps,
+                       "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms)}, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"], "host_prep_ms": stats["t_host_prep_ms"],
                        "pairs_per_step": pairs_all / args.steps, "n_sr": stats["n_sr"], "n_lr_kept": stats["n_lr_kept"],
                        "n_reruns": stats["n_reruns"], "n_candidates": stats["n_candidates"], "tiles_per_step_rank0": agg["n_tiles"] / args.steps,
                        "lr_links_approx": lra}}
