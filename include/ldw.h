@@ -252,6 +252,15 @@ LDW_API int ldw_run_aracne(int64_t n_chk, const double* chk_pos1, const double* 
 LDW_API int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n, const int64_t* rows, const int32_t* clust_c,
                      const double* srp_max, const double* aracne, int append);
 
+/* ldw_read_numeric_tsv reads a link file the way read_LongRangeLinks / read_ShortRangeLinks do
+ *   (read.table(path, sep = "\t", header = F, quote = "", comment.char = ""), R/io_functions.R:34,62; also
+ *   genomewide_LDMap, R/LDSummaryPlot.R:51-52): `ncols` numeric tab-separated fields per line, no header, "NA" -> NaN.
+ *   *cols_out is a library-owned column-major table (ncols x *nrows_out doubles: column k starts at k * nrows),
+ *   released by ldw_table_free.  A line with another number of fields is an error (message names the line).
+ */
+LDW_API int ldw_read_numeric_tsv(const char* path, int ncols, int64_t* nrows_out, double** cols_out);
+LDW_API void ldw_table_free(double* cols);
+
 /* Dense MI matrix of one block (debug / parity aid; nf x nt doubles, column-major, fp32-accurate values).
  * from/to are 0-based ascending global SNP ids, as `from`/`to` of perform_MI_computation_ACGTN. */
 LDW_API int ldw_mi_block_dense(ldw_mi_plan* plan, int64_t block_index, double* mi_out, int64_t* nf_out, int64_t* nt_out);

@@ -410,6 +410,72 @@ def write_sr_tsv(path: str, sr, rows: np.ndarray, clust_c: np.ndarray, srp_max: 
                                       1 if append else 0))
 
 
+def _read_numeric_tsv(path: str, names: Sequence[str]) -> dict:
+    n, cols = _lib.i64(0), _lib.P(_lib.f64)()
+    check(_lib.lib().ldw_read_numeric_tsv(os.fsencode(path), len(names), C.byref(n), C.byref(cols)))
+    try:
+        flat = _lib.copy_array(cols, int(n.value) * len(names), np.float64).reshape(len(names), int(n.value))
+    finally:
+        _lib.lib().ldw_table_free(cols)
+    return {k: flat[i] for i, k in enumerate(names)}
+
+
+def read_LongRangeLinks(lr_links_path: str, links_from_spydrpick: bool = False, sr_dist: float = 20000) -> dict:
+    """R/io_functions.R:32-47: lr_links.tsv as columns pos1, pos2, c1, c2, len, MI; rows with len < sr_dist are dropped
+    (:43).  Spydrpick output (space separated) is not read here."""
+    if links_from_spydrpick:
+        raise NotImplementedError("links_from_spydrpick = T (space-separated spydrpick output) is outside the hot path")
+    d = _read_numeric_tsv(lr_links_path, ["pos1", "pos2", "c1", "c2", "len", "MI"])
+    keep = ~(d["len"] < sr_dist)
+    return {k: v[keep] for k, v in d.items()} if not keep.all() else d
+
+
+def read_ShortRangeLinks(sr_links_path: str) -> dict:
+    """R/io_functions.R:61-66: sr_links.tsv as columns clust_c, pos1, pos2, clust1, clust2, len, MI, srp_max, ARACNE."""
+    return _read_numeric_tsv(sr_links_path, ["clust_c", "pos1", "pos2", "clust1", "clust2", "len", "MI", "srp_max", "ARACNE"])
+
+
+def _quantile7(x: np.ndarray, prob: float) -> float:
+    """stats::quantile.default(type = 7), one probability (selection instead of a full sort)."""
+    n = len(x)
+    index = 1 + max(n - 1, 0) * prob
+    lo, hi = int(np.floor(index)), int(np.ceil(index))
+    part = np.partition(x, sorted({lo - 1, hi - 1}))
+    qs = float(part[lo - 1])
+    if index > lo and part[hi - 1] != qs:
+        h = index - lo
+        qs = (1 - h) * qs + h * float(part[hi - 1])
+    return qs
+
+
+def analyse_long_range_links(lr_links: dict, sr_links: dict, are_lrlinks_ordered: bool = False) -> dict:
+    """The numerical part of R/lr_analyser.R:72-116 (what BASELINE config #5 feeds to runARACNE): Tukey outlier
+    thresholds on the long-range MI (quartiles by quantile type 7, :73-75), lr_links_red = MI > min(thresholds) (:91)
+    with the top-~5000 fallback (:94-99), the ARACNE check set = long-range + short-range links above the same threshold
+    (:105-108), runARACNE (native), ordering by MI (decreasing, stable; :113-116).  Plots and SnpEff annotation are out
+    of scope.  Returns the lr_links_red columns (+ ARACNE) and the two thresholds."""
+    mi = np.asarray(lr_links["MI"], dtype=np.float64)
+    q1, q3 = _quantile7(mi, 0.25), _quantile7(mi, 0.75)
+    thresholds = q3 + np.array([1.5, 3.0]) * (q3 - q1)
+    red = mi > thresholds.min()
+    if red.sum() < 5000 and len(mi) >= 5000:
+        import warnings
+        warnings.warn("Not enough lr links pass the Tukey criteria, ~5000 top links were retained instead")  # :95
+        thresholds = np.array([_quantile7(mi, 1 - (1 / len(mi) * k)) for k in (4000, 5000)])
+        red = mi > thresholds.min()
+    out = {k: np.asarray(v)[red] for k, v in lr_links.items()}
+    if "ARACNE" not in lr_links:
+        chk = {k: np.concatenate([np.asarray(lr_links[k], dtype=np.float64), np.asarray(sr_links[k], dtype=np.float64)])
+               for k in ("pos1", "pos2", "MI")}
+        m = chk["MI"] > thresholds.min()
+        out["ARACNE"] = runARACNE(out, {k: v[m] for k, v in chk.items()})
+    if not are_lrlinks_ordered:
+        o = np.argsort(-out["MI"], kind="stable")
+        out = {k: v[o] for k, v in out.items()}
+    out["thresholds"] = thresholds
+    return out
+
+
 def finish_sr_links(sr: dict, cds_var, sr_dist: float, srp_cutoff: float = 3, run_aracne: bool = True,
                     order_links: bool = True, sr_save_path: Optional[str] = None, plt_folder: Optional[str] = None):
     """Lines 118-143 of R/computePairwiseMI.R: mergeNsort_sr_links, ARACNE on sr_links_red against

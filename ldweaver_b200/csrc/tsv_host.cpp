@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -151,4 +152,85 @@ extern "C" int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n
     s.append(tmp, format_r_real(srp_max[i], tmp)); s.push_back('\t');
     s.append(tmp, format_r_real(aracne[i], tmp)); s.push_back('\n');
   });
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Reader of the two link files: read.table(path, sep = "\t", header = F, quote = "", comment.char = "") as
+// read_LongRangeLinks / read_ShortRangeLinks call it (R/io_functions.R:34,62): every column of these files is numeric,
+// so the table comes back as column-major doubles ("NA" -> NaN).  The file is cut at line ends into chunks that are
+// counted and then parsed on host threads.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" void ldw_table_free(double* cols) { free(cols); }
+
+extern "C" int ldw_read_numeric_tsv(const char* path, int ncols, int64_t* nrows_out, double** cols_out) {
+  if (!path || !nrows_out || !cols_out || ncols < 1) return ldw::set_error(LDW_ERR_ARG, "ldw_read_numeric_tsv: bad argument");
+  *nrows_out = 0;
+  *cols_out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return ldw::set_error(LDW_ERR_ARG, "ldw_read_numeric_tsv: can't open %s", path);
+  std::string buf;
+  {
+    char tmp[1 << 16];
+    size_t k;
+    while ((k = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.append(tmp, k);
+  }
+  fclose(f);
+  if (!buf.empty() && buf.back() != '\n') buf.push_back('\n');
+  const size_t len = buf.size();
+  if (len == 0) return 0;
+  const size_t target = 1 << 22;
+  std::vector<size_t> cut(1, 0);
+  while (cut.back() < len) {
+    size_t e = std::min(len, cut.back() + target);
+    while (e < len && buf[e - 1] != '\n') e++;
+    cut.push_back(e);
+  }
+  const int64_t nchunks = (int64_t)cut.size() - 1;
+  std::vector<int64_t> first(nchunks + 1, 0);
+  ldw::parallel_for(nchunks, 8, [&](int64_t c) {
+    int64_t n = 0;
+    for (size_t i = cut[c]; i < cut[c + 1]; i++) n += buf[i] == '\n';
+    first[c + 1] = n;
+  });
+  for (int64_t c = 0; c < nchunks; c++) first[c + 1] += first[c];
+  const int64_t nrows = first[nchunks];
+  double* cols = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(1, nrows) * ncols);
+  if (!cols) return ldw::set_error(LDW_ERR_NOMEM, "ldw_read_numeric_tsv: out of memory (%lld rows)", (long long)nrows);
+  std::vector<int64_t> bad(nchunks, -1);
+  ldw::parallel_for(nchunks, 8, [&](int64_t c) {
+    const char* p = buf.data() + cut[c];
+    const char* end = buf.data() + cut[c + 1];
+    int64_t row = first[c];
+    while (p < end) {
+      for (int k = 0; k < ncols; k++) {
+        double v;
+        if (p[0] == 'N' && p[1] == 'A' && (p[2] == '\t' || p[2] == '\n' || p[2] == '\r')) { v = NAN; p += 2; }
+        else {
+          char* q;
+          v = strtod(p, &q);
+          if (q == p) { if (bad[c] < 0) bad[c] = row; }
+          p = q;
+        }
+        cols[(size_t)k * nrows + row] = v;
+        const char sep = (k + 1 < ncols) ? '\t' : '\n';
+        if (*p == '\r' && sep == '\n') p++;
+        if (*p != sep) {  // wrong number of fields (or text in a field): skip to the end of the line, report it
+          if (bad[c] < 0) bad[c] = row;
+          while (*p != '\n') p++;
+          for (int j = k + 1; j < ncols; j++) cols[(size_t)j * nrows + row] = NAN;
+          k = ncols;
+        }
+        p++;
+      }
+      row++;
+    }
+  });
+  for (int64_t c = 0; c < nchunks; c++)
+    if (bad[c] >= 0) {
+      free(cols);
+      return ldw::set_error(LDW_ERR_ARG, "ldw_read_numeric_tsv: line %lld of %s did not have %d numeric fields", (long long)bad[c] + 1, path, ncols);
+    }
+  *nrows_out = nrows;
+  *cols_out = cols;
+  return 0;
 }

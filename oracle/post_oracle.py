@@ -347,3 +347,27 @@ def order_links_by_srp(srp_max: np.ndarray) -> np.ndarray:
     """order(srp_max, decreasing = TRUE): R's default radix method is stable, ties keep their original order
     (R/computePairwiseMI.R:134)."""
     return np.argsort(-np.asarray(srp_max), kind="stable")
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# analyse_long_range_links, numerical part  (R/lr_analyser.R:72-116)
+# --------------------------------------------------------------------------------------------------------------------
+def analyse_long_range_links(lr: Dict[str, np.ndarray], sr: Dict[str, np.ndarray], are_lrlinks_ordered: bool = False):
+    mi = np.asarray(lr["MI"], dtype=np.float64)
+    q13 = np.array([quantile_type7(mi, 0.25), quantile_type7(mi, 0.75)])          # :73
+    iqr = q13[1] - q13[0]                                                            # :74
+    thresholds = q13[1] + np.array([1.5, 3.0]) * iqr                                 # :75
+    red = mi > thresholds.min()                                                      # :91
+    if red.sum() < 5000 and len(mi) >= 5000:                                         # :94-99
+        thresholds = np.array([quantile_type7(mi, 1 - (1 / len(mi) * k)) for k in (4000, 5000)])
+        red = mi > thresholds.min()
+    p1 = np.concatenate([np.asarray(lr["pos1"], float), np.asarray(sr["pos1"], float)])   # :105-106
+    p2 = np.concatenate([np.asarray(lr["pos2"], float), np.asarray(sr["pos2"], float)])
+    mm = np.concatenate([mi, np.asarray(sr["MI"], float)])
+    k = mm > thresholds.min()                                                        # :107
+    ar = run_aracne(np.asarray(lr["pos1"], float)[red], np.asarray(lr["pos2"], float)[red], mi[red], p1[k], p2[k], mm[k])  # :108
+    idx = np.nonzero(red)[0]
+    if not are_lrlinks_ordered:                                                      # :113-116
+        o = np.argsort(-mi[idx], kind="stable")
+        idx, ar = idx[o], ar[o]
+    return idx, ar, thresholds

@@ -221,3 +221,59 @@ def test_tolerance_of_the_chain_under_scan_sized_mi_errors(fixture_expected):
         noisy["MI"] = (sr["MI"] + rng.uniform(-amp, amp, len(sr["MI"]))).astype(np.float32).astype(np.float64)
         red, post = ldw.finish_sr_links(noisy, ldw.CdsVar(paint, 3), 20000.0, 3.0, True, True, None)
         compare_sr_post_with_tolerance(red, post, ref, 3.0, 1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# link files back in, and the long-range ARACNE chain (BASELINE config #5: "long-range links fed to runARACNE")
+# ---------------------------------------------------------------------------------------------------------------------
+def test_link_files_round_trip_and_lr_aracne_chain(fixture_expected, tmp_path):
+    e = fixture_expected
+    tag = "g2M_b1000"
+    lr = {k: e[f"{tag}_lr_{k}"] for k in ("pos1", "pos2", "clust1", "clust2", "len", "MI")}
+    lr_path = tmp_path / "lr_links.tsv"
+    ldw.write_lr_tsv(str(lr_path), lr, append=False)
+    back = ldw.read_LongRangeLinks(str(lr_path))
+    assert list(back) == ["pos1", "pos2", "c1", "c2", "len", "MI"] and len(back["MI"]) == len(lr["MI"])
+    for a, b in (("pos1", "pos1"), ("pos2", "pos2"), ("c1", "clust1"), ("c2", "clust2"), ("len", "len")):
+        np.testing.assert_array_equal(back[a], lr[b].astype(np.float64))
+    # write.table keeps 15 significant digits: what comes back is the value R's read.table would see
+    assert np.array_equal(back["MI"], np.array([float(O.format_r_numeric(float(v))) for v in lr["MI"]]))
+    assert np.abs(back["MI"] / lr["MI"] - 1).max() < 1e-14
+    assert len(ldw.read_LongRangeLinks(str(lr_path), sr_dist=5e5)["MI"]) == int((lr["len"] >= 5e5).sum())   # :43
+    # sr_links.tsv
+    sr, paint = _fixture_sr(e)
+    sr_path = tmp_path / "sr_links.tsv"
+    red, _ = ldw.finish_sr_links(sr, ldw.CdsVar(paint, 3), 20000.0, 3.0, True, True, str(sr_path))
+    srb = ldw.read_ShortRangeLinks(str(sr_path))
+    assert len(srb["MI"]) == len(red["row"])
+    np.testing.assert_array_equal(srb["pos1"], red["pos1"].astype(float))
+    np.testing.assert_array_equal(srb["ARACNE"], red["ARACNE"])
+    np.testing.assert_array_equal(srb["clust_c"], red["clust_c"].astype(float))
+    assert np.abs(srb["srp_max"] / red["srp_max"] - 1).max() < 1e-14
+    # malformed files fail loudly
+    bad = tmp_path / "bad.tsv"
+    bad.write_text("1\t2\t1\t1\t5\t0.1\n3\t4\t1\t1\n")
+    with pytest.raises(_lib.LdwError, match="line 2 .* did not have 6 numeric fields"):
+        ldw.read_LongRangeLinks(str(bad))
+    with pytest.raises(_lib.LdwError, match="can't open"):
+        ldw.read_ShortRangeLinks(str(tmp_path / "missing.tsv"))
+    empty = tmp_path / "empty.tsv"
+    empty.write_text("")
+    assert len(ldw.read_ShortRangeLinks(str(empty))["MI"]) == 0
+    # the long-range chain on what was read back (R/lr_analyser.R:72-116)
+    got = ldw.analyse_long_range_links(back, srb)
+    idx, ar, thr = PO.analyse_long_range_links(back, srb)
+    assert np.array_equal(got["thresholds"], thr)
+    np.testing.assert_array_equal(got["pos1"], back["pos1"][idx])
+    np.testing.assert_array_equal(got["MI"], back["MI"][idx])
+    np.testing.assert_array_equal(got["ARACNE"], ar)
+    assert np.all(np.diff(got["MI"]) <= 0) and 0 < len(idx) < len(back["MI"])
+    # fewer than 5000 outliers among >= 5000 links: the top-~5000 fallback and its warning (:94-99)
+    rng = np.random.default_rng(4)
+    many = dict(pos1=rng.integers(1, 10 ** 6, 20000).astype(float), pos2=rng.integers(1, 10 ** 6, 20000).astype(float),
+                MI=rng.uniform(0.1, 0.2, 20000))
+    with pytest.warns(UserWarning, match="top links were retained"):
+        g2 = ldw.analyse_long_range_links(many, dict(pos1=np.zeros(0), pos2=np.zeros(0), MI=np.zeros(0)))
+    i2, a2, t2 = PO.analyse_long_range_links(many, dict(pos1=np.zeros(0), pos2=np.zeros(0), MI=np.zeros(0)))
+    assert np.array_equal(g2["thresholds"], t2) and np.array_equal(g2["MI"], many["MI"][i2]) and np.array_equal(g2["ARACNE"], a2)
+    assert 4990 <= len(i2) <= 5000
