@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--nrate", type=float, default=-1.0, help="override the per-cell N rate (debug only; invalidates the metric)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-post", action="store_true", help="skip the timing of the post-scan host steps")
     return ap.parse_args()
 
 
@@ -289,6 +290,22 @@ def main():
             t_plan += tb - ta; t_scan += tc - tb; t_close += td - tc
         barrier()
         te = allmax(time.perf_counter() - t0)
+        # what follows the scan in perform_MI_computation (R/computePairwiseMI.R:118-143), native host code, on the
+        # short-range table the last step left in pinned host memory: reported beside the metric, not part of it
+        post = None
+        if rank == 0 and world == 1 and not args.no_post:
+            try:
+                tp0 = time.perf_counter()
+                sp = api.mergeNsort_sr_links(ldw.CdsVar(sy.paint, 3), sr, SR_DIST, None, 3.0)
+                tp1 = time.perf_counter()
+                ar = api.runARACNE({k: sp.df[k][sp.red] for k in ("pos1", "pos2", "MI")}, {k: sp.df[k][sp.chk] for k in ("pos1", "pos2", "MI")})
+                tp2 = time.perf_counter()
+                post = {"mergeNsort_sr_links_s": tp1 - tp0, "runARACNE_s": tp2 - tp1, "n_sr_links": int(sr.n), "n_df": int(len(sp.df["row"])),
+                        "n_red": int(len(sp.red)), "n_aracne_check": int(len(sp.chk)), "aracne_kept": int(ar.sum()),
+                        "beta_shapes": [f["shape"].tolist() for f in sp.fits], "nm_evals": [f["nm_evals"] for f in sp.fits],
+                        "host_threads": os.cpu_count()}
+            except Exception as ex:  # noqa: BLE001 -- a failed fit must not take the metric down with it
+                post = {"error": str(ex)}
         pe_all = allsum(float(pe))
         h2d = codes_pin.nbytes + hdw.nbytes + sy.POS.nbytes + sy.paint.nbytes
         e2e = {"value": pe_all / te, "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h // e_steps),
@@ -337,7 +354,7 @@ def main():
             "vs_baseline": None, "dtype": "int8 (tcgen05 kind::i8 with int32 accumulation of 28-bit fixed-point weights; fp32 MI epilogue, fp64 refinement of long-range links)",
             "data": "synthetic", "config": config, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_all),
             "roofline": roofline, "cpu_baseline": cpu,
-            "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps,
+            "detail": {"wall_ms_per_step": 1e3 * wall_max / args.steps, "post_scan_host": post if not args.no_e2e else None,
                        "step_ms": {"min": min(step_ms), "median": sorted(step_ms)[len(step_ms) // 2], "max": max(step_ms)}, "hdw_s": t_hdw, "pack_ms": stats["t_pack_ms"], "host_prep_ms": stats["t_host_prep_ms"],
                        "pairs_per_step": pairs_all / args.steps, "n_sr": stats["n_sr"], "n_lr_kept": stats["n_lr_kept"],
                        "n_reruns": stats["n_reruns"], "n_candidates": stats["n_candidates"], "tiles_per_step_rank0": agg["n_tiles"] / args.steps,

@@ -43,6 +43,19 @@ class Links(C.Structure):
         self._keep = keep
         return self
 
+    def views(self) -> dict:
+        """Zero-copy NumPy views of the columns (valid as long as the owner keeps the buffers: the context until its next
+        scan, or the arrays passed to from_dict)."""
+        if hasattr(self, "_keep"):
+            return self._keep
+        n = int(self.n)
+        out = {}
+        for name, _ in self._fields_[1:]:
+            ptr = getattr(self, name)
+            if n and ptr:
+                out[name] = np.ctypeslib.as_array(ptr, shape=(n,))
+        return out
+
     def to_dict(self) -> dict:
         n = int(self.n)
         out = {}

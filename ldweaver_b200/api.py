@@ -371,7 +371,7 @@ def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[st
         cp = _lib.copy_array
         row = cp(out.row, out.n_df, np.int64)
         df = {"clust_c": cp(out.clust_c, out.n_df, np.int32), "row": row, "srp_max": cp(out.srp_max, out.n_df, np.float64)}
-        cols = links._keep if hasattr(links, "_keep") else links.to_dict()
+        cols = links.views()
         for k in ("pos1", "pos2", "clust1", "clust2", "len", "MI"):
             df[k] = np.asarray(cols[k])[row]
         off = cp(out.fit_off, nclust + 1, np.int64)
