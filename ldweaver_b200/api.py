@@ -207,13 +207,23 @@ class MIScanResult:
     sr: dict
     lr: dict
     borderline: dict
-    sr_links: List[np.ndarray]
+    nclust: int
     thr: np.ndarray
     prob: np.ndarray
     stats: dict
     lr_links_approx: Optional[float]
     sr_links_red: Optional[dict] = None   # what the reference returns (R/computePairwiseMI.R:143), column-wise
     sr_post: Optional["SrLinks"] = None
+    _by_cluster: Optional[List[np.ndarray]] = None
+
+    @property
+    def sr_links(self) -> List[np.ndarray]:
+        """Per-cluster routing (R/computePairwiseMI.R:372-376), built on first use: three passes over 9e7 rows cost more
+        than the scan itself, and the native post-processing does its own routing."""
+        if self._by_cluster is None:
+            self._by_cluster = [np.nonzero((self.sr["clust1"] == c) | (self.sr["clust2"] == c))[0]
+                                for c in range(1, self.nclust + 1)]
+        return self._by_cluster
 
 
 def round_half_even_thousands(x: float) -> int:
@@ -532,8 +542,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
             plan.close()
     if write_tsv and len(lr["MI"]):
         write_lr_tsv(lr_save_path, lr, append=True)
-    by_cluster = [np.nonzero((sr["clust1"] == c) | (sr["clust2"] == c))[0] for c in range(1, nclust + 1)]  # :372-376
-    res = MIScanResult(sr=sr, lr=lr, borderline=bd, sr_links=by_cluster, thr=thr, prob=prob, stats=stats,
+    res = MIScanResult(sr=sr, lr=lr, borderline=bd, nclust=nclust, thr=thr, prob=prob, stats=stats,
                        lr_links_approx=lr_links_approx)
     if postprocess if postprocess is not None else write_tsv:
         if write_tsv and sr_save_path is None:
