@@ -261,6 +261,26 @@ def partition_blocks(nsnp: int, blk: int, n_parts: int, part: int) -> List[int]:
     return [idx for _, idx in items if owner[idx] == part]
 
 
+def sr_pair_indices(pos: np.ndarray, blk: int, sr: dict):
+    """For every make_blocks block that holds short-range links: (block index, rows of ``sr``, from-local index,
+    to-local index) such that the link's MI is cell [from-local, to-local] of the block's MI matrix -- ``pos2`` is the
+    row ("from") SNP and ``pos1`` the column ("to") SNP on diagonal and off-diagonal blocks alike
+    (R/computePairwiseMI.R:319-323, quirk Q5)."""
+    pos = np.asarray(pos)
+    if np.any(np.diff(pos) <= 0):
+        raise ValueError("POS must be strictly increasing to map links back to SNPs")
+    blocks = make_blocks(len(pos), blk)
+    b = np.asarray(sr["block"])
+    order = np.argsort(b, kind="stable")
+    bounds = np.searchsorted(b[order], np.arange(len(blocks) + 1))
+    gi = np.searchsorted(pos, np.asarray(sr["pos2"]))
+    gj = np.searchsorted(pos, np.asarray(sr["pos1"]))
+    for k, (fs, fe, ts, te) in enumerate(blocks):
+        idx = order[bounds[k]:bounds[k + 1]]
+        if len(idx):
+            yield k, idx, (gi[idx] - (fs - 1)).astype(np.int32), (gj[idx] - (ts - 1)).astype(np.int32)
+
+
 class MIPlan:
     """Device-resident operands for one (snp.dat, hdw): ldw_mi_plan_create / ldw_mi_scan."""
 
@@ -303,6 +323,17 @@ class MIPlan:
         if copy:
             return sr.to_dict(), lr.to_dict(), bd.to_dict(), thr, prob, st.to_dict()
         return sr, lr, bd, thr, prob, st.to_dict()
+
+    def sr_exact(self, sr: dict) -> np.ndarray:
+        """fp64 MI, in the reference's own arithmetic (``ldw_mi_pairs_exact``, 1e-12 against the oracle), of every
+        short-range link of a scan of this plan.  The scan's short-range MI comes from the fp32 epilogue (|error| ~2e-7,
+        inside the 1e-6 bar); the statistics built on it afterwards (mergeNsort_sr_links' beta fit) amplify that error,
+        so ``perform_MI_computation(exact_sr=True)`` replaces the column by these values first.  Not available for
+        perform_SR_analysis_only scans (their local indices refer to the reduced SNP lists, quirk Q12)."""
+        out = np.array(sr["MI"], dtype=np.float64, copy=True)
+        for k, idx, il, jl in sr_pair_indices(self.pos, self.blk, sr):
+            out[idx] = self.pairs_exact(k, il, jl)
+        return out
 
     def block_dense(self, block_index: int) -> np.ndarray:
         nf, nt = C.c_int64(), C.c_int64()
@@ -514,13 +545,14 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
                            runARACNE: bool = True, perform_SR_analysis_only: bool = False, order_links: bool = True,
                            mega_dset: bool = False, lr_links_approx: Optional[float] = None, device: int = 0,
                            write_tsv: bool = True, plan: Optional[MIPlan] = None,
-                           postprocess: Optional[bool] = None) -> MIScanResult:
+                           postprocess: Optional[bool] = None, exact_sr: bool = False) -> MIScanResult:
     """R/computePairwiseMI.R:46-145.  Same arguments as the reference (``ncores`` is accepted and ignored by the GPU
     path; ``plt_folder`` is accepted, no plots are drawn).  The scan (:46-116) runs on the device; what follows it
     (:118-143: mergeNsort_sr_links, runARACNE, ordering, sr_links.tsv) runs in native host code and fills
     ``sr_links_red`` -- the data.frame the reference returns.  Extra keyword arguments are extensions:
     ``lr_links_approx`` overrides the R-RNG based estimate of :94-97; ``write_tsv=False`` returns the scan's link tables
-    without touching the file system and, unless ``postprocess=True``, without the post-processing."""
+    without touching the file system and, unless ``postprocess=True``, without the post-processing; ``exact_sr=True``
+    recomputes the MI of every short-range link in fp64 (``MIPlan.sr_exact``) before anything is derived from it."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -537,6 +569,10 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     try:
         flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
         sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags)
+        if exact_sr:
+            if perform_SR_analysis_only:
+                raise ValueError("exact_sr is not available with perform_SR_analysis_only")
+            sr["MI"] = plan.sr_exact(sr)
     finally:
         if own:
             plan.close()

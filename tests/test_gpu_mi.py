@@ -298,3 +298,37 @@ def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, t
     assert abs(float(first[6]) - red["MI"][0]) < 1e-14 and abs(float(first[7]) - red["srp_max"][0]) < 1e-12 * red["srp_max"][0] + 1e-14
     lrows = lr_path.read_text().splitlines()
     assert len(lrows) == len(res.lr["MI"]) and len(lrows[0].split("\t")) == 6
+
+
+def test_exact_short_range_mi_gives_tight_post_parity(fixture_snp, fixture_expected):
+    """exact_sr=True: every short-range MI recomputed in fp64 (reference arithmetic) -> the column matches the golden
+    fp64 values to 1e-12 and the statistics derived from it (percentiles, decay fit, beta fit, srp_max, the srp cut and
+    the ARACNE check set) match the oracle chain without the amplified fp32 tolerance."""
+    import ldw_oracle as O
+    import post_oracle as PO
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    tag = "g50k_b1000"
+    snp = _snp(fixture_snp, 50000)
+    res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), lr_retain_links=1e4, max_blk_sz=1000,
+                                     lr_links_approx=1e5, write_tsv=False, postprocess=True, exact_sr=True)
+    p1, p2, MI = e[f"{tag}_sr_pos1"], e[f"{tag}_sr_pos2"], e[f"{tag}_sr_MI"]
+    np.testing.assert_array_equal(res.sr["pos1"], p1.astype(np.int32))
+    err = np.abs(res.sr["MI"] - MI).max()
+    print("exact short-range MI: max abs err", err)
+    assert err < 1e-12
+    lut = np.zeros(int(snp.POS.max()) + 1, dtype=np.int32)
+    lut[snp.POS] = e["paint"]
+    sr = dict(pos1=p1, pos2=p2, clust1=lut[p1], clust2=lut[p2], len=O.circ_len(p1.astype(float), p2.astype(float), 50000.0), MI=MI)
+    ref = PO.merge_n_sort_sr_links(sr, 3, 20000.0, 3.0)
+    post = res.sr_post
+    np.testing.assert_array_equal(post.df["row"], ref.df["row"])
+    np.testing.assert_array_equal(post.df["clust_c"], ref.df["clust_c"])
+    for h, f in zip(post.fits, ref.fits):
+        assert np.abs(h["max"] - f.max).max() < 1e-12 and np.allclose(h["shape"], f.shape, rtol=1e-6)
+    assert np.allclose(post.df["srp_max"], ref.df["srp_max"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_array_equal(post.red, ref.red)
+    np.testing.assert_array_equal(post.chk, ref.chk)
+    with pytest.raises(ValueError, match="exact_sr is not available"):
+        ldw.perform_MI_computation(_snp(fixture_snp, 2221315), e["hdw"], ldw.CdsVar(e["paint"], 3), sr_dist=2000, max_blk_sz=1000,
+                                   perform_SR_analysis_only=True, write_tsv=False, exact_sr=True)

@@ -277,3 +277,30 @@ def test_link_files_round_trip_and_lr_aracne_chain(fixture_expected, tmp_path):
     i2, a2, t2 = PO.analyse_long_range_links(many, dict(pos1=np.zeros(0), pos2=np.zeros(0), MI=np.zeros(0)))
     assert np.array_equal(g2["thresholds"], t2) and np.array_equal(g2["MI"], many["MI"][i2]) and np.array_equal(g2["ARACNE"], a2)
     assert 4990 <= len(i2) <= 5000
+
+
+def test_sr_pair_indices_address_the_block_matrices(fixture_snp, fixture_expected):
+    """MIPlan.sr_exact() (fp64 MI of every short-range link) rests on mapping a link back to its cell of the block's
+    MI matrix: checked here without a device -- the oracle's dense block matrices, read at those cells, must reproduce
+    the golden short-range MI column exactly (diagonal and off-diagonal blocks, quirks Q1/Q5 included)."""
+    import c_oracle as CO
+    from ldweaver_b200 import api
+    e = fixture_expected
+    tag, blk = "g50k_b1000", 1000
+    p1, p2, MI = e[f"{tag}_sr_pos1"], e[f"{tag}_sr_pos2"], e[f"{tag}_sr_MI"]
+    # block id of every golden link: rows are in make_blocks order; rebuild it from the per-block SR counts
+    snp = fixture_snp
+    osr = O.perform_MI_scan(snp, e["hdw"], e["paint"], 3, max_blk_sz=blk, lr_links_approx=1e5, lr_retain_links=1e4, keep_blocks=True)
+    block = np.concatenate([np.full(int(b.sr_mask.sum()), k) for k, b in enumerate(osr.blocks)])
+    assert len(block) == len(MI) and np.array_equal(osr.sr["pos1"], p1)
+    sr = dict(pos1=p1, pos2=p2, MI=np.zeros(len(MI)), block=block)
+    seen = 0
+    for k, idx, il, jl in api.sr_pair_indices(snp.POS, blk, sr):
+        fs, fe, ts, te = O.make_blocks(snp.nsnp, blk)[k]
+        f, t = np.arange(fs - 1, fe), np.arange(ts - 1, te)
+        dense = CO.block_mi(snp.codes, e["hdw"], snp.r, snp.uqe, f, t)
+        assert np.abs(dense[il, jl] - MI[idx]).max() < 1e-12
+        seen += len(idx)
+    assert seen == len(MI)
+    with pytest.raises(ValueError, match="strictly increasing"):
+        list(api.sr_pair_indices(np.array([1, 5, 5, 9]), 1000, sr))
