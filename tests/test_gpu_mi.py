@@ -328,7 +328,12 @@ def test_exact_short_range_mi_gives_tight_post_parity(fixture_snp, fixture_expec
         assert np.abs(h["max"] - f.max).max() < 1e-12 and np.allclose(h["shape"], f.shape, rtol=1e-6)
     assert np.allclose(post.df["srp_max"], ref.df["srp_max"], rtol=1e-6, atol=1e-6)
     np.testing.assert_array_equal(post.red, ref.red)
-    np.testing.assert_array_equal(post.chk, ref.chk)
+    # sr_links_ARACNE_check is `MI >= min(sr_links_red$MI)` (:495): links that TIE with that minimum (duplicate SNP
+    # patterns give mathematically equal MI) are decided by the last ulp in any implementation -- only those may differ
+    mi_min = ref.df["MI"][ref.red].min()
+    diff = np.setxor1d(post.chk, ref.chk)
+    print("ARACNE check set:", len(ref.chk), "links,", len(diff), "ties with the minimum differ")
+    assert np.all(np.abs(ref.df["MI"][diff] - mi_min) < 1e-12) and len(diff) < 0.01 * len(ref.chk)
     with pytest.raises(ValueError, match="exact_sr is not available"):
         ldw.perform_MI_computation(_snp(fixture_snp, 2221315), e["hdw"], ldw.CdsVar(e["paint"], 3), sr_dist=2000, max_blk_sz=1000,
                                    perform_SR_analysis_only=True, write_tsv=False, exact_sr=True)
