@@ -261,6 +261,12 @@ LDW_API int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n, c
 LDW_API int ldw_read_numeric_tsv(const char* path, int ncols, int64_t* nrows_out, double** cols_out);
 LDW_API void ldw_table_free(double* cols);
 
+/* Cell of each link in the MI matrix of the block it came from (`links->block`): from_local[i] / to_local[i] are the
+ * 0-based local indices of the link's row ("from", pos2) and column ("to", pos1) SNPs (R/computePairwiseMI.R:319-323),
+ * i.e. what ldw_mi_pairs_exact takes.  Host only.  Not meaningful for LDW_SCAN_SR_ONLY scans (quirk Q12). */
+LDW_API int ldw_links_to_cells(const int32_t* pos, int64_t n_snp, int64_t blk, const ldw_links* links, int32_t* from_local,
+                       int32_t* to_local);
+
 /* Dense MI matrix of one block (debug / parity aid; nf x nt doubles, column-major, fp32-accurate values).
  * from/to are 0-based ascending global SNP ids, as `from`/`to` of perform_MI_computation_ACGTN. */
 LDW_API int ldw_mi_block_dense(ldw_mi_plan* plan, int64_t block_index, double* mi_out, int64_t* nf_out, int64_t* nt_out);

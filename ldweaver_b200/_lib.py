@@ -135,6 +135,7 @@ def lib():
     L.ldw_read_numeric_tsv.argtypes = [C.c_char_p, C.c_int, P(i64), P(P(f64))]
     L.ldw_table_free.argtypes = [P(f64)]
     L.ldw_table_free.restype = None
+    L.ldw_links_to_cells.argtypes = [C.c_void_p, i64, i64, P(Links), C.c_void_p, C.c_void_p]
     L.ldw_nm_rosenbrock.argtypes = [C.c_void_p, C.c_void_p, P(f64), P(C.c_int)]
     L.ldw_neg_log_pbeta_upper.argtypes = [C.c_void_p, i64, f64, f64, C.c_void_p]
     L.ldw_mi_pairs_exact.argtypes = [C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]

@@ -267,18 +267,23 @@ def sr_pair_indices(pos: np.ndarray, blk: int, sr: dict):
     row ("from") SNP and ``pos1`` the column ("to") SNP on diagonal and off-diagonal blocks alike
     (R/computePairwiseMI.R:319-323, quirk Q5)."""
     pos = np.asarray(pos)
-    if np.any(np.diff(pos) <= 0):
-        raise ValueError("POS must be strictly increasing to map links back to SNPs")
     blocks = make_blocks(len(pos), blk)
     b = np.asarray(sr["block"])
-    order = np.argsort(b, kind="stable")
-    bounds = np.searchsorted(b[order], np.arange(len(blocks) + 1))
-    gi = np.searchsorted(pos, np.asarray(sr["pos2"]))
-    gj = np.searchsorted(pos, np.asarray(sr["pos1"]))
-    for k, (fs, fe, ts, te) in enumerate(blocks):
-        idx = order[bounds[k]:bounds[k + 1]]
-        if len(idx):
-            yield k, idx, (gi[idx] - (fs - 1)).astype(np.int32), (gj[idx] - (ts - 1)).astype(np.int32)
+    n = len(b)
+    links = _lib.Links.from_dict({"pos1": sr["pos1"], "pos2": sr["pos2"], "block": b, "MI": np.zeros(n)})
+    pos32 = np.ascontiguousarray(pos, dtype=np.int32)
+    il, jl = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+    check(_lib.lib().ldw_links_to_cells(ptr(pos32), len(pos32), int(blk), C.byref(links), ptr(il), ptr(jl)))
+    if n == 0 or np.all(b[1:] >= b[:-1]):                       # the scan returns rows in make_blocks order
+        order = None
+        bounds = np.searchsorted(b, np.arange(len(blocks) + 1))
+    else:
+        order = np.argsort(b, kind="stable")
+        bounds = np.searchsorted(b[order], np.arange(len(blocks) + 1))
+    for k in range(len(blocks)):
+        if bounds[k + 1] > bounds[k]:
+            idx = slice(int(bounds[k]), int(bounds[k + 1])) if order is None else order[bounds[k]:bounds[k + 1]]
+            yield k, idx, il[idx], jl[idx]
 
 
 class MIPlan:

@@ -627,3 +627,50 @@ extern "C" int ldw_run_aracne(int64_t n_chk, const double* chk_pos1, const doubl
   });
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Link -> cell of its block's MI matrix (for the fp64 recomputation of short-range MI, ldw_mi_pairs_exact): pos2 is the
+// row ("from") SNP and pos1 the column ("to") SNP on diagonal and off-diagonal blocks alike (R/computePairwiseMI.R:
+// 319-323, quirk Q5); `block` is the make_blocks index the scan reported.  Binary searches over POS on host threads.
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int ldw_links_to_cells(const int32_t* pos, int64_t n_snp, int64_t blk, const ldw_links* links, int32_t* from_local,
+                                  int32_t* to_local) {
+  if (!pos || !links || n_snp < 1 || blk < 1) return ldw::set_error(LDW_ERR_ARG, "ldw_links_to_cells: bad argument");
+  const int64_t n = links->n;
+  if (n > 0 && (!links->pos1 || !links->pos2 || !links->block || !from_local || !to_local))
+    return ldw::set_error(LDW_ERR_ARG, "ldw_links_to_cells: null column");
+  for (int64_t i = 1; i < n_snp; i++)
+    if (pos[i] <= pos[i - 1]) return ldw::set_error(LDW_ERR_ARG, "ldw_links_to_cells: POS must be strictly increasing to map links back to SNPs");
+  const int64_t nr = (n_snp + blk - 1) / blk;
+  std::vector<int32_t> bf(nr * (nr + 1) / 2), bt(nr * (nr + 1) / 2);  // make_blocks order: (i, j >= i) row-major
+  {
+    int64_t k = 0;
+    for (int64_t i = 0; i < nr; i++) for (int64_t j = i; j < nr; j++) { bf[k] = (int32_t)(i * blk); bt[k] = (int32_t)(j * blk); k++; }
+  }
+  const int64_t nblocks = (int64_t)bf.size();
+  std::atomic<int64_t> bad(-1);
+  parallel_dynamic((n + kChunk - 1) / kChunk, [&](int64_t c) {
+    // the scan lists a block's links column by column (R/computePairwiseMI.R:309): the column SNP repeats and the row SNP
+    // advances by one, so the previous answers (or their successors) are right almost every time
+    int64_t ha = 0, hb = 0;
+    auto find = [&](int32_t q, int64_t& hint) -> const int32_t* {
+      if (pos[hint] == q) return pos + hint;
+      if (hint + 1 < n_snp && pos[hint + 1] == q) return pos + (++hint);
+      const int32_t* r = std::lower_bound(pos, pos + n_snp, q);
+      if (r != pos + n_snp) hint = r - pos;
+      return r;
+    };
+    for (int64_t i = c * kChunk; i < std::min(n, (c + 1) * kChunk); i++) {
+      const int32_t* a = find(links->pos2[i], ha);
+      const int32_t* b = find(links->pos1[i], hb);
+      const int64_t k = links->block[i];
+      if (a == pos + n_snp || *a != links->pos2[i] || b == pos + n_snp || *b != links->pos1[i] || k < 0 || k >= nblocks) { bad.store(i); continue; }
+      const int64_t fl = (a - pos) - bf[k], tl = (b - pos) - bt[k];
+      if (fl < 0 || fl >= blk || tl < 0 || tl >= blk) { bad.store(i); continue; }
+      from_local[i] = (int32_t)fl;
+      to_local[i] = (int32_t)tl;
+    }
+  });
+  if (bad.load() >= 0) return ldw::set_error(LDW_ERR_ARG, "ldw_links_to_cells: link %lld does not belong to the block it names", (long long)bad.load());
+  return 0;
+}

@@ -300,7 +300,17 @@ def test_sr_pair_indices_address_the_block_matrices(fixture_snp, fixture_expecte
         f, t = np.arange(fs - 1, fe), np.arange(ts - 1, te)
         dense = CO.block_mi(snp.codes, e["hdw"], snp.r, snp.uqe, f, t)
         assert np.abs(dense[il, jl] - MI[idx]).max() < 1e-12
-        seen += len(idx)
+        seen += len(MI[idx])
     assert seen == len(MI)
-    with pytest.raises(ValueError, match="strictly increasing"):
+    # rows in another order (not what the scan returns, but allowed): same cells
+    perm = np.random.default_rng(1).permutation(len(MI))
+    srp = {k: v[perm] for k, v in sr.items()}
+    for k, idx, il, jl in api.sr_pair_indices(snp.POS, blk, srp):
+        fs, fe, ts, te = O.make_blocks(snp.nsnp, blk)[k]
+        assert np.array_equal(snp.POS[fs - 1 + il], srp["pos2"][idx]) and np.array_equal(snp.POS[ts - 1 + jl], srp["pos1"][idx])
+    with pytest.raises(_lib.LdwError, match="strictly increasing"):
         list(api.sr_pair_indices(np.array([1, 5, 5, 9]), 1000, sr))
+    wrong = dict(sr)
+    wrong["block"] = np.where(np.arange(len(MI)) == 7, 2, block)      # a link filed under another block
+    with pytest.raises(_lib.LdwError, match="link 7 does not belong to the block it names"):
+        list(api.sr_pair_indices(snp.POS, blk, wrong))
