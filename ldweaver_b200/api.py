@@ -550,14 +550,16 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
                            runARACNE: bool = True, perform_SR_analysis_only: bool = False, order_links: bool = True,
                            mega_dset: bool = False, lr_links_approx: Optional[float] = None, device: int = 0,
                            write_tsv: bool = True, plan: Optional[MIPlan] = None,
-                           postprocess: Optional[bool] = None, exact_sr: bool = False) -> MIScanResult:
+                           postprocess: Optional[bool] = None, exact_sr: Optional[bool] = None) -> MIScanResult:
     """R/computePairwiseMI.R:46-145.  Same arguments as the reference (``ncores`` is accepted and ignored by the GPU
     path; ``plt_folder`` is accepted, no plots are drawn).  The scan (:46-116) runs on the device; what follows it
     (:118-143: mergeNsort_sr_links, runARACNE, ordering, sr_links.tsv) runs in native host code and fills
     ``sr_links_red`` -- the data.frame the reference returns.  Extra keyword arguments are extensions:
     ``lr_links_approx`` overrides the R-RNG based estimate of :94-97; ``write_tsv=False`` returns the scan's link tables
-    without touching the file system and, unless ``postprocess=True``, without the post-processing; ``exact_sr=True``
-    recomputes the MI of every short-range link in fp64 (``MIPlan.sr_exact``) before anything is derived from it."""
+    without touching the file system and, unless ``postprocess=True``, without the post-processing; ``exact_sr``
+    recomputes the MI of every short-range link in fp64 (``MIPlan.sr_exact``) before anything is derived from it -- by
+    default whenever the post-processing runs (its beta fit amplifies the fp32 epilogue's 2e-7 to ~1e-2 in srp_max; about
+    +0.5 s at 616 x 100k), never for perform_SR_analysis_only scans."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -574,6 +576,9 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     try:
         flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
         sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags)
+        do_post = postprocess if postprocess is not None else write_tsv
+        if exact_sr is None:
+            exact_sr = bool(do_post) and not perform_SR_analysis_only
         if exact_sr:
             if perform_SR_analysis_only:
                 raise ValueError("exact_sr is not available with perform_SR_analysis_only")
@@ -585,7 +590,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         write_lr_tsv(lr_save_path, lr, append=True)
     res = MIScanResult(sr=sr, lr=lr, borderline=bd, nclust=nclust, thr=thr, prob=prob, stats=stats,
                        lr_links_approx=lr_links_approx)
-    if postprocess if postprocess is not None else write_tsv:
+    if do_post:
         if write_tsv and sr_save_path is None:
             sr_save_path = os.path.join(os.getcwd(), "sr_links.tsv")  # :62
         res.sr_links_red, res.sr_post = finish_sr_links(sr, cds_var, sr_dist, srp_cutoff, runARACNE, order_links,

@@ -269,7 +269,8 @@ def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, t
     native mergeNsort_sr_links / runARACNE / ordering / sr_links.tsv + lr_links.tsv, against the oracle chain on the
     golden short-range table.  srp_max is a statistic of ALL short-range MI values (per-length percentiles, a decay fit,
     a beta fit whose likelihood weighs residuals near zero by their logarithm), so the 1e-6 tolerance on MI shows up
-    amplified: +-4e-7 on MI moves srp_max by up to ~2e-2 (tests/test_post_cpu.py covers the exact-input case)."""
+    amplified: +-4e-7 on MI moves srp_max by up to ~2e-2 (tests/test_post_cpu.py covers the exact-input case).  That is
+    why the default is exact_sr=True (next test); here the fp32 column is kept on purpose."""
     import ldw_oracle as O
     import post_oracle as PO
     import ldweaver_b200 as ldw
@@ -279,7 +280,7 @@ def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, t
     lr_path, sr_path = tmp_path / "lr_links.tsv", tmp_path / "sr_links.tsv"
     res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), ncores=1, lr_save_path=str(lr_path),
                                      sr_save_path=str(sr_path), plt_folder=str(tmp_path), sr_dist=20000, lr_retain_links=1e4,
-                                     max_blk_sz=1000, srp_cutoff=3, runARACNE=True, lr_links_approx=1e5)
+                                     max_blk_sz=1000, srp_cutoff=3, runARACNE=True, lr_links_approx=1e5, exact_sr=False)
     red = res.sr_links_red
     assert red is not None and len(red["row"]) > 0
     # oracle chain on the golden (fp64) short-range table
@@ -301,7 +302,7 @@ def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, t
 
 
 def test_exact_short_range_mi_gives_tight_post_parity(fixture_snp, fixture_expected):
-    """exact_sr=True: every short-range MI recomputed in fp64 (reference arithmetic) -> the column matches the golden
+    """exact_sr=True (the default whenever the post-processing runs): every short-range MI recomputed in fp64 (reference arithmetic) -> the column matches the golden
     fp64 values to 1e-12 and the statistics derived from it (percentiles, decay fit, beta fit, srp_max, the srp cut and
     the ARACNE check set) match the oracle chain without the amplified fp32 tolerance."""
     import ldw_oracle as O
@@ -311,7 +312,7 @@ def test_exact_short_range_mi_gives_tight_post_parity(fixture_snp, fixture_expec
     tag = "g50k_b1000"
     snp = _snp(fixture_snp, 50000)
     res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), lr_retain_links=1e4, max_blk_sz=1000,
-                                     lr_links_approx=1e5, write_tsv=False, postprocess=True, exact_sr=True)
+                                     lr_links_approx=1e5, write_tsv=False, postprocess=True)   # exact_sr defaults to True here
     p1, p2, MI = e[f"{tag}_sr_pos1"], e[f"{tag}_sr_pos2"], e[f"{tag}_sr_MI"]
     np.testing.assert_array_equal(res.sr["pos1"], p1.astype(np.int32))
     err = np.abs(res.sr["MI"] - MI).max()
