@@ -81,7 +81,9 @@ perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path =
   }
   res <- .Call("_LDWeaver_gpu_mi_scan", .snpdat_codes(snp.dat), snp.dat$nsnp, snp.dat$nseq, as.numeric(hdw),
                as.integer(snp.dat$POS), as.integer(cds_var$paint), as.numeric(snp.dat$g), sr_dist, lr_retain_links,
-               lr_links_approx, max_blk_sz, perform_SR_analysis_only, PACKAGE = "LDWeaver")
+               lr_links_approx, max_blk_sz, perform_SR_analysis_only,
+               isTRUE(getOption("LDWeaver.exact_sr", TRUE)),   # fp64 MI for the short-range links (the fp32 epilogue's 2e-7 is amplified by the beta fit below)
+               PACKAGE = "LDWeaver")
   if (length(res$lr$MI) > 0)   # same rows, same order as the per-block appends of R/computePairwiseMI.R:362
     write.table(x = as.data.frame(res$lr[1:6]), file = lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
   if (!isTRUE(getOption("LDWeaver.native_post", TRUE))) {
@@ -91,7 +93,8 @@ perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path =
     sr_links_red <- sr_links_all$sr_links_red
     sr_links_ARACNE_check <- sr_links_all$sr_links_ARACNE_check
   } else {
-    post <- .Call("_LDWeaver_gpu_sr_post", res$sr$pos1, res$sr$pos2, res$sr$clust1, res$sr$clust2, res$sr$len, res$sr$MI,
+    post <- .Call("_LDWeaver_gpu_sr_post", as.integer(res$sr$pos1), as.integer(res$sr$pos2), res$sr$clust1, res$sr$clust2,
+                  as.integer(res$sr$len), res$sr$MI,
                   as.integer(cds_var$nclust), sr_dist, srp_cutoff, PACKAGE = "LDWeaver")
     frame <- function(idx) {   # columns of sr_links_df (R/computePairwiseMI.R:470): clust_c + the six link columns + srp_max
       r <- post$row[idx]

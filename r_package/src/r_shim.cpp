@@ -128,11 +128,12 @@ SEXP LDWeaver_gpu_hdw(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP thr_) {
   return w;
 }
 
-// .Call("_LDWeaver_gpu_mi_scan", codes, nsnp, nseq, hdw, POS, paint, g, sr_dist, lr_retain_links, lr_links_approx, blk, sr_only)
-//   -> list(sr = <columns>, lr = <columns>, borderline = <columns>, thr = numeric(nblocks))
-// scan part of perform_MI_computation (R/computePairwiseMI.R:69-116)
+// .Call("_LDWeaver_gpu_mi_scan", codes, nsnp, nseq, hdw, POS, paint, g, sr_dist, lr_retain_links, lr_links_approx, blk, sr_only,
+//       exact_sr) -> list(sr = <columns>, lr = <columns>, borderline = <columns>, thr = numeric(nblocks))
+// scan part of perform_MI_computation (R/computePairwiseMI.R:69-116).  exact_sr = TRUE replaces the fp32-accurate MI of the
+// short-range links by fp64 values (ldw_links_to_cells + ldw_mi_pairs_exact per block) before R derives statistics from them.
 SEXP LDWeaver_gpu_mi_scan(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP hdw_, SEXP pos_, SEXP paint_, SEXP g_, SEXP srd_, SEXP retain_,
-                          SEXP approx_, SEXP blk_, SEXP sronly_) {
+                          SEXP approx_, SEXP blk_, SEXP sronly_, SEXP exact_) {
   int64_t n = (int64_t)Rf_asReal(nsnp_), S = (int64_t)Rf_asReal(nseq_), blk = (int64_t)Rf_asReal(blk_);
   ldw_mi_plan* plan = nullptr;
   if (ldw_mi_plan_create(ctx(), RAW(codes_), n, S, REAL(hdw_), INTEGER(pos_), INTEGER(paint_), blk, &plan) != 0)
@@ -149,8 +150,33 @@ SEXP LDWeaver_gpu_mi_scan(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP hdw_, SEXP p
     UNPROTECT(1);
     Rf_error("%s", ldw_last_error());
   }
+  // cells of the short-range links in their blocks' MI matrices (host only), while the library-owned columns are at hand
+  const bool exact = Rf_asLogical(exact_) && !(flags & LDW_SCAN_SR_ONLY) && sr.n > 0;
+  std::vector<int32_t> fl, tl, blk_of;
+  if (exact) {
+    fl.resize((size_t)sr.n); tl.resize((size_t)sr.n);
+    if (ldw_links_to_cells(INTEGER(pos_), n, blk, &sr, fl.data(), tl.data()) != 0) {
+      ldw_mi_plan_destroy(plan);
+      UNPROTECT(1);
+      Rf_error("%s", ldw_last_error());
+    }
+    blk_of.assign(sr.block, sr.block + sr.n);
+  }
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 4));
   SET_VECTOR_ELT(out, 0, links_to_list(sr));
+  if (exact) {  // rows are in make_blocks order: one ldw_mi_pairs_exact call per run of equal block ids, written in place
+    double* mi = REAL(VECTOR_ELT(VECTOR_ELT(out, 0), 5));
+    for (int64_t lo = 0; lo < sr.n;) {
+      int64_t hi = lo;
+      while (hi < sr.n && blk_of[hi] == blk_of[lo]) hi++;
+      if (ldw_mi_pairs_exact(plan, blk_of[lo], fl.data() + lo, tl.data() + lo, hi - lo, mi + lo) != 0) {
+        ldw_mi_plan_destroy(plan);
+        UNPROTECT(2);
+        Rf_error("%s", ldw_last_error());
+      }
+      lo = hi;
+    }
+  }
   SET_VECTOR_ELT(out, 1, links_to_list(lr));
   SET_VECTOR_ELT(out, 2, links_to_list(bd));
   SET_VECTOR_ELT(out, 3, thr);
@@ -222,7 +248,7 @@ SEXP LDWeaver_gpu_sr_post(SEXP p1_, SEXP p2_, SEXP c1_, SEXP c2_, SEXP len_, SEX
 static const R_CallMethodDef CallEntries[] = {
     {"_LDWeaver_gpu_encode", (DL_FUNC)&LDWeaver_gpu_encode, 4},
     {"_LDWeaver_gpu_hdw", (DL_FUNC)&LDWeaver_gpu_hdw, 4},
-    {"_LDWeaver_gpu_mi_scan", (DL_FUNC)&LDWeaver_gpu_mi_scan, 12},
+    {"_LDWeaver_gpu_mi_scan", (DL_FUNC)&LDWeaver_gpu_mi_scan, 13},
     {"_LDWeaver_gpu_ACGTN2num", (DL_FUNC)&LDWeaver_gpu_ACGTN2num, 3},
     {"_LDWeaver_gpu_runARACNE", (DL_FUNC)&LDWeaver_gpu_runARACNE, 6},
     {"_LDWeaver_gpu_sr_post", (DL_FUNC)&LDWeaver_gpu_sr_post, 9},

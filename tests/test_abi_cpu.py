@@ -72,3 +72,11 @@ def test_r_shim_type_checks_against_the_abi():
     for name, nargs in re.findall(r'\{"(_LDWeaver_gpu_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim):
         calls = re.findall(r'\.Call\("%s",(.*?)PACKAGE = "LDWeaver"\)' % name, rcode, flags=re.S)
         assert calls or name == "_LDWeaver_gpu_ACGTN2num", f"{name} registered but never called from gpu_hotpath.R"
+        for body in calls:  # the registered argument count must be the number of arguments the R side passes
+            body = re.sub(r"#[^\n]*", "", body)
+            depth, nargs_r = 0, 0
+            for ch in body:
+                depth += ch in "([{"
+                depth -= ch in ")]}"
+                nargs_r += ch == "," and depth == 0
+            assert nargs_r == int(nargs), f"{name}: R passes {nargs_r} arguments, the shim registers {nargs}"
