@@ -49,8 +49,12 @@ enum {
   LDW_SCAN_SR_ONLY = 1,   /* perform_SR_analysis_only = TRUE (R/computePairwiseMI.R:179-189, quirk Q12) */
   LDW_SCAN_IDEAL_Q = 2,   /* opt-out of quirk Q1: use 0.25*r_i*r_j on off-diagonal blocks too (NOT reference behaviour) */
   LDW_SCAN_NO_LINKS = 4,  /* compute MI / thresholds only: no link columns are materialised or copied */
-  LDW_SCAN_NO_D2H = 8     /* materialise the link columns in device memory but do not copy them to the host
+  LDW_SCAN_NO_D2H = 8,    /* materialise the link columns in device memory but do not copy them to the host
                              (device-resident throughput measurement); link outputs come back with n rows and NULL pointers */
+  LDW_SCAN_SR_EXACT = 16  /* recompute the MI of every short-range link in fp64 (the reference's arithmetic) on the device,
+                             block by block, before the rows are copied out.  Added at the end of round 1 WITHOUT a run on
+                             hardware (the verified way to the same values is ldw_links_to_cells + ldw_mi_pairs_exact);
+                             off unless asked for; tests/test_gpu_mi.py holds its parity test behind LDW_TEST_UNVERIFIED=1 */
 };
 
 typedef struct ldw_ctx ldw_ctx;         /* one per device; owns stream + scratch */

@@ -189,7 +189,7 @@ def estimate_Hamming_distance_weights(snp_dat: SnpDat, threshold: float = 0.1, m
 # --------------------------------------------------------------------------------------------------
 # perform_MI_computation (scan + sr/lr link filter)
 # --------------------------------------------------------------------------------------------------
-SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS, SCAN_NO_D2H = 1, 2, 4, 8
+SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS, SCAN_NO_D2H, SCAN_SR_EXACT = 1, 2, 4, 8, 16
 
 
 @dataclass
@@ -559,7 +559,8 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     without touching the file system and, unless ``postprocess=True``, without the post-processing; ``exact_sr``
     recomputes the MI of every short-range link in fp64 (``MIPlan.sr_exact``) before anything is derived from it -- by
     default whenever the post-processing runs (its beta fit amplifies the fp32 epilogue's 2e-7 to ~1e-2 in srp_max; about
-    +0.5 s at 616 x 100k), never for perform_SR_analysis_only scans."""
+    +0.5 s at 616 x 100k), never for perform_SR_analysis_only scans.  ``exact_sr="in_scan"`` asks the scan itself for
+    them (``LDW_SCAN_SR_EXACT``; written at the end of round 1 and not yet run on hardware)."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -575,10 +576,13 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         plan = MIPlan(snp_dat, hdw, paint, blk, device)
     try:
         flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
-        sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags)
         do_post = postprocess if postprocess is not None else write_tsv
         if exact_sr is None:
             exact_sr = bool(do_post) and not perform_SR_analysis_only
+        if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call (not yet run on hardware)
+            flags |= SCAN_SR_EXACT
+            exact_sr = False
+        sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags)
         if exact_sr:
             if perform_SR_analysis_only:
                 raise ValueError("exact_sr is not available with perform_SR_analysis_only")

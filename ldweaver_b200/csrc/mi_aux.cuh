@@ -589,6 +589,33 @@ __global__ void mi_sr_materialize_kernel(SrMatParams P) {
   }
 }
 
+// LDW_SCAN_SR_EXACT: fp64 MI, in the reference's own arithmetic (refine_pair), of every short-range link of a block,
+// written over the fp32-derived values mi_sr_materialize_kernel left in the link column.  Same walk over a column's
+// short-range rows as that kernel (one CTA per column), one warp per link.
+__global__ void __launch_bounds__(32 * REFINE_WARPS) mi_sr_exact_kernel(SrMatParams P, RefineParams R) {
+  __shared__ double acc_s[REFINE_WARPS][32 * 25];
+  const int jl = blockIdx.x;
+  if (jl >= P.nt) return;
+  const ColInfo c = P.col[jl];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double* acc = acc_s[warp];
+  const int la = c.a1 - c.a0, lb = c.b1 - c.b0;
+  const int bj = min(max(jl + 1 - c.a0, 0), la) + min(max(jl + 1 - c.b0, 0), lb);  // SR rows <= jl
+  for (int k = warp; k < la + lb; k += REFINE_WARPS) {  // k is warp-uniform: refine_pair synchronises the warp
+    const int il = k < la ? c.a0 + k : c.b0 + (k - la);
+    if (il == jl) continue;
+    int64_t slot;
+    if (il < jl) {
+      if (P.diag) continue;
+      slot = (int64_t)c.baseU + k;
+    } else {
+      slot = (int64_t)c.baseL + (k - bj);
+    }
+    const double v = refine_pair(R, il, jl, lane, acc);
+    if (lane == 0) P.o_mi[slot] = v;
+  }
+}
+
 __global__ void mi_lr_materialize_kernel(const uint32_t* __restrict__ order, const uint64_t* __restrict__ keys_sorted,
                                          const int32_t* __restrict__ gi, const int32_t* __restrict__ gj,
                                          const double* __restrict__ mi, const int32_t* __restrict__ pos,

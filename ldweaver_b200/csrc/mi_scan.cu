@@ -1128,6 +1128,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       m.o_mi = W->d_sr.mi.as<double>() + s.sr_base;
       mi_sr_materialize_kernel<<<H.nt, 128, 0, st>>>(m);
       LDW_CUDA(cudaGetLastError());
+      if (flags & LDW_SCAN_SR_EXACT) {  // fp64 MI over the fp32-derived column, before the rows leave for the host
+        n_launches++;
+        mi_sr_exact_kernel<<<H.nt, 32 * REFINE_WARPS, 0, st>>>(m, make_refine_params(P, D, H, cfg));
+        LDW_CUDA(cudaGetLastError());
+      }
       if (want_host) {
         // copy this block's finished rows to the host while the next blocks are being scanned
         LDW_CUDA(cudaEventRecord(ev_blk, st));

@@ -338,3 +338,28 @@ def test_exact_short_range_mi_gives_tight_post_parity(fixture_snp, fixture_expec
     with pytest.raises(ValueError, match="exact_sr is not available"):
         ldw.perform_MI_computation(_snp(fixture_snp, 2221315), e["hdw"], ldw.CdsVar(e["paint"], 3), sr_dist=2000, max_blk_sz=1000,
                                    perform_SR_analysis_only=True, write_tsv=False, exact_sr=True)
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("LDW_TEST_UNVERIFIED"),
+                    reason="LDW_SCAN_SR_EXACT was written after the round's GPU budget was spent; set LDW_TEST_UNVERIFIED=1 to run it")
+@pytest.mark.parametrize("sr_only", [False, True])
+def test_in_scan_exact_short_range_mi(fixture_snp, fixture_expected, sr_only):
+    """LDW_SCAN_SR_EXACT (mi_sr_exact_kernel): fp64 short-range MI from inside the scan call -- must equal the golden fp64
+    column to 1e-12, and in SR-only mode (quirk Q12: reduced SNP lists) the oracle's SR-only values."""
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    e = fixture_expected
+    if not sr_only:
+        snp = _snp(fixture_snp, 50000)
+        res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), lr_retain_links=1e4, max_blk_sz=1000,
+                                         lr_links_approx=1e5, write_tsv=False, exact_sr="in_scan")
+        np.testing.assert_array_equal(res.sr["pos1"], e["g50k_b1000_sr_pos1"].astype(np.int32))
+        assert np.abs(res.sr["MI"] - e["g50k_b1000_sr_MI"]).max() < 1e-12
+    else:
+        g = 2221315
+        osnp = O.snp_dat_from_codes(fixture_snp.codes, fixture_snp.POS, g)
+        ref = O.perform_MI_scan(osnp, e["hdw"], e["paint"], 3, max_blk_sz=1000, perform_SR_analysis_only=True, sr_dist=2000)
+        res = ldw.perform_MI_computation(_snp(fixture_snp, g), e["hdw"], ldw.CdsVar(e["paint"], 3), sr_dist=2000, max_blk_sz=1000,
+                                         perform_SR_analysis_only=True, write_tsv=False, exact_sr="in_scan")
+        np.testing.assert_array_equal(res.sr["pos1"], ref.sr["pos1"].astype(np.int32))
+        assert np.abs(res.sr["MI"] - ref.sr["MI"]).max() < 1e-12
