@@ -52,9 +52,9 @@ enum {
   LDW_SCAN_NO_D2H = 8,    /* materialise the link columns in device memory but do not copy them to the host
                              (device-resident throughput measurement); link outputs come back with n rows and NULL pointers */
   LDW_SCAN_SR_EXACT = 16  /* recompute the MI of every short-range link in fp64 (the reference's arithmetic) on the device,
-                             block by block, before the rows are copied out.  Added at the end of round 1 WITHOUT a run on
-                             hardware (the verified way to the same values is ldw_links_to_cells + ldw_mi_pairs_exact);
-                             off unless asked for; tests/test_gpu_mi.py holds its parity test behind LDW_TEST_UNVERIFIED=1 */
+                             block by block, before the rows are copied out (mi_sr_exact_kernel; also valid with
+                             LDW_SCAN_SR_ONLY).  Parity-checked on the fixture in both modes (1e-12); not yet timed at
+                             616 x 100k, so the host mirror still defaults to ldw_links_to_cells + ldw_mi_pairs_exact */
 };
 
 typedef struct ldw_ctx ldw_ctx;         /* one per device; owns stream + scratch */

@@ -560,7 +560,8 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     recomputes the MI of every short-range link in fp64 (``MIPlan.sr_exact``) before anything is derived from it -- by
     default whenever the post-processing runs (its beta fit amplifies the fp32 epilogue's 2e-7 to ~1e-2 in srp_max; about
     +0.5 s at 616 x 100k), never for perform_SR_analysis_only scans.  ``exact_sr="in_scan"`` asks the scan itself for
-    them (``LDW_SCAN_SR_EXACT``; written at the end of round 1 and not yet run on hardware)."""
+    them (``LDW_SCAN_SR_EXACT``, also valid with perform_SR_analysis_only; parity-checked on the fixture, not yet timed at
+    full size, hence not the default)."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -579,7 +580,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         do_post = postprocess if postprocess is not None else write_tsv
         if exact_sr is None:
             exact_sr = bool(do_post) and not perform_SR_analysis_only
-        if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call (not yet run on hardware)
+        if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call
             flags |= SCAN_SR_EXACT
             exact_sr = False
         sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags)

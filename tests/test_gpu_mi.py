@@ -340,8 +340,6 @@ def test_exact_short_range_mi_gives_tight_post_parity(fixture_snp, fixture_expec
                                    perform_SR_analysis_only=True, write_tsv=False, exact_sr=True)
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("LDW_TEST_UNVERIFIED"),
-                    reason="LDW_SCAN_SR_EXACT was written after the round's GPU budget was spent; set LDW_TEST_UNVERIFIED=1 to run it")
 @pytest.mark.parametrize("sr_only", [False, True])
 def test_in_scan_exact_short_range_mi(fixture_snp, fixture_expected, sr_only):
     """LDW_SCAN_SR_EXACT (mi_sr_exact_kernel): fp64 short-range MI from inside the scan call -- must equal the golden fp64
