@@ -18,6 +18,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <atomic>
@@ -64,6 +65,26 @@ struct PhaseTimer {  // LDW_DBG_TIMING=1: phase times on stderr (never stdout)
     fprintf(stderr, "[ldw_sr_postprocess] cluster %d %-28s %8.2f ms\n", c, what, std::chrono::duration<double, std::milli>(n - t).count());
     t = n;
   }
+};
+
+// Scratch array on transparent huge pages where the kernel grants them (madvise): the counting sort below writes through
+// tens of thousands of cursors spread over hundreds of MB, which with 4 KB pages is one TLB miss per element.
+template <class T>
+struct HugeArray {
+  T* p = nullptr;
+  size_t n = 0;
+  explicit HugeArray(size_t count) : n(count) {
+    const size_t bytes = std::max<size_t>(sizeof(T) * count, 1), two_mb = size_t(2) << 20;
+    void* q = nullptr;
+    if (posix_memalign(&q, two_mb, (bytes + two_mb - 1) / two_mb * two_mb) != 0) q = nullptr;
+    if (q) madvise(q, (bytes + two_mb - 1) / two_mb * two_mb, MADV_HUGEPAGE);
+    p = (T*)q;
+  }
+  ~HugeArray() { free(p); }
+  HugeArray(const HugeArray&) = delete;
+  HugeArray& operator=(const HugeArray&) = delete;
+  T* data() { return p; }
+  T& operator[](size_t i) { return p[i]; }
 };
 
 constexpr int64_t kChunk = 1 << 16;  // fixed, so that chunked sums do not depend on the number of threads
@@ -313,149 +334,186 @@ extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr
   std::vector<int64_t> dup_row;
   std::vector<int32_t> dup_c;
   std::vector<double> dup_srp;
-  const int64_t nchunks = (N + kChunk - 1) / kChunk;
-
+  // Every pass below walks the link table ONCE for all clusters (a link belongs to clust1 and, if different, clust2;
+  // R/computePairwiseMI.R:372-376), in a fixed number of contiguous pieces so that the results do not depend on the
+  // number of host threads.
   PhaseTimer tm;
-  for (int32_t c = 1; c <= nclust; c++) {
-    // ---- cluster list c (R/computePairwiseMI.R:372-376) with the filters of :417-419, in scan order ----
-    std::vector<int64_t> cnt(nchunks + 1, 0);
-    int32_t maxlen = 0;
-    {
-      std::vector<int32_t> mx(nchunks, 0);
-      parallel_dynamic(nchunks, [&](int64_t k) {
-        const int64_t lo = k * kChunk, hi = std::min(N, lo + kChunk);
-        int64_t m = 0;
-        int32_t ml = 0;
-        for (int64_t i = lo; i < hi; i++) {
-          const int32_t l = sr->len[i];
-          if ((sr->clust1[i] == c || sr->clust2[i] == c) && (double)l < sr_dist && l > 0) { m++; ml = std::max(ml, l); }
-        }
-        cnt[k + 1] = m;
-        mx[k] = ml;
-      });
-      for (int64_t k = 0; k < nchunks; k++) { cnt[k + 1] += cnt[k]; maxlen = std::max(maxlen, mx[k]); }
-    }
-    const int64_t nrow = cnt[nchunks];
-    if (nrow == 0) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d holds no short-range link with 0 < len < sr_dist", (int)c);
-    std::vector<int64_t> rows(nrow);
-    parallel_dynamic(nchunks, [&](int64_t k) {
-      const int64_t lo = k * kChunk, hi = std::min(N, lo + kChunk);
-      int64_t o = cnt[k];
-      for (int64_t i = lo; i < hi; i++) {
-        const int32_t l = sr->len[i];
-        if ((sr->clust1[i] == c || sr->clust2[i] == c) && (double)l < sr_dist && l > 0) rows[o++] = i;
+  auto member = [&](int64_t i, int32_t& ca, int32_t& cb) -> bool {  // filters of :417-419; clusters the link is listed under
+    const int32_t l = sr->len[i];
+    if (!(l > 0 && (double)l < sr_dist)) return false;
+    ca = sr->clust1[i]; cb = sr->clust2[i];
+    if (ca < 1 || ca > nclust) ca = 0;
+    if (cb < 1 || cb > nclust || cb == ca) cb = 0;
+    return (ca | cb) != 0;
+  };
+  // ---- longest length present (sizes the histograms): len < sr_dist bounds it unless sr_dist is huge ----
+  int32_t maxlen = 0;
+  if (sr_dist <= (double)(1 << 18)) {
+    maxlen = (int32_t)std::max(0.0, ceil(sr_dist) - 1.0);
+  } else {
+    const int64_t P0 = 256, p0sz = (N + P0 - 1) / P0;
+    std::vector<int32_t> mx0(P0, 0);
+    parallel_dynamic(P0, [&](int64_t k) {
+      int32_t ml = 0;
+      for (int64_t i = k * p0sz; i < std::min(N, (k + 1) * p0sz); i++) {
+        int32_t ca, cb;
+        if (member(i, ca, cb)) ml = std::max(ml, sr->len[i]);
       }
+      mx0[k] = ml;
     });
+    for (int64_t k = 0; k < P0; k++) maxlen = std::max(maxlen, mx0[k]);
+    tm.lap("longest length", 0);
+  }
 
-    tm.lap("cluster rows", c);
-    // ---- group_by(len) %>% summarise(quantile(MI, 0.95))  (:422): counting sort by length, then one selection per group ----
-    const int64_t rchunks = (nrow + kChunk - 1) / kChunk;
-    const int64_t nl = (int64_t)maxlen + 1;
-    std::vector<int64_t> gcount(nl, 0);
-    std::vector<std::vector<int32_t>> hist(rchunks);  // per chunk: how many rows of each length (chunks are short: int32 suffices)
-    parallel_dynamic(rchunks, [&](int64_t k) {
-      std::vector<int32_t>& h = hist[k];
-      h.assign(nl, 0);
-      const int64_t lo = k * kChunk, hi = std::min(nrow, lo + kChunk);
-      for (int64_t i = lo; i < hi; i++) h[sr->len[rows[i]]]++;
-    });
-    for (int64_t k = 0; k < rchunks; k++) for (int64_t l = 0; l < nl; l++) gcount[l] += hist[k][l];
-    std::vector<int64_t> goff(nl + 1, 0);
-    for (int64_t l = 0; l < nl; l++) goff[l + 1] = goff[l] + gcount[l];
-    {  // turn the per-chunk histograms into write cursors
-      std::vector<int64_t> run(goff.begin(), goff.end() - 1);
-      std::vector<std::vector<int64_t>> cur(rchunks);
-      for (int64_t k = 0; k < rchunks; k++) {
-        cur[k].resize(nl);
-        for (int64_t l = 0; l < nl; l++) { cur[k][l] = run[l]; run[l] += hist[k][l]; }
-        std::vector<int32_t>().swap(hist[k]);
+  // ---- group_by(len) %>% summarise(quantile(MI, 0.95))  (:422): counting sort by (cluster, length) -- per-piece
+  //      histograms turned into write cursors, so the scatter is parallel and deterministic -- then one selection per group ----
+  const int64_t nl = (int64_t)maxlen + 1;
+  const int64_t G = (int64_t)nclust * nl;                       // group id = (c - 1) * nl + len
+  int64_t B = std::min<int64_t>(64, std::max<int64_t>(1, (int64_t)(128ll << 20) / (G * 4)));  // histogram memory <= 128 MB
+  B = std::max<int64_t>(1, std::min<int64_t>(B, (N + kChunk - 1) / kChunk));
+  const int64_t bsz = (N + B - 1) / B;
+  std::vector<std::vector<int32_t>> hist(B);
+  parallel_dynamic(B, [&](int64_t k) {
+    std::vector<int32_t>& h = hist[k];
+    h.assign((size_t)G, 0);
+    for (int64_t i = k * bsz; i < std::min(N, (k + 1) * bsz); i++) {
+      int32_t ca, cb;
+      if (!member(i, ca, cb)) continue;
+      const int64_t l = sr->len[i];
+      if (ca) h[(ca - 1) * nl + l]++;
+      if (cb) h[(cb - 1) * nl + l]++;
+    }
+  });
+  std::vector<int64_t> gcount((size_t)G, 0), goff((size_t)G + 1, 0);
+  for (int64_t k = 0; k < B; k++) for (int64_t g = 0; g < G; g++) gcount[g] += hist[k][g];
+  for (int64_t g = 0; g < G; g++) goff[g + 1] = goff[g] + gcount[g];
+  for (int32_t c = 1; c <= nclust; c++)
+    if (goff[(int64_t)c * nl] == goff[(int64_t)(c - 1) * nl])
+      return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d holds no short-range link with 0 < len < sr_dist", (int)c);
+  std::vector<int64_t> glist;                                   // non-empty groups, cluster-major, ascending length
+  for (int64_t g = 0; g < G; g++) if (gcount[g] > 0) glist.push_back(g);
+  std::vector<double> gq((size_t)glist.size());
+  {
+    HugeArray<double> grouped((size_t)goff[G]);
+    if (!grouped.data()) return ldw::set_error(LDW_ERR_NOMEM, "ldw_sr_postprocess: out of memory (%lld values)", (long long)goff[G]);
+    std::vector<std::vector<int64_t>> cur(B);
+    std::vector<int64_t> run(goff.begin(), goff.end() - 1);
+    for (int64_t k = 0; k < B; k++) {
+      cur[k].resize((size_t)G);
+      for (int64_t g = 0; g < G; g++) { cur[k][g] = run[g]; run[g] += hist[k][g]; }
+      std::vector<int32_t>().swap(hist[k]);
+    }
+    parallel_dynamic(B, [&](int64_t k) {
+      std::vector<int64_t>& cu = cur[k];
+      for (int64_t i = k * bsz; i < std::min(N, (k + 1) * bsz); i++) {
+        int32_t ca, cb;
+        if (!member(i, ca, cb)) continue;
+        const int64_t l = sr->len[i];
+        const double v = sr->MI[i];
+        if (ca) grouped[cu[(ca - 1) * nl + l]++] = v;
+        if (cb) grouped[cu[(cb - 1) * nl + l]++] = v;
       }
-      std::vector<double> grouped(nrow);
-      parallel_dynamic(rchunks, [&](int64_t k) {
-        std::vector<int64_t>& cu = cur[k];
-        const int64_t lo = k * kChunk, hi = std::min(nrow, lo + kChunk);
-        for (int64_t i = lo; i < hi; i++) { const int64_t r = rows[i]; grouped[cu[sr->len[r]]++] = sr->MI[r]; }
-      });
-      std::vector<std::vector<int64_t>>().swap(cur);
-      tm.lap("counting sort by len", c);
-      std::vector<int32_t> ulen;
-      for (int64_t l = 1; l < nl; l++) if (gcount[l] > 0) ulen.push_back((int32_t)l);
-      const int64_t ng = (int64_t)ulen.size();
+    });
+    std::vector<std::vector<int64_t>>().swap(cur);
+    tm.lap("counting sort by (cluster, len)", 0);
+    parallel_dynamic((int64_t)glist.size(), [&](int64_t t) {
+      const int64_t g = glist[t];
+      gq[t] = quantile7(grouped.data() + goff[g], gcount[g], 0.95);
+    });
+    tm.lap("quantiles", 0);
+  }
+  // ---- fastLm(cbind(log(len), 1), log(max)); fit = exp(fitted)  (:428-429), per cluster ----
+  {
+    size_t t = 0;
+    for (int32_t c = 1; c <= nclust; c++) {
+      std::vector<double> lx, ly;
+      const size_t base = S->fit_len.size();
+      for (; t < glist.size() && glist[t] < (int64_t)c * nl; t++) {
+        const int32_t l = (int32_t)(glist[t] - (int64_t)(c - 1) * nl);
+        S->fit_len.push_back(l);
+        S->fit_q95.push_back(gq[t]);
+        lx.push_back(log((double)l));
+        ly.push_back(log(gq[t]));
+      }
+      const int64_t ng = (int64_t)lx.size();
       if (ng < 2) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d has fewer than two distinct link lengths", (int)c);
-      std::vector<double> q95(ng);
-      parallel_dynamic(ng, [&](int64_t gi) {
-        const int64_t l = ulen[gi];
-        q95[gi] = quantile7(grouped.data() + goff[l], gcount[l], 0.95);
-      });
-      tm.lap("quantiles", c);
-      // ---- fastLm(cbind(log(len), 1), log(max)); fit = exp(fitted)  (:428-429) ----
-      std::vector<double> lx(ng), ly(ng);
-      for (int64_t gi = 0; gi < ng; gi++) { lx[gi] = log((double)ulen[gi]); ly[gi] = log(q95[gi]); }
       double coef[2];
       ols2(lx, ly, coef);
-      const size_t base = S->fit_len.size();
-      S->fit_len.insert(S->fit_len.end(), ulen.begin(), ulen.end());
-      S->fit_q95.insert(S->fit_q95.end(), q95.begin(), q95.end());
       S->fit_val.resize(base + ng);
       for (int64_t gi = 0; gi < ng; gi++) S->fit_val[base + gi] = exp(lx[gi] * coef[0] + coef[1]);
       S->fit_off.push_back((int64_t)(base + ng));
       S->coef.push_back(coef[0]);
       S->coef.push_back(coef[1]);
     }
-    const int64_t ng = S->fit_off[c] - S->fit_off[c - 1];
-    const double* mean_dist = S->fit_val.data() + S->fit_off[c - 1];
+  }
+  tm.lap("decay fits", 0);
 
-    tm.lap("decay fit", c);
-    // ---- residuals above the fit (:448-450).  `mean_dist[sr_links_t$len]` subscripts the fitted values with the VALUE of
-    //      len (position in maxvls), which is the group of that length only when no shorter length is missing; a length
-    //      beyond the number of groups gives NA and the link drops out of which(diff > 0).  Reproduced as is. ----
-    std::vector<int64_t> pcnt(rchunks + 1, 0);
-    std::vector<double> cs1(rchunks, 0), cs2(rchunks, 0), csum(rchunks, 0);
-    std::atomic<int> bad(0);
-    parallel_dynamic(rchunks, [&](int64_t k) {
-      const int64_t lo = k * kChunk, hi = std::min(nrow, lo + kChunk);
-      int64_t m = 0;
-      double s1 = 0, s2 = 0, s = 0;
-      for (int64_t i = lo; i < hi; i++) {
-        const int64_t r = rows[i];
-        const int64_t l = sr->len[r];
-        if (l > ng) continue;
-        const double d = sr->MI[r] - mean_dist[l - 1];
-        if (d > 0) {
-          if (d > 1) bad.store(1);
-          m++; s1 += log(d); s2 += log1p(-d); s += d;
-        }
+  // ---- residuals above the fit (:448-450).  `mean_dist[sr_links_t$len]` subscripts the fitted values with the VALUE of
+  //      len (position in maxvls), which is the group of that length only when no shorter length is missing; a length
+  //      beyond the number of groups gives NA and the link drops out of which(diff > 0).  Reproduced as is. ----
+  const int64_t R = std::max<int64_t>(1, std::min<int64_t>(256, (N + kChunk - 1) / kChunk));
+  const int64_t rsz = (N + R - 1) / R;
+  const int C1 = nclust + 1;
+  std::vector<int64_t> pcnt((size_t)(R + 1) * C1, 0);
+  std::vector<double> cs1((size_t)R * C1, 0), cs2((size_t)R * C1, 0), csum((size_t)R * C1, 0);
+  std::vector<std::vector<int64_t>> lrow((size_t)R * C1);      // per piece and cluster: links above the fit, in scan order
+  std::vector<std::vector<double>> lx((size_t)R * C1);
+  std::atomic<int> bad(0);
+  auto residual = [&](int64_t i, int32_t c, double& d) -> bool {
+    const int64_t l = sr->len[i];
+    if (l > S->fit_off[c] - S->fit_off[c - 1]) return false;
+    d = sr->MI[i] - S->fit_val[S->fit_off[c - 1] + l - 1];
+    return d > 0;
+  };
+  parallel_dynamic(R, [&](int64_t k) {
+    for (int64_t i = k * rsz; i < std::min(N, (k + 1) * rsz); i++) {
+      int32_t cc[2];
+      if (!member(i, cc[0], cc[1])) continue;
+      for (int q = 0; q < 2; q++) {
+        double d;
+        if (!cc[q] || !residual(i, cc[q], d)) continue;
+        if (d > 1) bad.store(cc[q]);
+        const size_t o = (size_t)k * C1 + cc[q];
+        lrow[o].push_back(i); lx[o].push_back(d);
+        cs1[o] += log(d); cs2[o] += log1p(-d); csum[o] += d;
       }
-      pcnt[k + 1] = m; cs1[k] = s1; cs2[k] = s2; csum[k] = s;
-    });
-    if (bad.load()) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d: values must be in [0-1] to fit a beta distribution", (int)c);
-    for (int64_t k = 0; k < rchunks; k++) pcnt[k + 1] += pcnt[k];
-    const int64_t npos = pcnt[rchunks];
+    }
+    for (int c = 1; c <= nclust; c++) pcnt[(size_t)(k + 1) * C1 + c] = (int64_t)lrow[(size_t)k * C1 + c].size();
+  });
+  if (bad.load()) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d: values must be in [0-1] to fit a beta distribution", bad.load());
+  for (int64_t k = 0; k < R; k++) for (int c = 1; c <= nclust; c++) pcnt[(size_t)(k + 1) * C1 + c] += pcnt[(size_t)k * C1 + c];
+  std::vector<std::vector<int64_t>> prow(C1);
+  std::vector<std::vector<double>> px(C1);
+  for (int32_t c = 1; c <= nclust; c++) {
+    const int64_t npos = pcnt[(size_t)R * C1 + c];
     if (npos < 2) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d has fewer than two links above the fitted decay", (int)c);
-    std::vector<int64_t> prow(npos);
-    std::vector<double> px(npos);
-    parallel_dynamic(rchunks, [&](int64_t k) {
-      const int64_t lo = k * kChunk, hi = std::min(nrow, lo + kChunk);
-      int64_t o = pcnt[k];
-      for (int64_t i = lo; i < hi; i++) {
-        const int64_t r = rows[i];
-        const int64_t l = sr->len[r];
-        if (l > ng) continue;
-        const double d = sr->MI[r] - mean_dist[l - 1];
-        if (d > 0) { prow[o] = r; px[o] = d; o++; }
-      }
-    });
-    tm.lap("residuals", c);
+    prow[c].resize((size_t)npos);
+    px[c].resize((size_t)npos);
+  }
+  parallel_dynamic(R, [&](int64_t k) {
+    for (int c = 1; c <= nclust; c++) {
+      const size_t o = (size_t)k * C1 + c;
+      std::copy(lrow[o].begin(), lrow[o].end(), prow[c].begin() + pcnt[o]);
+      std::copy(lx[o].begin(), lx[o].end(), px[c].begin() + pcnt[o]);
+      std::vector<int64_t>().swap(lrow[o]);
+      std::vector<double>().swap(lx[o]);
+    }
+  });
+  tm.lap("residuals", 0);
+
+  for (int32_t c = 1; c <= nclust; c++) {
+    const int64_t npos = (int64_t)px[c].size();
+    const std::vector<double>& x = px[c];
     // ---- fitdist(x, "beta") (:452): moment start values, then optim's Nelder-Mead on the negative log-likelihood ----
     long double s1 = 0, s2 = 0, sm = 0;
-    for (int64_t k = 0; k < rchunks; k++) { s1 += cs1[k]; s2 += cs2[k]; sm += csum[k]; }
+    for (int64_t k = 0; k < R; k++) { s1 += cs1[(size_t)k * C1 + c]; s2 += cs2[(size_t)k * C1 + c]; sm += csum[(size_t)k * C1 + c]; }
     const double mean = (double)(sm / (long double)npos);
     const int64_t pchunks = (npos + kChunk - 1) / kChunk;
     std::vector<double> cvar(pchunks, 0);
     parallel_dynamic(pchunks, [&](int64_t k) {
       const int64_t lo = k * kChunk, hi = std::min(npos, lo + kChunk);
       double s = 0;
-      for (int64_t i = lo; i < hi; i++) { const double t = px[i] - mean; s += t * t; }
+      for (int64_t i = lo; i < hi; i++) { const double t = x[i] - mean; s += t * t; }
       cvar[k] = s;
     });
     long double ss = 0;
@@ -481,18 +539,20 @@ extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr
     std::vector<double> psrp(npos);
     parallel_dynamic(pchunks, [&](int64_t k) {
       const int64_t lo = k * kChunk, hi = std::min(npos, lo + kChunk);
-      for (int64_t i = lo; i < hi; i++) psrp[i] = px[i] < 1.0 ? neg_log_upper_beta(px[i], par[0], par[1], lbeta) : INFINITY;
+      for (int64_t i = lo; i < hi; i++) psrp[i] = x[i] < 1.0 ? neg_log_upper_beta(x[i], par[0], par[1], lbeta) : INFINITY;
     });
     tm.lap("srp", c);
     // ---- same-cluster links go to sr_links_df, links between clusters to duplink_df (:460-468) ----
+    S->row.reserve(S->row.size() + (size_t)npos); S->clust_c.reserve(S->clust_c.size() + (size_t)npos); S->srp.reserve(S->srp.size() + (size_t)npos);
     for (int64_t i = 0; i < npos; i++) {
-      const int64_t r = prow[i];
+      const int64_t r = prow[c][i];
       if (std::isnan(psrp[i])) continue;  // :458
       if (sr->clust1[r] != sr->clust2[r]) { dup_row.push_back(r); dup_c.push_back(c); dup_srp.push_back(psrp[i]); }
       else { S->row.push_back(r); S->clust_c.push_back(c); S->srp.push_back(psrp[i]); }
     }
+    std::vector<int64_t>().swap(prow[c]);
+    std::vector<double>().swap(px[c]);
   }
-
   tm.lap("(last cluster's append)", nclust);
   // ---- links seen from two clusters: one row per distinct link, the one with the larger srp_max; groups in order of first
   //      appearance, first maximum wins (:474-483, data.table `.I[which.max(srp_max)], by = keys`) ----
