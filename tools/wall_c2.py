@@ -21,6 +21,8 @@ def main():
     snp = ldw.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
     lra = synth.exact_lr_links_approx(sy.POS, sy.g, 20000.0)
     exact_sr = "--exact-sr" in sys.argv   # fp64 MI for every short-range link before the statistics are derived
+    if "--exact-sr-in-scan" in sys.argv:  # the same from inside the scan call (LDW_SCAN_SR_EXACT)
+        exact_sr = "in_scan"
     out = None
     for it in range(2):
         with tempfile.TemporaryDirectory() as d:
