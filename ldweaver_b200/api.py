@@ -407,8 +407,9 @@ class SrLinks:
 def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[str] = None, srp_cutoff: float = 3) -> SrLinks:
     """R/computePairwiseMI.R:400-495 through ``ldw_sr_postprocess`` (native host code).  ``sr_links`` is the scan's
     short-range table (dict of columns, all clusters together -- the per-cluster lists of the reference are the rows
-    with clust1 == c or clust2 == c, :372-376).  ``plt_path`` is accepted for signature compatibility: no plots or .rds
-    files are written, the fitted curves come back in ``fits``."""
+    with clust1 == c or clust2 == c, :372-376).  No plots are drawn; the fitted curves come back in ``fits`` and, when
+    ``plt_path`` is given, each cluster's ``maxvls`` table (len, max, fit -- what the reference saves as
+    c<i>_fit_data.rds, :437) is written there as c<i>_fit_data.tsv."""
     nclust = int(cds_var.nclust if hasattr(cds_var, "nclust") else cds_var["nclust"])
     links = sr_links if isinstance(sr_links, _lib.Links) else _lib.Links.from_dict(sr_links)
     out = _lib.SrPost()
@@ -428,6 +429,12 @@ def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[st
         fits = [dict(len=fl[off[c]:off[c + 1]], max=fq[off[c]:off[c + 1]], fit=fv[off[c]:off[c + 1]], coef=coef[c],
                      shape=shape[c], start=start[c], n_pos=int(npos[c]), nm_evals=int(ev[c]), nm_fail=int(fail[c]))
                 for c in range(nclust)]
+        if plt_path is not None:  # stand-in for c<i>_fit_data.rds (:437): the maxvls table of each cluster as text
+            os.makedirs(plt_path, exist_ok=True)
+            for c, f in enumerate(fits, start=1):
+                with open(os.path.join(plt_path, f"c{c}_fit_data.tsv"), "w") as fh:
+                    fh.write("len\tmax\tfit\n")
+                    fh.writelines(f"{int(a)}\t{b:.15g}\t{v:.15g}\n" for a, b, v in zip(f["len"], f["max"], f["fit"]))
         return SrLinks(df=df, red=cp(out.red, out.n_red, np.int64), chk=cp(out.chk, out.n_chk, np.int64), fits=fits)
     finally:
         _lib.lib().ldw_sr_post_free(C.byref(out))

@@ -202,9 +202,13 @@ def test_finish_sr_links_and_tsv(fixture_expected, tmp_path):
     # appending (the reference's write.table(append = T))
     ldw.write_sr_tsv(str(path), sr, red["row"][:3], red["clust_c"][:3], red["srp_max"][:3], red["ARACNE"][:3], append=True)
     assert len(path.read_text().splitlines()) == len(lines) + 3
-    # runARACNE = FALSE: warning, constant 1 (:128-129); order_links = FALSE keeps sr_links_df order
+    # runARACNE = FALSE: warning, constant 1 (:128-129); order_links = FALSE keeps sr_links_df order; plt_folder receives
+    # the per-cluster maxvls tables (the reference's c<i>_fit_data.rds, as text)
     with pytest.warns(UserWarning, match="ARACNE not run"):
-        red2, _ = ldw.finish_sr_links(sr, ldw.CdsVar(paint, 3), 20000.0, 3.0, False, False, None)
+        red2, post2 = ldw.finish_sr_links(sr, ldw.CdsVar(paint, 3), 20000.0, 3.0, False, False, None, str(tmp_path / "PLOTS"))
+    for c in (1, 2, 3):
+        tab = np.loadtxt(tmp_path / "PLOTS" / f"c{c}_fit_data.tsv", skiprows=1)
+        assert np.array_equal(tab[:, 0], post2.fits[c - 1]["len"]) and np.allclose(tab[:, 2], post2.fits[c - 1]["fit"], rtol=1e-14)
     assert np.all(red2["ARACNE"] == 1) and np.array_equal(red2["row"], d["row"][ref.red])
 
 
