@@ -318,3 +318,41 @@ def test_sr_pair_indices_address_the_block_matrices(fixture_snp, fixture_expecte
     wrong["block"] = np.where(np.arange(len(MI)) == 7, 2, block)      # a link filed under another block
     with pytest.raises(_lib.LdwError, match="link 7 does not belong to the block it names"):
         list(api.sr_pair_indices(snp.POS, blk, wrong))
+
+
+def test_post_chain_against_committed_golden(fixture_expected):
+    """tests/golden/post_expected.npz (tests/golden/make_golden_post.py): the oracle today and the native code must both
+    still produce the committed sr_links_red table (rows, clusters, srp_max, ARACNE, order) and the long-range chain."""
+    import os
+    from conftest import GOLDEN
+    g = dict(np.load(os.path.join(GOLDEN, "post_expected.npz")))
+    sr, paint = _fixture_sr(fixture_expected)
+    # native
+    red, post = ldw.finish_sr_links(sr, ldw.CdsVar(paint, 3), 20000.0, 3.0, True, True, None)
+    assert len(post.df["row"]) == int(g["n_df"]) and len(post.chk) == int(g["n_chk"])
+    assert int(np.sum(post.df["row"] * (np.arange(len(post.df["row"])) % 1009 + 1))) == int(g["df_row_checksum"])
+    # same links; links with (mathematically) equal srp_max -- duplicate SNP patterns -- may swap places in the ordering,
+    # their values agreeing to 1e-9 rather than bitwise, so the tables are compared link by link
+    a, b = np.argsort(red["row"], kind="stable"), np.argsort(g["red_row"], kind="stable")
+    np.testing.assert_array_equal(red["row"][a], g["red_row"][b])
+    np.testing.assert_array_equal(red["clust_c"][a], g["red_clust_c"][b])
+    np.testing.assert_array_equal(red["ARACNE"][a], g["red_aracne"][b].astype(float))
+    assert np.allclose(red["srp_max"][a], g["red_srp_max"][b], rtol=1e-7, atol=0)
+    assert np.all(np.diff(red["srp_max"]) <= 0)
+    moved = red["row"] != g["red_row"]
+    assert moved.mean() < 0.02 and np.allclose(red["srp_max"][moved], g["red_srp_max"][moved], rtol=1e-7)
+    assert np.allclose([f["shape"] for f in post.fits], g["shape"], rtol=1e-9)
+    assert np.allclose([f["coef"] for f in post.fits], g["coef"], rtol=1e-11)
+    assert [f["nm_evals"] for f in post.fits] == g["nm_evals"].tolist() and [f["n_pos"] for f in post.fits] == g["n_pos"].tolist()
+    assert np.allclose([f["max"].sum() for f in post.fits], g["q95_sum"], rtol=1e-14)
+    # oracle (guards the oracle itself against drift)
+    ref = PO.merge_n_sort_sr_links(sr, 3, 20000.0, 3.0)
+    o = PO.order_links_by_srp(ref.df["srp_max"][ref.red])
+    np.testing.assert_array_equal(ref.df["row"][ref.red][o], g["red_row"])
+    assert np.array_equal(ref.df["srp_max"][ref.red][o], g["red_srp_max"])
+    # long-range chain (g = 2 221 315 tables) through the native ARACNE
+    lr = {k: fixture_expected[f"g2M_b1000_lr_{k}"] for k in ("pos1", "pos2", "MI")}
+    got = ldw.analyse_long_range_links(lr, {k: red[k] for k in ("pos1", "pos2", "MI")})
+    assert np.array_equal(got["thresholds"], g["lr_thresholds"])
+    np.testing.assert_array_equal(got["MI"], lr["MI"][g["lr_idx"]])
+    np.testing.assert_array_equal(got["ARACNE"], g["lr_aracne"])
