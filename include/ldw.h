@@ -271,6 +271,11 @@ LDW_API void ldw_table_free(double* cols);
 LDW_API int ldw_links_to_cells(const int32_t* pos, int64_t n_snp, int64_t blk, const ldw_links* links, int32_t* from_local,
                        int32_t* to_local);
 
+/* Copies a link table (library-owned, e.g. what ldw_mi_scan returned) into caller-allocated columns of src->n elements on
+ * host threads; a NULL destination skips that column. */
+LDW_API int ldw_links_copy(const ldw_links* src, int32_t* pos1, int32_t* pos2, int32_t* clust1, int32_t* clust2, int32_t* len,
+                   double* MI, int32_t* block);
+
 /* Dense MI matrix of one block (debug / parity aid; nf x nt doubles, column-major, fp32-accurate values).
  * from/to are 0-based ascending global SNP ids, as `from`/`to` of perform_MI_computation_ACGTN. */
 LDW_API int ldw_mi_block_dense(ldw_mi_plan* plan, int64_t block_index, double* mi_out, int64_t* nf_out, int64_t* nt_out);

@@ -57,16 +57,14 @@ class Links(C.Structure):
         return out
 
     def to_dict(self) -> dict:
+        """Copies of the columns as NumPy arrays (``ldw_links_copy``: host threads, 2.9 GB at 616 x 100k)."""
         n = int(self.n)
-        out = {}
-        for name, ct, dt in (("pos1", C.c_int32, np.int32), ("pos2", C.c_int32, np.int32), ("clust1", C.c_int32, np.int32),
-                             ("clust2", C.c_int32, np.int32), ("len", C.c_int32, np.int32), ("MI", f64, np.float64),
-                             ("block", C.c_int32, np.int32)):
-            ptr = getattr(self, name)
-            if n == 0 or not ptr:
-                out[name] = np.zeros(0, dtype=dt)
-            else:
-                out[name] = np.ctypeslib.as_array(ptr, shape=(n,)).copy()
+        cols = (("pos1", np.int32), ("pos2", np.int32), ("clust1", np.int32), ("clust2", np.int32), ("len", np.int32),
+                ("MI", np.float64), ("block", np.int32))
+        out = {name: np.empty(n if (n and getattr(self, name)) else 0, dtype=dt) for name, dt in cols}
+        if n:
+            dst = [out[name].ctypes.data_as(C.c_void_p) if len(out[name]) else None for name, _ in cols]
+            check(lib().ldw_links_copy(C.byref(self), *dst))
         return out
 
 
@@ -136,6 +134,7 @@ def lib():
     L.ldw_table_free.argtypes = [P(f64)]
     L.ldw_table_free.restype = None
     L.ldw_links_to_cells.argtypes = [C.c_void_p, i64, i64, P(Links), C.c_void_p, C.c_void_p]
+    L.ldw_links_copy.argtypes = [P(Links)] + [C.c_void_p] * 7
     L.ldw_nm_rosenbrock.argtypes = [C.c_void_p, C.c_void_p, P(f64), P(C.c_int)]
     L.ldw_neg_log_pbeta_upper.argtypes = [C.c_void_p, i64, f64, f64, C.c_void_p]
     L.ldw_mi_pairs_exact.argtypes = [C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]

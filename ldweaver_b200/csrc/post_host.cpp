@@ -734,3 +734,28 @@ extern "C" int ldw_links_to_cells(const int32_t* pos, int64_t n_snp, int64_t blk
   if (bad.load() >= 0) return ldw::set_error(LDW_ERR_ARG, "ldw_links_to_cells: link %lld does not belong to the block it names", (long long)bad.load());
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Copy of a library-owned link table into caller-allocated columns (R vectors, NumPy arrays) on host threads: 2.9 GB at
+// 616 x 100k, which one thread moves at memcpy speed minus the page faults of a fresh destination.
+// Any destination pointer may be NULL (column skipped).
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int ldw_links_copy(const ldw_links* src, int32_t* pos1, int32_t* pos2, int32_t* clust1, int32_t* clust2, int32_t* len,
+                              double* MI, int32_t* block) {
+  if (!src) return ldw::set_error(LDW_ERR_ARG, "ldw_links_copy: null table");
+  const int64_t n = src->n;
+  if (n <= 0) return 0;
+  const int32_t* si[6] = {src->pos1, src->pos2, src->clust1, src->clust2, src->len, src->block};
+  int32_t* di[6] = {pos1, pos2, clust1, clust2, len, block};
+  for (int k = 0; k < 6; k++)
+    if (di[k] && !si[k]) return ldw::set_error(LDW_ERR_ARG, "ldw_links_copy: the table has no such column (materialised without host copies?)");
+  if (MI && !src->MI) return ldw::set_error(LDW_ERR_ARG, "ldw_links_copy: the table has no MI column");
+  const int64_t piece = 1 << 20;
+  parallel_dynamic((n + piece - 1) / piece, [&](int64_t c) {
+    const int64_t lo = c * piece, m = std::min(n, lo + piece) - lo;
+    for (int k = 0; k < 6; k++)
+      if (di[k]) memcpy(di[k] + lo, si[k] + lo, sizeof(int32_t) * (size_t)m);
+    if (MI) memcpy(MI + lo, src->MI + lo, sizeof(double) * (size_t)m);
+  });
+  return 0;
+}

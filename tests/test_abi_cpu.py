@@ -80,3 +80,23 @@ def test_r_shim_type_checks_against_the_abi():
                 depth -= ch in ")]}"
                 nargs_r += ch == "," and depth == 0
             assert nargs_r == int(nargs), f"{name}: R passes {nargs_r} arguments, the shim registers {nargs}"
+
+
+def test_links_copy_matches_the_columns():
+    """Links.to_dict() (ldw_links_copy, host threads) is how every scan result reaches NumPy: exact copies, right dtypes,
+    NULL columns (LDW_SCAN_NO_D2H results) come back empty."""
+    import numpy as np
+    from ldweaver_b200 import _lib
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 5, 1 << 20, (1 << 20) + 7, 2_500_001):
+        d = dict(pos1=rng.integers(0, 1e6, n), pos2=rng.integers(0, 1e6, n), clust1=rng.integers(1, 4, n), clust2=rng.integers(1, 4, n),
+                 len=rng.integers(1, 20000, n), MI=rng.random(n), block=rng.integers(0, 55, n))
+        a = _lib.Links.from_dict(d)
+        b = _lib.Links()
+        C.memmove(C.byref(b), C.byref(a), C.sizeof(a))      # a table that only holds pointers, like one returned by ldw_mi_scan
+        o = b.to_dict()
+        for k in d:
+            assert o[k].dtype == (np.float64 if k == "MI" else np.int32) and np.array_equal(o[k], np.asarray(d[k]).astype(o[k].dtype))
+    e = _lib.Links()
+    e.n = 10
+    assert all(len(v) == 0 for v in e.to_dict().values())
