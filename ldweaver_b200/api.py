@@ -329,15 +329,23 @@ class MIPlan:
             return sr.to_dict(), lr.to_dict(), bd.to_dict(), thr, prob, st.to_dict()
         return sr, lr, bd, thr, prob, st.to_dict()
 
-    def sr_exact(self, sr: dict) -> np.ndarray:
+    def sr_exact(self, sr: dict, inplace: bool = False) -> np.ndarray:
         """fp64 MI, in the reference's own arithmetic (``ldw_mi_pairs_exact``, 1e-12 against the oracle), of every
         short-range link of a scan of this plan.  The scan's short-range MI comes from the fp32 epilogue (|error| ~2e-7,
         inside the 1e-6 bar); the statistics built on it afterwards (mergeNsort_sr_links' beta fit) amplify that error,
-        so ``perform_MI_computation(exact_sr=True)`` replaces the column by these values first.  Not available for
-        perform_SR_analysis_only scans (their local indices refer to the reduced SNP lists, quirk Q12)."""
-        out = np.array(sr["MI"], dtype=np.float64, copy=True)
+        so ``perform_MI_computation`` replaces the column by these values first.  ``inplace`` writes into ``sr["MI"]``
+        instead of a copy.  Not available for perform_SR_analysis_only scans (their local indices refer to the reduced
+        SNP lists, quirk Q12; ``LDW_SCAN_SR_EXACT`` covers that mode)."""
+        mi = sr["MI"]
+        if inplace and isinstance(mi, np.ndarray) and mi.dtype == np.float64 and mi.flags.c_contiguous and mi.flags.writeable:
+            out = mi
+        else:
+            out = np.array(mi, dtype=np.float64, copy=True)
         for k, idx, il, jl in sr_pair_indices(self.pos, self.blk, sr):
-            out[idx] = self.pairs_exact(k, il, jl)
+            if isinstance(idx, slice):
+                self.pairs_exact(k, il, jl, out=out[idx])      # rows of a block are contiguous: written in place
+            else:
+                out[idx] = self.pairs_exact(k, il, jl)
         return out
 
     def block_dense(self, block_index: int) -> np.ndarray:
@@ -347,10 +355,13 @@ class MIPlan:
         check(_lib.lib().ldw_mi_block_dense(self.handle, block_index, ptr(out), C.byref(nf), C.byref(nt)))
         return out
 
-    def pairs_exact(self, block_index: int, from_local: np.ndarray, to_local: np.ndarray) -> np.ndarray:
+    def pairs_exact(self, block_index: int, from_local: np.ndarray, to_local: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         f = np.ascontiguousarray(from_local, dtype=np.int32)
         t = np.ascontiguousarray(to_local, dtype=np.int32)
-        out = np.zeros(len(f), dtype=np.float64)
+        if out is None:
+            out = np.zeros(len(f), dtype=np.float64)
+        elif not (out.dtype == np.float64 and out.flags.c_contiguous and out.flags.writeable and out.shape == (len(f),)):
+            raise ValueError("out must be a writeable C-contiguous float64 array with one element per pair")
         check(_lib.lib().ldw_mi_pairs_exact(self.handle, block_index, ptr(f), ptr(t), len(f), ptr(out)))
         return out
 
@@ -594,7 +605,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         if exact_sr:
             if perform_SR_analysis_only:
                 raise ValueError("exact_sr is not available with perform_SR_analysis_only")
-            sr["MI"] = plan.sr_exact(sr)
+            sr["MI"] = plan.sr_exact(sr, inplace=True)
     finally:
         if own:
             plan.close()

@@ -356,3 +356,44 @@ def test_post_chain_against_committed_golden(fixture_expected):
     assert np.array_equal(got["thresholds"], g["lr_thresholds"])
     np.testing.assert_array_equal(got["MI"], lr["MI"][g["lr_idx"]])
     np.testing.assert_array_equal(got["ARACNE"], g["lr_aracne"])
+
+
+def test_sr_exact_writes_every_link_once(fixture_snp, fixture_expected):
+    """MIPlan.sr_exact without a device: pairs_exact stubbed by the oracle's dense block matrices.  In place and copying,
+    block-ordered and shuffled rows must all give the golden fp64 column."""
+    import c_oracle as CO
+    from ldweaver_b200 import api
+    e = fixture_expected
+    snp, blk = fixture_snp, 1000
+    MI = e["g50k_b1000_sr_MI"]
+    osr = O.perform_MI_scan(snp, e["hdw"], e["paint"], 3, max_blk_sz=blk, lr_links_approx=1e5, lr_retain_links=1e4, keep_blocks=True)
+    block = np.concatenate([np.full(int(b.sr_mask.sum()), k) for k, b in enumerate(osr.blocks)]).astype(np.int32)
+    dense = {}
+    for k, (fs, fe, ts, te) in enumerate(O.make_blocks(snp.nsnp, blk)):
+        dense[k] = CO.block_mi(snp.codes, e["hdw"], snp.r, snp.uqe, np.arange(fs - 1, fe), np.arange(ts - 1, te))
+
+    class StubPlan(api.MIPlan):
+        def __init__(self):  # no device, no library handle
+            self.pos, self.blk, self.handle = np.asarray(snp.POS, dtype=np.int32), blk, None
+            self.calls = 0
+
+        def pairs_exact(self, block_index, from_local, to_local, out=None):
+            self.calls += 1
+            v = dense[block_index][from_local, to_local]
+            if out is None:
+                return v
+            assert out.flags.c_contiguous and out.shape == v.shape
+            out[:] = v
+            return out
+
+    sr = dict(pos1=e["g50k_b1000_sr_pos1"], pos2=e["g50k_b1000_sr_pos2"], block=block, MI=MI.astype(np.float32).astype(np.float64))
+    plan = StubPlan()
+    got = plan.sr_exact(sr)                                    # copy: the input column is left alone
+    assert np.abs(got - MI).max() < 1e-12 and np.abs(sr["MI"] - MI).max() > 1e-9
+    same = plan.sr_exact(sr, inplace=True)
+    assert same is sr["MI"] and np.abs(sr["MI"] - MI).max() < 1e-12
+    perm = np.random.default_rng(5).permutation(len(MI))
+    shuffled = {k: v[perm] for k, v in sr.items()}
+    shuffled["MI"] = np.zeros(len(MI))
+    assert np.abs(plan.sr_exact(shuffled) - MI[perm]).max() < 1e-12
+    StubPlan.__del__ = lambda self: None
