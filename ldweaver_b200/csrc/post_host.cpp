@@ -36,7 +36,11 @@
 
 namespace {
 
-int host_threads() {
+int host_threads() {  // LDW_HOST_THREADS=<n> overrides (results never depend on it: every pass works on fixed pieces)
+  if (const char* e = getenv("LDW_HOST_THREADS")) {
+    const int v = atoi(e);
+    if (v >= 1) return std::min(v, 256);
+  }
   unsigned h = std::thread::hardware_concurrency();
   if (h == 0) h = 4;
   return (int)std::min<unsigned>(h, 32);

@@ -397,3 +397,25 @@ def test_sr_exact_writes_every_link_once(fixture_snp, fixture_expected):
     shuffled["MI"] = np.zeros(len(MI))
     assert np.abs(plan.sr_exact(shuffled) - MI[perm]).max() < 1e-12
     StubPlan.__del__ = lambda self: None
+
+
+def test_post_results_do_not_depend_on_the_thread_count(fixture_expected, tmp_path):
+    """ldw_sr_postprocess cuts every pass into a fixed number of pieces, so one host thread and eight must give the same
+    bits (LDW_HOST_THREADS overrides the thread count)."""
+    import os
+    import subprocess
+    import sys
+    sr, paint = _fixture_sr(fixture_expected)
+    np.savez(tmp_path / "sr.npz", paint=paint, **sr)
+    code = ("import sys, numpy as np; sys.path[:0] = [%r]; import ldweaver_b200 as ldw; d = dict(np.load(sys.argv[1])); paint = d.pop('paint');"
+            "p = ldw.mergeNsort_sr_links(ldw.CdsVar(paint, 3), d, 20000.0, None, 3.0);"
+            "np.savez(sys.argv[2], row=p.df['row'], srp=p.df['srp_max'], red=p.red, chk=p.chk, shape=np.array([f['shape'] for f in p.fits]),"
+            "fit=np.concatenate([f['fit'] for f in p.fits]))") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for nt in ("1", "3", "8"):
+        out = tmp_path / f"o{nt}.npz"
+        subprocess.run([sys.executable, "-c", code, str(tmp_path / "sr.npz"), str(out)], check=True, env=dict(os.environ, LDW_HOST_THREADS=nt))
+        outs.append(dict(np.load(out)))
+    for o in outs[1:]:
+        for k in outs[0]:
+            assert np.array_equal(o[k], outs[0][k]), k
