@@ -577,9 +577,9 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     without touching the file system and, unless ``postprocess=True``, without the post-processing; ``exact_sr``
     recomputes the MI of every short-range link in fp64 (``MIPlan.sr_exact``) before anything is derived from it -- by
     default whenever the post-processing runs (its beta fit amplifies the fp32 epilogue's 2e-7 to ~1e-2 in srp_max; about
-    +0.5 s at 616 x 100k), never for perform_SR_analysis_only scans.  ``exact_sr="in_scan"`` asks the scan itself for
-    them (``LDW_SCAN_SR_EXACT``, also valid with perform_SR_analysis_only; parity-checked on the fixture, not yet timed at
-    full size, hence not the default)."""
+    +0.5 s at 616 x 100k).  ``exact_sr="in_scan"`` asks the scan itself for them (``LDW_SCAN_SR_EXACT``; parity-checked
+    on the fixture, not yet timed at full size, hence the default only for perform_SR_analysis_only scans, which
+    ``MIPlan.sr_exact`` cannot serve)."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -596,8 +596,8 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     try:
         flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
         do_post = postprocess if postprocess is not None else write_tsv
-        if exact_sr is None:
-            exact_sr = bool(do_post) and not perform_SR_analysis_only
+        if exact_sr is None:  # SR-only scans index reduced SNP lists (Q12): only the in-scan kernel can refine them
+            exact_sr = ("in_scan" if perform_SR_analysis_only else True) if do_post else False
         if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call
             flags |= SCAN_SR_EXACT
             exact_sr = False
