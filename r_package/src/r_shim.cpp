@@ -143,6 +143,9 @@ SEXP LDWeaver_gpu_mi_scan(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP hdw_, SEXP p
   ldw_links sr, lr, bd;
   ldw_scan_stats st;
   int flags = Rf_asLogical(sronly_) ? LDW_SCAN_SR_ONLY : 0;
+  // SR-only scans index reduced SNP lists (quirk Q12), which ldw_links_to_cells cannot address: there the scan itself
+  // refines the short-range MI (mi_sr_exact_kernel)
+  if ((flags & LDW_SCAN_SR_ONLY) && Rf_asLogical(exact_)) flags |= LDW_SCAN_SR_EXACT;
   int rc = ldw_mi_scan(plan, Rf_asReal(g_), Rf_asReal(srd_), Rf_asReal(retain_), Rf_asReal(approx_), flags, 1, 0, &sr, &lr, &bd,
                        REAL(thr), nullptr, &st);
   if (rc != 0) {
