@@ -419,3 +419,28 @@ def test_post_results_do_not_depend_on_the_thread_count(fixture_expected, tmp_pa
     for o in outs[1:]:
         for k in outs[0]:
             assert np.array_equal(o[k], outs[0][k]), k
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_merge_n_sort_differential_fuzz(seed):
+    """Random tables against the literal oracle: 1-5 clusters, cluster ids outside 1..nclust, links listed under two
+    clusters, lengths 0 and >= sr_dist, fractional sr_dist, missing lengths (the subscript-by-value quirk), tied MI values."""
+    rng = np.random.default_rng(seed)
+    nclust = int(rng.integers(1, 6))
+    n = int(rng.integers(3000, 30000))
+    sr_dist = float(rng.choice([50, 200.5, 1000, 5000]))
+    ln = rng.integers(0, int(sr_dist * rng.choice([0.5, 1.0, 1.3])) + 2, n)
+    if rng.random() < 0.5:
+        ln = ln * 2
+    pos1 = rng.integers(1, 10 ** 6, n)
+    c1 = rng.integers(0, nclust + 2, n)
+    c2 = np.where(rng.random(n) < 0.7, c1, rng.integers(1, nclust + 1, n))
+    mi = rng.beta(0.8, rng.choice([20, 60, 200]), n) * (np.maximum(ln, 1) ** -rng.choice([0.0, 0.3]))
+    k = rng.integers(0, n, n // 10)
+    mi[k] = mi[rng.integers(0, n, n // 10)]
+    sr = dict(pos1=pos1, pos2=pos1 + ln, clust1=c1, clust2=c2, len=ln.astype(float), MI=mi)
+    cutoff = float(rng.choice([1.0, 3.0]))
+    ref = PO.merge_n_sort_sr_links(sr, nclust, sr_dist, cutoff)
+    got = ldw.mergeNsort_sr_links(ldw.CdsVar(None, nclust), sr, sr_dist, None, cutoff)
+    _compare_post(got, ref)
+    assert [f["nm_evals"] for f in got.fits] == [f.nm_evals for f in ref.fits]
