@@ -444,3 +444,29 @@ def test_merge_n_sort_differential_fuzz(seed):
     got = ldw.mergeNsort_sr_links(ldw.CdsVar(None, nclust), sr, sr_dist, None, cutoff)
     _compare_post(got, ref)
     assert [f["nm_evals"] for f in got.fits] == [f.nm_evals for f in ref.fits]
+
+
+def test_links_to_cells_random_blocks():
+    """ldw_links_to_cells against a NumPy restatement: random positions, ragged last block, diagonal and off-diagonal
+    blocks, rows in block order and shuffled."""
+    from ldweaver_b200 import api
+    rng = np.random.default_rng(9)
+    for n, blk in ((2500, 1000), (4096, 1024), (130, 128), (5000, 3000)):
+        pos = np.sort(rng.choice(np.arange(1, 10 * n), n, replace=False)).astype(np.int32)
+        blocks = api.make_blocks(n, blk)
+        rows = []
+        for k, (fs, fe, ts, te) in enumerate(blocks):
+            m = int(rng.integers(0, 400))
+            i = rng.integers(fs - 1, fe, m)
+            j = rng.integers(ts - 1, te, m)
+            rows.append(np.stack([np.full(m, k), i, j], axis=1))
+        t = np.concatenate(rows)
+        for order in (np.arange(len(t)), rng.permutation(len(t))):
+            b, gi, gj = t[order, 0], t[order, 1], t[order, 2]
+            sr = dict(pos1=pos[gj], pos2=pos[gi], block=b.astype(np.int32))
+            seen = np.zeros(len(b), dtype=bool)
+            for k, idx, il, jl in api.sr_pair_indices(pos, blk, sr):
+                fs, fe, ts, te = blocks[k]
+                assert np.array_equal(il, gi[idx] - (fs - 1)) and np.array_equal(jl, gj[idx] - (ts - 1)) and np.all(b[idx] == k)
+                seen[idx] = True
+            assert seen.all()
