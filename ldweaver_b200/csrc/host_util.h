@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <exception>
+#include <new>
 
 #include <string>
 #include <thread>
@@ -28,6 +30,20 @@ int set_error(int code, const char* fmt, ...);
     if (e__ != cudaSuccess)                                                                                \
       return ldw::set_error(LDW_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
+
+// No exception crosses the C ABI (include/ldw.h): a host entry point runs its body through this.
+template <class F>
+inline int guarded(const char* who, F body) {
+  try {
+    return body();
+  } catch (const std::bad_alloc&) {
+    return set_error(LDW_ERR_NOMEM, "%s: out of host memory", who);
+  } catch (const std::exception& e) {
+    return set_error(LDW_ERR_INTERNAL, "%s: %s", who, e.what());
+  } catch (...) {
+    return set_error(LDW_ERR_INTERNAL, "%s: unknown failure", who);
+  }
+}
 
 #define LDW_TRY(call)        \
   do {                       \

@@ -22,6 +22,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <exception>
+#include <new>
 #include <chrono>
 #include <memory>
 #include <mutex>
@@ -52,12 +54,25 @@ void parallel_dynamic(int64_t n, F fn) {
   const int nt = (int)std::min<int64_t>(host_threads(), n);
   if (nt <= 1) { for (int64_t i = 0; i < n; i++) fn(i); return; }
   std::atomic<int64_t> next(0);
+  std::exception_ptr err;  // first exception of a worker (std::bad_alloc of a growing vector), rethrown on the caller
+  std::mutex err_mu;
   std::vector<std::thread> th;
   th.reserve(nt);
   for (int t = 0; t < nt; t++)
-    th.emplace_back([&]() { for (;;) { const int64_t i = next.fetch_add(1); if (i >= n) break; fn(i); } });
+    th.emplace_back([&]() {
+      try {
+        for (;;) { const int64_t i = next.fetch_add(1); if (i >= n) break; fn(i); }
+      } catch (...) {
+        std::lock_guard<std::mutex> g(err_mu);
+        if (!err) err = std::current_exception();
+        next.store(n);
+      }
+    });
   for (auto& x : th) x.join();
+  if (err) std::rethrow_exception(err);
 }
+
+using ldw::guarded;
 
 struct PhaseTimer {  // LDW_DBG_TIMING=1: phase times on stderr (never stdout)
   bool on;
@@ -327,6 +342,7 @@ extern "C" void ldw_sr_post_free(ldw_sr_post* p) {
 }
 
 extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr_dist, double srp_cutoff, ldw_sr_post* out) {
+  return guarded("ldw_sr_postprocess", [&]() -> int {
   if (!sr || !out) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: null argument");
   memset(out, 0, sizeof(*out));
   if (nclust < 1) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: nclust must be >= 1");
@@ -600,20 +616,24 @@ extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr
   out->n_pos = S->n_pos.data(); out->nm_evals = S->nm_evals.data(); out->nm_fail = S->nm_fail.data();
   out->priv = S.release();
   return 0;
+  });
 }
 
 // Building blocks exposed for the parity tests: the Nelder-Mead iteration on Rosenbrock's function (the example of R's
 // ?optim, whose printed result pins the restatement: par 1.000260 1.000506, value 8.825241e-08, 195 evaluations) and the
 // log upper beta tail.
 extern "C" int ldw_nm_rosenbrock(const double* start, double* par_out, double* value_out, int* count_out) {
+  return guarded("ldw_nm_rosenbrock", [&]() -> int {
   if (!start || !par_out || !value_out || !count_out) return ldw::set_error(LDW_ERR_ARG, "ldw_nm_rosenbrock: null argument");
   struct Fr { double operator()(const double* x) const { const double t = x[1] - x[0] * x[0], u = 1 - x[0]; return 100 * t * t + u * u; } };
   const int fail = nmmin2(Fr(), start, par_out, value_out, count_out);
   if (fail < 0) return ldw::set_error(LDW_ERR_ARG, "ldw_nm_rosenbrock: function cannot be evaluated at initial parameters");
   return 0;
+  });
 }
 
 extern "C" int ldw_neg_log_pbeta_upper(const double* x, int64_t n, double shape1, double shape2, double* out) {
+  return guarded("ldw_neg_log_pbeta_upper", [&]() -> int {
   if (n < 0 || (n > 0 && (!x || !out))) return ldw::set_error(LDW_ERR_ARG, "ldw_neg_log_pbeta_upper: bad argument");
   if (!(shape1 > 0 && shape2 > 0)) return ldw::set_error(LDW_ERR_ARG, "ldw_neg_log_pbeta_upper: shapes must be positive");
   int sg;
@@ -623,6 +643,7 @@ extern "C" int ldw_neg_log_pbeta_upper(const double* x, int64_t n, double shape1
       out[i] = x[i] <= 0 ? 0.0 : x[i] >= 1 ? INFINITY : neg_log_upper_beta(x[i], shape1, shape2, lbeta);
   });
   return 0;
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -630,6 +651,7 @@ extern "C" int ldw_neg_log_pbeta_upper(const double* x, int64_t n, double shape1
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" int ldw_run_aracne(int64_t n_chk, const double* chk_pos1, const double* chk_pos2, const double* chk_MI, int64_t n_full,
                               const double* full_pos1, const double* full_pos2, const double* full_MI, uint8_t* aracne_out) {
+  return guarded("ldw_run_aracne", [&]() -> int {
   if (n_chk < 0 || n_full < 0) return ldw::set_error(LDW_ERR_ARG, "ldw_run_aracne: negative size");
   if ((n_chk > 0 && (!chk_pos1 || !chk_pos2 || !chk_MI || !aracne_out)) || (n_full > 0 && (!full_pos1 || !full_pos2 || !full_MI)))
     return ldw::set_error(LDW_ERR_ARG, "ldw_run_aracne: null argument");
@@ -690,6 +712,7 @@ extern "C" int ldw_run_aracne(int64_t n_chk, const double* chk_pos1, const doubl
     }
   });
   return 0;
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -699,6 +722,7 @@ extern "C" int ldw_run_aracne(int64_t n_chk, const double* chk_pos1, const doubl
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" int ldw_links_to_cells(const int32_t* pos, int64_t n_snp, int64_t blk, const ldw_links* links, int32_t* from_local,
                                   int32_t* to_local) {
+  return guarded("ldw_links_to_cells", [&]() -> int {
   if (!pos || !links || n_snp < 1 || blk < 1) return ldw::set_error(LDW_ERR_ARG, "ldw_links_to_cells: bad argument");
   const int64_t n = links->n;
   if (n > 0 && (!links->pos1 || !links->pos2 || !links->block || !from_local || !to_local))
@@ -737,6 +761,7 @@ extern "C" int ldw_links_to_cells(const int32_t* pos, int64_t n_snp, int64_t blk
   });
   if (bad.load() >= 0) return ldw::set_error(LDW_ERR_ARG, "ldw_links_to_cells: link %lld does not belong to the block it names", (long long)bad.load());
   return 0;
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -746,6 +771,7 @@ extern "C" int ldw_links_to_cells(const int32_t* pos, int64_t n_snp, int64_t blk
 // ---------------------------------------------------------------------------------------------------------------------
 extern "C" int ldw_links_copy(const ldw_links* src, int32_t* pos1, int32_t* pos2, int32_t* clust1, int32_t* clust2, int32_t* len,
                               double* MI, int32_t* block) {
+  return guarded("ldw_links_copy", [&]() -> int {
   if (!src) return ldw::set_error(LDW_ERR_ARG, "ldw_links_copy: null table");
   const int64_t n = src->n;
   if (n <= 0) return 0;
@@ -762,4 +788,5 @@ extern "C" int ldw_links_copy(const ldw_links* src, int32_t* pos1, int32_t* pos2
     if (MI) memcpy(MI + lo, src->MI + lo, sizeof(double) * (size_t)m);
   });
   return 0;
+  });
 }

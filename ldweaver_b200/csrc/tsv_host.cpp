@@ -84,12 +84,14 @@ int format_r_whole(int64_t v, char* out) {
 }  // namespace
 
 extern "C" int ldw_format_r_real(double x, char* out, int cap) {
+  return ldw::guarded("ldw_format_r_real", [&]() -> int {
   char buf[512];
   int n = format_r_real(x, buf);
   if (!out || cap <= n) return ldw::set_error(LDW_ERR_ARG, "ldw_format_r_real: buffer too small");
   memcpy(out, buf, n);
   out[n] = 0;
   return 0;
+  });
 }
 
 namespace {
@@ -120,6 +122,7 @@ int write_rows(const char* who, const char* path, int append, int64_t n, RowFn r
 }  // namespace
 
 extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int append) {
+  return ldw::guarded("ldw_write_lr_tsv", [&]() -> int {
   if (!path || !lr) return ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: null argument");
   return write_rows("ldw_write_lr_tsv", path, append, lr->n, [&](int64_t i, std::string& s) {
     char tmp[512];
@@ -130,12 +133,14 @@ extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int appen
     s.append(tmp, format_r_whole(lr->len[i], tmp)); s.push_back('\t');
     s.append(tmp, format_r_real(lr->MI[i], tmp)); s.push_back('\n');
   });
+  });
 }
 
 // sr_links.tsv (R/computePairwiseMI.R:140): clust_c is the integer loop index of mergeNsort_sr_links (:411,470), pos1 / pos2
 // integer, clust1 / clust2 / len / MI / srp_max doubles, ARACNE = as.numeric(logical) (:126) or the constant 1 (:129).
 extern "C" int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n, const int64_t* rows, const int32_t* clust_c,
                                 const double* srp_max, const double* aracne, int append) {
+  return ldw::guarded("ldw_write_sr_tsv", [&]() -> int {
   if (!path || !sr || (n > 0 && (!rows || !clust_c || !srp_max || !aracne))) return ldw::set_error(LDW_ERR_ARG, "ldw_write_sr_tsv: null argument");
   for (int64_t i = 0; i < n; i++)
     if (rows[i] < 0 || rows[i] >= sr->n) return ldw::set_error(LDW_ERR_ARG, "ldw_write_sr_tsv: row %lld outside the link table", (long long)rows[i]);
@@ -152,6 +157,7 @@ extern "C" int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n
     s.append(tmp, format_r_real(srp_max[i], tmp)); s.push_back('\t');
     s.append(tmp, format_r_real(aracne[i], tmp)); s.push_back('\n');
   });
+  });
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -163,6 +169,7 @@ extern "C" int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n
 extern "C" void ldw_table_free(double* cols) { free(cols); }
 
 extern "C" int ldw_read_numeric_tsv(const char* path, int ncols, int64_t* nrows_out, double** cols_out) {
+  return ldw::guarded("ldw_read_numeric_tsv", [&]() -> int {
   if (!path || !nrows_out || !cols_out || ncols < 1) return ldw::set_error(LDW_ERR_ARG, "ldw_read_numeric_tsv: bad argument");
   *nrows_out = 0;
   *cols_out = nullptr;
@@ -233,4 +240,5 @@ extern "C" int ldw_read_numeric_tsv(const char* path, int ncols, int64_t* nrows_
   *nrows_out = nrows;
   *cols_out = cols;
   return 0;
+  });
 }
