@@ -101,6 +101,14 @@ LDW_API int ldw_extract_snps(ldw_ctx* ctx, const uint8_t* aln, int64_t nseq, int
                      int64_t n_snp, uint8_t* codes_out, double* table_out);
 LDW_API int ldw_read_fasta(const char* path, int64_t* nseq_out, int64_t* seq_len_out, uint8_t* aln_out, int64_t aln_cap,
                    char* names_out, int64_t names_cap);
+/* ldw_read_fasta_alloc: the same tokeniser in ONE pass over the file (the reference opens the gz
+ *   file three times, src/getACGTNsites.cpp:33,44,212): inflate on a reader thread, tokenising on the caller's, the
+ *   matrix in a library-allocated buffer.  *aln_out (nseq x seq_len bytes, row-major; NULL when the records differ in
+ *   length, *seq_len_out = -1, or when there is no sequence) and *names_out (*names_len_out bytes: NUL-terminated names
+ *   back to back) are released with ldw_buffer_free. */
+LDW_API int ldw_read_fasta_alloc(const char* path, int64_t* nseq_out, int64_t* seq_len_out, uint8_t** aln_out, char** names_out,
+                         int64_t* names_len_out);
+LDW_API void ldw_buffer_free(void* p);
 
 /* ldw_acgtn2num replaces `.ACGTN2num(nv, cv, ncores)` (R/RcppExports.R:4-6 -> _LDWeaver_ACGTN2num,
  *   src/RcppExports.cpp:16; body src/ACGTN2num_parallel.cpp:10-43).  In place on nv (5 x n doubles,

@@ -114,6 +114,9 @@ def lib():
     L.ldw_aln_param.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_int, f64, f64, C.c_void_p, P(i64), C.c_void_p]
     L.ldw_extract_snps.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p]
     L.ldw_read_fasta.argtypes = [C.c_char_p, P(i64), P(i64), C.c_void_p, i64, C.c_void_p, i64]
+    L.ldw_read_fasta_alloc.argtypes = [C.c_char_p, P(i64), P(i64), P(C.c_void_p), P(C.c_void_p), P(i64)]
+    L.ldw_buffer_free.argtypes = [C.c_void_p]
+    L.ldw_buffer_free.restype = None
     L.ldw_acgtn2num.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, i64]
     L.ldw_hdw.argtypes = [C.c_void_p, C.c_void_p, i64, i64, f64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.ldw_mi_plan_create.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_void_p, C.c_void_p, C.c_void_p, i64,

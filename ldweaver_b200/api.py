@@ -64,28 +64,43 @@ def _method_to_filter(method: str) -> int:
     return 0
 
 
+class _LibraryBuffer:
+    """A buffer the library allocated (ldw_read_fasta_alloc): exposed to NumPy without a copy, released with
+    ldw_buffer_free when the last array viewing it goes away."""
+
+    def __init__(self, addr: int, nbytes: int):
+        self._addr = addr
+        self.__array_interface__ = {"data": (addr, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        try:
+            _lib.lib().ldw_buffer_free(self._addr)
+        except Exception:
+            pass
+
+
 def read_fasta_matrix(aln_path: str):
-    """gz/plain multi-FASTA -> (names, uint8 matrix [nseq, seq_len]) via the library's host reader."""
+    """gz/plain multi-FASTA -> (names, uint8 matrix [nseq, seq_len]) via the library's single-pass host reader
+    (``ldw_read_fasta_alloc``: inflate on a reader thread, tokenising beside it; the reference opens the file three
+    times, src/getACGTNsites.cpp:33,44,212)."""
     L = _lib.lib()
-    nseq, slen = C.c_int64(), C.c_int64()
-    check(L.ldw_read_fasta(aln_path.encode(), C.byref(nseq), C.byref(slen), None, 0, None, 0))
+    nseq, slen, nlen = C.c_int64(), C.c_int64(), C.c_int64()
+    aln_p, names_p = C.c_void_p(), C.c_void_p()
+    check(L.ldw_read_fasta_alloc(os.fsencode(aln_path), C.byref(nseq), C.byref(slen), C.byref(aln_p), C.byref(names_p), C.byref(nlen)))
+    try:
+        raw = C.string_at(names_p, nlen.value) if names_p else b""
+    finally:
+        L.ldw_buffer_free(names_p)
+    owner = _LibraryBuffer(aln_p.value, nseq.value * max(slen.value, 0)) if aln_p else None
     if slen.value == -1:
         raise ValueError("Error! sequences are of different lengths!")  # R/extractSNPs.R:41
     if nseq.value == 0:
         raise ValueError("File does not contain any sequences!")  # :42
-    aln = np.empty((nseq.value, slen.value), dtype=np.uint8)
-    names = C.create_string_buffer(1 << 16)
-    cap = 1 << 16
-    while True:
-        n2, l2 = C.c_int64(), C.c_int64(slen.value)
-        rc = L.ldw_read_fasta(aln_path.encode(), C.byref(n2), C.byref(l2), ptr(aln), aln.size, names, cap)
-        if rc != 0 and b"names buffer" in L.ldw_last_error():
-            cap *= 8
-            names = C.create_string_buffer(cap)
-            continue
-        check(rc)
-        break
-    name_list = names.raw.split(b"\0")[:nseq.value]
+    if owner is None:
+        aln = np.empty((nseq.value, 0), dtype=np.uint8)
+    else:
+        aln = np.asarray(owner).reshape(nseq.value, slen.value)
+    name_list = raw.split(b"\0")[:nseq.value]
     return [n.decode(errors="replace") for n in name_list], aln
 
 
