@@ -70,37 +70,39 @@ extern "C" {
 // stands in for .extractAlnParam + .extractSNPs (R/extractSNPs.R:39,45)
 SEXP LDWeaver_gpu_encode(SEXP path_, SEXP filter_, SEXP gap_, SEXP maf_) {
   const char* path = CHAR(STRING_ELT(path_, 0));
-  int64_t nseq = 0, slen = 0;
-  if (ldw_read_fasta(path, &nseq, &slen, nullptr, 0, nullptr, 0) != 0) Rf_error("%s", ldw_last_error());
+  int64_t nseq = 0, slen = 0, names_len = 0, nsnp = 0;
+  uint8_t* aln = nullptr;   // library-allocated (ldw_read_fasta_alloc: one pass over the file), released before any Rf_error
+  char* names = nullptr;
+  int32_t* pos = nullptr;
+  auto release = [&]() { ldw_buffer_free(aln); ldw_buffer_free(names); free(pos); aln = nullptr; names = nullptr; pos = nullptr; };
+  if (ldw_read_fasta_alloc(path, &nseq, &slen, &aln, &names, &names_len) != 0) Rf_error("%s", ldw_last_error());
   if (slen == -1 || nseq == 0) {  // sentinel values the R wrapper turns into stop() (R/extractSNPs.R:41-42)
+    release();
     SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
     SET_VECTOR_ELT(out, 0, Rf_ScalarInteger((int)nseq));
     SET_VECTOR_ELT(out, 1, Rf_ScalarInteger((int)slen));
     UNPROTECT(1);
     return out;
   }
-  std::vector<uint8_t> aln((size_t)nseq * slen);
-  std::vector<char> names((size_t)nseq * 256);
-  int64_t l2 = slen, n2 = 0;
-  if (ldw_read_fasta(path, &n2, &l2, aln.data(), (int64_t)aln.size(), names.data(), (int64_t)names.size()) != 0)
+  pos = (int32_t*)malloc(sizeof(int32_t) * (size_t)(slen > 0 ? slen : 1));
+  if (!pos) { release(); Rf_error("out of memory"); }
+  if (ldw_aln_param(ctx(), aln, nseq, slen, Rf_asInteger(filter_), Rf_asReal(gap_), Rf_asReal(maf_), pos, &nsnp, nullptr) != 0) {
+    release();
     Rf_error("%s", ldw_last_error());
-  std::vector<int32_t> pos((size_t)slen);
-  int64_t nsnp = 0;
-  if (ldw_aln_param(ctx(), aln.data(), nseq, slen, Rf_asInteger(filter_), Rf_asReal(gap_), Rf_asReal(maf_), pos.data(), &nsnp,
-                    nullptr) != 0)
-    Rf_error("%s", ldw_last_error());
+  }
   SEXP codes = PROTECT(Rf_allocVector(RAWSXP, nsnp * nseq));
   SEXP table = PROTECT(Rf_allocMatrix(REALSXP, 5, (int)nsnp));
-  if (nsnp > 0 &&
-      ldw_extract_snps(ctx(), aln.data(), nseq, slen, pos.data(), nsnp, RAW(codes), REAL(table)) != 0) {
+  if (nsnp > 0 && ldw_extract_snps(ctx(), aln, nseq, slen, pos, nsnp, RAW(codes), REAL(table)) != 0) {
+    release();
     UNPROTECT(2);
     Rf_error("%s", ldw_last_error());
   }
   SEXP rpos = PROTECT(Rf_allocVector(INTSXP, nsnp));
-  if (nsnp) memcpy(INTEGER(rpos), pos.data(), sizeof(int) * (size_t)nsnp);
+  if (nsnp) memcpy(INTEGER(rpos), pos, sizeof(int) * (size_t)nsnp);
   SEXP rnames = PROTECT(Rf_allocVector(STRSXP, nseq));
-  const char* q = names.data();
+  const char* q = names;
   for (int64_t i = 0; i < nseq; i++) { SET_STRING_ELT(rnames, i, Rf_mkChar(q)); q += strlen(q) + 1; }
+  release();
   const char* nm[] = {"num.seqs", "num.snps", "seq.length", "seq.names", "pos", "codes", "ACGTN_table"};
   SEXP out = PROTECT(Rf_allocVector(VECSXP, 7));
   SEXP onm = PROTECT(Rf_allocVector(STRSXP, 7));
