@@ -11,8 +11,10 @@
  * Rf_error(ldw_last_error()) after releasing its own resources (reference convention:
  * BEGIN_RCPP/END_RCPP, src/RcppExports.cpp:17,24).
  *
- * There is NO CPU fallback behind these functions: without a CUDA device they fail with
- * LDW_ERR_CUDA.
+ * There is NO CPU fallback behind the device entry points (encoding, weights, scan): without a CUDA
+ * device they fail with LDW_ERR_CUDA.  The entry points marked "host only" (FASTA / TSV I/O and the
+ * steps that follow the scan inside perform_MI_computation) are not fallbacks of device code: they
+ * replace parts of the reference that are host code there too, and work on host buffers.
  *
  * Each entry point names the reference interface it replaces (paths relative to the LDWeaver
  * source tree, v1.5.2).
