@@ -423,11 +423,16 @@ class SrLinks:
     """Result of ``mergeNsort_sr_links``: ``df`` holds sr_links_df column-wise (clust_c, pos1, pos2, clust1, clust2, len,
     MI, srp_max, plus ``row`` = index into the scan's short-range table); ``red`` / ``chk`` are the row indices of
     sr_links_red / sr_links_ARACNE_check inside it (R/computePairwiseMI.R:494-495); ``fits`` the per-cluster decay and
-    beta fits (what the reference stores as c<i>_fit_data.rds / plots)."""
+    beta fits (what the reference stores as c<i>_fit_data.rds / plots).  Both selections are threshold tests on
+    floating-point values (``srp_max > srp_cutoff``, ``MI >= min(MI of the selected)``); rows sitting on a threshold --
+    ties between links with mathematically equal MI are common -- are decided by the last ulp in any implementation
+    and are listed explicitly in ``borderline_red`` / ``borderline_chk``, like the long-range borderline pairs."""
     df: dict
     red: np.ndarray
     chk: np.ndarray
     fits: List[dict]
+    borderline_red: Optional[np.ndarray] = None   # df rows whose srp_max lies within 1e-9 (relative) of srp_cutoff
+    borderline_chk: Optional[np.ndarray] = None   # df rows whose MI lies within 1e-12 of min(sr_links_red$MI)
 
 
 def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[str] = None, srp_cutoff: float = 3) -> SrLinks:
@@ -461,7 +466,10 @@ def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[st
                 with open(os.path.join(plt_path, f"c{c}_fit_data.tsv"), "w") as fh:
                     fh.write("len\tmax\tfit\n")
                     fh.writelines(f"{int(a)}\t{b:.15g}\t{v:.15g}\n" for a, b, v in zip(f["len"], f["max"], f["fit"]))
-        return SrLinks(df=df, red=cp(out.red, out.n_red, np.int64), chk=cp(out.chk, out.n_chk, np.int64), fits=fits)
+        red, chk = cp(out.red, out.n_red, np.int64), cp(out.chk, out.n_chk, np.int64)
+        b_red = np.nonzero(np.abs(df["srp_max"] - srp_cutoff) <= 1e-9 * max(abs(float(srp_cutoff)), 1.0))[0]
+        b_chk = np.nonzero(np.abs(df["MI"] - df["MI"][red].min()) <= 1e-12)[0] if len(red) else np.zeros(0, np.int64)
+        return SrLinks(df=df, red=red, chk=chk, fits=fits, borderline_red=b_red, borderline_chk=b_chk)
     finally:
         _lib.lib().ldw_sr_post_free(C.byref(out))
 

@@ -101,6 +101,11 @@ def test_merge_n_sort_matches_oracle_on_fixture(fixture_expected):
     assert [f["nm_evals"] for f in got.fits] == [f.nm_evals for f in ref.fits]
     assert len(got.red) > 0 and np.all(got.df["srp_max"][got.red] > 3.0)
     assert np.all(got.df["MI"][got.chk] >= got.df["MI"][got.red].min())
+    # rows sitting on the two thresholds are listed: the link that sets min(MI) is one of them, and so are its ties
+    mi_min = got.df["MI"][got.red].min()
+    assert len(got.borderline_chk) >= 1 and np.all(np.abs(got.df["MI"][got.borderline_chk] - mi_min) <= 1e-12)
+    assert set(np.nonzero(got.df["MI"] == mi_min)[0]) <= set(got.borderline_chk.tolist())
+    assert len(got.borderline_red) == int((np.abs(got.df["srp_max"] - 3.0) <= 3e-9).sum())
 
 
 def test_missing_lengths_shift_the_fit_lookup_like_the_reference():
