@@ -86,8 +86,8 @@ struct PhaseTimer {  // LDW_DBG_TIMING=1: phase times on stderr (never stdout)
   }
 };
 
-// Scratch array on transparent huge pages where the kernel grants them (madvise): the counting sort below writes through
-// tens of thousands of cursors spread over hundreds of MB, which with 4 KB pages is one TLB miss per element.
+// Large scratch array, 2 MB-aligned.  LDW_THP=1 asks for transparent huge pages (madvise); off by default: the grouping
+// below is organised so that it does not need them, and huge-page faults can stall on compaction.
 template <class T>
 struct HugeArray {
   T* p = nullptr;
@@ -96,7 +96,7 @@ struct HugeArray {
     const size_t bytes = std::max<size_t>(sizeof(T) * count, 1), two_mb = size_t(2) << 20;
     void* q = nullptr;
     if (posix_memalign(&q, two_mb, (bytes + two_mb - 1) / two_mb * two_mb) != 0) q = nullptr;
-    if (q) madvise(q, (bytes + two_mb - 1) / two_mb * two_mb, MADV_HUGEPAGE);
+    if (q && getenv("LDW_THP")) madvise(q, (bytes + two_mb - 1) / two_mb * two_mb, MADV_HUGEPAGE);
     p = (T*)q;
   }
   ~HugeArray() { free(p); }
@@ -414,33 +414,60 @@ extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr
   for (int64_t g = 0; g < G; g++) if (gcount[g] > 0) glist.push_back(g);
   std::vector<double> gq((size_t)glist.size());
   {
-    HugeArray<double> grouped((size_t)goff[G]);
-    if (!grouped.data()) return ldw::set_error(LDW_ERR_NOMEM, "ldw_sr_postprocess: out of memory (%lld values)", (long long)goff[G]);
-    std::vector<std::vector<int64_t>> cur(B);
-    std::vector<int64_t> run(goff.begin(), goff.end() - 1);
-    for (int64_t k = 0; k < B; k++) {
-      cur[k].resize((size_t)G);
-      for (int64_t g = 0; g < G; g++) { cur[k][g] = run[g]; run[g] += hist[k][g]; }
-      std::vector<int32_t>().swap(hist[k]);
+    // Two levels, so that no pass writes through more than a few hundred cursors (with ~6 x 10^4 groups a direct scatter
+    // costs a TLB miss per element): first into <= 512 buckets of consecutive groups -- each bucket's slice of the array is
+    // where its groups will finally live --, then bucket by bucket (a few MB each, one thread per bucket) into a local
+    // scratch ordered by group, from which the bucket's percentiles are taken.
+    int sh = 0;
+    while (((G - 1) >> sh) + 1 > 512) sh++;
+    const int64_t NB = ((G - 1) >> sh) + 1;
+    const int64_t E = goff[G];
+    HugeArray<double> tmp_mi((size_t)E);
+    HugeArray<uint32_t> tmp_g((size_t)E);
+    if (!tmp_mi.data() || !tmp_g.data()) return ldw::set_error(LDW_ERR_NOMEM, "ldw_sr_postprocess: out of memory (%lld values)", (long long)E);
+    std::vector<int64_t> bcur((size_t)B * NB);
+    {
+      std::vector<int64_t> run((size_t)NB);
+      for (int64_t b = 0; b < NB; b++) run[b] = goff[b << sh];
+      for (int64_t k = 0; k < B; k++) {
+        for (int64_t b = 0; b < NB; b++) {
+          bcur[(size_t)k * NB + b] = run[b];
+          int64_t c = 0;
+          for (int64_t g = b << sh; g < std::min(G, (b + 1) << sh); g++) c += hist[k][g];
+          run[b] += c;
+        }
+        std::vector<int32_t>().swap(hist[k]);
+      }
     }
     parallel_dynamic(B, [&](int64_t k) {
-      std::vector<int64_t>& cu = cur[k];
+      int64_t* cu = bcur.data() + (size_t)k * NB;
       for (int64_t i = k * bsz; i < std::min(N, (k + 1) * bsz); i++) {
-        int32_t ca, cb;
-        if (!member(i, ca, cb)) continue;
+        int32_t cc[2];
+        if (!member(i, cc[0], cc[1])) continue;
         const int64_t l = sr->len[i];
         const double v = sr->MI[i];
-        if (ca) grouped[cu[(ca - 1) * nl + l]++] = v;
-        if (cb) grouped[cu[(cb - 1) * nl + l]++] = v;
+        for (int q = 0; q < 2; q++) {
+          if (!cc[q]) continue;
+          const int64_t g = (int64_t)(cc[q] - 1) * nl + l, b = g >> sh, at = cu[b]++;
+          tmp_mi[(size_t)at] = v;
+          tmp_g[(size_t)at] = (uint32_t)(g - (b << sh));
+        }
       }
     });
-    std::vector<std::vector<int64_t>>().swap(cur);
-    tm.lap("counting sort by (cluster, len)", 0);
-    parallel_dynamic((int64_t)glist.size(), [&](int64_t t) {
-      const int64_t g = glist[t];
-      gq[t] = quantile7(grouped.data() + goff[g], gcount[g], 0.95);
+    tm.lap("scatter into buckets", 0);
+    std::vector<double> gq_by_group((size_t)G, 0.0);
+    parallel_dynamic(NB, [&](int64_t b) {
+      const int64_t g0 = b << sh, g1 = std::min(G, (b + 1) << sh), lo = goff[g0], hi = goff[g1];
+      if (hi == lo) return;
+      std::vector<double> sc((size_t)(hi - lo));
+      std::vector<int64_t> cur((size_t)(g1 - g0));
+      for (int64_t g = g0; g < g1; g++) cur[g - g0] = goff[g] - lo;
+      for (int64_t e = lo; e < hi; e++) sc[(size_t)cur[tmp_g[(size_t)e]]++] = tmp_mi[(size_t)e];
+      for (int64_t g = g0; g < g1; g++)
+        if (gcount[g] > 0) gq_by_group[g] = quantile7(sc.data() + (goff[g] - lo), gcount[g], 0.95);
     });
-    tm.lap("quantiles", 0);
+    for (size_t t = 0; t < glist.size(); t++) gq[t] = gq_by_group[glist[t]];
+    tm.lap("group + quantiles", 0);
   }
   // ---- fastLm(cbind(log(len), 1), log(max)); fit = exp(fitted)  (:428-429), per cluster ----
   {
