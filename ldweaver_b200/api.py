@@ -509,10 +509,15 @@ def _read_numeric_tsv(path: str, names: Sequence[str]) -> dict:
 
 def read_LongRangeLinks(lr_links_path: str, links_from_spydrpick: bool = False, sr_dist: float = 20000) -> dict:
     """R/io_functions.R:32-47: lr_links.tsv as columns pos1, pos2, c1, c2, len, MI; rows with len < sr_dist are dropped
-    (:43).  Spydrpick output (space separated) is not read here."""
-    if links_from_spydrpick:
-        raise NotImplementedError("links_from_spydrpick = T (space-separated spydrpick output) is outside the hot path")
-    d = _read_numeric_tsv(lr_links_path, ["pos1", "pos2", "c1", "c2", "len", "MI"])
+    (:43); ``links_from_spydrpick`` reads spydrpick's space-separated 4- or 5-column output instead (:36-41)."""
+    if links_from_spydrpick:  # :36-41 space-separated spydrpick output with 5 (pos1 pos2 len ARACNE MI) or 4 columns; small files
+        tab = np.loadtxt(lr_links_path, dtype=np.float64, ndmin=2)
+        names = {5: ["pos1", "pos2", "len", "ARACNE", "MI"], 4: ["pos1", "pos2", "len", "MI"]}.get(tab.shape[1])
+        if names is None:
+            raise ValueError(f"spydrpick link files have 4 or 5 columns, {lr_links_path} has {tab.shape[1]}")
+        d = {k: np.ascontiguousarray(tab[:, i]) for i, k in enumerate(names)}
+    else:
+        d = _read_numeric_tsv(lr_links_path, ["pos1", "pos2", "c1", "c2", "len", "MI"])
     keep = ~(d["len"] < sr_dist)
     return {k: v[keep] for k, v in d.items()} if not keep.all() else d
 

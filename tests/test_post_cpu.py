@@ -249,6 +249,13 @@ def test_link_files_round_trip_and_lr_aracne_chain(fixture_expected, tmp_path):
     assert np.array_equal(back["MI"], np.array([float(O.format_r_numeric(float(v))) for v in lr["MI"]]))
     assert np.abs(back["MI"] / lr["MI"] - 1).max() < 1e-14
     assert len(ldw.read_LongRangeLinks(str(lr_path), sr_dist=5e5)["MI"]) == int((lr["len"] >= 5e5).sum())   # :43
+    # spydrpick output: space separated, 5 or 4 columns (R/io_functions.R:36-41), same len filter
+    sp = tmp_path / "spydrpick.txt"
+    sp.write_text("10 50000 49990 1 0.25\n20 30 10 0 0.5\n")
+    got5 = ldw.read_LongRangeLinks(str(sp), links_from_spydrpick=True)
+    assert list(got5) == ["pos1", "pos2", "len", "ARACNE", "MI"] and got5["MI"].tolist() == [0.25] and got5["ARACNE"].tolist() == [1.0]
+    sp.write_text("10 50000 49990 0.25\n")
+    assert list(ldw.read_LongRangeLinks(str(sp), links_from_spydrpick=True)) == ["pos1", "pos2", "len", "MI"]
     # sr_links.tsv
     sr, paint = _fixture_sr(e)
     sr_path = tmp_path / "sr_links.tsv"
