@@ -34,27 +34,97 @@ ALLELES = "ACGTN"
 # FASTA reading (host side of src/getACGTNsites.cpp: kseq over gzread)
 # --------------------------------------------------------------------------------------
 def read_fasta(path: str) -> Tuple[List[str], List[bytes]]:
-    """Minimal multi-FASTA reader (gz or plain) standing in for klib kseq
-    (reference src/kseq2.h:167 ``kseq_read``): name = first word after '>', sequence =
-    concatenation of the following lines with whitespace removed."""
-    opener = gzip.open if path.endswith(".gz") else open
+    """Multi-FASTA reader (gz or plain) restating klib's ``kseq_read`` as vendored in src/kseq2.h:167-207, as its
+    callers see the records (``strlen(seq->seq.s)`` / C string of ``seq->name.s``, src/getACGTNsites.cpp:36,51-52).
+
+    * :171-174 skip to the first '>' or '@' (anywhere) when no header character is pending;
+    * :176-178 name = up to the first isspace() byte; the rest of the line is a comment unless that byte was '\n';
+    * :183-186 line by line: first byte '>' / '@' -> next record, '+' -> quality section, ANY other first byte
+      (a '\n' of an empty line, '\r', blank) is appended and so is everything up to the next '\n' -- CR of CRLF files
+      and inner blanks are sequence bytes, an empty line glues the following line onto the sequence;
+    * :196-205 after '+': drop that line, append whole lines to qual until len(qual) >= len(seq); a mismatch or a
+      missing quality section returns -2, which ends the callers' ``while ((l = kseq_read(seq)) >= 0)`` loops;
+    * :87-98/:176 a header character that is the very last byte of the stream gives no record unless the stream length
+      is a multiple of the 16384-byte buffer (EOF not yet known to ks_getuntil).
+    Pinned against the compiled reference reader in tests/test_fasta_ref_cpu.py / tests/test_ref_pins_cpu.py."""
+    opener = gzip.open if _is_gz(path) else open
+    with opener(path, "rb") as fh:
+        buf = fh.read()
+    n = len(buf)
     names: List[str] = []
     seqs: List[bytes] = []
-    cur: List[bytes] = []
-    with opener(path, "rb") as fh:
-        for line in fh:
-            line = line.rstrip(b"\r\n")
-            if line.startswith(b">"):
-                if names:
-                    seqs.append(b"".join(cur))
-                    cur = []
-                hdr = line[1:].split()
-                names.append(hdr[0].decode() if hdr else "")
-            elif names:
-                cur.append(line.replace(b" ", b"").replace(b"\t", b""))
-        if names:
-            seqs.append(b"".join(cur))
+    space = b" \t\n\v\f\r"
+    i = 0
+    pending_header = False
+    while True:
+        if not pending_header:  # :171-174
+            while i < n and buf[i] not in b">@":
+                i += 1
+            if i >= n:
+                break
+            i += 1
+        pending_header = False
+        if i >= n and n % 16384 != 0:  # ks_getuntil returns -1 at a known EOF (:88)
+            break
+        j = i
+        while j < n and buf[j] not in space:
+            j += 1
+        name = buf[i:j]
+        delim = buf[j] if j < n else 0
+        i = j + 1
+        if delim != 0x0A:  # comment up to '\n' (:178)
+            k = buf.find(b"\n", i)
+            i = n if k < 0 else k + 1
+        seq = bytearray()
+        c = -1
+        while i < n:  # :183-186
+            c = buf[i]
+            i += 1
+            if c in b">+@":
+                break
+            seq.append(c)
+            k = buf.find(b"\n", i)
+            if k < 0:
+                seq += buf[i:]
+                i = n
+            else:
+                seq += buf[i:k]
+                i = k + 1
+            c = -1
+        if c != -1 and c in b">@":
+            pending_header = True
+        ok = True
+        if c == 0x2B:  # '+'  (:196-205)
+            k = buf.find(b"\n", i)
+            if k < 0:
+                ok = False
+                i = n
+            else:
+                i = k + 1
+                qual = 0
+                while True:
+                    if i >= n:
+                        break
+                    k = buf.find(b"\n", i)
+                    if k < 0:
+                        qual += n - i
+                        i = n
+                    else:
+                        qual += k - i
+                        i = k + 1
+                    if qual >= len(seq):
+                        break
+                ok = qual == len(seq)
+            if not ok:
+                break  # return -2: the callers' loops end
+        names.append(name.split(b"\0", 1)[0].decode("latin-1"))
+        seqs.append(bytes(seq).split(b"\0", 1)[0])
     return names, seqs
+
+
+def _is_gz(path: str) -> bool:
+    with open(path, "rb") as fh:
+        return fh.read(2) == b"\x1f\x8b"  # gzread inflates by magic number, not by file name
 
 
 def classify_bytes(arr: np.ndarray) -> np.ndarray:
@@ -405,9 +475,20 @@ def quantile_type7(x: np.ndarray, prob: float) -> float:
 # --------------------------------------------------------------------------------------
 # a7-a9  perform_MI_computation_ACGTN / computeMI_Sprase / fastHadamard
 # --------------------------------------------------------------------------------------
+# When set (tests/test_ref_pins_cpu.py, tests/golden/make_golden_ref.py: ``ref_lib.fastHadamard``), the element-wise
+# finish below is executed by the reference's own compiled src/computeMI.cpp instead of the NumPy restatement.
+HADAMARD_IMPL = None
+
+
 def fast_hadamard(MI, den, uq, pxy, pxpy, RXY, pXrX, pYrY) -> None:
     """src/computeMI.cpp:11-21 -- linear (column-major) index over nf*nt; ``RXY`` may have
     a different shape (nt x nf) and is consumed by the same linear index (quirk Q1)."""
+    if HADAMARD_IMPL is not None:
+        f = [np.asfortranarray(m, dtype=np.float64) for m in (MI, den, uq, pxy, pxpy, RXY, pXrX, pYrY)]
+        f[0] = np.array(MI, dtype=np.float64, order="F")  # private copy: modified in place (quirk Q11)
+        HADAMARD_IMPL(*f)
+        MI[...] = f[0]
+        return
     mi = MI.reshape(-1, order="F")
     d = den.reshape(-1, order="F")
     u = uq.reshape(-1, order="F")

@@ -23,6 +23,62 @@ def test_encode_fixture_bit_exact(fixture_input, fixture_expected):
         np.testing.assert_array_equal(snp.codes, fixture_expected["codes"])
 
 
+@pytest.fixture(scope="module")
+def ref_expected():
+    import os
+    from conftest import GOLDEN
+    return dict(np.load(os.path.join(GOLDEN, "ref_expected.npz")))
+
+
+def test_encode_vs_reference_object_code_goldens(fixture_input, ref_expected):
+    """a1/a2 against tests/golden/ref_expected.npz = outputs of the reference's OWN compiled .extractAlnParam /
+    .extractSNPs (oracle/_ref, tests/golden/make_golden_ref.py) on the bundled fixture, six (filter, gap, maf)."""
+    ldw = _lib()
+    e = ref_expected
+    aln = fixture_input["aln"]
+    k = 0
+    while f"enc{k}_setting" in e:
+        filt, gap, maf = e[f"enc{k}_setting"]
+        method = "default" if filt == 0 else "relaxed"
+        snp = ldw.snp_dat_from_alignment_matrix(aln, fixture_input["names"], method=method, gap_freq=float(gap), maf_freq=float(maf))
+        assert snp.nseq == int(e[f"enc{k}_num_seqs"]) and snp.g == int(e[f"enc{k}_seq_length"])
+        np.testing.assert_array_equal(snp.POS, e[f"enc{k}_pos"])
+        np.testing.assert_array_equal(snp.codes, e[f"enc{k}_codes"])
+        np.testing.assert_array_equal(snp.uqe, (e[f"enc{k}_table"] > 0).T.astype(float))
+        k += 1
+    assert k == 6
+
+
+def test_whole_parse_chain_on_the_crlf_edge_file_vs_reference_goldens(ref_expected, tmp_path):
+    """File bytes -> ldw_read_fasta_alloc (kseq grammar: CR columns kept) -> device count/filter/gather, against what the
+    reference's compiled code returned for the very same file."""
+    ldw = _lib()
+    e = ref_expected
+    p = tmp_path / "edge.fa"
+    p.write_bytes(e["edge_file"].tobytes())
+    for k, (method, gap, maf) in enumerate([("default", 0.15, 0.01), ("relaxed", 0.15, 0.01), ("default", 0.05, 0.10),
+                                            ("relaxed", 0.05, 0.10)]):
+        if int(e[f"edge{k}_num_snps"]) == 0:
+            with pytest.raises(ValueError, match="any SNPs"):
+                ldw.parse_fasta_alignment(str(p), gap_freq=gap, maf_freq=maf, method=method)
+            continue
+        snp = ldw.parse_fasta_alignment(str(p), gap_freq=gap, maf_freq=maf, method=method)
+        assert snp.g == int(e[f"edge{k}_seq_length"]) == 426 and snp.nseq == 60
+        assert snp.seq_names == [str(x) for x in e["edge_names"]]
+        np.testing.assert_array_equal(snp.POS, e[f"edge{k}_pos"])
+        np.testing.assert_array_equal(snp.codes, e[f"edge{k}_codes"])
+        np.testing.assert_array_equal(snp.uqe, (e[f"edge{k}_table"] > 0).T.astype(float))
+
+
+def test_acgtn2num_vs_reference_object_code_golden(ref_expected):
+    ldw = _lib()
+    e = ref_expected
+    cv = [chr(c) for c in e["a2n_cv"]]
+    nv = np.ones((5, 256), order="F")
+    ldw.acgtn2num(nv, cv)
+    np.testing.assert_array_equal(nv, e["a2n_nv"])
+
+
 def test_encode_filters_vs_oracle_ragged():
     """Filters that bite, lower case, gaps, IUPAC, odd sizes (unaligned rows)."""
     import c_oracle as CO

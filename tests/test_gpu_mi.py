@@ -52,6 +52,34 @@ def test_dense_block_mi_offdiag_and_ragged(fixture_snp, fixture_expected):
     plan.close()
 
 
+def test_dense_blocks_vs_reference_hadamard_goldens(fixture_input):
+    """a7-a9 with quirk Q1 against tests/golden/ref_expected.npz: per-block MI (max_blk_sz 500: diagonal, square
+    off-diagonal, ragged) whose element-wise finish was executed by the reference's compiled .fastHadamard
+    (src/computeMI.cpp:11-21; tests/golden/make_golden_ref.py).  fp32 epilogue within 1e-6, fp64 refinement 1e-12."""
+    import os
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    from conftest import GOLDEN
+    e = dict(np.load(os.path.join(GOLDEN, "ref_expected.npz")))
+    POS = fixture_input["pos"][e["enc1_pos"].astype(np.int64) - 1]
+    snp = ldw.snp_dat_from_codes(e["enc1_codes"], POS, 50000)
+    hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    np.testing.assert_array_equal(hdw, e["mi_hdw"])
+    plan = ldw.MIPlan(snp, hdw, np.ones(snp.nsnp, dtype=np.int64), int(e["mi_blk"]))
+    worst32 = worst64 = 0.0
+    for bi, (fs, fe, ts, te) in enumerate(O.make_blocks(snp.nsnp, int(e["mi_blk"]))):
+        rows, want = e[f"mi_b{bi}_rows"], e[f"mi_b{bi}"]
+        MI = plan.block_dense(bi)
+        worst32 = max(worst32, float(np.abs(MI[rows] - want).max()))
+        il = np.repeat(rows, want.shape[1])
+        jl = np.tile(np.arange(want.shape[1]), len(rows))
+        got = plan.pairs_exact(bi, il, jl).reshape(want.shape)
+        worst64 = max(worst64, float(np.abs(got - want).max()))
+    print("vs reference .fastHadamard goldens: fp32 epilogue", worst32, "fp64 refinement", worst64)
+    assert worst32 < MI_TOL and worst64 < 1e-12
+    plan.close()
+
+
 def test_exact_pairs_fp64(fixture_snp, fixture_expected):
     import c_oracle as CO
     import ldw_oracle as O
