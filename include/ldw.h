@@ -294,6 +294,49 @@ LDW_API int ldw_mi_block_dense(ldw_mi_plan* plan, int64_t block_index, double* m
 LDW_API int ldw_mi_pairs_exact(ldw_mi_plan* plan, int64_t block_index, const int32_t* from_local, const int32_t* to_local,
                        int64_t n_pairs, double* mi_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: device groups (one box, NCCL over NVLink / NVSwitch).
+ *
+ * Replaces nothing the reference has -- its block loop is serial (R/computePairwiseMI.R:103-116) -- but the blocks are
+ * independent given codes, hdw, POS and paint, and the long-range threshold is per block (quirk Q3), so dealing whole
+ * blocks to devices reproduces the single-device tables bit for bit.
+ *
+ * A group holds this process's members of the job: ALL of them (ldw_group_create: the form an R session or a Python
+ * process uses; one host thread per device while an operation runs) or ONE rank of a multi-process job
+ * (ldw_group_create_rank: rank 0 makes an id with ldw_group_unique_id and the launcher hands it to every rank).
+ * Every call below is collective: all processes of the job make it with the same arguments.
+ *
+ * ldw_group_load_codes: the class matrix (nsnp x nseq, as ldw_mi_plan_create takes it) goes host -> device ONCE, on the
+ *   member with rank 0 (other processes may pass NULL), and reaches the other devices by ncclBroadcast; it stays
+ *   resident for the calls that follow.
+ * ldw_group_hdw: estimate_Hamming_distance_weights on the resident matrix.  The distance GEMM's upper-triangle tiles are
+ *   dealt to the ranks, the partial neighbour counts are summed with ncclAllReduce and every rank forms the weights
+ *   (so no separate weight broadcast is needed); problems too small to share are computed whole on every rank
+ *   (*sharded_out tells which; LDW_HDW_FORCE_SHARD always deals).  Results are bit-identical to ldw_hdw.
+ * ldw_group_mi_scan: ldw_mi_plan_create + ldw_mi_scan over the group.  Every member packs its operands from the resident
+ *   matrix and scans its share of the make_blocks blocks (dealt by cost exactly as ldw_mi_scan's n_parts / part).
+ *   Short-range rows are copied by each device directly to their final rows of ONE pinned host table; long-range and
+ *   borderline rows are merged into make_blocks order.  The tables (group-owned, valid until the next scan on the group)
+ *   are identical to a single-device ldw_mi_scan when the group holds the whole job; a one-rank group of a
+ *   multi-process job returns the rows of its own blocks.  stats_out: one entry per LOCAL member; t_plan_ms_out: wall
+ *   time of the operand packing.
+ */
+typedef struct ldw_group ldw_group;
+#define LDW_GROUP_ID_BYTES 128
+enum { LDW_HDW_FORCE_SHARD = 1 };
+LDW_API int ldw_group_create(const int* devices, int n_devices, ldw_group** out);
+LDW_API int ldw_group_unique_id(char* id_out /* LDW_GROUP_ID_BYTES */);
+LDW_API int ldw_group_create_rank(int device, int rank, int world, const char* id /* LDW_GROUP_ID_BYTES */, ldw_group** out);
+LDW_API void ldw_group_destroy(ldw_group* g);
+LDW_API int ldw_group_info(const ldw_group* g, int* world_out, int* n_local_out, int* first_rank_out);
+LDW_API ldw_ctx* ldw_group_ctx(ldw_group* g, int local_index);
+LDW_API int ldw_group_load_codes(ldw_group* g, const uint8_t* codes, int64_t n_snp, int64_t nseq);
+LDW_API int ldw_group_hdw(ldw_group* g, double threshold, int flags, int32_t* cnt_out, double* hdw_out, int* sharded_out);
+LDW_API int ldw_group_mi_scan(ldw_group* g, const double* hdw, const int32_t* pos, const int32_t* paint, int64_t blk, double g_len,
+                      double sr_dist, double lr_retain_links, double lr_links_approx, int flags, ldw_links* sr_out,
+                      ldw_links* lr_out, ldw_links* borderline_out, double* thr_out, double* prob_out,
+                      ldw_scan_stats* stats_out, double* t_plan_ms_out);
+
 #ifdef __cplusplus
 }
 #endif

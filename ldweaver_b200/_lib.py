@@ -141,8 +141,43 @@ def lib():
     L.ldw_nm_rosenbrock.argtypes = [C.c_void_p, C.c_void_p, P(f64), P(C.c_int)]
     L.ldw_neg_log_pbeta_upper.argtypes = [C.c_void_p, i64, f64, f64, C.c_void_p]
     L.ldw_mi_pairs_exact.argtypes = [C.c_void_p, i64, C.c_void_p, C.c_void_p, i64, C.c_void_p]
+    L.ldw_group_create.argtypes = [C.c_void_p, C.c_int, P(C.c_void_p)]
+    L.ldw_group_unique_id.argtypes = [C.c_char_p]
+    L.ldw_group_create_rank.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, P(C.c_void_p)]
+    L.ldw_group_destroy.argtypes = [C.c_void_p]
+    L.ldw_group_destroy.restype = None
+    L.ldw_group_info.argtypes = [C.c_void_p, P(C.c_int), P(C.c_int), P(C.c_int)]
+    L.ldw_group_ctx.argtypes = [C.c_void_p, C.c_int]
+    L.ldw_group_ctx.restype = C.c_void_p
+    L.ldw_group_load_codes.argtypes = [C.c_void_p, C.c_void_p, i64, i64]
+    L.ldw_group_hdw.argtypes = [C.c_void_p, f64, C.c_int, C.c_void_p, C.c_void_p, P(C.c_int)]
+    L.ldw_group_mi_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i64, f64, f64, f64, f64, C.c_int,
+                                    P(Links), P(Links), P(Links), C.c_void_p, C.c_void_p, C.c_void_p, P(f64)]
     _lib = L
     return L
+
+
+_nccl_preloaded = False
+
+
+def preload_nccl() -> None:
+    """libldwgpu binds NCCL at run time by soname (csrc/group.cu); a later ``import torch`` needs its own bundled,
+    newer libnccl.so.2.  Loading that copy first (when the nvidia-nccl wheel is installed) keeps a process on ONE copy
+    whichever order the imports come in.  No wheel: the system library is found by the loader."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations if spec and spec.submodule_search_locations else []):
+            so = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(so):
+                C.CDLL(so, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
 
 
 def check(rc: int) -> None:

@@ -185,9 +185,18 @@ def acgtn2num(nv: np.ndarray, cv, ncores: int = 1, device: int = 0) -> None:
 
 
 def estimate_Hamming_distance_weights(snp_dat: SnpDat, threshold: float = 0.1, mega_dset: bool = False,
-                                      device: int = 0, return_parts: bool = False):
+                                      device: int = 0, return_parts: bool = False, devices: Optional[Sequence[int]] = None):
     """R/performPopulationStuctureCorrection.R:20-81.  Returns the weight vector (``hdw``); with
-    ``return_parts`` also the neighbour counts and the integer Hamming-distance matrix."""
+    ``return_parts`` also the neighbour counts and the integer Hamming-distance matrix.  ``devices`` (or ``LDW_GPUS``)
+    runs it on a device group: tiles of the distance GEMM dealt across the GPUs, counts all-reduced with NCCL."""
+    if devices is None and not return_parts:
+        devices = devices_from_env()
+    if devices is not None and len(devices) > 1:
+        if return_parts:
+            raise ValueError("the distance matrix (return_parts) is a single-device output")
+        grp = default_group(devices)
+        grp.load_codes(snp_dat.codes)
+        return grp.hdw(threshold)
     ctx = _lib.default_context(device)
     codes = np.ascontiguousarray(snp_dat.codes, dtype=np.uint8)
     n, S = codes.shape
@@ -418,6 +427,119 @@ def write_lr_tsv(path: str, lr, append: bool = True) -> None:
     check(_lib.lib().ldw_write_lr_tsv(os.fsencode(path), C.byref(links), 1 if append else 0))
 
 
+class DeviceGroup:
+    """A device group (``ldw_group_*``): the multi-GPU form of the weights and of the scan.
+
+    ``DeviceGroup([0, 1, 2, 3])`` holds the whole job in this process (what an R session does; one host thread per device
+    while a call runs).  ``DeviceGroup.from_rank(device, rank, world, unique_id)`` is one rank of a multi-process job
+    (torchrun): rank 0 calls ``DeviceGroup.unique_id()`` and the launcher broadcasts the bytes.  Every method is
+    collective over the job.  The class matrix is uploaded once (rank 0) and broadcast with NCCL (``load_codes``);
+    ``hdw`` deals the distance GEMM's tiles and all-reduces the neighbour counts; ``mi_scan`` deals make_blocks blocks by
+    cost and assembles ONE link table (identical to the single-device one when the group holds the whole job)."""
+
+    def __init__(self, devices: Sequence[int]):
+        devs = np.ascontiguousarray(list(devices), dtype=np.int32)
+        self.handle = C.c_void_p()
+        if len(devs) > 1:
+            _lib.preload_nccl()
+        check(_lib.lib().ldw_group_create(ptr(devs), len(devs), C.byref(self.handle)))
+        self._after_create()
+
+    def _after_create(self):
+        w, nl, fr = C.c_int(), C.c_int(), C.c_int()
+        check(_lib.lib().ldw_group_info(self.handle, C.byref(w), C.byref(nl), C.byref(fr)))
+        self.world, self.n_local, self.first_rank = w.value, nl.value, fr.value
+        self.n_snp = self.nseq = 0
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.preload_nccl()
+        check(_lib.lib().ldw_group_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def from_rank(cls, device: int, rank: int, world: int, unique_id: Optional[bytes]):
+        self = cls.__new__(cls)
+        self.handle = C.c_void_p()
+        _lib.preload_nccl()
+        check(_lib.lib().ldw_group_create_rank(int(device), int(rank), int(world), unique_id, C.byref(self.handle)))
+        self._after_create()
+        return self
+
+    def close(self):
+        if getattr(self, "handle", None):
+            _lib.lib().ldw_group_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_codes(self, codes: Optional[np.ndarray], n_snp: Optional[int] = None, nseq: Optional[int] = None) -> None:
+        """``codes`` [nsnp, nseq] uint8 on the process that holds rank 0; other processes pass None and the shape."""
+        if codes is not None:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            n_snp, nseq = codes.shape
+        check(_lib.lib().ldw_group_load_codes(self.handle, ptr(codes) if codes is not None else None, int(n_snp), int(nseq)))
+        self.n_snp, self.nseq = int(n_snp), int(nseq)
+
+    def hdw(self, threshold: float = 0.1, force_shard: bool = False, return_parts: bool = False):
+        cnt = np.empty(self.nseq, dtype=np.int32)
+        w = np.empty(self.nseq, dtype=np.float64)
+        sharded = C.c_int()
+        check(_lib.lib().ldw_group_hdw(self.handle, float(threshold), 1 if force_shard else 0, ptr(cnt), ptr(w), C.byref(sharded)))
+        return (w, cnt, bool(sharded.value)) if return_parts else w
+
+    def mi_scan(self, hdw, pos, paint, blk: int, g: float, sr_dist: float, lr_retain_links: float, lr_links_approx: float,
+                flags: int = 0, copy: bool = True):
+        hdw = np.ascontiguousarray(hdw, dtype=np.float64)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        paint = np.ascontiguousarray(paint, dtype=np.int32)
+        if len(hdw) != self.nseq or len(pos) != self.n_snp or len(paint) != self.n_snp:
+            raise ValueError("hdw / POS / paint do not match the matrix given to load_codes")
+        nr = -(-self.n_snp // int(blk))
+        nblk = nr * (nr + 1) // 2
+        sr, lr, bd = _lib.Links(), _lib.Links(), _lib.Links()
+        thr, prob = np.full(nblk, np.nan), np.full(nblk, np.nan)
+        stats = (_lib.ScanStats * self.n_local)()
+        t_plan = _lib.f64()
+        check(_lib.lib().ldw_group_mi_scan(self.handle, ptr(hdw), ptr(pos), ptr(paint), int(blk), float(g), float(sr_dist),
+                                           float(lr_retain_links), float(lr_links_approx if lr_links_approx else 0.0), int(flags),
+                                           C.byref(sr), C.byref(lr), C.byref(bd), ptr(thr), ptr(prob), stats, C.byref(t_plan)))
+        st = [s_.to_dict() for s_ in stats]
+        for d in st:
+            d["t_plan_ms"] = t_plan.value
+        if copy:
+            return sr.to_dict(), lr.to_dict(), bd.to_dict(), thr, prob, st
+        return sr, lr, bd, thr, prob, st
+
+
+_groups = {}
+
+
+def default_group(devices: Sequence[int]) -> DeviceGroup:
+    """One cached in-process group per device list (NCCL communicator set-up costs ~0.1-1 s)."""
+    key = tuple(int(d) for d in devices)
+    if key not in _groups:
+        _groups[key] = DeviceGroup(key)
+    return _groups[key]
+
+
+def devices_from_env() -> Optional[List[int]]:
+    """``LDW_GPUS`` ("0,1,2,3" or a count "4"): the devices the hot path uses when the caller names none -- the Python
+    mirror of ``options(LDWeaver.gpus = )`` in r_package/R/gpu_hotpath.R."""
+    v = os.environ.get("LDW_GPUS", "").strip()
+    if not v:
+        return None
+    if "," in v:
+        return [int(x) for x in v.split(",") if x.strip() != ""]
+    n = int(v)
+    return list(range(n)) if n > 1 else None
+
+
 @dataclass
 class SrLinks:
     """Result of ``mergeNsort_sr_links``: ``df`` holds sr_links_df column-wise (clust_c, pos1, pos2, clust1, clust2, len,
@@ -596,7 +718,8 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
                            runARACNE: bool = True, perform_SR_analysis_only: bool = False, order_links: bool = True,
                            mega_dset: bool = False, lr_links_approx: Optional[float] = None, device: int = 0,
                            write_tsv: bool = True, plan: Optional[MIPlan] = None,
-                           postprocess: Optional[bool] = None, exact_sr: Optional[bool] = None) -> MIScanResult:
+                           postprocess: Optional[bool] = None, exact_sr: Optional[bool] = None,
+                           devices: Optional[Sequence[int]] = None) -> MIScanResult:
     """R/computePairwiseMI.R:46-145.  Same arguments as the reference (``ncores`` is accepted and ignored by the GPU
     path; ``plt_folder`` is accepted, no plots are drawn).  The scan (:46-116) runs on the device; what follows it
     (:118-143: mergeNsort_sr_links, runARACNE, ordering, sr_links.tsv) runs in native host code and fills
@@ -618,12 +741,36 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     if not perform_SR_analysis_only and lr_links_approx is None:
         from .rrng import lr_links_approx as _lra
         lr_links_approx = _lra(np.asarray(snp_dat.POS), float(snp_dat.g), float(sr_dist))  # :94-97
+    if devices is None and plan is None:
+        devices = devices_from_env()
+    multi = devices is not None and len(devices) > 1
+    do_post = postprocess if postprocess is not None else write_tsv
+    if multi:
+        # device group: matrix uploaded once + NCCL broadcast, blocks dealt by cost, one link table.  The fp64
+        # short-range MI comes from inside the scan (LDW_SCAN_SR_EXACT): the host-driven refinement is single-device.
+        grp = default_group(devices)
+        grp.load_codes(snp_dat.codes)
+        flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
+        if exact_sr is None:
+            exact_sr = do_post
+        if exact_sr:
+            flags |= SCAN_SR_EXACT
+        sr, lr, bd, thr, prob, st_list = grp.mi_scan(hdw, snp_dat.POS, paint, blk, float(snp_dat.g), sr_dist, lr_retain_links,
+                                                     lr_links_approx or 0.0, flags)
+        stats = dict(st_list[0])
+        for k in ("n_blocks", "n_pairs", "n_sr", "n_lr_total", "n_lr_kept", "n_borderline", "n_reruns", "n_candidates",
+                  "n_scan_launches", "n_launches", "n_tiles", "exec_int8_ops"):
+            stats[k] = sum(d[k] for d in st_list)
+        for k in ("t_pack_ms", "t_scan_ms", "t_select_ms", "t_d2h_ms", "t_kernel_ms", "t_host_prep_ms"):
+            stats[k] = max(d[k] for d in st_list)
+        stats["per_device"] = st_list
+        return _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff,
+                                      runARACNE, order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder)
     own = plan is None
     if own:
         plan = MIPlan(snp_dat, hdw, paint, blk, device)
     try:
         flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
-        do_post = postprocess if postprocess is not None else write_tsv
         if exact_sr is None:  # SR-only scans index reduced SNP lists (Q12): only the in-scan kernel can refine them
             exact_sr = ("in_scan" if perform_SR_analysis_only else True) if do_post else False
         if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call
@@ -637,6 +784,13 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     finally:
         if own:
             plan.close()
+    return _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff,
+                                  runARACNE, order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder)
+
+
+def _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff, run_aracne,
+                           order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder) -> MIScanResult:
+    """What follows the scan in perform_MI_computation (R/computePairwiseMI.R:118-143), for one device or a group."""
     if write_tsv and len(lr["MI"]):
         write_lr_tsv(lr_save_path, lr, append=True)
     res = MIScanResult(sr=sr, lr=lr, borderline=bd, nclust=nclust, thr=thr, prob=prob, stats=stats,
@@ -644,6 +798,6 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     if do_post:
         if write_tsv and sr_save_path is None:
             sr_save_path = os.path.join(os.getcwd(), "sr_links.tsv")  # :62
-        res.sr_links_red, res.sr_post = finish_sr_links(sr, cds_var, sr_dist, srp_cutoff, runARACNE, order_links,
+        res.sr_links_red, res.sr_post = finish_sr_links(sr, cds_var, sr_dist, srp_cutoff, run_aracne, order_links,
                                                         sr_save_path if write_tsv else None, plt_folder)
     return res

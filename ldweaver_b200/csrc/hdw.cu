@@ -17,6 +17,8 @@
 
 #include "umma.cuh"
 
+#include <vector>
+
 namespace ldw {
 
 // ------------------------------------------------------------------------------------------------
@@ -165,7 +167,7 @@ constexpr int HDW_BM = 128, HDW_BN = 256, HDW_BK = 128;  // BK in bytes == int8 
 constexpr int HDW_STAGES = 4;
 constexpr int HDW_THREADS = 192;
 constexpr uint32_t HDW_STAGE_A = HDW_BM * HDW_BK, HDW_STAGE_B = HDW_BN * HDW_BK;
-constexpr uint32_t HDW_SMEM = HDW_STAGES * (HDW_STAGE_A + HDW_STAGE_B) + 1024 /*align*/ + 256 /*barriers*/ + HDW_BN * 4;
+constexpr uint32_t HDW_SMEM = HDW_STAGES * (HDW_STAGE_A + HDW_STAGE_B) + 1024 /*align*/ + 256 /*barriers*/ + 2 * HDW_BN * 4;
 
 struct HdwGemmParams {
   int32_t S;         // real sequences
@@ -176,6 +178,10 @@ struct HdwGemmParams {
   const int32_t* cnt_z;  // per-sequence z counts
   int32_t* neigh;        // per-sequence neighbour counts (fused mode)
   int32_t* g;            // [t * ldg + s] partial G (non-fused mode)
+  // G is symmetric: only tiles that hold at least one pair s <= t are computed (the upper triangle of the tile grid),
+  // and in multi-GPU runs each rank takes every n_parts-th of them.  tile_list[k] = (tm, tn) of this launch's tiles.
+  const int2* tile_list;
+  int32_t n_tiles;
 };
 
 __global__ void __launch_bounds__(HDW_THREADS, 1)
@@ -190,7 +196,8 @@ hdw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* tfull = bars + 2 * HDW_STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  int32_t* s_cnt = reinterpret_cast<int32_t*>(bars + 32);  // [2][HDW_BN/2]? -> one buffer of BN ints per accumulator stage not needed: reloaded per tile
+  int32_t* s_cnt = reinterpret_cast<int32_t*>(bars + 32);  // z counts of the tile's column sequences, reloaded per tile
+  int32_t* s_col = s_cnt + HDW_BN;                         // neighbours found for the column sequences (pairs s < t)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -206,15 +213,16 @@ hdw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_work = p.tiles_m * p.tiles_n * p.ksplit;
+  const int total_work = p.n_tiles * p.ksplit;
   const int kb_per = (p.nkb + p.ksplit - 1) / p.ksplit;
 
   if (warp == 0) {
     if (lane == 0) {
       int st = 0; uint32_t ph = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        int ks = w % p.ksplit, tile = w / p.ksplit;
-        int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+        int ks = w % p.ksplit;
+        const int2 tl = p.tile_list[w / p.ksplit];
+        int tm = tl.x, tn = tl.y;
         int kb0 = ks * kb_per, kb1 = min(p.nkb, kb0 + kb_per);
         for (int kb = kb0; kb < kb1; kb++) {
           mbar_wait(&empty[st], ph ^ 1, 1);
@@ -255,8 +263,9 @@ hdw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int et = (warp - 2) * 32 + lane;  // 0..127 linear epilogue thread id
     int as = 0; uint32_t aph = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-      int ks = w % p.ksplit, tile = w / p.ksplit;
-      int tm = tile % p.tiles_m, tn = tile / p.tiles_m;
+      int ks = w % p.ksplit;
+      const int2 tl = p.tile_list[w / p.ksplit];
+      int tm = tl.x, tn = tl.y;
       int kb0 = ks * kb_per;
       bool has_k = kb0 < p.nkb;
       // stage the column sequences' z counts
@@ -264,6 +273,7 @@ hdw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int c = et; c < HDW_BN; c += 128) {
         int t = tn * HDW_BN + c;
         s_cnt[c] = (t < p.S) ? p.cnt_z[t] : 0;
+        s_col[c] = 0;
       }
       asm volatile("bar.sync 1, 128;");
       mbar_wait(&tfull[as], aph, 4);
@@ -283,8 +293,13 @@ hdw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           int t = tn * HDW_BN + c0 + j;
           int gval = has_k ? (int)v[j] : 0;
           if (p.fused) {
+            // dist(s,t) == dist(t,s): a pair s < t counts for both sequences, the diagonal once, s > t is the mirror
+            // image of a pair another (or this) tile counts
             int dist = cs + s_cnt[c0 + j] - gval;
-            local += (t < p.S && dist < p.thresh) ? 1 : 0;
+            const bool near = (t < p.S && s < p.S && dist < p.thresh);
+            local += (near && s <= t) ? 1 : 0;
+            const unsigned m = __ballot_sync(0xffffffffu, near && s < t);
+            if (m && lane == 0) atomicAdd(&s_col[c0 + j], __popc(m));
           } else if (s < p.S && t < p.S && gval != 0) {
             atomicAdd(&p.g[(int64_t)t * p.ldg + s], gval);
           }
@@ -292,7 +307,14 @@ hdw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
-      if (p.fused && s < p.S && local) atomicAdd(&p.neigh[s], local);
+      if (p.fused) {
+        if (s < p.S && local) atomicAdd(&p.neigh[s], local);
+        asm volatile("bar.sync 1, 128;");
+        for (int c = et; c < HDW_BN; c += 128) {
+          const int t = tn * HDW_BN + c, v = s_col[c];
+          if (v && t < p.S) atomicAdd(&p.neigh[t], v);
+        }
+      }
       if (++as == 2) { as = 0; aph ^= 1; }
     }
   }
@@ -311,7 +333,8 @@ __global__ void hdw_finish_kernel(const int32_t* __restrict__ g, int32_t ldg, co
   if (s >= S) return;
   int cs = cnt_z[s], c = 0;
   for (int t = 0; t < S; t++) {
-    int d = cs + cnt_z[t] - g[(int64_t)t * ldg + s];
+    // only tiles of the upper triangle were accumulated: G(s,t) for s <= t sits at [t][s], else at [s][t]
+    int d = cs + cnt_z[t] - (s <= t ? g[(int64_t)t * ldg + s] : g[(int64_t)s * ldg + t]);
     c += d < thresh;
     if (dist_out) dist_out[(int64_t)t * S + s] = d;
   }
@@ -340,10 +363,10 @@ int exclusive_scan_i32(cudaStream_t st, const int32_t* d_in, int64_t n, int32_t*
 }
 
 int hdw_device(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, int32_t thresh, int32_t* d_neigh,
-               double* d_hdw, int32_t* d_dist, int num_sms) {
+               double* d_hdw, int32_t* d_dist, int num_sms, const HdwShard* shard) {
   if (S <= 0 || n <= 0) return set_error(LDW_ERR_ARG, "hdw: empty input (nsnp=%lld nseq=%lld)", (long long)n, (long long)S);
   if (n >= (1 << 24)) return set_error(LDW_ERR_UNSUPPORTED, "hdw: nsnp >= 2^24 not supported");
-  DevBuf table, mask, r, npl, poff, total, desc, A, B, cntz, g;
+  DevBuf table, mask, r, npl, poff, total, desc, A, B, cntz, g, tiles_dev;
   LDW_TRY(table.alloc(n * 5 * 4));
   LDW_TRY(mask.alloc(n));
   LDW_TRY(r.alloc(n));
@@ -378,12 +401,33 @@ int hdw_device(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, in
   LDW_TRY(make_tmap_u8_sw128(&tmB, B.p, (uint64_t)S_pad, (uint64_t)Kh, HDW_BN));
 
   HdwGemmParams p;
+  memset(&p, 0, sizeof(p));
   p.S = (int32_t)S;
   p.tiles_m = (int32_t)((S + HDW_BM - 1) / HDW_BM);
   p.tiles_n = (int32_t)((S + HDW_BN - 1) / HDW_BN);
   p.nkb = (int32_t)(Kh / HDW_BK);
-  int tiles = p.tiles_m * p.tiles_n;
-  int ks = (2 * num_sms) / tiles;
+  // Upper triangle of the tile grid: tile (tm, tn) holds a pair s <= t iff its first row does not lie below its last column.
+  std::vector<int2> tri;
+  for (int tn = 0; tn < p.tiles_n; tn++)
+    for (int tm = 0; tm < p.tiles_m; tm++)
+      if ((int64_t)tm * HDW_BM <= (int64_t)tn * HDW_BN + HDW_BN - 1) tri.push_back(make_int2(tm, tn));
+  // Multi-GPU: when every rank still gets more than a wave of whole-K tiles, the triangle's tiles are
+  // dealt round-robin, each rank counts the neighbours its tiles reveal and the partial counts are summed across ranks
+  // (the `allreduce` callback: ncclAllReduce).  Smaller problems are computed whole on every rank -- identical results,
+  // no collective -- because split-K (which they need to fill the SMs) leaves no per-rank share to count from.
+  // The decision depends on S, the rank count and the SM count only, so all ranks of a homogeneous box agree.
+  int n_parts = 1, part = 0;
+  if (shard && shard->n_parts > 1 && d_dist == nullptr &&
+      (shard->force || (int64_t)tri.size() >= (int64_t)shard->n_parts * 2 * num_sms)) {
+    n_parts = shard->n_parts;
+    part = shard->part;
+  }
+  std::vector<int2> mine;
+  for (size_t k = 0; k < tri.size(); k++)
+    if ((int)(k % (size_t)n_parts) == part) mine.push_back(tri[k]);
+  const int tiles = (int)mine.size();
+  int ks = tiles > 0 ? (2 * num_sms) / tiles : 1;
+  if (n_parts > 1) ks = 1;
   if (ks < 1) ks = 1;
   if (ks > p.nkb) ks = p.nkb;
   // every split must own at least one k-block
@@ -395,20 +439,31 @@ int hdw_device(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, in
   p.cnt_z = cntz.as<int32_t>();
   p.neigh = d_neigh;
   p.g = nullptr;
+  p.n_tiles = tiles;
+  LDW_TRY(tiles_dev.alloc(std::max<size_t>(mine.size(), 1) * sizeof(int2)));
+  if (tiles) LDW_CUDA(cudaMemcpyAsync(tiles_dev.p, mine.data(), mine.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+  p.tile_list = tiles_dev.as<int2>();
   if (!p.fused) {
     LDW_TRY(g.alloc((size_t)S_pad * S_pad * 4));
     LDW_CUDA(cudaMemsetAsync(g.p, 0, (size_t)S_pad * S_pad * 4, st));
     p.g = g.as<int32_t>();
   }
   LDW_CUDA(cudaFuncSetAttribute(hdw_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HDW_SMEM));
-  int grid = tiles * ks < num_sms ? tiles * ks : num_sms;
-  hdw_gemm_kernel<<<grid, HDW_THREADS, HDW_SMEM, st>>>(tmA, tmB, p);
-  LDW_CUDA(cudaGetLastError());
+  if (tiles > 0) {
+    int grid = tiles * ks < num_sms ? tiles * ks : num_sms;
+    hdw_gemm_kernel<<<grid, HDW_THREADS, HDW_SMEM, st>>>(tmA, tmB, p);
+    LDW_CUDA(cudaGetLastError());
+  }
   if (!p.fused) {
     hdw_finish_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(g.as<int32_t>(), p.ldg, cntz.as<int32_t>(), (int32_t)S, thresh,
                                                                    d_neigh, d_dist);
     LDW_CUDA(cudaGetLastError());
   }
+  if (n_parts > 1) {
+    if (!shard->allreduce) return set_error(LDW_ERR_INTERNAL, "hdw: sharded run without a reduction");
+    LDW_TRY(shard->allreduce(d_neigh, S, st));  // sum of the ranks' partial neighbour counts, in place, on every rank
+  }
+  if (shard && shard->sharded_out) *shard->sharded_out = n_parts > 1 ? 1 : 0;
   hdw_weights_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>(d_neigh, (int32_t)S, d_hdw);
   LDW_CUDA(cudaGetLastError());
   LDW_CUDA(cudaStreamSynchronize(st));

@@ -16,6 +16,7 @@
 #include "hdw.h"
 #include "mi_aux.cuh"
 #include "mi_kernel.cuh"
+#include "mi_scan.h"
 
 using namespace ldw;
 
@@ -121,6 +122,7 @@ struct ldw_mi_plan {
   bool pos_sorted = true;
   // device, static
   DevBuf d_codes, d_w, d_p64, d_rec, d_r, d_mask, d_pos, d_paint, d_ops, d_dig;
+  const uint8_t* codes_dev = nullptr;  // the class matrix on this device: d_codes, or a buffer the device group owns
   TmapSet tm;
   std::vector<BlockResult> results;
   double t_pack_ms = 0;
@@ -129,7 +131,10 @@ struct ldw_mi_plan {
 namespace {
 
 // ---------------------------------------------------------------------------------------------- plan
-int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const int32_t* pos, const int32_t* paint) {
+// codes: host class matrix (uploaded here), or NULL when `codes_dev` already holds it on this device (multi-GPU: the
+// group uploads once and broadcasts, ldw_group_load_codes)
+int build_plan(ldw_mi_plan* P, const uint8_t* codes, const uint8_t* codes_dev, const double* hdw, const int32_t* pos,
+               const int32_t* paint) {
   ldw_ctx* ctx = P->ctx;
   cudaStream_t st = ctx->stream;
   const int64_t n = P->n, S = P->S, blk = P->blk;
@@ -219,13 +224,18 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   P->neffL = (int32_t)sumL;
   blap("weights/digits");
   // ---- upload codes, per-SNP allele statistics
-  LDW_TRY(P->d_codes.alloc((size_t)n * S));
+  if (codes) {
+    LDW_TRY(P->d_codes.alloc((size_t)n * S));
+    P->codes_dev = static_cast<const uint8_t*>(P->d_codes.p);
+  } else {
+    P->codes_dev = codes_dev;
+  }
   LDW_TRY(P->d_mask.alloc((size_t)n));
   LDW_TRY(P->d_r.alloc((size_t)n));
   DevBuf d_table;
   LDW_TRY(d_table.alloc((size_t)n * 5 * 4));
-  LDW_CUDA(cudaMemcpyAsync(P->d_codes.p, codes, (size_t)n * S, cudaMemcpyHostToDevice, st));
-  LDW_TRY(snp_allele_stats(st, P->d_codes.as<uint8_t>(), n, S, d_table.as<int32_t>(), P->d_mask.as<uint8_t>(), P->d_r.as<uint8_t>()));
+  if (codes) LDW_CUDA(cudaMemcpyAsync(P->d_codes.p, codes, (size_t)n * S, cudaMemcpyHostToDevice, st));
+  LDW_TRY(snp_allele_stats(st, P->codes_dev, n, S, d_table.as<int32_t>(), P->d_mask.as<uint8_t>(), P->d_r.as<uint8_t>()));
   P->r.resize(n);
   P->mask.resize(n);
   LDW_CUDA(cudaMemcpyAsync(P->r.data(), P->d_r.p, (size_t)n, cudaMemcpyDeviceToHost, st));
@@ -303,7 +313,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   {
     int wpb = 8;
     mi_build_rec_kernel<<<(unsigned)((slot + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-        P->d_codes.as<uint8_t>(), S, d_slot_snp.as<int32_t>(), slot, P->d_mask.as<uint8_t>(), P->d_w.as<double>(),
+        P->codes_dev, S, d_slot_snp.as<int32_t>(), slot, P->d_mask.as<uint8_t>(), P->d_w.as<double>(),
         d_wH.as<int32_t>(), d_wL.as<int32_t>(), P->d_rec.as<Rec>(), slot, P->d_p64.as<double>(), P->sa, P->sb, P->M);
     LDW_CUDA(cudaGetLastError());
   }
@@ -314,7 +324,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const double* hdw, const in
   {
     int64_t total = row * (P->Kpad / 16);
     if (total > 0) {
-      mi_pack_operands_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P->d_codes.as<uint8_t>(), S, P->Kpad,
+      mi_pack_operands_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(P->codes_dev, S, P->Kpad,
                                                                                d_row_info.as<uint32_t>(), row,
                                                                                P->d_ops.as<uint8_t>());
       LDW_CUDA(cudaGetLastError());
@@ -651,7 +661,7 @@ int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st, int
 
 RefineParams make_refine_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& H, const ScanCfg& cfg) {
   RefineParams R;
-  R.codes = P->d_codes.as<uint8_t>();
+  R.codes = P->codes_dev;
   R.S = P->S;
   R.w = P->d_w.as<double>();
   R.p64 = P->d_p64.as<double>();
@@ -682,14 +692,22 @@ extern "C" {
 
 int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, const double* hdw,
                        const int32_t* pos, const int32_t* paint, int64_t blk, ldw_mi_plan** out) {
+  if (!codes) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: null argument");
+  return ldw::mi_plan_create_impl(ctx, codes, nullptr, n_snp, nseq, hdw, pos, paint, blk, out);
+}
+
+}  // extern "C"
+
+int ldw::mi_plan_create_impl(ldw_ctx* ctx, const uint8_t* codes, const uint8_t* codes_dev, int64_t n_snp, int64_t nseq,
+                             const double* hdw, const int32_t* pos, const int32_t* paint, int64_t blk, ldw_mi_plan** out) {
   LDW_TRY(ctx_bind(ctx));
   if (!out) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: null out");
   *out = nullptr;
-  if (!codes || !hdw || !pos || !paint) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: null argument");
+  if ((!codes && !codes_dev) || !hdw || !pos || !paint) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: null argument");
   if (n_snp < 2 || nseq < 1) return set_error(LDW_ERR_ARG, "ldw_mi_plan_create: need at least 2 SNPs and 1 sequence");
   if (nseq > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: nseq > 65535 not supported by the 15-bit digit accumulation");
   if (blk < 128 || blk > 65535) return set_error(LDW_ERR_UNSUPPORTED, "ldw_mi_plan_create: block size %lld outside [128, 65535]", (long long)blk);
-  {
+  if (codes) {
     // every code must be 0..4; eight bytes per step (a byte > 4 sets bit 7 of byte + 0x7B, or has it set already),
     // chunks spread over a few host threads
     const int64_t total = n_snp * nseq;
@@ -714,11 +732,13 @@ int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_
   ldw_mi_plan* P = new ldw_mi_plan();
   P->ctx = ctx;
   P->n = n_snp; P->S = nseq; P->blk = blk;
-  int rc = build_plan(P, codes, hdw, pos, paint);
+  int rc = build_plan(P, codes, codes_dev, hdw, pos, paint);
   if (rc != 0) { delete P; return rc; }
   *out = P;
   return 0;
 }
+
+extern "C" {
 
 void ldw_mi_plan_destroy(ldw_mi_plan* plan) {
   if (!plan) return;
@@ -814,6 +834,65 @@ int ldw_mi_pairs_exact(ldw_mi_plan* P, int64_t block_index, const int32_t* from_
 int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links, double lr_links_approx, int flags,
                 int n_parts, int part, ldw_links* sr_out, ldw_links* lr_out, ldw_links* borderline_out, double* thr_out,
                 double* prob_out, ldw_scan_stats* stats_out) {
+  return ldw::mi_scan_impl(P, g, sr_dist, lr_retain_links, lr_links_approx, flags, n_parts, part, nullptr, sr_out, lr_out,
+                           borderline_out, thr_out, prob_out, stats_out);
+}
+
+}  // extern "C"
+
+// Sizes of every make_blocks block (pairs, short-range, long-range) on host threads: positions only, no device work.
+int ldw::mi_block_sizes(const ldw_mi_plan* P, double g, double sr_dist, int flags, std::vector<BlockSizes>& out) {
+  if (!P) return set_error(LDW_ERR_ARG, "null plan");
+  ScanCfg cfg{g, sr_dist, 0, 0, flags};
+  LDW_TRY(validate_scan(P, cfg));
+  std::vector<std::pair<int, int>> bl;
+  for (int i = 0; i < P->nranges; i++)
+    for (int j = i; j < P->nranges; j++) bl.push_back({i, j});
+  out.assign(bl.size(), BlockSizes{0, 0, 0, 0});
+  parallel_for((int64_t)bl.size(), 16, [&](int64_t b) {
+    BlockHost tmp;
+    int e = prepare_block(P, bl[b].first, bl[b].second, cfg, tmp, true);
+    out[b] = BlockSizes{tmp.n_pairs, tmp.n_sr, tmp.n_lr, e};
+  });
+  for (size_t b = 0; b < bl.size(); b++)
+    if (out[b].err > 1) {  // re-run on this thread so that the (thread-local) error message is the caller's
+      BlockHost t2;
+      return prepare_block(P, bl[b].first, bl[b].second, cfg, t2, true);
+    }
+  return 0;
+}
+
+// Blocks are dealt by cost (pairs), largest first, each to the least-loaded part (lowest part on ties): diagonal blocks
+// cost half of the others, so plain round-robin would leave up to 12 % imbalance at 8 parts.  Deterministic: every rank
+// derives the same assignment (ldweaver_b200/api.py:partition_blocks mirrors it).
+void ldw::mi_block_owners(const ldw_mi_plan* P, int n_parts, std::vector<int>& owner) {
+  struct Item { int64_t cost, idx; };
+  std::vector<Item> items;
+  int64_t idx = 0;
+  for (int i = 0; i < P->nranges; i++)
+    for (int j = i; j < P->nranges; j++, idx++) {
+      const int64_t ni = std::min<int64_t>(P->n, (int64_t)(i + 1) * P->blk) - (int64_t)i * P->blk;
+      const int64_t nj = std::min<int64_t>(P->n, (int64_t)(j + 1) * P->blk) - (int64_t)j * P->blk;
+      items.push_back({i == j ? ni * (ni - 1) / 2 : ni * nj, idx});
+    }
+  std::vector<Item> order = items;
+  std::stable_sort(order.begin(), order.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
+  std::vector<int64_t> load(n_parts, 0);
+  owner.assign(items.size(), 0);
+  for (const Item& it : order) {
+    int best = 0;
+    for (int p = 1; p < n_parts; p++)
+      if (load[p] < load[best]) best = p;
+    owner[it.idx] = best;
+    load[best] += it.cost;
+  }
+}
+
+int64_t ldw::mi_plan_nblocks(const ldw_mi_plan* P) { return (int64_t)P->nranges * (P->nranges + 1) / 2; }
+
+int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links, double lr_links_approx, int flags,
+                      int n_parts, int part, const ScanShared* shared, ldw_links* sr_out, ldw_links* lr_out,
+                      ldw_links* borderline_out, double* thr_out, double* prob_out, ldw_scan_stats* stats_out) {
   if (!P) return set_error(LDW_ERR_ARG, "null plan");
   const auto t_entry = std::chrono::steady_clock::now();
   LDW_TRY(ctx_bind(P->ctx));
@@ -831,28 +910,12 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   struct Blk { int bf, bt; int64_t index; };
   std::vector<Blk> blocks;
   {
-    struct Item { int64_t cost, idx; int bf, bt; };
-    std::vector<Item> items;
+    std::vector<int> owner;
+    mi_block_owners(P, n_parts, owner);
     int64_t idx = 0;
     for (int i = 0; i < P->nranges; i++)
-      for (int j = i; j < P->nranges; j++, idx++) {
-        const int64_t ni = std::min<int64_t>(P->n, (int64_t)(i + 1) * P->blk) - (int64_t)i * P->blk;
-        const int64_t nj = std::min<int64_t>(P->n, (int64_t)(j + 1) * P->blk) - (int64_t)j * P->blk;
-        items.push_back({i == j ? ni * (ni - 1) / 2 : ni * nj, idx, i, j});
-      }
-    std::vector<Item> order = items;
-    std::stable_sort(order.begin(), order.end(), [](const Item& a, const Item& b) { return a.cost > b.cost; });
-    std::vector<int64_t> load(n_parts, 0);
-    std::vector<int> owner(items.size(), 0);
-    for (const Item& it : order) {
-      int best = 0;
-      for (int p = 1; p < n_parts; p++)
-        if (load[p] < load[best]) best = p;
-      owner[it.idx] = best;
-      load[best] += it.cost;
-    }
-    for (const Item& it : items)
-      if (owner[it.idx] == part) blocks.push_back({it.bf, it.bt, it.idx});
+      for (int j = i; j < P->nranges; j++, idx++)
+        if (owner[idx] == part) blocks.push_back({i, j, idx});
   }
   const int64_t nblk_total = (int64_t)P->nranges * (P->nranges + 1) / 2;
   if (thr_out) for (int64_t b = 0; b < nblk_total; b++) thr_out[b] = NAN;
@@ -863,7 +926,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
 
   // ---- pass 1 (host): per-block sizes -> output offsets and long-range selection ranks
   struct Sel { int64_t n_lr = 0, n_sr = 0, n_pairs = 0; double prob = NAN; uint64_t k_lo = 0, k_hi = 0; double h = 0; int interp = 0;
-               int emit_all = 0; uint32_t kprime = 0, delta = 1, cap = 0; int64_t sr_base = 0; int skip = 0; };
+               int emit_all = 0; uint32_t kprime = 0, delta = 1, cap = 0; int64_t sr_base = 0, sr_hbase = 0; int skip = 0; };
   std::vector<Sel> sel(blocks.size());
   int64_t total_sr = 0, total_pairs = 0, total_lr = 0;
   uint64_t max_cap = 1, sum_keep = 0;
@@ -882,10 +945,16 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
         if (first_guess >= 0) first_rc = prepare_block(P, blocks[first_guess].bf, blocks[first_guess].bt, cfg, W->hring[0]);
         return;
       }
+      Sel& s = sel[b];
+      if (shared) {  // the device group sized every block once for all its ranks
+        const BlockSizes& z = shared->sizes[blocks[b].index];
+        perr[b] = z.err;
+        s.n_lr = z.n_lr; s.n_sr = z.n_sr; s.n_pairs = z.n_pairs;
+        return;
+      }
       BlockHost tmp;
       int e = prepare_block(P, blocks[b].bf, blocks[b].bt, cfg, tmp, true);
       perr[b] = e;
-      Sel& s = sel[b];
       s.n_lr = tmp.n_lr; s.n_sr = tmp.n_sr; s.n_pairs = tmp.n_pairs;
     });
     for (size_t b = 0; b < blocks.size(); b++) {
@@ -898,6 +967,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       s.skip = (e == 1);
       struct { int64_t n_lr, n_sr, n_pairs; } tmp{s.n_lr, s.n_sr, s.n_pairs};
       s.sr_base = total_sr;
+      s.sr_hbase = shared ? shared->sr_hbase[blocks[b].index] : total_sr;  // row of the block in the host table
       total_sr += tmp.n_sr; total_pairs += tmp.n_pairs; total_lr += tmp.n_lr;
       if (!sr_only && tmp.n_lr > 0) {
         const double m = (double)tmp.n_lr;
@@ -964,8 +1034,11 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   const bool want_host = !(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_NO_D2H));
   cudaStream_t cst = P->ctx->copy_stream;
   cudaEvent_t ev_blk = nullptr;  // "this block's SR columns are materialised"
+  // short-range rows go to this context's pinned table, or -- multi-GPU -- straight to the group's table, every rank
+  // at the final offsets of its blocks (the table is complete when the last rank finishes: no merge pass)
+  HostLinks& hsr = shared ? *shared->h_sr : P->ctx->h_sr;
   if (want_host) {
-    LDW_TRY(P->ctx->h_sr.ensure(total_sr));
+    if (!shared) LDW_TRY(hsr.ensure(total_sr));
     LDW_CUDA(cudaEventCreateWithFlags(&ev_blk, cudaEventDisableTiming));
   }
   auto tpre = std::chrono::steady_clock::now();
@@ -1137,8 +1210,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
         // copy this block's finished rows to the host while the next blocks are being scanned
         LDW_CUDA(cudaEventRecord(ev_blk, st));
         LDW_CUDA(cudaStreamWaitEvent(cst, ev_blk, 0));
-        HostLinks& h = P->ctx->h_sr;
-        const size_t o = (size_t)s.sr_base, nb4 = (size_t)s.n_sr * 4, nb8 = (size_t)s.n_sr * 8;
+        HostLinks& h = hsr;
+        const size_t o = (size_t)s.sr_hbase, nb4 = (size_t)s.n_sr * 4, nb8 = (size_t)s.n_sr * 8;
         LDW_CUDA(cudaMemcpyAsync(h.pos1.as<int32_t>() + o, m.o_pos1, nb4, cudaMemcpyDeviceToHost, cst));
         LDW_CUDA(cudaMemcpyAsync(h.pos2.as<int32_t>() + o, m.o_pos2, nb4, cudaMemcpyDeviceToHost, cst));
         LDW_CUDA(cudaMemcpyAsync(h.c1.as<int32_t>() + o, m.o_c1, nb4, cudaMemcpyDeviceToHost, cst));
@@ -1256,7 +1329,7 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
       LDW_CUDA(cudaMemcpyAsync(h.mi.p, d.mi.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
       return 0;
     };
-    P->ctx->h_sr.n = total_sr;  // short-range rows were streamed out block by block on the copy stream
+    if (!shared) P->ctx->h_sr.n = total_sr;  // short-range rows were streamed out block by block on the copy stream
     LDW_TRY(d2h(P->ctx->h_lr, W->d_lr, (int64_t)n_kept));
   }
   LDW_CUDA(cudaEventRecord(ev3, st));
@@ -1295,7 +1368,8 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
     if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = total_sr; }
     if (lr_out) { memset(lr_out, 0, sizeof(*lr_out)); lr_out->n = (int64_t)n_kept; }
   } else {
-    P->ctx->h_sr.fill(sr_out);
+    if (shared) { if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = total_sr; } }
+    else P->ctx->h_sr.fill(sr_out);
     P->ctx->h_lr.fill(lr_out);
   }
   for (size_t b = 0; b < blocks.size(); b++) {
@@ -1376,5 +1450,3 @@ int ldw_mi_scan(ldw_mi_plan* P, double g, double sr_dist, double lr_retain_links
   lap("borderline + stats (host)");
   return 0;
 }
-
-}  // extern "C"
