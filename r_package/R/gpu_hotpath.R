@@ -5,6 +5,26 @@
 # drop-in for the exported runARACNE, used by analyse_long_range_links, R/lr_analyser.R:101-108).  Setting
 # options(LDWeaver.native_post = FALSE) keeps the reference's own R code for those steps.
 
+# Devices (SURVEY section 5): options(LDWeaver.gpus = c(0, 1, 2, 3)) or the environment variable LDW_GPUS ("0,1,2,3", or
+# a count "4" meaning devices 0..3); default: device 0.  More than one device runs the weights and the scan on a device
+# group (ldw_group_*): the class matrix is uploaded once and broadcast with NCCL, blocks are dealt across the GPUs and
+# ONE link table comes back -- results are bit-identical to the single-device run.
+.ldw_gpus <- function() {
+  g <- getOption("LDWeaver.gpus", NULL)
+  if (is.null(g)) {
+    e <- Sys.getenv("LDW_GPUS", "")
+    if (nzchar(e)) g <- if (grepl(",", e)) as.integer(strsplit(e, ",")[[1]]) else seq_len(as.integer(e)) - 1L
+  }
+  if (is.null(g) || length(g) == 0) g <- 0L
+  as.integer(g)
+}
+
+# Drop-in for the Rcpp stub of the same name (R/RcppExports.R:4-6; caller R/estimateCDSDiversity.R:85): masks the
+# reference allele of each SNP in the 5 x nsnp matrix `nv` IN PLACE and returns NULL (quirk Q11).
+.ACGTN2num <- function(nv, cv, ncores) {
+  invisible(.Call("_LDWeaver_ACGTN2num", nv, cv, ncores, PACKAGE = "LDWeaver"))
+}
+
 .codes_to_snpdat <- function(enc, pos = NULL) {
   if (enc$seq.length == -1) stop("Error! sequences are of different lengths!")
   if (enc$num.seqs == 0) stop("File does not contain any sequences!")
@@ -40,7 +60,7 @@ parse_fasta_alignment <- function(aln_path, gap_freq = 0.15, maf_freq = 0.01, me
   aln_path <- normalizePath(aln_path)
   if (!file.exists(aln_path)) stop(paste("Can't locate file", aln_path))
   filter <- if (method == "relaxed") 1L else { if (method != "default") warning("Unkown filtering method, using default..."); 0L }
-  enc <- .Call("_LDWeaver_gpu_encode", aln_path, filter, gap_freq, maf_freq, PACKAGE = "LDWeaver")
+  enc <- .Call("_LDWeaver_gpu_encode", aln_path, filter, gap_freq, maf_freq, .ldw_gpus(), PACKAGE = "LDWeaver")
   .codes_to_snpdat(enc)
 }
 
@@ -48,14 +68,14 @@ parse_fasta_SNP_alignment <- function(aln_path, pos, gap_freq = 0.15, maf_freq =
   aln_path <- normalizePath(aln_path)
   if (!file.exists(aln_path)) stop(paste("Can't locate file", aln_path))
   filter <- if (method == "relaxed") 1L else { if (method != "default") warning("Unkown filtering method, using default..."); 0L }
-  enc <- .Call("_LDWeaver_gpu_encode", aln_path, filter, gap_freq, maf_freq, PACKAGE = "LDWeaver")
+  enc <- .Call("_LDWeaver_gpu_encode", aln_path, filter, gap_freq, maf_freq, .ldw_gpus(), PACKAGE = "LDWeaver")
   if (enc$seq.length > 0 && length(pos) != enc$seq.length) stop("Error! Number of positions do not match the fasta sequence length")
   .codes_to_snpdat(enc, pos)
 }
 
 estimate_Hamming_distance_weights <- function(snp.dat, threshold = 0.1, mega_dset = F) {
   t0 <- Sys.time()
-  hdw <- .Call("_LDWeaver_gpu_hdw", .snpdat_codes(snp.dat), snp.dat$nsnp, snp.dat$nseq, threshold, PACKAGE = "LDWeaver")
+  hdw <- .Call("_LDWeaver_gpu_hdw", .snpdat_codes(snp.dat), snp.dat$nsnp, snp.dat$nseq, threshold, .ldw_gpus(), PACKAGE = "LDWeaver")
   names(hdw) <- snp.dat$seq.names
   cat(paste("Done in", round(difftime(Sys.time(), t0, units = "secs"), 2), "s\n"))
   hdw
@@ -83,7 +103,7 @@ perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path =
                as.integer(snp.dat$POS), as.integer(cds_var$paint), as.numeric(snp.dat$g), sr_dist, lr_retain_links,
                lr_links_approx, max_blk_sz, perform_SR_analysis_only,
                isTRUE(getOption("LDWeaver.exact_sr", TRUE)),   # fp64 MI for the short-range links (the fp32 epilogue's 2e-7 is amplified by the beta fit below)
-               PACKAGE = "LDWeaver")
+               .ldw_gpus(), PACKAGE = "LDWeaver")
   if (length(res$lr$MI) > 0)   # same rows, same order as the per-block appends of R/computePairwiseMI.R:362
     write.table(x = as.data.frame(res$lr[1:6]), file = lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
   if (!isTRUE(getOption("LDWeaver.native_post", TRUE))) {

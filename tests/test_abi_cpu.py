@@ -69,9 +69,11 @@ def test_r_shim_type_checks_against_the_abi():
     assert r.returncode == 0, r.stderr
     shim = open(os.path.join(ROOT, "r_package", "src", "r_shim.cpp")).read()
     rcode = open(os.path.join(ROOT, "r_package", "R", "gpu_hotpath.R")).read()
-    for name, nargs in re.findall(r'\{"(_LDWeaver_gpu_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim):
+    entries = re.findall(r'\{"(_LDWeaver_\w+)", \(DL_FUNC\)&\w+, (\d+)\}', shim)
+    assert {n for n, _ in entries} >= {"_LDWeaver_gpu_encode", "_LDWeaver_gpu_hdw", "_LDWeaver_gpu_mi_scan", "_LDWeaver_ACGTN2num"}
+    for name, nargs in entries:
         calls = re.findall(r'\.Call\("%s",(.*?)PACKAGE = "LDWeaver"\)' % name, rcode, flags=re.S)
-        assert calls or name == "_LDWeaver_gpu_ACGTN2num", f"{name} registered but never called from gpu_hotpath.R"
+        assert calls, f"{name} registered but never called from gpu_hotpath.R"
         for body in calls:  # the registered argument count must be the number of arguments the R side passes
             body = re.sub(r"#[^\n]*", "", body)
             depth, nargs_r = 0, 0
@@ -80,6 +82,12 @@ def test_r_shim_type_checks_against_the_abi():
                 depth -= ch in ")]}"
                 nargs_r += ch == "," and depth == 0
             assert nargs_r == int(nargs), f"{name}: R passes {nargs_r} arguments, the shim registers {nargs}"
+    # Rf_error is a longjmp: the shim must hold no object with a destructor
+    code = re.sub(r"//[^\n]*", "", shim)
+    assert "std::" not in code and "#include <vector>" not in code and "#include <string>" not in code
+    # the reference's own stub name is bound (R/RcppExports.R:4-6) and devices come from options()/LDW_GPUS
+    assert re.search(r"^\.ACGTN2num <- function\(nv, cv, ncores\)", rcode, flags=re.M)
+    assert "LDWeaver.gpus" in rcode and "LDW_GPUS" in rcode and "ldw_group_mi_scan" in shim
 
 
 def test_links_copy_matches_the_columns():
