@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LDW_ABI_VERSION 1
+#define LDW_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define LDW_API __attribute__((visibility("default")))
@@ -53,10 +53,13 @@ enum {
   LDW_SCAN_NO_LINKS = 4,  /* compute MI / thresholds only: no link columns are materialised or copied */
   LDW_SCAN_NO_D2H = 8,    /* materialise the link columns in device memory but do not copy them to the host
                              (device-resident throughput measurement); link outputs come back with n rows and NULL pointers */
-  LDW_SCAN_SR_EXACT = 16  /* recompute the MI of every short-range link in fp64 (the reference's arithmetic) on the device,
+  LDW_SCAN_SR_EXACT = 16, /* recompute the MI of every short-range link in fp64 (the reference's arithmetic) on the device,
                              block by block, before the rows are copied out (mi_sr_exact_kernel; also valid with
-                             LDW_SCAN_SR_ONLY).  Parity-checked on the fixture in both modes (1e-12); not yet timed at
-                             616 x 100k, so the host mirror still defaults to ldw_links_to_cells + ldw_mi_pairs_exact */
+                             LDW_SCAN_SR_ONLY).  Parity-checked on the fixture in both modes (1e-12) */
+  LDW_SCAN_LR_ONLY = 32   /* no short-range link table (sr_out->n = 0): only the long-range rows, thresholds and statistics.
+                             For inputs whose short-range table would not fit host memory (2000 x 500k SNPs in a 2.2 Mb
+                             genome: 2.3e9 short-range links = 72 GB of columns) and for callers that only feed the
+                             long-range links on (analyse_long_range_links, R/lr_analyser.R:72-108) */
 };
 
 typedef struct ldw_ctx ldw_ctx;         /* one per device; owns stream + scratch */
@@ -168,6 +171,7 @@ typedef struct ldw_scan_stats {
   int64_t n_tiles;       /* tiles processed */
   double exec_int8_ops;  /* int8 tensor operations actually issued (2 * MACs) */
   double t_host_prep_ms; /* host time spent building and staging the per-block tables (overlaps the device work) */
+  double exec_mufu_ops;  /* MUFU (LG2 / RCP) instructions x lanes the epilogue executed */
 } ldw_scan_stats;
 
 LDW_API int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, const double* hdw,

@@ -73,7 +73,7 @@ class ScanStats(C.Structure):
     _fields_ = [("n_blocks", i64), ("n_pairs", i64), ("n_sr", i64), ("n_lr_total", i64), ("n_lr_kept", i64),
                 ("n_borderline", i64), ("n_reruns", i64), ("n_candidates", i64), ("t_pack_ms", f64), ("t_scan_ms", f64), ("t_select_ms", f64),
                 ("t_d2h_ms", f64), ("t_kernel_ms", f64), ("n_scan_launches", i64), ("n_launches", i64), ("n_tiles", i64),
-                ("exec_int8_ops", f64), ("t_host_prep_ms", f64)]
+                ("exec_int8_ops", f64), ("t_host_prep_ms", f64), ("exec_mufu_ops", f64)]
 
     def to_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}

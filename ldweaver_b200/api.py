@@ -213,7 +213,7 @@ def estimate_Hamming_distance_weights(snp_dat: SnpDat, threshold: float = 0.1, m
 # --------------------------------------------------------------------------------------------------
 # perform_MI_computation (scan + sr/lr link filter)
 # --------------------------------------------------------------------------------------------------
-SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS, SCAN_NO_D2H, SCAN_SR_EXACT = 1, 2, 4, 8, 16
+SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS, SCAN_NO_D2H, SCAN_SR_EXACT, SCAN_LR_ONLY = 1, 2, 4, 8, 16, 32
 
 
 @dataclass
@@ -719,7 +719,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
                            mega_dset: bool = False, lr_links_approx: Optional[float] = None, device: int = 0,
                            write_tsv: bool = True, plan: Optional[MIPlan] = None,
                            postprocess: Optional[bool] = None, exact_sr: Optional[bool] = None,
-                           devices: Optional[Sequence[int]] = None) -> MIScanResult:
+                           devices: Optional[Sequence[int]] = None, scan_flags: int = 0) -> MIScanResult:
     """R/computePairwiseMI.R:46-145.  Same arguments as the reference (``ncores`` is accepted and ignored by the GPU
     path; ``plt_folder`` is accepted, no plots are drawn).  The scan (:46-116) runs on the device; what follows it
     (:118-143: mergeNsort_sr_links, runARACNE, ordering, sr_links.tsv) runs in native host code and fills
@@ -730,7 +730,8 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     default whenever the post-processing runs (its beta fit amplifies the fp32 epilogue's 2e-7 to ~1e-2 in srp_max; about
     +0.5 s at 616 x 100k).  ``exact_sr="in_scan"`` asks the scan itself for them (``LDW_SCAN_SR_EXACT``; parity-checked
     on the fixture, not yet timed at full size, hence the default only for perform_SR_analysis_only scans, which
-    ``MIPlan.sr_exact`` cannot serve)."""
+    ``MIPlan.sr_exact`` cannot serve).  ``scan_flags``: extra LDW_SCAN_* bits, e.g. ``SCAN_LR_ONLY`` for inputs whose
+    short-range table would not fit host memory; ``devices`` (or ``LDW_GPUS``): run on a device group."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -750,7 +751,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         # short-range MI comes from inside the scan (LDW_SCAN_SR_EXACT): the host-driven refinement is single-device.
         grp = default_group(devices)
         grp.load_codes(snp_dat.codes)
-        flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
+        flags = (SCAN_SR_ONLY if perform_SR_analysis_only else 0) | int(scan_flags)
         if exact_sr is None:
             exact_sr = do_post
         if exact_sr:
@@ -759,7 +760,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
                                                      lr_links_approx or 0.0, flags)
         stats = dict(st_list[0])
         for k in ("n_blocks", "n_pairs", "n_sr", "n_lr_total", "n_lr_kept", "n_borderline", "n_reruns", "n_candidates",
-                  "n_scan_launches", "n_launches", "n_tiles", "exec_int8_ops"):
+                  "n_scan_launches", "n_launches", "n_tiles", "exec_int8_ops", "exec_mufu_ops"):
             stats[k] = sum(d[k] for d in st_list)
         for k in ("t_pack_ms", "t_scan_ms", "t_select_ms", "t_d2h_ms", "t_kernel_ms", "t_host_prep_ms"):
             stats[k] = max(d[k] for d in st_list)
@@ -770,7 +771,7 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     if own:
         plan = MIPlan(snp_dat, hdw, paint, blk, device)
     try:
-        flags = SCAN_SR_ONLY if perform_SR_analysis_only else 0
+        flags = (SCAN_SR_ONLY if perform_SR_analysis_only else 0) | int(scan_flags)
         if exact_sr is None:  # SR-only scans index reduced SNP lists (Q12): only the in-scan kernel can refine them
             exact_sr = ("in_scan" if perform_SR_analysis_only else True) if do_post else False
         if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call

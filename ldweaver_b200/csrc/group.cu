@@ -356,6 +356,8 @@ int ldw_group_mi_scan(ldw_group* G, const double* hdw, const int32_t* pos, const
     sh.h_sr = &G->h_sr;
     const bool want_host = !(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_NO_D2H));
     G->h_sr.n = 0; G->h_lr.n = 0; G->h_border.n = 0;
+    const bool sr_rows = !(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_LR_ONLY));
+    if (!sr_rows) total_sr = 0;
     if (want_host) {
       rc = G->h_sr.ensure(total_sr);
       if (rc != 0) { destroy_plans(); return rc; }

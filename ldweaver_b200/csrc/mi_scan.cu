@@ -1020,7 +1020,8 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
   LDW_TRY(W->d_kept_gj.ensure(kept_cap * 4));
   LDW_TRY(W->d_kept_mi.ensure(kept_cap * 8));
   LDW_TRY(W->d_kept_count.ensure(16));
-  LDW_TRY(W->d_sr.ensure(total_sr));
+  const bool sr_rows = !(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_LR_ONLY));  // short-range link columns wanted at all
+  if (sr_rows) LDW_TRY(W->d_sr.ensure(total_sr));
   LDW_CUDA(cudaMemsetAsync(W->d_kept_count.p, 0, 16, st));
   uint32_t* d_kept_overflow = W->d_state.as<uint32_t>() + 3;
   // Threshold seed for the next blocks: ONE word, overwritten by every selection and read by every block's begin
@@ -1038,13 +1039,13 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
   // at the final offsets of its blocks (the table is complete when the last rank finishes: no merge pass)
   HostLinks& hsr = shared ? *shared->h_sr : P->ctx->h_sr;
   if (want_host) {
-    if (!shared) LDW_TRY(hsr.ensure(total_sr));
+    if (!shared && sr_rows) LDW_TRY(hsr.ensure(total_sr));
     LDW_CUDA(cudaEventCreateWithFlags(&ev_blk, cudaEventDisableTiming));
   }
   auto tpre = std::chrono::steady_clock::now();
   LDW_CUDA(cudaEventRecord(ev0, st));
   int64_t n_reruns = 0, n_launches = 0, n_scan_launches = 0, n_tiles = 0;
-  double exec_ops = 0;
+  double exec_ops = 0, exec_mufu = 0;
   std::vector<cudaEvent_t> kev;  // pairs of events around every scan-kernel launch
   auto kev_cleanup = [&]() { for (auto e : kev) cudaEventDestroy(e); kev.clear(); };
   int64_t dbg_block = -1;
@@ -1153,6 +1154,10 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       for (int32_t ti = 0; ti < H.n_real_tiles; ti++) {  // 4 K-passes x 2 ops/MAC x 128 rows x (PA*PB*NJ) columns x Kpad
         const TileDesc& td = H.tiles[ti];
         exec_ops += 8.0 * 128.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;  // 2 passes x 2 halves
+        // MUFU instructions of the epilogue, per lane-pair of the tile (all 128 x NJ lanes execute): one LG2 per cell of the
+        // (PA+1) x (PB+1) table, plus -- Q1 form, off-diagonal blocks -- one RCP per two cells of a row (mi_row)
+        const int RA = td.PA + 1, RB = td.PB + 1;
+        exec_mufu += 128.0 * (double)(1 << td.njlog2) * (double)(RA * (RB + (sp.qcorr ? (RB + 1) / 2 : 0)));
       }
     }
     if (lr) {
@@ -1188,7 +1193,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       L.used = true;
       D.used2 = true;
     }
-    if (s.n_sr > 0 && !(flags & LDW_SCAN_NO_LINKS)) {
+    if (s.n_sr > 0 && sr_rows) {
       n_launches++;
       SrMatParams m;
       m.col = D.colinfo.as<ColInfo>(); m.from_idx = D.from_idx.as<int32_t>(); m.to_idx = D.to_idx.as<int32_t>();
@@ -1206,7 +1211,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
         mi_sr_exact_kernel<<<H.nt, 32 * REFINE_WARPS, 0, st>>>(m, make_refine_params(P, D, H, cfg));
         LDW_CUDA(cudaGetLastError());
       }
-      if (want_host) {
+      if (want_host) {  // (sr_rows holds here)
         // copy this block's finished rows to the host while the next blocks are being scanned
         LDW_CUDA(cudaEventRecord(ev_blk, st));
         LDW_CUDA(cudaStreamWaitEvent(cst, ev_blk, 0));
@@ -1329,7 +1334,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       LDW_CUDA(cudaMemcpyAsync(h.mi.p, d.mi.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
       return 0;
     };
-    if (!shared) P->ctx->h_sr.n = total_sr;  // short-range rows were streamed out block by block on the copy stream
+    if (!shared) P->ctx->h_sr.n = sr_rows ? total_sr : 0;  // short-range rows were streamed out block by block on the copy stream
     LDW_TRY(d2h(P->ctx->h_lr, W->d_lr, (int64_t)n_kept));
   }
   LDW_CUDA(cudaEventRecord(ev3, st));
@@ -1368,7 +1373,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
     if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = total_sr; }
     if (lr_out) { memset(lr_out, 0, sizeof(*lr_out)); lr_out->n = (int64_t)n_kept; }
   } else {
-    if (shared) { if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = total_sr; } }
+    if (shared) { if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = sr_rows ? total_sr : 0; } }
     else P->ctx->h_sr.fill(sr_out);
     P->ctx->h_lr.fill(lr_out);
   }
@@ -1429,6 +1434,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
     stats_out->n_tiles = n_tiles;
     stats_out->exec_int8_ops = exec_ops;
     stats_out->t_host_prep_ms = host_prep_ms;
+    stats_out->exec_mufu_ops = exec_mufu;
   }
   if (dbg_block >= 0 && W->d_dbg.p) {
     std::vector<unsigned long long> h(4096 * 16);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     L = _lib.lib()
     for s in _declared_symbols():
         assert hasattr(L, s), f"{s} declared in include/ldw.h but not exported"
-    assert L.ldw_abi_version() == 1
+    assert L.ldw_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_device():

@@ -207,8 +207,100 @@ def test_c3_full_hamming_weights_10000_by_50000():
     assert np.array_equal(dist, dist.T) and np.all(np.diag(dist) == 0)
     assert np.array_equal(cnt, (dist < thresh).sum(axis=0))                       # strict <, self included (Q7)
     assert np.array_equal(hdw, 1.0 / (cnt + 1.0))
+    # the fused path (upper-triangle tiles, neighbours counted straight from TMEM, no distance matrix) gives the same weights
+    assert np.array_equal(ldw.estimate_Hamming_distance_weights(snp, 0.1), hdw)
     rng = np.random.default_rng(3)
     for s in rng.choice(S, 12, replace=False):                                     # exact distances of sampled rows
         ref = (codes != codes[:, s][:, None]).sum(axis=0)
         assert np.array_equal(ref, dist[:, s])
     assert len(np.unique(cnt)) > 10
+
+
+def _dense_cells_check(plan, snp_o, hdw, blocks, b, rng, n_cells=3000, tol=1e-6):
+    """Sampled cells of one block's dense MI matrix (the fp32 epilogue path that feeds the short-range slots) against the
+    oracle's per-pair closed form."""
+    fs, fe, ts, te = blocks[b]
+    f, t = np.arange(fs - 1, fe), np.arange(ts - 1, te)
+    MI = plan.block_dense(b)
+    il = rng.integers(0, len(f), n_cells)
+    jl = rng.integers(0, len(t), n_cells)
+    ref = O.pair_mi_closed_form(snp_o, hdw, f, t, il, jl)
+    err = float(np.abs(MI[il, jl] - ref).max())
+    assert err < tol, f"block {b}: max |MI - oracle| = {err}"
+    return err
+
+
+def _full_size_scan_checks(tag, snp, hdw, paint, codes, retain):
+    """Whole scan at a BASELINE shape whose short-range table is too large to bring to the host (C4: 8.2e8 rows, C5: 2.3e9):
+    LDW_SCAN_LR_ONLY.  Checked: pair / short-range / long-range counts against an independent count from the positions,
+    per-block kept counts against the type-7 rank arithmetic, every kept link >= its threshold and longer than sr_dist,
+    sampled long-range rows (fp64) and sampled cells of dense blocks (fp32 epilogue) against the oracle's closed form."""
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import api, synth
+    blk = 10000
+    lra = synth.exact_lr_links_approx(snp.POS, snp.g, SR_DIST)
+    plan = ldw.MIPlan(snp, hdw, paint, blk)
+    sr, lr, bd, thr, prob, st = plan.scan(snp.g, SR_DIST, retain, lra, api.SCAN_LR_ONLY)
+    n_pairs, n_sr = _expected_sr_pairs(snp.POS, snp.g, blk, SR_DIST)
+    assert st["n_pairs"] == n_pairs and st["n_sr"] == n_sr and len(sr["MI"]) == 0
+    assert st["n_lr_total"] == n_pairs - n_sr and st["n_lr_kept"] == len(lr["MI"])
+    blocks = api.make_blocks(snp.nsnp, blk)
+    assert st["n_blocks"] == len(blocks)
+    kept = np.bincount(lr["block"], minlength=len(blocks))
+    has_lr = ~np.isnan(thr)
+    assert np.all(kept[~has_lr] == 0) and np.all(kept[has_lr] > 0)
+    thr_of_row = thr[lr["block"]]
+    assert np.all(lr["MI"] >= thr_of_row) and np.all(lr["len"] > SR_DIST)
+    assert np.all(np.diff(lr["block"]) >= 0)
+    assert abs(len(lr["MI"]) - retain) < 0.02 * retain + len(bd["MI"]) + 2 * len(blocks)   # ~lr_retain_links rows in total
+    rng = np.random.default_rng(21)
+    snp_o = O.snp_dat_from_codes(codes, snp.POS, snp.g)
+    pick = sorted(set([0, 1, len(blocks) // 3, len(blocks) // 2, len(blocks) - 2, len(blocks) - 1]))
+    w_lr = _sample_check(snp_o, hdw, lr, blocks, pick, 200, rng, tol=1e-9)
+    nr = -(-snp.nsnp // blk)
+    w_d = max(_dense_cells_check(plan, snp_o, hdw, blocks, b, rng) for b in (0, 1, nr))   # diagonal, off-diagonal, next diagonal
+    print(f"{tag} full: {snp.nseq} x {snp.nsnp}, {st['n_pairs']:.3e} pairs, {len(blocks)} blocks, kept {len(lr['MI'])}, lr max err {w_lr:.2e}, "
+          f"dense (fp32) max err {w_d:.2e}, reruns {st['n_reruns']}, scan {st['t_scan_ms'] + st['t_select_ms']:.0f} ms")
+    plan.close()
+
+
+def test_c4_full_5000_by_300000():
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import synth
+    S, n, seed, probs, nrate = synth.CONFIGS["C4"]
+    codes = _cheap_codes(S, n, seed, nrate, probs)
+    rng = np.random.default_rng(seed)
+    POS = np.sort(rng.choice(np.arange(1, synth.G_DEFAULT + 1), n, replace=False)).astype(np.int32)
+    paint = (1 + np.arange(n) * 3 // n).astype(np.int32)
+    snp = ldw.snp_dat_from_codes(codes, POS, synth.G_DEFAULT)
+    hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    assert len(np.unique(hdw)) > 3
+    _full_size_scan_checks("C4", snp, hdw, paint, codes, 1e6)
+
+
+def test_c5_full_2000_by_500000_snp_only_through_the_encoder():
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import api, synth
+    S, n, seed, probs, nrate = synth.CONFIGS["C5"]
+    codes = _cheap_codes(S, n, seed, nrate, probs)
+    rng = np.random.default_rng(seed)
+    pos_in = np.sort(rng.choice(np.arange(1, synth.G_DEFAULT + 1), n, replace=False)).astype(np.int32)
+    aln = synth.codes_to_alignment(codes, lowercase_frac=0.3)             # [S, n] ASCII: gaps, N, lowercase
+    snp = ldw.snp_dat_from_alignment_matrix(aln, pos=pos_in, method="relaxed")   # SNP-only input: positions given, g from the annotation
+    del aln
+    snp.g = synth.G_DEFAULT
+    assert snp.nsnp > 0.9 * n
+    keep = np.searchsorted(pos_in, snp.POS)
+    assert np.array_equal(pos_in[keep], snp.POS) and np.array_equal(snp.codes, codes[keep])   # the encoder reproduces the generator's classes
+    hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    paint = (1 + np.arange(snp.nsnp) * 3 // snp.nsnp).astype(np.int32)
+    _full_size_scan_checks("C5", snp, hdw, paint, snp.codes, 1e6)
+    # "long-range links fed to runARACNE" (R/lr_analyser.R:72-108) on the full-size output
+    lra = synth.exact_lr_links_approx(snp.POS, snp.g, SR_DIST)
+    res = ldw.perform_MI_computation(snp, hdw, ldw.CdsVar(paint, 3), sr_dist=SR_DIST, lr_retain_links=1e6, lr_links_approx=lra,
+                                     write_tsv=False, scan_flags=api.SCAN_LR_ONLY)
+    lr = {"pos1": res.lr["pos1"].astype(float), "pos2": res.lr["pos2"].astype(float), "c1": res.lr["clust1"], "c2": res.lr["clust2"],
+          "len": res.lr["len"].astype(float), "MI": res.lr["MI"]}
+    out = api.analyse_long_range_links(lr, {k: np.zeros(0) for k in ("pos1", "pos2", "MI")})
+    assert len(out["MI"]) >= 4000 and np.all(np.diff(out["MI"]) <= 0) and set(np.unique(out["ARACNE"])) <= {0, 1, True, False}
+    print(f"C5 full: {len(res.lr['MI'])} long-range links -> {len(out['MI'])} above the Tukey threshold, ARACNE keeps {int(np.sum(out['ARACNE']))}")
