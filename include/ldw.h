@@ -104,6 +104,14 @@ LDW_API int ldw_aln_param(ldw_ctx* ctx, const uint8_t* aln, int64_t nseq, int64_
                   double maf_thresh, int32_t* pos_out, int64_t* n_snp_out, double* counts_out);
 LDW_API int ldw_extract_snps(ldw_ctx* ctx, const uint8_t* aln, int64_t nseq, int64_t seq_len, const int32_t* pos,
                      int64_t n_snp, uint8_t* codes_out, double* table_out);
+/* ldw_encode_alignment = ldw_aln_param + ldw_extract_snps in ONE call (what parse_fasta_alignment needs,
+ *   R/extractSNPs.R:39-45): the alignment is uploaded once when it fits one device chunk (8 GiB by default), otherwise
+ *   it streams through in row chunks -- device memory stays O(chunk), as the reference's record-by-record passes
+ *   (src/getACGTNsites.cpp:49-85) need O(seq_len).  *pos_out (n_snp int32), *codes_out (n_snp x nseq) and *table_out
+ *   (5 x n_snp doubles, column-major) are library-allocated and released with ldw_buffer_free; all NULL when
+ *   *n_snp_out == 0 ("File does not contain any SNPs", R/extractSNPs.R:43). */
+LDW_API int ldw_encode_alignment(ldw_ctx* ctx, const uint8_t* aln, int64_t nseq, int64_t seq_len, int filter, double gap_thresh,
+                         double maf_thresh, int64_t* n_snp_out, int32_t** pos_out, uint8_t** codes_out, double** table_out);
 LDW_API int ldw_read_fasta(const char* path, int64_t* nseq_out, int64_t* seq_len_out, uint8_t* aln_out, int64_t aln_cap,
                    char* names_out, int64_t names_cap);
 /* ldw_read_fasta_alloc: the same tokeniser in ONE pass over the file (the reference opens the gz
@@ -162,7 +170,7 @@ typedef struct ldw_scan_stats {
   int64_t n_lr_total;    /* len > sr_dist (before the quantile filter) */
   int64_t n_lr_kept;
   int64_t n_borderline;  /* LR candidates within borderline_tol of their block threshold (listed in `borderline`) */
-  int64_t n_reruns;      /* blocks re-run because the candidate threshold guess was too high */
+  int64_t n_reruns;      /* blocks re-run: candidate threshold guess too high, or measured epilogue error above the margin's head room */
   int64_t n_candidates;  /* long-range candidates collected by the scan kernel (before refinement / selection) */
   double t_pack_ms, t_scan_ms, t_select_ms, t_d2h_ms; /* CUDA-event phase timings of the last scan (library stream) */
   double t_kernel_ms;    /* sum of the scan kernel's own launch durations (CUDA events around each launch) */
@@ -172,6 +180,8 @@ typedef struct ldw_scan_stats {
   double exec_int8_ops;  /* int8 tensor operations actually issued (2 * MACs) */
   double t_host_prep_ms; /* host time spent building and staging the per-block tables (overlaps the device work) */
   double exec_mufu_ops;  /* MUFU (LG2 / RCP) instructions x lanes the epilogue executed */
+  double eps_obs_max;    /* largest |fp32 epilogue MI - fp64 MI| the long-range selection observed on its refined candidates
+                            (it re-runs a block with wider margins when 4x this exceeds the selection margin, 4e-6) */
 } ldw_scan_stats;
 
 LDW_API int ldw_mi_plan_create(ldw_ctx* ctx, const uint8_t* codes, int64_t n_snp, int64_t nseq, const double* hdw,

@@ -73,7 +73,7 @@ class ScanStats(C.Structure):
     _fields_ = [("n_blocks", i64), ("n_pairs", i64), ("n_sr", i64), ("n_lr_total", i64), ("n_lr_kept", i64),
                 ("n_borderline", i64), ("n_reruns", i64), ("n_candidates", i64), ("t_pack_ms", f64), ("t_scan_ms", f64), ("t_select_ms", f64),
                 ("t_d2h_ms", f64), ("t_kernel_ms", f64), ("n_scan_launches", i64), ("n_launches", i64), ("n_tiles", i64),
-                ("exec_int8_ops", f64), ("t_host_prep_ms", f64), ("exec_mufu_ops", f64)]
+                ("exec_int8_ops", f64), ("t_host_prep_ms", f64), ("exec_mufu_ops", f64), ("eps_obs_max", f64)]
 
     def to_dict(self) -> dict:
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -113,6 +113,8 @@ def lib():
     L.ldw_destroy.restype = None
     L.ldw_aln_param.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_int, f64, f64, C.c_void_p, P(i64), C.c_void_p]
     L.ldw_extract_snps.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_void_p, i64, C.c_void_p, C.c_void_p]
+    L.ldw_encode_alignment.argtypes = [C.c_void_p, C.c_void_p, i64, i64, C.c_int, f64, f64, P(i64), P(C.c_void_p), P(C.c_void_p),
+                                       P(C.c_void_p)]
     L.ldw_read_fasta.argtypes = [C.c_char_p, P(i64), P(i64), C.c_void_p, i64, C.c_void_p, i64]
     L.ldw_read_fasta_alloc.argtypes = [C.c_char_p, P(i64), P(i64), P(C.c_void_p), P(C.c_void_p), P(i64)]
     L.ldw_buffer_free.argtypes = [C.c_void_p]

@@ -110,18 +110,25 @@ def _build_snp_dat(aln: np.ndarray, names: Sequence[str], filt: int, gap_freq: f
     ctx = _lib.default_context(device)
     aln = np.ascontiguousarray(aln, dtype=np.uint8)
     nseq, slen = aln.shape
-    pos_idx = np.empty(slen, dtype=np.int32)
+    # one call: counts + filter + class matrix + ACGTN table, the alignment crossing PCIe once (ldw_encode_alignment)
     n_snp = C.c_int64()
-    check(L.ldw_aln_param(ctx.handle, ptr(aln), nseq, slen, filt, gap_freq, maf_freq, ptr(pos_idx), C.byref(n_snp), None))
+    pos_p, codes_p, table_p = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    check(L.ldw_encode_alignment(ctx.handle, ptr(aln), nseq, slen, filt, gap_freq, maf_freq, C.byref(n_snp), C.byref(pos_p),
+                                 C.byref(codes_p), C.byref(table_p)))
     n = int(n_snp.value)
     if n == 0:
         raise ValueError("File does not contain any SNPs")  # R/extractSNPs.R:43
     if pos is not None and len(pos) != slen:
+        for p_ in (pos_p, codes_p, table_p):
+            L.ldw_buffer_free(p_)
         raise ValueError("Error! Number of positions do not match the fasta sequence length")  # :194
-    pos_idx = np.ascontiguousarray(pos_idx[:n])
-    codes = np.empty((n, nseq), dtype=np.uint8)
-    table = np.empty(5 * n, dtype=np.float64)
-    check(L.ldw_extract_snps(ctx.handle, ptr(aln), nseq, slen, ptr(pos_idx), n, ptr(codes), ptr(table)))
+    try:
+        pos_idx = np.frombuffer(C.string_at(pos_p, n * 4), dtype=np.int32).copy()
+        table = np.frombuffer(C.string_at(table_p, n * 5 * 8), dtype=np.float64).copy()
+    finally:
+        L.ldw_buffer_free(pos_p)
+        L.ldw_buffer_free(table_p)
+    codes = np.asarray(_LibraryBuffer(codes_p.value, n * nseq)).reshape(n, nseq)  # library buffer, no copy
     table = table.reshape(n, 5)  # == t(ACGTN_table)
     uqe = (table > 0).astype(np.float64)  # R/extractSNPs.R:47
     if pos is None:

@@ -13,50 +13,87 @@ __device__ __forceinline__ int classify_char(unsigned c) {
   return u == 'a' ? 0 : u == 'c' ? 1 : u == 'g' ? 2 : u == 't' ? 3 : 4;
 }
 
-// Column histogram.  Each thread owns 4 adjacent columns and walks a slice of the rows, so a warp reads
-// 128 contiguous bytes per row; per-thread counters are flushed with one atomic per (column, class).
-// counts: int32 [L x 5] (== 5 x L column-major).  The "other" class is rows - sum(ACGT).
-__global__ void __launch_bounds__(256) column_count_kernel(const uint8_t* __restrict__ aln, int64_t S, int64_t L,
+// Column histogram (src/getACGTNsites.cpp:50-85), HBM-bound: S*L bytes read once, 20 L bytes of counters written.
+//
+// A thread owns 16 adjacent columns -- one 128-bit load per row, a warp reads 512 contiguous bytes -- and walks a slice
+// of at most 255 rows.  The sixteen bytes are classified four at a time inside their 32-bit words: for each nucleotide
+// x, (w | 0x20202020) ^ x_x4 has a zero byte exactly where the column holds x or X, and the zero bytes are counted into
+// byte-lane accumulators (4 columns per register, 16 registers: 4 words x 4 nucleotides; 255 rows cannot overflow a
+// lane).  ~5 integer instructions per byte and class instead of a compare/select chain per byte.  At the end of the
+// slice the lanes are unpacked and added to counts[L x 5] with one red.add per (column, class); "other" = rows - ACGT.
+// Rows start at multiples of `pitch` (>= L, a multiple of 16: the upload pads them), so every load is aligned.
+__device__ __forceinline__ uint32_t zero_bytes_to_ones(uint32_t t) {
+  // 0x01 in every byte lane of t that is zero, 0x00 elsewhere (exact: no carries cross lanes)
+  const uint32_t nz = ((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t;  // bit 7 of a lane set <=> lane != 0
+  return (~nz & 0x80808080u) >> 7;
+}
+
+constexpr int CC_COLS = 16;          // columns per thread
+constexpr int CC_MAX_ROWS = 255;     // rows per slice (byte-lane counters)
+
+__global__ void __launch_bounds__(256) column_count_kernel(const uint8_t* __restrict__ aln, int64_t S, int64_t L, int64_t pitch,
                                                            int rows_per_slice, int32_t* counts) {
-  int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int64_t j0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * CC_COLS;
   if (j0 >= L) return;
-  int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
-  int64_t r1 = r0 + rows_per_slice < S ? r0 + rows_per_slice : S;
-  int c[4][4];
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t r1 = r0 + rows_per_slice < S ? r0 + rows_per_slice : S;
+  if (r0 >= r1) return;
+  uint32_t acc[4][4];  // [word][nucleotide], four byte lanes each
 #pragma unroll
   for (int q = 0; q < 4; q++)
 #pragma unroll
-    for (int a = 0; a < 4; a++) c[q][a] = 0;
-  const bool vec = ((L & 3) == 0) && ((reinterpret_cast<uintptr_t>(aln) & 3) == 0) && (j0 + 3 < L);
-  for (int64_t s = r0; s < r1; s++) {
-    uint32_t w;
-    if (vec) {
-      w = *reinterpret_cast<const uint32_t*>(aln + s * L + j0);
-    } else {
-      w = 0;
+    for (int a = 0; a < 4; a++) acc[q][a] = 0;
+  const uint4* p = reinterpret_cast<const uint4*>(aln + r0 * pitch + j0);
+  const int64_t step = pitch / 16;
+  int64_t s = r0;
+  // four rows in flight per thread
+  for (; s + 4 <= r1; s += 4) {
+    uint4 v[4];
 #pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (j0 + q < L) w |= (uint32_t)aln[s * L + j0 + q] << (8 * q);
+    for (int u = 0; u < 4; u++) v[u] = __ldg(p + u * step);
+    p += 4 * step;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const uint32_t lw = w[q] | 0x20202020u;  // folds 'A'..'Z' onto 'a'..'z'; no other byte aliases onto a, c, g, t
+        acc[q][0] += zero_bytes_to_ones(lw ^ 0x61616161u);
+        acc[q][1] += zero_bytes_to_ones(lw ^ 0x63636363u);
+        acc[q][2] += zero_bytes_to_ones(lw ^ 0x67676767u);
+        acc[q][3] += zero_bytes_to_ones(lw ^ 0x74747474u);
+      }
     }
+  }
+  for (; s < r1; s++) {
+    const uint4 v = __ldg(p);
+    p += step;
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      int k = classify_char((w >> (8 * q)) & 0xFF);
-#pragma unroll
-      for (int a = 0; a < 4; a++) c[q][a] += (k == a);
+      const uint32_t lw = w[q] | 0x20202020u;
+      acc[q][0] += zero_bytes_to_ones(lw ^ 0x61616161u);
+      acc[q][1] += zero_bytes_to_ones(lw ^ 0x63636363u);
+      acc[q][2] += zero_bytes_to_ones(lw ^ 0x67676767u);
+      acc[q][3] += zero_bytes_to_ones(lw ^ 0x74747474u);
     }
   }
-  int rows = (int)(r1 - r0);
+  const int rows = (int)(r1 - r0);
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    if (j0 + q >= L) break;
-    int sum = 0;
+  for (int q = 0; q < 4; q++)
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-      if (c[q][a]) atomicAdd(&counts[(j0 + q) * 5 + a], c[q][a]);
-      sum += c[q][a];
+    for (int b = 0; b < 4; b++) {
+      const int64_t j = j0 + q * 4 + b;
+      if (j >= L) continue;  // padding columns of the last group
+      int sum = 0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int c = (int)((acc[q][a] >> (8 * b)) & 0xFFu);
+        if (c) atomicAdd(&counts[j * 5 + a], c);
+        sum += c;
+      }
+      if (rows - sum) atomicAdd(&counts[j * 5 + 4], rows - sum);
     }
-    if (rows - sum) atomicAdd(&counts[(j0 + q) * 5 + 4], rows - sum);
-  }
 }
 
 // Site filter (src/getACGTNsites.cpp:104-166; quirk Q9).  flag[j] = 1 if column j is retained.
@@ -107,19 +144,35 @@ __global__ void counts_to_double_kernel(const int32_t* __restrict__ in, int64_t 
   if (i < n) out[i] = (double)in[i];
 }
 
-// Gather retained columns and classify: codes[k][s] = class(aln[s][pos[k]-1]).  32x32 tiles through shared
-// memory so the writes are contiguous along sequences.
-__global__ void __launch_bounds__(1024) extract_codes_kernel(const uint8_t* __restrict__ aln, int64_t S, int64_t L,
-                                                             const int32_t* __restrict__ pos, int64_t n, uint8_t* codes) {
-  __shared__ uint8_t tile[32][33];
-  int64_t k0 = (int64_t)blockIdx.x * 32, s0 = (int64_t)blockIdx.y * 32;
-  int tx = threadIdx.x, ty = threadIdx.y;
-  int64_t k = k0 + tx, s = s0 + ty;
-  if (k < n && s < S) tile[tx][ty] = (uint8_t)classify_char(aln[s * L + (pos[k] - 1)]);
+// Gather retained columns and classify (src/getACGTNsites.cpp:222-267): codes[k][s] = class(aln[s][pos[k]-1]).
+// HBM-bound gather: retained columns are sparse in the row (one in ~22 at 616 x 2.2 Mb), so the useful unit is the
+// 32-byte sector; a warp takes 32 consecutive SNPs of ONE row, so neighbouring SNPs share sectors and every sector of the
+// row that holds a SNP is fetched once.  A block covers 32 rows x 128 SNPs (four loads in flight per thread before the
+// first use) and transposes through shared memory so that the writes are contiguous along sequences.
+constexpr int EX_K = 128;  // SNPs per block
+// `aln` holds rows [row0, row0 + S) of an alignment of S_total records (row chunks of a streamed upload).
+__global__ void __launch_bounds__(1024) extract_codes_kernel(const uint8_t* __restrict__ aln, int64_t S, int64_t L, int64_t pitch,
+                                                             const int32_t* __restrict__ pos, int64_t n, uint8_t* codes,
+                                                             int64_t row0, int64_t S_total) {
+  __shared__ uint8_t tile[EX_K][33];
+  const int64_t k0 = (int64_t)blockIdx.x * EX_K, s0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int64_t s = s0 + ty;
+  uint8_t v[EX_K / 32];
+#pragma unroll
+  for (int u = 0; u < EX_K / 32; u++) {
+    const int64_t k = k0 + u * 32 + tx;
+    v[u] = (k < n && s < S) ? __ldg(aln + s * pitch + (__ldg(pos + k) - 1)) : (uint8_t)0;
+  }
+#pragma unroll
+  for (int u = 0; u < EX_K / 32; u++) tile[u * 32 + tx][ty] = (uint8_t)classify_char(v[u]);
   __syncthreads();
-  k = k0 + ty;
-  s = s0 + tx;
-  if (k < n && s < S) codes[k * S + s] = tile[ty][tx];
+  const int64_t so = s0 + tx;
+#pragma unroll
+  for (int u = 0; u < EX_K / 32; u++) {
+    const int64_t k = k0 + u * 32 + ty;
+    if (k < n && so < S) codes[k * S_total + row0 + so] = tile[u * 32 + ty][tx];
+  }
 }
 
 // src/ACGTN2num_parallel.cpp:18-41: uppercase A/C/G/T, and 'N' or '-' -> row 4; anything else untouched.
@@ -131,14 +184,20 @@ __global__ void acgtn2num_kernel(double* nv, const char* __restrict__ ref, int64
   if (row >= 0) nv[c * 5 + row] = 0.0;
 }
 
-int column_counts_device(cudaStream_t st, const uint8_t* d_aln, int64_t S, int64_t L, int32_t* d_counts) {
-  LDW_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)L * 5 * 4, st));
-  int slices = (int)((S + 63) / 64);
-  if (slices > 64) slices = 64;
-  if (slices < 1) slices = 1;
-  int rps = (int)((S + slices - 1) / slices);
-  dim3 grid((unsigned)((L + 4 * 256 - 1) / (4 * 256)), (unsigned)slices);
-  column_count_kernel<<<grid, 256, 0, st>>>(d_aln, S, L, rps, d_counts);
+int column_counts_device(cudaStream_t st, const uint8_t* d_aln, int64_t S, int64_t L, int64_t pitch, int32_t* d_counts,
+                         bool accumulate) {
+  if (pitch < L || (pitch & 15) || (reinterpret_cast<uintptr_t>(d_aln) & 15))
+    return set_error(LDW_ERR_INTERNAL, "column_counts_device: rows must be 16-byte aligned (pitch %lld)", (long long)pitch);
+  if (!accumulate) LDW_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)L * 5 * 4, st));
+  // slices of at most 255 rows (byte-lane counters); more of them when the column groups alone cannot fill the SMs
+  const int64_t groups = (L + CC_COLS - 1) / CC_COLS;
+  const int64_t col_blocks = (groups + 255) / 256;
+  int64_t slices = (S + CC_MAX_ROWS - 1) / CC_MAX_ROWS;
+  while (slices * col_blocks < 4 * 148 && slices * 2 <= S && slices < 65535) slices *= 2;
+  if (slices > 65535) return set_error(LDW_ERR_UNSUPPORTED, "alignment with more than 16.7 M sequences");
+  const int rps = (int)((S + slices - 1) / slices);
+  dim3 grid((unsigned)col_blocks, (unsigned)slices);
+  column_count_kernel<<<grid, 256, 0, st>>>(d_aln, S, L, pitch, rps, d_counts);
   LDW_CUDA(cudaGetLastError());
   return 0;
 }
@@ -172,11 +231,12 @@ int counts_to_double_device(cudaStream_t st, const int32_t* d_in, int64_t n, dou
   return 0;
 }
 
-int extract_codes_device(cudaStream_t st, const uint8_t* d_aln, int64_t S, int64_t L, const int32_t* d_pos, int64_t n,
-                         uint8_t* d_codes) {
+int extract_codes_device(cudaStream_t st, const uint8_t* d_aln, int64_t S, int64_t L, int64_t pitch, const int32_t* d_pos,
+                         int64_t n, uint8_t* d_codes, int64_t row0, int64_t S_total) {
   if (n == 0 || S == 0) return 0;
-  dim3 grid((unsigned)((n + 31) / 32), (unsigned)((S + 31) / 32));
-  extract_codes_kernel<<<grid, dim3(32, 32), 0, st>>>(d_aln, S, L, d_pos, n, d_codes);
+  if ((S + 31) / 32 > 65535) return set_error(LDW_ERR_UNSUPPORTED, "alignment with more than 2 M sequences");
+  dim3 grid((unsigned)((n + EX_K - 1) / EX_K), (unsigned)((S + 31) / 32));
+  extract_codes_kernel<<<grid, dim3(32, 32), 0, st>>>(d_aln, S, L, pitch, d_pos, n, d_codes, row0, S_total);
   LDW_CUDA(cudaGetLastError());
   return 0;
 }

@@ -251,31 +251,38 @@ int ldw_group_load_codes(ldw_group* G, const uint8_t* codes, int64_t n_snp, int6
   bool have_root = false;
   for (auto& mb : G->m) have_root |= (mb.rank == 0);
   if (have_root && !codes) return set_error(LDW_ERR_ARG, "ldw_group_load_codes: the process that holds rank 0 must pass the matrix");
-  if (have_root) {  // same validation as ldw_mi_plan_create: every class is 0..4
-    const int64_t total = n_snp * nseq, chunk = (int64_t)1 << 22, nchunks = (total + chunk - 1) / chunk;
-    std::vector<int64_t> bad_at(nchunks, -1);
-    parallel_for(nchunks, 8, [&](int64_t c) {
-      const int64_t end = std::min<int64_t>(total, (c + 1) * chunk);
-      for (int64_t i = c * chunk; i < end; i++)
-        if (codes[i] > 4) { bad_at[c] = i; break; }
-    });
-    for (int64_t c = 0; c < nchunks; c++)
-      if (bad_at[c] >= 0) return set_error(LDW_ERR_ARG, "ldw_group_load_codes: codes[%lld] = %d outside 0..4", (long long)bad_at[c], (int)codes[bad_at[c]]);
-  }
   G->n_snp = n_snp;
   G->nseq = nseq;
   const size_t bytes = (size_t)n_snp * (size_t)nseq;
   const NcclApi* nccl = nullptr;
   if (G->world > 1) LDW_TRY(nccl_api(&nccl));
-  return for_members(G, [&](int k) -> int {
+  int bad_code = 0;
+  int rc_all = for_members(G, [&](int k) -> int {
     ldw_group::Member& mb = G->m[k];
     cudaStream_t st = mb.ctx->stream;
     LDW_TRY(mb.d_codes.ensure(bytes));
-    if (mb.rank == 0) LDW_CUDA(cudaMemcpyAsync(mb.d_codes.p, codes, bytes, cudaMemcpyHostToDevice, st));
+    if (mb.rank == 0) {
+      LDW_CUDA(cudaMemcpyAsync(mb.d_codes.p, codes, bytes, cudaMemcpyHostToDevice, st));
+      // every class must be 0..4 (as ldw_mi_plan_create checks on the host): one pass at HBM speed on the device
+      DevBuf d_max;
+      LDW_TRY(d_max.alloc(4));
+      LDW_CUDA(cudaMemsetAsync(d_max.p, 0, 4, st));
+      LDW_TRY(max_byte_device(st, mb.d_codes.as<uint8_t>(), (int64_t)bytes, d_max.as<uint32_t>()));
+      uint32_t mx = 0;
+      LDW_CUDA(cudaMemcpyAsync(&mx, d_max.p, 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaStreamSynchronize(st));
+      if (mx > 4) bad_code = (int)mx;  // reported after the collective below, so that no rank is left waiting in it
+    }
     if (G->world > 1) LDW_NCCL(nccl->Broadcast(mb.d_codes.p, mb.d_codes.p, bytes, ncclUint8, 0, mb.comm, st));
     LDW_CUDA(cudaStreamSynchronize(st));
     return 0;
   });
+  if (rc_all != 0) return rc_all;
+  if (bad_code) {
+    G->n_snp = G->nseq = 0;
+    return set_error(LDW_ERR_ARG, "ldw_group_load_codes: the matrix holds a class %d outside 0..4", bad_code);
+  }
+  return 0;
 }
 
 int ldw_group_hdw(ldw_group* G, double threshold, int flags, int32_t* cnt_out, double* hdw_out, int* sharded_out) {
@@ -337,6 +344,15 @@ int ldw_group_mi_scan(ldw_group* G, const double* hdw, const int32_t* pos, const
     });
     if (rc != 0) { destroy_plans(); return rc; }
     if (t_plan_ms_out) *t_plan_ms_out = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+    if (G->world == 1) {  // one device, one process: exactly ldw_mi_scan (its own sizing pass, its own tables, nothing to merge)
+      ldw_scan_stats st1;
+      rc = mi_scan_impl(plans[0], g, sr_dist, lr_retain_links, lr_links_approx, flags, 1, 0, nullptr, sr_out, lr_out, borderline_out,
+                        thr_out, prob_out, &st1);
+      if (rc != 0) { std::string keep = last_error_ref(); destroy_plans(); return set_error(rc, "%s", keep.c_str()); }
+      destroy_plans();
+      if (stats_out) stats_out[0] = st1;
+      return 0;
+    }
     // ---- one layout for the job's short-range table: block sizes once, rows of the blocks this process scans
     ScanShared sh;
     rc = mi_block_sizes(plans[0], g, sr_dist, flags, sh.sizes);

@@ -346,6 +346,28 @@ __global__ void hdw_weights_kernel(const int32_t* __restrict__ neigh, int32_t S,
   if (s < S) w[s] = 1.0 / (double)(neigh[s] + 1);
 }
 
+// Largest byte of a buffer (input validation of a device-resident class matrix), atomicMax into *out.
+__global__ void max_byte_kernel(const uint8_t* __restrict__ p, int64_t n, uint32_t* out) {
+  uint32_t m = 0;
+  const int64_t n16 = n / 16;
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(q + i);
+    m = __vmaxu4(m, __vmaxu4(__vmaxu4(v.x, v.y), __vmaxu4(v.z, v.w)));
+  }
+  for (int64_t i = n16 * 16 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = __vmaxu4(m, (uint32_t)p[i]);
+  m = max(max(m & 0xFFu, (m >> 8) & 0xFFu), max((m >> 16) & 0xFFu, m >> 24));
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+int max_byte_device(cudaStream_t st, const uint8_t* d, int64_t n, uint32_t* d_out) {
+  if (n <= 0) return 0;
+  max_byte_kernel<<<148 * 8, 256, 0, st>>>(d, n, d_out);
+  LDW_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 int snp_allele_stats(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, int32_t* d_table, uint8_t* d_mask,
                      uint8_t* d_r) {

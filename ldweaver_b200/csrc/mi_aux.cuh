@@ -356,7 +356,10 @@ struct BlockResult {
   uint32_t n_cand;
   uint32_t n_kept;
   uint32_t n_border;
-  uint32_t bad;  // 1: candidate buffer overflowed; 2: fewer candidates than needed; 4: threshold guess not provably safe
+  uint32_t bad;  // 1: candidate buffer overflowed; 2: fewer candidates than needed; 4: threshold guess not provably safe;
+                 // 8: the fp32 epilogue's error observed on this block's refined candidates is too large for the margins used
+  float eps_obs; // max |fp32 MI - fp64 MI| over the refined candidates
+  uint32_t pad;
 };
 
 struct SelectParams {
@@ -491,6 +494,23 @@ __global__ void __launch_bounds__(1024) mi_select_kernel(SelectParams P) {
       if (!(v_lo >= tc + P.tol_safe)) bad |= 4;
     }
   }
+  // The pre-selection kept the candidates with fp32 MI >= v32 - tol_safe and the completeness test above uses the same
+  // margin; both are sound when the epilogue's error eps satisfies 2 eps <= tol_safe.  That error depends on the input
+  // (fixed-point weight rounding adds up coherently inside large clusters of equal weights), so it is MEASURED here on
+  // the refined candidates -- the pairs around the threshold, where it matters -- and the block is sent back for a
+  // re-run with wider margins unless there is a factor 2 of head room (4 eps_obs <= tol_safe).
+  __shared__ float s_eps;
+  if (threadIdx.x == 0) s_eps = 0.f;
+  __syncthreads();
+  {
+    float e = 0.f;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) e = fmaxf(e, (float)fabs((double)P.cand[i].mi - P.mi64[i]));
+    for (int o = 16; o > 0; o >>= 1) e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<uint32_t*>(&s_eps), __float_as_uint(e));  // e >= 0: bit order == value order
+  }
+  __syncthreads();
+  const float eps_obs = s_eps;
+  if (4.0 * (double)eps_obs > P.tol_safe) bad |= 8;
   if (threadIdx.x == 0) { s_kept = 0; s_border = 0; }
   __syncthreads();
   if (!bad) {
@@ -523,6 +543,7 @@ __global__ void __launch_bounds__(1024) mi_select_kernel(SelectParams P) {
     }
     BlockResult r;
     r.thr = thr; r.v_lo = v_lo; r.n_cand = raw; r.n_kept = s_kept; r.n_border = s_border; r.bad = bad;
+    r.eps_obs = eps_obs; r.pad = 0;
     *P.result = r;
   }
 }

@@ -1061,7 +1061,12 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
   float force_seed = -1.f;
   if (const char* e = getenv("LDW_DBG_FORCE_SEED")) force_seed = (float)atof(e);
   // b: index into this rank's block list (output offsets, results); seq: position in the execution order (ring slots)
-  auto run_block = [&](size_t b, size_t seq, int force_emit_all, uint32_t cap_override, bool use_chain) -> int {
+  // margin of the long-range selection (pre-selection window and completeness test): sound while twice the fp32
+  // epilogue's error stays below it; the selection kernel measures that error per block and asks for a re-run with a
+  // wider margin when it does not (BlockResult.bad & 8)
+  double sel_margin0 = 4e-6;
+  if (const char* e = getenv("LDW_DBG_SEL_MARGIN")) sel_margin0 = atof(e);  // test hook: a tiny margin exercises that re-run
+  auto run_block = [&](size_t b, size_t seq, int force_emit_all, uint32_t cap_override, bool use_chain, double sel_margin) -> int {
     Sel& s = sel[b];
     if (s.skip) return 0;
     int slot = (int)(seq % ScanWS::RING);
@@ -1168,7 +1173,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       RefineParams R = make_refine_params(P, D, H, cfg);
       // candidates that can reach the exact K-th largest value (fp32 pre-selection), then their fp64 refinement
       n_launches++;
-      mi_presel_kernel<<<1, 1024, 0, sst>>>(L.cand.as<Cand>(), d_count, cap, d_tcand, emit_all, (unsigned long long)s.k_lo, 4e-6f,
+      mi_presel_kernel<<<1, 1024, 0, sst>>>(L.cand.as<Cand>(), d_count, cap, d_tcand, emit_all, (unsigned long long)s.k_lo, (float)sel_margin,
                                            L.vcand.as<Cand>(), d_count + 5);
       LDW_CUDA(cudaGetLastError());
       mi_refine_list_kernel<<<P->ctx->num_sms * 4, 32 * REFINE_WARPS, 0, sst>>>(R, L.vcand.as<Cand>(), d_count + 5, L.mi64.as<double>());
@@ -1178,7 +1183,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       q.cand = L.vcand.as<Cand>(); q.mi64 = L.mi64.as<double>(); q.vcount = d_count + 5; q.count = d_count; q.cap = cap;
       q.overflow = d_overflow; q.tcand_bits = d_tcand; q.emit_all = emit_all;
       q.k_lo = s.k_lo; q.k_hi = s.k_hi; q.h = s.h; q.interpolate = s.interp;
-      q.tol_safe = 4e-6; q.tol_border = 1e-9;
+      q.tol_safe = sel_margin; q.tol_border = 1e-9;
       q.from_idx = D.from_idx.as<int32_t>(); q.to_idx = D.to_idx.as<int32_t>();
       q.nf = H.nf; q.nt = H.nt; q.diag = H.diag; q.block = (int32_t)blocks[b].index;
       q.kept_key = W->d_kept_key.as<uint64_t>(); q.kept_gi = W->d_kept_gi.as<int32_t>(); q.kept_gj = W->d_kept_gj.as<int32_t>();
@@ -1235,7 +1240,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
   std::vector<size_t> order;
   for (size_t b = 0; b < blocks.size(); b++) if (sel[b].n_sr > 0) order.push_back(b);
   for (size_t b = 0; b < blocks.size(); b++) if (!(sel[b].n_sr > 0)) order.push_back(b);
-  for (size_t k = 0; k < order.size(); k++) LDW_TRY(run_block(order[k], k, 0, 0, true));
+  for (size_t k = 0; k < order.size(); k++) LDW_TRY(run_block(order[k], k, 0, 0, true, sel_margin0));
   for (auto& l : W->lr)
     if (l.used) LDW_CUDA(cudaStreamWaitEvent(st, l.sel_done, 0));  // join the select stream
   LDW_CUDA(cudaEventRecord(ev1, st));
@@ -1262,8 +1267,11 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       if (P->results[b].bad) {
         // second attempt: no chained seed (collect from zero, the histogram places the threshold); last resort:
         // collect every long-range pair of the block
+        double margin = sel_margin0;
         for (int attempt = 0; attempt < 2 && P->results[b].bad; attempt++) {
           n_reruns++;
+          // measured epilogue error too large for the margin: widen it to 8x the observation (the test wants 4x)
+          if (P->results[b].bad & 8) margin = std::max(std::max(margin, 4e-6), 8.0 * (double)P->results[b].eps_obs);
           uint32_t cap = 0;
           if (attempt == 1) {
             if ((uint64_t)sel[b].n_lr > 0xFFFFFFF0ull) return set_error(LDW_ERR_UNSUPPORTED, "block %lld needs an exhaustive long-range pass over more than 2^32 links", (long long)blocks[b].index);
@@ -1273,7 +1281,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
             LDW_TRY(L.mi64.ensure((size_t)cap * 8));
             LDW_TRY(L.vcand.ensure((size_t)cap * sizeof(Cand)));
           }
-          LDW_TRY(run_block(b, 0, attempt == 1, cap, false));
+          LDW_TRY(run_block(b, 0, attempt == 1, cap, false, margin));
           LDW_CUDA(cudaStreamWaitEvent(st, W->lr[0].sel_done, 0));
           LDW_CUDA(cudaStreamSynchronize(st));
           P->results[b] = W->h_results.as<BlockResult>()[b];
@@ -1435,6 +1443,12 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
     stats_out->exec_int8_ops = exec_ops;
     stats_out->t_host_prep_ms = host_prep_ms;
     stats_out->exec_mufu_ops = exec_mufu;
+    {
+      double em = 0;
+      for (size_t b = 0; b < blocks.size(); b++)
+        if (!sel[b].skip && sel[b].n_lr > 0 && !sr_only) em = std::max(em, (double)P->results[b].eps_obs);
+      stats_out->eps_obs_max = em;
+    }
   }
   if (dbg_block >= 0 && W->d_dbg.p) {
     std::vector<unsigned long long> h(4096 * 16);

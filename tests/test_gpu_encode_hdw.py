@@ -10,6 +10,9 @@ def _lib():
     return ldw
 
 
+_lib_ = _lib
+
+
 def test_encode_fixture_bit_exact(fixture_input, fixture_expected):
     import ldw_oracle as O
     ldw = _lib()
@@ -104,6 +107,51 @@ def test_encode_filters_vs_oracle_ragged():
                 np.testing.assert_array_equal(snp.codes, codes_c)
                 np.testing.assert_array_equal(snp.uqe, (table_c > 0).T.astype(float))
                 assert snp.g == L
+
+
+def test_encode_streams_in_row_chunks_and_separate_entry_points_agree(monkeypatch):
+    """The alignment goes to the device in row chunks (8 GiB by default; a few kilobytes here): counts accumulate across
+    chunks, every chunk's classes land in its own sequence range.  The two reference-shaped entry points (ldw_aln_param,
+    ldw_extract_snps: what `.extractAlnParam` / `.extractSNPs` map to) must agree with the one-call encoder, for row
+    lengths that are and are not multiples of 16 (rows are padded to 16 bytes on the device)."""
+    import ctypes as C
+    import c_oracle as CO
+    from ldweaver_b200 import _lib
+    ldw = _lib_()
+    rng = np.random.default_rng(5)
+    for (S, L) in ((300, 1000), (517, 1601), (64, 16), (1, 33)):
+        alphabet = np.frombuffer(b"ACGTacgtNn-RYK", dtype=np.uint8)
+        aln = alphabet[rng.integers(0, 4, size=L)][None, :].repeat(S, axis=0).copy()
+        mut = rng.random((S, L)) < rng.random(L)[None, :] * 0.4
+        aln[mut] = alphabet[rng.integers(0, len(alphabet), size=int(mut.sum()))]
+        pos_c, counts_c = CO.aln_param(aln, 1, 0.3, 0.0)
+        if len(pos_c) == 0:
+            continue
+        codes_c, table_c = CO.extract_snps(aln, pos_c)
+        for chunk in (None, 7 * ((L + 15) // 16 * 16), 1):     # one chunk / 7 rows per chunk / one row per chunk
+            if chunk is None:
+                monkeypatch.delenv("LDW_ENCODE_CHUNK_BYTES", raising=False)
+            else:
+                monkeypatch.setenv("LDW_ENCODE_CHUNK_BYTES", str(chunk))
+            snp = ldw.snp_dat_from_alignment_matrix(aln, method="relaxed", gap_freq=0.3, maf_freq=0.0)
+            np.testing.assert_array_equal(snp.POS, pos_c)
+            np.testing.assert_array_equal(snp.codes, codes_c)
+            np.testing.assert_array_equal(snp.uqe, (table_c > 0).T.astype(float))
+            # the separate entry points
+            Lb = _lib.lib()
+            ctx = _lib.default_context(0)
+            pos = np.empty(L, dtype=np.int32)
+            n = C.c_int64()
+            counts = np.empty(5 * L, dtype=np.float64)
+            _lib.check(Lb.ldw_aln_param(ctx.handle, _lib.ptr(aln), S, L, 1, 0.3, 0.0, _lib.ptr(pos), C.byref(n), _lib.ptr(counts)))
+            np.testing.assert_array_equal(pos[:n.value], pos_c)
+            np.testing.assert_array_equal(counts.reshape(L, 5).T, counts_c)
+            codes = np.empty((n.value, S), dtype=np.uint8)
+            table = np.empty(5 * n.value, dtype=np.float64)
+            _lib.check(Lb.ldw_extract_snps(ctx.handle, _lib.ptr(aln), S, L, _lib.ptr(pos_c), n.value, _lib.ptr(codes), _lib.ptr(table)))
+            np.testing.assert_array_equal(codes, codes_c)
+            np.testing.assert_array_equal(table.reshape(n.value, 5).T, table_c)
+    monkeypatch.delenv("LDW_ENCODE_CHUNK_BYTES", raising=False)
 
 
 def test_acgtn2num_vs_oracle():

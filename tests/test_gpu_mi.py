@@ -292,6 +292,69 @@ def test_rerun_path_after_a_failed_threshold_seed(monkeypatch):
     plan.close()
 
 
+def test_selection_margin_is_verified_and_widened(monkeypatch):
+    """The long-range selection measures the fp32 epilogue's error on its refined candidates (BlockResult.eps_obs) and re-runs
+    a block with a wider margin when 4 x that exceeds the margin in use.  A tiny initial margin (test hook) must trigger the
+    re-run on every block and still give exactly the undisturbed result."""
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import synth
+    sy = synth.generate(nseq=300, nsnp=6000, seed=22)
+    snp = ldw.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
+    hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    lra = synth.exact_lr_links_approx(sy.POS, sy.g, 20000.0)
+    plan = ldw.MIPlan(snp, hdw, sy.paint, 2000)
+    ref = plan.scan(sy.g, 20000.0, 5e4, lra)
+    assert 0 < ref[5]["eps_obs_max"] < 1e-6        # the observed error itself stays inside the MI bar
+    monkeypatch.setenv("LDW_DBG_SEL_MARGIN", "1e-8")
+    got = plan.scan(sy.g, 20000.0, 5e4, lra)
+    monkeypatch.delenv("LDW_DBG_SEL_MARGIN")
+    assert got[5]["n_reruns"] >= 6                  # every block with a long-range branch was sent back
+    for which in (0, 1):
+        for col in ("pos1", "pos2", "clust1", "clust2", "len", "MI", "block"):
+            assert np.array_equal(ref[which][col], got[which][col]), (which, col)
+    assert np.array_equal(ref[3], got[3], equal_nan=True)
+    plan.close()
+
+
+def test_strongly_clonal_weights_at_5000_sequences():
+    """one clonal cluster of 5000 near-identical sequences (weights 1/5001, coherently rounded in the 28-bit
+    fixed-point unit whose scale is set by the largest weight, 0.5 for the singletons) is where the epilogue error is
+    largest.  Thresholds and link sets must still match the oracle, with the observed error reported."""
+    import c_oracle as CO
+    import ldw_oracle as O
+    import ldweaver_b200 as ldw
+    rng = np.random.default_rng(77)
+    S_big, S_single, n = 5000, 12, 260
+    base = rng.integers(0, 2, size=n).astype(np.uint8)
+    clone = np.repeat(base[:, None], S_big, axis=1)
+    flip = rng.random((n, S_big)) < 0.02                       # within-cluster variation: distances far below 0.1 n
+    clone[flip] ^= 1
+    singles = rng.integers(0, 2, size=(n, S_single)).astype(np.uint8)
+    codes = np.ascontiguousarray(np.concatenate([clone, singles], axis=1))
+    codes[rng.random(codes.shape) < 0.01] = 4
+    POS = np.sort(rng.choice(np.arange(1, 400000), n, replace=False)).astype(np.int32)
+    g = 500000
+    snp = ldw.snp_dat_from_codes(codes, POS, g)
+    hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    hdw_c, _ = CO.hdw(codes, 0.1)
+    np.testing.assert_array_equal(hdw, hdw_c)
+    assert hdw.max() == 0.5 and np.sum(hdw < 1e-3) >= S_big - 5     # one huge cluster, isolated singletons
+    osnp = O.snp_dat_from_codes(codes, POS, g)
+    idx = np.arange(n)
+    MI = CO.block_mi(codes, hdw, osnp.r, osnp.uqe, idx, idx)
+    L = CO.block_links(MI, POS.astype(np.float64), idx, idx, float(g), 20000.0, 3000.0, 2e4)
+    res = ldw.perform_MI_computation(snp, hdw, ldw.CdsVar(np.ones(n, dtype=np.int32), 1), sr_dist=20000, lr_retain_links=3000,
+                                     max_blk_sz=1000, lr_links_approx=2e4, write_tsv=False)
+    print("clonal 5000: eps_obs_max", res.stats["eps_obs_max"], "reruns", res.stats["n_reruns"],
+          "max |dMI| SR", float(np.abs(res.sr["MI"] - L["MI"][L["is_sr"]]).max()))
+    assert abs(res.thr[0] - L["thr"]) < 1e-12
+    P = POS.astype(np.float64)
+    compare_lr_sets(P[L["col"]][L["lr_keep"]], P[L["row"]][L["lr_keep"]], L["MI"][L["lr_keep"]],
+                    res.lr["pos1"], res.lr["pos2"], res.lr["MI"], L["thr"])
+    assert np.abs(res.sr["MI"] - L["MI"][L["is_sr"]]).max() < MI_TOL
+    assert 4 * res.stats["eps_obs_max"] <= max(4e-6, 8 * res.stats["eps_obs_max"])   # whatever was observed, the margin used covered it
+
+
 def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, tmp_path):
     """perform_MI_computation as the reference runs it (R/computePairwiseMI.R:46-145): scan on the device, then the
     native mergeNsort_sr_links / runARACNE / ordering / sr_links.tsv + lr_links.tsv, against the oracle chain on the
