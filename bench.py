@@ -474,7 +474,7 @@ def main():
                         t2 = time.perf_counter()
                     extra["wall_to_links_s"] = t2 - t0
                     extra["wall_to_links"] = {"hdw_s": t1 - t0, "perform_MI_computation_s": t2 - t1, "n_sr_links": int(len(res.sr["MI"])), "n_lr_links": int(len(res.lr["MI"])),
-                                              "n_sr_links_red": int(len(res.sr_links_red["row"])), "exact_sr": "in_scan (fp64 MI of every short-range link, LDW_SCAN_SR_EXACT)",
+                                              "n_sr_links_red": int(len(res.sr_links_red["row"])), "phases_s": res.stats.get("phases"), "exact_sr": "in_scan (fp64 MI of every short-range link, LDW_SCAN_SR_EXACT)",
                                               "includes": "hdw + upload/packing + scan + D2H of all links + NumPy copies + lr_links.tsv + mergeNsort_sr_links + runARACNE + ordering + sr_links.tsv",
                                               "host_threads": ncpu}
                     del res

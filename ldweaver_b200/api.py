@@ -775,8 +775,12 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         return _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff,
                                       runARACNE, order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder)
     own = plan is None
+    import time as _time
+    t_phase = {}
+    _t0 = _time.perf_counter()
     if own:
         plan = MIPlan(snp_dat, hdw, paint, blk, device)
+    t_phase["plan_create_s"] = _time.perf_counter() - _t0
     try:
         flags = (SCAN_SR_ONLY if perform_SR_analysis_only else 0) | int(scan_flags)
         if exact_sr is None:  # SR-only scans index reduced SNP lists (Q12): only the in-scan kernel can refine them
@@ -784,14 +788,22 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call
             flags |= SCAN_SR_EXACT
             exact_sr = False
-        sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags)
+        _t0 = _time.perf_counter()
+        sr, lr, bd, thr, prob, stats = plan.scan(float(snp_dat.g), sr_dist, lr_retain_links, lr_links_approx or 0.0, flags, copy=False)
+        t_phase["scan_call_s"] = _time.perf_counter() - _t0
+        _t0 = _time.perf_counter()
+        sr, lr, bd = sr.to_dict(), lr.to_dict(), bd.to_dict()     # library-owned pinned columns -> NumPy arrays the caller owns
+        t_phase["copy_links_s"] = _time.perf_counter() - _t0
         if exact_sr:
             if perform_SR_analysis_only:
                 raise ValueError("exact_sr is not available with perform_SR_analysis_only")
+            _t0 = _time.perf_counter()
             sr["MI"] = plan.sr_exact(sr, inplace=True)
+            t_phase["exact_sr_host_driven_s"] = _time.perf_counter() - _t0
     finally:
         if own:
             plan.close()
+    stats["phases"] = t_phase
     return _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff,
                                   runARACNE, order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder)
 
@@ -799,8 +811,13 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
 def _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff, run_aracne,
                            order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder) -> MIScanResult:
     """What follows the scan in perform_MI_computation (R/computePairwiseMI.R:118-143), for one device or a group."""
+    import time as _time
+    ph = stats.setdefault("phases", {})
+    _t0 = _time.perf_counter()
     if write_tsv and len(lr["MI"]):
         write_lr_tsv(lr_save_path, lr, append=True)
+    ph["write_lr_tsv_s"] = _time.perf_counter() - _t0
+    _t0 = _time.perf_counter()
     res = MIScanResult(sr=sr, lr=lr, borderline=bd, nclust=nclust, thr=thr, prob=prob, stats=stats,
                        lr_links_approx=lr_links_approx)
     if do_post:
@@ -808,4 +825,5 @@ def _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx
             sr_save_path = os.path.join(os.getcwd(), "sr_links.tsv")  # :62
         res.sr_links_red, res.sr_post = finish_sr_links(sr, cds_var, sr_dist, srp_cutoff, run_aracne, order_links,
                                                         sr_save_path if write_tsv else None, plt_folder)
+    ph["finish_sr_links_s"] = _time.perf_counter() - _t0
     return res

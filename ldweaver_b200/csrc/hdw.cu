@@ -429,10 +429,16 @@ int hdw_device(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, in
   p.tiles_n = (int32_t)((S + HDW_BN - 1) / HDW_BN);
   p.nkb = (int32_t)(Kh / HDW_BK);
   // Upper triangle of the tile grid: tile (tm, tn) holds a pair s <= t iff its first row does not lie below its last column.
+  // Listed supertile by supertile (16 row tiles x 8 column tiles = 2048 x 2048 sequences, about one wave of CTAs): the
+  // CTAs that run at the same time then share 16 A tiles and 8 B tiles through L2 instead of streaming ~80 different A
+  // tiles (every tile re-reads its operands over the whole K: the kernel is HBM-bound without that reuse).
   std::vector<int2> tri;
-  for (int tn = 0; tn < p.tiles_n; tn++)
-    for (int tm = 0; tm < p.tiles_m; tm++)
-      if ((int64_t)tm * HDW_BM <= (int64_t)tn * HDW_BN + HDW_BN - 1) tri.push_back(make_int2(tm, tn));
+  constexpr int SUP_M = 16, SUP_N = 8;
+  for (int sn = 0; sn < p.tiles_n; sn += SUP_N)
+    for (int sm = 0; sm < p.tiles_m; sm += SUP_M)
+      for (int tn = sn; tn < std::min(sn + SUP_N, p.tiles_n); tn++)
+        for (int tm = sm; tm < std::min(sm + SUP_M, p.tiles_m); tm++)
+          if ((int64_t)tm * HDW_BM <= (int64_t)tn * HDW_BN + HDW_BN - 1) tri.push_back(make_int2(tm, tn));
   // Multi-GPU: when every rank still gets more than a wave of whole-K tiles, the triangle's tiles are
   // dealt round-robin, each rank counts the neighbours its tiles reveal and the partial counts are summed across ranks
   // (the `allreduce` callback: ncclAllReduce).  Smaller problems are computed whole on every rank -- identical results,

@@ -207,10 +207,32 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const uint8_t* codes_dev, c
   std::vector<uint8_t> dig((size_t)4 * P->Kpad, 0);  // rows: aH, aL, bH, bL (shared-memory slot order)
   std::vector<int32_t> wH(S), wL(S);
   int64_t sumH = 0, sumL = 0;
+  // Rounding with error diffusion along the sequences ordered by weight: the fixed-point unit is set by the LARGEST
+  // weight, so the members of a big clonal cluster (thousands of equal weights 1/(m+1), a singleton at 0.5 elsewhere) carry
+  // only ~17 significant bits each, and round-to-nearest would give all of them the SAME rounding error -- it adds up
+  // coherently in every joint count (measured: 1.1e-6 on MI at m = 5000).  Diffusing the residual to the next sequence of
+  // the same (or the nearest) weight keeps every weight within one unit of its value, makes each cluster's total exact to
+  // half a unit and turns the error of a subset sum into a zero-mean walk of ~0.3 sqrt(m) units instead of a bias of up to m / 2.
+  std::vector<int64_t> Wq(S);
+  {
+    std::vector<int32_t> order(S);
+    for (int64_t s = 0; s < S; s++) order[s] = (int32_t)s;
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return hdw[a] < hdw[b]; });
+    double carry = 0.0;
+    for (int64_t k = 0; k < S; k++) {
+      const int32_t s = order[k];
+      const double x = hdw[s] * P->scale + carry;
+      int64_t W = (int64_t)std::llround(x);
+      if (W < 0) W = 0;
+      if (W > 268435455) W = 268435455;
+      carry = x - (double)W;
+      if (carry > 1.0) carry = 1.0;
+      if (carry < -1.0) carry = -1.0;
+      Wq[s] = W;
+    }
+  }
   for (int64_t s = 0; s < S; s++) {
-    int64_t W = (int64_t)std::llround(hdw[s] * P->scale);
-    if (W < 0) W = 0;
-    if (W > 268435455) W = 268435455;
+    int64_t W = Wq[s];
     int32_t H = (int32_t)(W >> 14), L = (int32_t)(W & 16383);
     wH[s] = H; wL[s] = L;
     sumH += H; sumL += L;

@@ -34,7 +34,10 @@
 #include <vector>
 
 #include "host_util.h"
+#include "post_host.h"
 #include "../../include/ldw.h"
+
+using ldwpost::SrPostPriv;
 
 namespace {
 
@@ -313,18 +316,6 @@ double neg_log_upper_beta(double x, double a, double b, double lbeta) {
   return -log1p(-exp(lp));
 }
 
-struct SrPostPriv {
-  std::vector<int32_t> clust_c;
-  std::vector<int64_t> row;
-  std::vector<double> srp;
-  std::vector<int64_t> red, chk;
-  std::vector<int64_t> fit_off;
-  std::vector<int32_t> fit_len;
-  std::vector<double> fit_q95, fit_val, coef, shape, start;
-  std::vector<int64_t> n_pos;
-  std::vector<int32_t> nm_evals, nm_fail;
-};
-
 struct KeyHash {
   size_t operator()(const std::pair<int64_t, int64_t>& k) const {
     uint64_t h = (uint64_t)k.first * 0x9E3779B97F4A7C15ull ^ ((uint64_t)k.second + 0x7F4A7C15ull + ((uint64_t)k.first << 6));
@@ -334,6 +325,108 @@ struct KeyHash {
 };
 
 }  // namespace
+
+namespace ldwpost {
+
+int decay_fits(SrPostPriv& S, int32_t nclust, int64_t nl, const std::vector<int64_t>& glist, const std::vector<double>& gq) {
+  size_t t = 0;
+  for (int32_t c = 1; c <= nclust; c++) {
+    std::vector<double> lx, ly;
+    const size_t base = S.fit_len.size();
+    for (; t < glist.size() && glist[t] < (int64_t)c * nl; t++) {
+      const int32_t l = (int32_t)(glist[t] - (int64_t)(c - 1) * nl);
+      S.fit_len.push_back(l);
+      S.fit_q95.push_back(gq[t]);
+      lx.push_back(log((double)l));
+      ly.push_back(log(gq[t]));
+    }
+    const int64_t ng = (int64_t)lx.size();
+    if (ng < 2) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d has fewer than two distinct link lengths", (int)c);
+    double coef[2];
+    ols2(lx, ly, coef);
+    S.fit_val.resize(base + ng);
+    for (int64_t gi = 0; gi < ng; gi++) S.fit_val[base + gi] = exp(lx[gi] * coef[0] + coef[1]);
+    S.fit_off.push_back((int64_t)(base + ng));
+    S.coef.push_back(coef[0]);
+    S.coef.push_back(coef[1]);
+  }
+  return 0;
+}
+
+// fitdist(x, "beta") (:452) from the sufficient statistics: moment start values (v = biased variance), then optim's
+// Nelder-Mead on the negative log-likelihood n lbeta(a, b) - (a - 1) sum(log x) - (b - 1) sum(log(1 - x)).
+int beta_fit(SrPostPriv& S, int32_t c, int64_t npos, double s1, double s2, double mean, double v, double par[2]) {
+  const double aux = mean * (1 - mean) / v - 1;
+  const double start[2] = {mean * aux, (1 - mean) * aux};
+  BetaNll nll{(double)npos, s1, s2};
+  double fmin;
+  int evals = 0;
+  const int fail = nmmin2(nll, start, par, &fmin, &evals);
+  if (fail < 0) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d: the beta likelihood cannot be evaluated at the initial parameters (%g, %g)", (int)c, start[0], start[1]);
+  S.shape.push_back(par[0]); S.shape.push_back(par[1]);
+  S.start.push_back(start[0]); S.start.push_back(start[1]);
+  S.n_pos.push_back(npos);
+  S.nm_evals.push_back(evals);
+  S.nm_fail.push_back(fail);
+  return 0;
+}
+
+double lbeta_fn(double a, double b) {
+  int sg;
+  return lgamma_r(a, &sg) + lgamma_r(b, &sg) - lgamma_r(a + b, &sg);
+}
+
+// Links seen from two clusters: one row per distinct link, the one with the larger srp_max; groups in order of first
+// appearance, first maximum wins (:474-483, data.table `.I[which.max(srp_max)], by = keys`).  Then
+// sr_links_red = srp_max > srp_cutoff; sr_links_ARACNE_check = MI >= min(sr_links_red$MI)  (:494-495).
+// `cols` are link columns addressed by the entries of dup_at / df_at (rows of the full table on the host path, positions
+// in the gathered df table on the device path); dup_row are the rows of the full table that go into S.row.
+void dedup_and_select(SrPostPriv& S, const LinkCols& cols, const std::vector<int64_t>& dup_row, const std::vector<int64_t>& dup_at,
+                      const std::vector<int32_t>& dup_c, const std::vector<double>& dup_srp, std::vector<int64_t>& df_at, double srp_cutoff) {
+  if (!dup_row.empty()) {
+    struct Grp { int64_t first, best; };
+    std::unordered_map<std::pair<int64_t, int64_t>, std::vector<int64_t>, KeyHash> index;  // (pos1, pos2) -> groups
+    index.reserve(dup_row.size());
+    std::vector<Grp> groups;
+    groups.reserve(dup_row.size());
+    auto same = [&](int64_t a, int64_t b) {
+      return cols.pos1[a] == cols.pos1[b] && cols.pos2[a] == cols.pos2[b] && cols.clust1[a] == cols.clust1[b] &&
+             cols.clust2[a] == cols.clust2[b] && cols.len[a] == cols.len[b] && cols.MI[a] == cols.MI[b];
+    };
+    for (int64_t k = 0; k < (int64_t)dup_row.size(); k++) {
+      const int64_t r = dup_at[k];
+      auto& lst = index[{(int64_t)cols.pos1[r], (int64_t)cols.pos2[r]}];
+      int64_t g = -1;
+      for (int64_t gi : lst) if (same(dup_at[groups[gi].first], r)) { g = gi; break; }
+      if (g < 0) { lst.push_back((int64_t)groups.size()); groups.push_back({k, k}); }
+      else if (dup_srp[k] > dup_srp[groups[g].best]) groups[g].best = k;
+    }
+    const bool separate = (&df_at != &S.row);
+    for (const Grp& g : groups) {
+      S.row.push_back(dup_row[g.best]); S.clust_c.push_back(dup_c[g.best]); S.srp.push_back(dup_srp[g.best]);
+      if (separate) df_at.push_back(dup_at[g.best]);
+    }
+  }
+  const int64_t ndf = (int64_t)S.row.size();
+  double min_mi = INFINITY;
+  for (int64_t i = 0; i < ndf; i++)
+    if (S.srp[i] > srp_cutoff) { S.red.push_back(i); min_mi = std::min(min_mi, cols.MI[df_at[i]]); }
+  for (int64_t i = 0; i < ndf; i++)
+    if (cols.MI[df_at[i]] >= min_mi) S.chk.push_back(i);
+}
+
+void publish(SrPostPriv& S, int32_t nclust, ldw_sr_post* out) {
+  out->n_df = (int64_t)S.row.size();
+  out->clust_c = S.clust_c.data(); out->row = S.row.data(); out->srp_max = S.srp.data();
+  out->n_red = (int64_t)S.red.size(); out->red = S.red.data();
+  out->n_chk = (int64_t)S.chk.size(); out->chk = S.chk.data();
+  out->nclust = nclust;
+  out->fit_off = S.fit_off.data(); out->fit_len = S.fit_len.data(); out->fit_q95 = S.fit_q95.data(); out->fit_val = S.fit_val.data();
+  out->coef = S.coef.data(); out->shape = S.shape.data(); out->start = S.start.data();
+  out->n_pos = S.n_pos.data(); out->nm_evals = S.nm_evals.data(); out->nm_fail = S.nm_fail.data();
+}
+
+}  // namespace ldwpost
 
 extern "C" void ldw_sr_post_free(ldw_sr_post* p) {
   if (!p) return;
@@ -470,29 +563,7 @@ extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr
     tm.lap("group + quantiles", 0);
   }
   // ---- fastLm(cbind(log(len), 1), log(max)); fit = exp(fitted)  (:428-429), per cluster ----
-  {
-    size_t t = 0;
-    for (int32_t c = 1; c <= nclust; c++) {
-      std::vector<double> lx, ly;
-      const size_t base = S->fit_len.size();
-      for (; t < glist.size() && glist[t] < (int64_t)c * nl; t++) {
-        const int32_t l = (int32_t)(glist[t] - (int64_t)(c - 1) * nl);
-        S->fit_len.push_back(l);
-        S->fit_q95.push_back(gq[t]);
-        lx.push_back(log((double)l));
-        ly.push_back(log(gq[t]));
-      }
-      const int64_t ng = (int64_t)lx.size();
-      if (ng < 2) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d has fewer than two distinct link lengths", (int)c);
-      double coef[2];
-      ols2(lx, ly, coef);
-      S->fit_val.resize(base + ng);
-      for (int64_t gi = 0; gi < ng; gi++) S->fit_val[base + gi] = exp(lx[gi] * coef[0] + coef[1]);
-      S->fit_off.push_back((int64_t)(base + ng));
-      S->coef.push_back(coef[0]);
-      S->coef.push_back(coef[1]);
-    }
-  }
+  if (int rc = ldwpost::decay_fits(*S, nclust, nl, glist, gq)) return rc;
   tm.lap("decay fits", 0);
 
   // ---- residuals above the fit (:448-450).  `mean_dist[sr_links_t$len]` subscripts the fitted values with the VALUE of
@@ -567,18 +638,8 @@ extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr
     for (double v : cvar) ss += v;
     const double var_unbiased = (double)(ss / (long double)(npos - 1));
     const double v = (double)(npos - 1) / (double)npos * var_unbiased;
-    const double aux = mean * (1 - mean) / v - 1;
-    const double start[2] = {mean * aux, (1 - mean) * aux};
-    BetaNll nll{(double)npos, (double)s1, (double)s2};
-    double par[2], fmin;
-    int evals = 0;
-    const int fail = nmmin2(nll, start, par, &fmin, &evals);
-    if (fail < 0) return ldw::set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d: the beta likelihood cannot be evaluated at the initial parameters (%g, %g)", (int)c, start[0], start[1]);
-    S->shape.push_back(par[0]); S->shape.push_back(par[1]);
-    S->start.push_back(start[0]); S->start.push_back(start[1]);
-    S->n_pos.push_back(npos);
-    S->nm_evals.push_back(evals);
-    S->nm_fail.push_back(fail);
+    double par[2];
+    if (int rc = ldwpost::beta_fit(*S, c, npos, (double)s1, (double)s2, mean, v, par)) return rc;
     tm.lap("beta fit", c);
     // ---- srp = -pbeta(x, shape1, shape2, lower.tail = F, log.p = T)  (:453) ----
     int sg;
@@ -601,46 +662,11 @@ extern "C" int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr
     std::vector<double>().swap(px[c]);
   }
   tm.lap("(last cluster's append)", nclust);
-  // ---- links seen from two clusters: one row per distinct link, the one with the larger srp_max; groups in order of first
-  //      appearance, first maximum wins (:474-483, data.table `.I[which.max(srp_max)], by = keys`) ----
-  if (!dup_row.empty()) {
-    struct Grp { int64_t first, best; };
-    std::unordered_map<std::pair<int64_t, int64_t>, std::vector<int64_t>, KeyHash> index;  // (pos1, pos2) -> groups
-    index.reserve(dup_row.size());
-    std::vector<Grp> groups;
-    groups.reserve(dup_row.size());
-    auto same = [&](int64_t a, int64_t b) {
-      return sr->pos1[a] == sr->pos1[b] && sr->pos2[a] == sr->pos2[b] && sr->clust1[a] == sr->clust1[b] &&
-             sr->clust2[a] == sr->clust2[b] && sr->len[a] == sr->len[b] && sr->MI[a] == sr->MI[b];
-    };
-    for (int64_t k = 0; k < (int64_t)dup_row.size(); k++) {
-      const int64_t r = dup_row[k];
-      auto& lst = index[{(int64_t)sr->pos1[r], (int64_t)sr->pos2[r]}];
-      int64_t g = -1;
-      for (int64_t gi : lst) if (same(dup_row[groups[gi].first], r)) { g = gi; break; }
-      if (g < 0) { lst.push_back((int64_t)groups.size()); groups.push_back({k, k}); }
-      else if (dup_srp[k] > dup_srp[groups[g].best]) groups[g].best = k;
-    }
-    for (const Grp& g : groups) { S->row.push_back(dup_row[g.best]); S->clust_c.push_back(dup_c[g.best]); S->srp.push_back(dup_srp[g.best]); }
-  }
-
-  // ---- sr_links_red = srp_max > srp_cutoff; sr_links_ARACNE_check = MI >= min(sr_links_red$MI)  (:494-495) ----
-  const int64_t ndf = (int64_t)S->row.size();
-  double min_mi = INFINITY;
-  for (int64_t i = 0; i < ndf; i++)
-    if (S->srp[i] > srp_cutoff) { S->red.push_back(i); min_mi = std::min(min_mi, sr->MI[S->row[i]]); }
-  for (int64_t i = 0; i < ndf; i++)
-    if (sr->MI[S->row[i]] >= min_mi) S->chk.push_back(i);
+  ldwpost::LinkCols cols{sr->pos1, sr->pos2, sr->clust1, sr->clust2, sr->len, sr->MI};
+  ldwpost::dedup_and_select(*S, cols, dup_row, dup_row, dup_c, dup_srp, S->row, srp_cutoff);
 
   tm.lap("dedup + red/chk", 0);
-  out->n_df = ndf;
-  out->clust_c = S->clust_c.data(); out->row = S->row.data(); out->srp_max = S->srp.data();
-  out->n_red = (int64_t)S->red.size(); out->red = S->red.data();
-  out->n_chk = (int64_t)S->chk.size(); out->chk = S->chk.data();
-  out->nclust = nclust;
-  out->fit_off = S->fit_off.data(); out->fit_len = S->fit_len.data(); out->fit_q95 = S->fit_q95.data(); out->fit_val = S->fit_val.data();
-  out->coef = S->coef.data(); out->shape = S->shape.data(); out->start = S->start.data();
-  out->n_pos = S->n_pos.data(); out->nm_evals = S->nm_evals.data(); out->nm_fail = S->nm_fail.data();
+  ldwpost::publish(*S, nclust, out);
   out->priv = S.release();
   return 0;
   });
