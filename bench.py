@@ -461,22 +461,27 @@ def main():
                 # wall time "to sr/lr links" through the public API (the metric's second half): hdw + perform_MI_computation with both TSVs
                 snp = ldw.snp_dat_from_codes(codes_pin, POS, g)
                 with tempfile.TemporaryDirectory() as d:
-                    for it in range(2):  # second call reported (the first allocates pinned buffers)
-                        for f in ("lr_links.tsv", "sr_links.tsv"):
-                            if os.path.exists(os.path.join(d, f)):
-                                os.unlink(os.path.join(d, f))
-                        t0 = time.perf_counter()
-                        h2 = ldw.estimate_Hamming_distance_weights(snp, 0.1, device=local_rank)
-                        t1 = time.perf_counter()
-                        res = ldw.perform_MI_computation(snp, h2, ldw.CdsVar(paint, 3), ncores=1, lr_save_path=os.path.join(d, "lr_links.tsv"),
-                                                         sr_save_path=os.path.join(d, "sr_links.tsv"), plt_folder=d, sr_dist=SR_DIST, lr_retain_links=LR_RETAIN,
-                                                         max_blk_sz=MAX_BLK, srp_cutoff=3, runARACNE=True, lr_links_approx=lra, device=local_rank, exact_sr="in_scan")
-                        t2 = time.perf_counter()
-                    extra["wall_to_links_s"] = t2 - t0
-                    extra["wall_to_links"] = {"hdw_s": t1 - t0, "perform_MI_computation_s": t2 - t1, "n_sr_links": int(len(res.sr["MI"])), "n_lr_links": int(len(res.lr["MI"])),
-                                              "n_sr_links_red": int(len(res.sr_links_red["row"])), "phases_s": res.stats.get("phases"), "exact_sr": "in_scan (fp64 MI of every short-range link, LDW_SCAN_SR_EXACT)",
-                                              "includes": "hdw + upload/packing + scan + D2H of all links + NumPy copies + lr_links.tsv + mergeNsort_sr_links + runARACNE + ordering + sr_links.tsv",
-                                              "host_threads": ncpu}
+                    for variant, kw in (("host_post", dict(exact_sr="in_scan")), ("device_post", dict(device_post=True))):
+                        for it in range(2):  # second call reported (the first allocates pinned buffers)
+                            for f in ("lr_links.tsv", "sr_links.tsv"):
+                                if os.path.exists(os.path.join(d, f)):
+                                    os.unlink(os.path.join(d, f))
+                            t0 = time.perf_counter()
+                            h2 = ldw.estimate_Hamming_distance_weights(snp, 0.1, device=local_rank)
+                            t1 = time.perf_counter()
+                            res = ldw.perform_MI_computation(snp, h2, ldw.CdsVar(paint, 3), ncores=1, lr_save_path=os.path.join(d, "lr_links.tsv"),
+                                                             sr_save_path=os.path.join(d, "sr_links.tsv"), plt_folder=d, sr_dist=SR_DIST, lr_retain_links=LR_RETAIN,
+                                                             max_blk_sz=MAX_BLK, srp_cutoff=3, runARACNE=True, lr_links_approx=lra, device=local_rank, **kw)
+                            t2 = time.perf_counter()
+                        extra["wall_to_links_" + variant] = {
+                            "total_s": t2 - t0, "hdw_s": t1 - t0, "perform_MI_computation_s": t2 - t1, "n_sr_links": int(res.stats["n_sr"]),
+                            "n_lr_links": int(len(res.lr["MI"])), "n_sr_links_red": int(len(res.sr_links_red["row"])), "phases_s": res.stats.get("phases"),
+                            "short_range_MI": "fp64, recomputed inside the scan (LDW_SCAN_SR_EXACT)",
+                            "includes": "hdw + upload/packing + scan + lr_links.tsv + mergeNsort_sr_links + runARACNE + ordering + sr_links.tsv"
+                                        + (" + D2H of the whole short-range table and its NumPy copies; mergeNsort_sr_links on host threads" if variant == "host_post"
+                                           else "; short-range table kept in device memory, mergeNsort_sr_links on the device (ldw_sr_postprocess_dev)"),
+                            "host_threads": ncpu}
+                    extra["wall_to_links_s"] = extra["wall_to_links_device_post"]["total_s"]
                     del res
         except Exception as ex:  # noqa: BLE001
             extra["error"] = repr(ex)

@@ -56,6 +56,10 @@ enum {
   LDW_SCAN_SR_EXACT = 16, /* recompute the MI of every short-range link in fp64 (the reference's arithmetic) on the device,
                              block by block, before the rows are copied out (mi_sr_exact_kernel; also valid with
                              LDW_SCAN_SR_ONLY).  Parity-checked on the fixture in both modes (1e-12) */
+  LDW_SCAN_SR_ON_DEVICE = 64, /* the short-range rows are materialised in device memory and STAY there (sr_out comes back with n rows
+                             and NULL columns); long-range and borderline rows are copied as usual.  For ldw_sr_postprocess_dev,
+                             which derives sr_links_red / the ARACNE check set from the device-resident table, so that the
+                             2.9 GB (616 x 100k) of short-range columns never cross PCIe */
   LDW_SCAN_LR_ONLY = 32   /* no short-range link table (sr_out->n = 0): only the long-range rows, thresholds and statistics.
                              For inputs whose short-range table would not fit host memory (2000 x 500k SNPs in a 2.2 Mb
                              genome: 2.3e9 short-range links = 72 GB of columns) and for callers that only feed the
@@ -255,6 +259,17 @@ typedef struct ldw_sr_post {
 } ldw_sr_post;
 LDW_API int ldw_sr_postprocess(const ldw_links* sr, int32_t nclust, double sr_dist, double srp_cutoff, ldw_sr_post* out);
 LDW_API void ldw_sr_post_free(ldw_sr_post* p);
+
+/* ldw_sr_postprocess_dev: the same mergeNsort_sr_links, computed from the short-range table the last ldw_mi_scan on `ctx`
+ *   left in DEVICE memory (whole job on this device: n_parts = 1; any flags but LDW_SCAN_NO_LINKS / LDW_SCAN_LR_ONLY; with
+ *   LDW_SCAN_SR_ON_DEVICE the table never crosses PCIe).  Every pass over the links is a device kernel (group histogram,
+ *   per-group order statistics, residual flags and sufficient statistics, srp_max); the decay fits, the beta fit and the
+ *   cross-cluster de-duplication are the host code ldw_sr_postprocess uses.  Percentiles, fits and row sets are identical to
+ *   ldw_sr_postprocess on the same table; the beta start values / shapes and srp_max agree to ~1e-12 relative (the sums are
+ *   formed in another order).  `out->row` indexes the device table (= the rows ldw_mi_scan would have returned);
+ *   *df_rows_out receives the link columns of the out->n_df rows of sr_links_df (owned by `out`, released by ldw_sr_post_free),
+ *   which is all that sr_links_red / sr_links_ARACNE_check / sr_links.tsv need. */
+LDW_API int ldw_sr_postprocess_dev(ldw_ctx* ctx, int32_t nclust, double sr_dist, double srp_cutoff, ldw_sr_post* out, ldw_links* df_rows_out);
 
 /* Building blocks of ldw_sr_postprocess, exposed for parity tests: stats::optim's Nelder-Mead (restated from R's nmmin)
  * run on Rosenbrock's function, the example of R's ?optim -- from c(-1.2, 1) R prints par 1.000260 1.000506, value

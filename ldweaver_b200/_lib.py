@@ -131,6 +131,7 @@ def lib():
     L.ldw_write_lr_tsv.argtypes = [C.c_char_p, P(Links), C.c_int]
     L.ldw_format_r_real.argtypes = [f64, C.c_char_p, C.c_int]
     L.ldw_sr_postprocess.argtypes = [P(Links), C.c_int32, f64, f64, P(SrPost)]
+    L.ldw_sr_postprocess_dev.argtypes = [C.c_void_p, C.c_int32, f64, f64, P(SrPost), P(Links)]
     L.ldw_sr_post_free.argtypes = [P(SrPost)]
     L.ldw_sr_post_free.restype = None
     L.ldw_run_aracne.argtypes = [i64, C.c_void_p, C.c_void_p, C.c_void_p, i64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

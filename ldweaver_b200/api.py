@@ -220,7 +220,7 @@ def estimate_Hamming_distance_weights(snp_dat: SnpDat, threshold: float = 0.1, m
 # --------------------------------------------------------------------------------------------------
 # perform_MI_computation (scan + sr/lr link filter)
 # --------------------------------------------------------------------------------------------------
-SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS, SCAN_NO_D2H, SCAN_SR_EXACT, SCAN_LR_ONLY = 1, 2, 4, 8, 16, 32
+SCAN_SR_ONLY, SCAN_IDEAL_Q, SCAN_NO_LINKS, SCAN_NO_D2H, SCAN_SR_EXACT, SCAN_LR_ONLY, SCAN_SR_ON_DEVICE = 1, 2, 4, 8, 16, 32, 64
 
 
 @dataclass
@@ -564,6 +564,34 @@ class SrLinks:
     borderline_chk: Optional[np.ndarray] = None   # df rows whose MI lies within 1e-12 of min(sr_links_red$MI)
 
 
+def _unpack_sr_post(out, nclust: int, cols: dict, row_is_position: bool, plt_path: Optional[str], srp_cutoff: float) -> SrLinks:
+    """ldw_sr_post -> SrLinks.  ``cols``: link columns; addressed by ``out.row`` (host path: the full table) or by the position
+    of the df row itself (device path: the gathered df rows)."""
+    cp = _lib.copy_array
+    row = cp(out.row, out.n_df, np.int64)
+    df = {"clust_c": cp(out.clust_c, out.n_df, np.int32), "row": row, "srp_max": cp(out.srp_max, out.n_df, np.float64)}
+    for k in ("pos1", "pos2", "clust1", "clust2", "len", "MI"):
+        df[k] = np.array(cols[k], copy=True) if row_is_position else np.asarray(cols[k])[row]
+    off = cp(out.fit_off, nclust + 1, np.int64)
+    nfit = int(off[-1])
+    fl, fq, fv = cp(out.fit_len, nfit, np.int32), cp(out.fit_q95, nfit, np.float64), cp(out.fit_val, nfit, np.float64)
+    coef, shape, start = (cp(x, 2 * nclust, np.float64).reshape(nclust, 2) for x in (out.coef, out.shape, out.start))
+    npos, ev, fail = cp(out.n_pos, nclust, np.int64), cp(out.nm_evals, nclust, np.int32), cp(out.nm_fail, nclust, np.int32)
+    fits = [dict(len=fl[off[c]:off[c + 1]], max=fq[off[c]:off[c + 1]], fit=fv[off[c]:off[c + 1]], coef=coef[c],
+                 shape=shape[c], start=start[c], n_pos=int(npos[c]), nm_evals=int(ev[c]), nm_fail=int(fail[c]))
+            for c in range(nclust)]
+    if plt_path is not None:  # stand-in for c<i>_fit_data.rds (:437): the maxvls table of each cluster as text
+        os.makedirs(plt_path, exist_ok=True)
+        for c, f in enumerate(fits, start=1):
+            with open(os.path.join(plt_path, f"c{c}_fit_data.tsv"), "w") as fh:
+                fh.write("len\tmax\tfit\n")
+                fh.writelines(f"{int(a)}\t{b:.15g}\t{v:.15g}\n" for a, b, v in zip(f["len"], f["max"], f["fit"]))
+    red, chk = cp(out.red, out.n_red, np.int64), cp(out.chk, out.n_chk, np.int64)
+    b_red = np.nonzero(np.abs(df["srp_max"] - srp_cutoff) <= 1e-9 * max(abs(float(srp_cutoff)), 1.0))[0]
+    b_chk = np.nonzero(np.abs(df["MI"] - df["MI"][red].min()) <= 1e-12)[0] if len(red) else np.zeros(0, np.int64)
+    return SrLinks(df=df, red=red, chk=chk, fits=fits, borderline_red=b_red, borderline_chk=b_chk)
+
+
 def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[str] = None, srp_cutoff: float = 3) -> SrLinks:
     """R/computePairwiseMI.R:400-495 through ``ldw_sr_postprocess`` (native host code).  ``sr_links`` is the scan's
     short-range table (dict of columns, all clusters together -- the per-cluster lists of the reference are the rows
@@ -575,30 +603,22 @@ def mergeNsort_sr_links(cds_var, sr_links, sr_dist: float, plt_path: Optional[st
     out = _lib.SrPost()
     check(_lib.lib().ldw_sr_postprocess(C.byref(links), nclust, float(sr_dist), float(srp_cutoff), C.byref(out)))
     try:
-        cp = _lib.copy_array
-        row = cp(out.row, out.n_df, np.int64)
-        df = {"clust_c": cp(out.clust_c, out.n_df, np.int32), "row": row, "srp_max": cp(out.srp_max, out.n_df, np.float64)}
-        cols = links.views()
-        for k in ("pos1", "pos2", "clust1", "clust2", "len", "MI"):
-            df[k] = np.asarray(cols[k])[row]
-        off = cp(out.fit_off, nclust + 1, np.int64)
-        nfit = int(off[-1])
-        fl, fq, fv = cp(out.fit_len, nfit, np.int32), cp(out.fit_q95, nfit, np.float64), cp(out.fit_val, nfit, np.float64)
-        coef, shape, start = (cp(x, 2 * nclust, np.float64).reshape(nclust, 2) for x in (out.coef, out.shape, out.start))
-        npos, ev, fail = cp(out.n_pos, nclust, np.int64), cp(out.nm_evals, nclust, np.int32), cp(out.nm_fail, nclust, np.int32)
-        fits = [dict(len=fl[off[c]:off[c + 1]], max=fq[off[c]:off[c + 1]], fit=fv[off[c]:off[c + 1]], coef=coef[c],
-                     shape=shape[c], start=start[c], n_pos=int(npos[c]), nm_evals=int(ev[c]), nm_fail=int(fail[c]))
-                for c in range(nclust)]
-        if plt_path is not None:  # stand-in for c<i>_fit_data.rds (:437): the maxvls table of each cluster as text
-            os.makedirs(plt_path, exist_ok=True)
-            for c, f in enumerate(fits, start=1):
-                with open(os.path.join(plt_path, f"c{c}_fit_data.tsv"), "w") as fh:
-                    fh.write("len\tmax\tfit\n")
-                    fh.writelines(f"{int(a)}\t{b:.15g}\t{v:.15g}\n" for a, b, v in zip(f["len"], f["max"], f["fit"]))
-        red, chk = cp(out.red, out.n_red, np.int64), cp(out.chk, out.n_chk, np.int64)
-        b_red = np.nonzero(np.abs(df["srp_max"] - srp_cutoff) <= 1e-9 * max(abs(float(srp_cutoff)), 1.0))[0]
-        b_chk = np.nonzero(np.abs(df["MI"] - df["MI"][red].min()) <= 1e-12)[0] if len(red) else np.zeros(0, np.int64)
-        return SrLinks(df=df, red=red, chk=chk, fits=fits, borderline_red=b_red, borderline_chk=b_chk)
+        return _unpack_sr_post(out, nclust, links.views(), False, plt_path, srp_cutoff)
+    finally:
+        _lib.lib().ldw_sr_post_free(C.byref(out))
+
+
+def mergeNsort_sr_links_device(cds_var, sr_dist: float, plt_path: Optional[str] = None, srp_cutoff: float = 3, device: int = 0) -> SrLinks:
+    """The same, computed on the device from the short-range table the last whole-job scan on ``device`` left in HBM
+    (``ldw_sr_postprocess_dev``): the table itself never crosses PCIe -- only the rows of sr_links_df do.  ``df["row"]`` indexes
+    that table (the rows a scan without ``SCAN_SR_ON_DEVICE`` would have returned)."""
+    nclust = int(cds_var.nclust if hasattr(cds_var, "nclust") else cds_var["nclust"])
+    ctx = _lib.default_context(device)
+    out, rows = _lib.SrPost(), _lib.Links()
+    check(_lib.lib().ldw_sr_postprocess_dev(ctx.handle, nclust, float(sr_dist), float(srp_cutoff), C.byref(out), C.byref(rows)))
+    try:
+        return _unpack_sr_post(out, nclust, rows.views() if int(rows.n) else {k: np.zeros(0) for k in ("pos1", "pos2", "clust1", "clust2", "len", "MI")},
+                               True, plt_path, srp_cutoff)
     finally:
         _lib.lib().ldw_sr_post_free(C.byref(out))
 
@@ -697,12 +717,14 @@ def analyse_long_range_links(lr_links: dict, sr_links: dict, are_lrlinks_ordered
     return out
 
 
-def finish_sr_links(sr: dict, cds_var, sr_dist: float, srp_cutoff: float = 3, run_aracne: bool = True,
-                    order_links: bool = True, sr_save_path: Optional[str] = None, plt_folder: Optional[str] = None):
+def finish_sr_links(sr: Optional[dict], cds_var, sr_dist: float, srp_cutoff: float = 3, run_aracne: bool = True,
+                    order_links: bool = True, sr_save_path: Optional[str] = None, plt_folder: Optional[str] = None,
+                    post: Optional[SrLinks] = None):
     """Lines 118-143 of R/computePairwiseMI.R: mergeNsort_sr_links, ARACNE on sr_links_red against
     sr_links_ARACNE_check, the optional ordering by srp_max (stable, decreasing) and the append to sr_links.tsv.
     Returns (sr_links_red as a dict of columns incl. ``ARACNE``, the SrLinks it came from)."""
-    post = mergeNsort_sr_links(cds_var, sr, sr_dist, plt_folder, srp_cutoff)
+    if post is None:
+        post = mergeNsort_sr_links(cds_var, sr, sr_dist, plt_folder, srp_cutoff)
     red = {k: v[post.red] for k, v in post.df.items()}
     if run_aracne:
         chk = {k: post.df[k][post.chk] for k in ("pos1", "pos2", "MI")}
@@ -714,8 +736,8 @@ def finish_sr_links(sr: dict, cds_var, sr_dist: float, srp_cutoff: float = 3, ru
     if order_links:
         o = np.argsort(-red["srp_max"], kind="stable")  # :134 order(decreasing = T): ties keep their order
         red = {k: v[o] for k, v in red.items()}
-    if sr_save_path is not None:
-        write_sr_tsv(sr_save_path, sr, red["row"], red["clust_c"], red["srp_max"], red["ARACNE"], append=True)
+    if sr_save_path is not None:  # rows come from the columns of sr_links_red themselves (the full table may live on the device only)
+        write_sr_tsv(sr_save_path, red, np.arange(len(red["row"]), dtype=np.int64), red["clust_c"], red["srp_max"], red["ARACNE"], append=True)
     return red, post
 
 
@@ -726,7 +748,8 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
                            mega_dset: bool = False, lr_links_approx: Optional[float] = None, device: int = 0,
                            write_tsv: bool = True, plan: Optional[MIPlan] = None,
                            postprocess: Optional[bool] = None, exact_sr: Optional[bool] = None,
-                           devices: Optional[Sequence[int]] = None, scan_flags: int = 0) -> MIScanResult:
+                           devices: Optional[Sequence[int]] = None, scan_flags: int = 0,
+                           device_post: bool = False) -> MIScanResult:
     """R/computePairwiseMI.R:46-145.  Same arguments as the reference (``ncores`` is accepted and ignored by the GPU
     path; ``plt_folder`` is accepted, no plots are drawn).  The scan (:46-116) runs on the device; what follows it
     (:118-143: mergeNsort_sr_links, runARACNE, ordering, sr_links.tsv) runs in native host code and fills
@@ -738,7 +761,10 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
     +0.5 s at 616 x 100k).  ``exact_sr="in_scan"`` asks the scan itself for them (``LDW_SCAN_SR_EXACT``; parity-checked
     on the fixture, not yet timed at full size, hence the default only for perform_SR_analysis_only scans, which
     ``MIPlan.sr_exact`` cannot serve).  ``scan_flags``: extra LDW_SCAN_* bits, e.g. ``SCAN_LR_ONLY`` for inputs whose
-    short-range table would not fit host memory; ``devices`` (or ``LDW_GPUS``): run on a device group."""
+    short-range table would not fit host memory; ``devices`` (or ``LDW_GPUS``): run on a device group.
+    ``device_post=True`` (single device): the short-range table stays in device memory (``SCAN_SR_ON_DEVICE``, fp64 MI from
+    inside the scan) and mergeNsort_sr_links runs there (``ldw_sr_postprocess_dev``); the result's ``sr`` is then empty --
+    the reference's function does not return that table either -- and only sr_links_red / its ARACNE check set come to the host."""
     if snp_dat.g is None:
         raise ValueError("snp.dat$g is NULL: set the genome length first (R/BacGWES.R:338-345)")
     paint = np.asarray(cds_var.paint if hasattr(cds_var, "paint") else cds_var["paint"])
@@ -785,6 +811,10 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         flags = (SCAN_SR_ONLY if perform_SR_analysis_only else 0) | int(scan_flags)
         if exact_sr is None:  # SR-only scans index reduced SNP lists (Q12): only the in-scan kernel can refine them
             exact_sr = ("in_scan" if perform_SR_analysis_only else True) if do_post else False
+        if device_post and do_post:
+            flags |= SCAN_SR_ON_DEVICE
+            if exact_sr:
+                exact_sr = "in_scan"
         if exact_sr == "in_scan":   # LDW_SCAN_SR_EXACT: the same values from inside the scan call
             flags |= SCAN_SR_EXACT
             exact_sr = False
@@ -804,12 +834,17 @@ def perform_MI_computation(snp_dat: SnpDat, hdw: np.ndarray, cds_var, ncores: in
         if own:
             plan.close()
     stats["phases"] = t_phase
+    post = None
+    if device_post and do_post:
+        _t0 = _time.perf_counter()
+        post = mergeNsort_sr_links_device(cds_var, sr_dist, plt_folder, srp_cutoff, device)
+        t_phase["sr_post_device_s"] = _time.perf_counter() - _t0
     return _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff,
-                                  runARACNE, order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder)
+                                  runARACNE, order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder, post)
 
 
 def _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx, cds_var, sr_dist, srp_cutoff, run_aracne,
-                           order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder) -> MIScanResult:
+                           order_links, write_tsv, do_post, lr_save_path, sr_save_path, plt_folder, post=None) -> MIScanResult:
     """What follows the scan in perform_MI_computation (R/computePairwiseMI.R:118-143), for one device or a group."""
     import time as _time
     ph = stats.setdefault("phases", {})
@@ -824,6 +859,6 @@ def _finish_mi_computation(sr, lr, bd, thr, prob, stats, nclust, lr_links_approx
         if write_tsv and sr_save_path is None:
             sr_save_path = os.path.join(os.getcwd(), "sr_links.tsv")  # :62
         res.sr_links_red, res.sr_post = finish_sr_links(sr, cds_var, sr_dist, srp_cutoff, run_aracne, order_links,
-                                                        sr_save_path if write_tsv else None, plt_folder)
+                                                        sr_save_path if write_tsv else None, plt_folder, post)
     ph["finish_sr_links_s"] = _time.perf_counter() - _t0
     return res

@@ -168,16 +168,18 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const uint8_t* codes_dev, c
   }
   P->neff = neff;
   {
-    // count unit of the epilogue: t = (H << sa) + (L >> sb).  H < 16384 * S; one spare bit so that t + (pseudocounts)
-    // stays below 2^32 (the pseudocount of a whole table, r r' / 2 <= 12.5, is below the total weight whenever
-    // neff >= 12.5; the spare bit covers that and validate below covers the rest)
-    uint64_t hmax = 2 * 16383ull * (uint64_t)S;
+    // count unit of the epilogue: t = (H << sa) + (L >> sb), sa + sb = 14, i.e. 2^sb weight units.  t must hold the total
+    // of a joint table, (neff + r r' / 2) * scale <= (neff + 12.5) * 2^28 / max(w) weight units, in 32 bits -- sized from
+    // the ACTUAL total weight, not from the worst case nseq * max(w): a population of a few large clusters (neff of a
+    // handful at thousands of sequences) would otherwise lose 8-10 low bits of every cell to the floor below, which showed
+    // as 1.1e-6 on MI with one clonal cluster of 5000 (tests/test_gpu_mi.py).
+    const double total = (neff + 12.5) * 268435456.0 / wmax;
     int bits = 0;
-    while ((hmax >> bits) != 0) bits++;
-    int sa_ = std::min(14, 32 - bits);
-    if (sa_ < 0) sa_ = 0;
-    P->sa = (uint32_t)sa_;
-    P->sb = (uint32_t)(14 - sa_);
+    while (std::ldexp(1.0, bits) <= total) bits++;
+    int sb_ = std::max(0, bits - 32);
+    if (sb_ > 14) sb_ = 14;
+    P->sb = (uint32_t)sb_;
+    P->sa = (uint32_t)(14 - sb_);
   }
   // weights are W_s = round(w_s * scale) <= 2^28 - 1, with the scale chosen such that the pseudocount 0.5 is an
   // integer number M of count units (2^sb weight units each): scale = M * 2^(sb+1)
@@ -1055,12 +1057,14 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
   cudaStream_t sst = P->ctx->select_stream;
 
   const bool want_host = !(flags & (LDW_SCAN_NO_LINKS | LDW_SCAN_NO_D2H));
+  const bool sr_to_host = want_host && !(flags & LDW_SCAN_SR_ON_DEVICE);  // short-range rows cross PCIe at all?
+  P->ctx->dev_sr.n = -1;
   cudaStream_t cst = P->ctx->copy_stream;
   cudaEvent_t ev_blk = nullptr;  // "this block's SR columns are materialised"
   // short-range rows go to this context's pinned table, or -- multi-GPU -- straight to the group's table, every rank
   // at the final offsets of its blocks (the table is complete when the last rank finishes: no merge pass)
   HostLinks& hsr = shared ? *shared->h_sr : P->ctx->h_sr;
-  if (want_host) {
+  if (sr_to_host) {
     if (!shared && sr_rows) LDW_TRY(hsr.ensure(total_sr));
     LDW_CUDA(cudaEventCreateWithFlags(&ev_blk, cudaEventDisableTiming));
   }
@@ -1238,7 +1242,7 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
         mi_sr_exact_kernel<<<H.nt, 32 * REFINE_WARPS, 0, st>>>(m, make_refine_params(P, D, H, cfg));
         LDW_CUDA(cudaGetLastError());
       }
-      if (want_host) {  // (sr_rows holds here)
+      if (sr_to_host) {  // (sr_rows holds here)
         // copy this block's finished rows to the host while the next blocks are being scanned
         LDW_CUDA(cudaEventRecord(ev_blk, st));
         LDW_CUDA(cudaStreamWaitEvent(cst, ev_blk, 0));
@@ -1364,13 +1368,13 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       LDW_CUDA(cudaMemcpyAsync(h.mi.p, d.mi.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
       return 0;
     };
-    if (!shared) P->ctx->h_sr.n = sr_rows ? total_sr : 0;  // short-range rows were streamed out block by block on the copy stream
+    if (!shared) P->ctx->h_sr.n = (sr_rows && sr_to_host) ? total_sr : 0;  // short-range rows were streamed out block by block on the copy stream
     LDW_TRY(d2h(P->ctx->h_lr, W->d_lr, (int64_t)n_kept));
   }
   LDW_CUDA(cudaEventRecord(ev3, st));
   LDW_CUDA(cudaStreamSynchronize(st));
   lap("lr d2h");
-  if (want_host) LDW_CUDA(cudaStreamSynchronize(cst));
+  if (sr_to_host) LDW_CUDA(cudaStreamSynchronize(cst));
   lap("copy stream drain");
   if (ev_blk) cudaEventDestroy(ev_blk);
 
@@ -1403,9 +1407,17 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
     if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = total_sr; }
     if (lr_out) { memset(lr_out, 0, sizeof(*lr_out)); lr_out->n = (int64_t)n_kept; }
   } else {
-    if (shared) { if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = sr_rows ? total_sr : 0; } }
+    if (shared || !sr_to_host) { if (sr_out) { memset(sr_out, 0, sizeof(*sr_out)); sr_out->n = sr_rows ? total_sr : 0; } }
     else P->ctx->h_sr.fill(sr_out);
+
     P->ctx->h_lr.fill(lr_out);
+  }
+  if (sr_rows && n_parts == 1) {  // the whole job's table is in this context's device memory, in reference order
+    ldw_ctx::DevSr& d = P->ctx->dev_sr;
+    d.pos1 = W->d_sr.pos1.as<int32_t>(); d.pos2 = W->d_sr.pos2.as<int32_t>(); d.c1 = W->d_sr.c1.as<int32_t>();
+    d.c2 = W->d_sr.c2.as<int32_t>(); d.len = W->d_sr.len.as<int32_t>(); d.blk = W->d_sr.blk.as<int32_t>();
+    d.mi = W->d_sr.mi.as<double>();
+    d.n = total_sr;
   }
   for (size_t b = 0; b < blocks.size(); b++) {
     if (sel[b].skip || sel[b].n_lr == 0 || sr_only) continue;

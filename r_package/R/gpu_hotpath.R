@@ -99,11 +99,28 @@ perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path =
       sum((0.5 * snp.dat$g - abs((x - snp.dat$POS) %% snp.dat$g - 0.5 * snp.dat$g)) > sr_dist))
     lr_links_approx <- sum(lr_link_count) / snp_subset * snp.dat$nsnp / 2
   }
+  gpus <- .ldw_gpus()
+  if (length(gpus) == 1 && isTRUE(getOption("LDWeaver.native_post", TRUE)) && isTRUE(getOption("LDWeaver.device_post", TRUE))) {
+    # default on one GPU: the short-range table (9e7 rows at 616 x 100k) stays in device memory; the scan refines its MI in
+    # fp64 and mergeNsort_sr_links runs on the device (ldw_sr_postprocess_dev) -- only the rows of sr_links_df come back
+    res <- .Call("_LDWeaver_gpu_mi_scan_post", .snpdat_codes(snp.dat), snp.dat$nsnp, snp.dat$nseq, as.numeric(hdw),
+                 as.integer(snp.dat$POS), as.integer(cds_var$paint), as.numeric(snp.dat$g), sr_dist, lr_retain_links,
+                 lr_links_approx, max_blk_sz, perform_SR_analysis_only, as.integer(cds_var$nclust), srp_cutoff, gpus,
+                 PACKAGE = "LDWeaver")
+    if (length(res$lr$MI) > 0)
+      write.table(x = as.data.frame(res$lr[1:6]), file = lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
+    post <- res$post
+    frame <- function(idx) data.frame(clust_c = post$clust_c[idx], pos1 = post$rows$pos1[idx], pos2 = post$rows$pos2[idx],
+                                      clust1 = as.numeric(post$rows$clust1[idx]), clust2 = as.numeric(post$rows$clust2[idx]),
+                                      len = post$rows$len[idx], MI = post$rows$MI[idx], srp_max = post$srp_max[idx])
+    sr_links_red <- frame(post$red)
+    sr_links_ARACNE_check <- frame(post$chk)
+  } else {
   res <- .Call("_LDWeaver_gpu_mi_scan", .snpdat_codes(snp.dat), snp.dat$nsnp, snp.dat$nseq, as.numeric(hdw),
                as.integer(snp.dat$POS), as.integer(cds_var$paint), as.numeric(snp.dat$g), sr_dist, lr_retain_links,
                lr_links_approx, max_blk_sz, perform_SR_analysis_only,
                isTRUE(getOption("LDWeaver.exact_sr", TRUE)),   # fp64 MI for the short-range links (the fp32 epilogue's 2e-7 is amplified by the beta fit below)
-               .ldw_gpus(), PACKAGE = "LDWeaver")
+               gpus, PACKAGE = "LDWeaver")
   if (length(res$lr$MI) > 0)   # same rows, same order as the per-block appends of R/computePairwiseMI.R:362
     write.table(x = as.data.frame(res$lr[1:6]), file = lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
   if (!isTRUE(getOption("LDWeaver.native_post", TRUE))) {
@@ -123,6 +140,7 @@ perform_MI_computation <- function(snp.dat, hdw, cds_var, ncores, lr_save_path =
     }
     sr_links_red <- frame(post$red)
     sr_links_ARACNE_check <- frame(post$chk)
+  }
   }
   if (runARACNE) {
     sr_links_red$ARACNE <- as.numeric(runARACNE(sr_links_red, sr_links_ARACNE_check))

@@ -226,6 +226,55 @@ SEXP LDWeaver_gpu_mi_scan(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP hdw_, SEXP p
   return out;
 }
 
+// .Call("_LDWeaver_gpu_mi_scan_post", <the 12 scan arguments up to sr_only>, nclust, srp_cutoff, gpu)
+//   -> list(lr, borderline, thr, post = list(clust_c, pos1, pos2, clust1, clust2, len, MI, srp_max, red (1-based), chk (1-based)))
+// perform_MI_computation's scan AND mergeNsort_sr_links (R/computePairwiseMI.R:69-116, 400-495) with the short-range table kept
+// in device memory: fp64 short-range MI inside the scan (LDW_SCAN_SR_EXACT), LDW_SCAN_SR_ON_DEVICE, ldw_sr_postprocess_dev.
+// Only the rows of sr_links_df (a few per cent of the table) cross PCIe.  One device (the first of `gpus`).
+SEXP LDWeaver_gpu_mi_scan_post(SEXP codes_, SEXP nsnp_, SEXP nseq_, SEXP hdw_, SEXP pos_, SEXP paint_, SEXP g_, SEXP srd_, SEXP retain_,
+                               SEXP approx_, SEXP blk_, SEXP sronly_, SEXP nclust_, SEXP cut_, SEXP gpus_) {
+  int64_t n = (int64_t)Rf_asReal(nsnp_), S = (int64_t)Rf_asReal(nseq_), blk = (int64_t)Rf_asReal(blk_);
+  if (blk < 1) Rf_error("max_blk_sz must be positive");
+  int64_t nr = (n + blk - 1) / blk, nblk = nr * (nr + 1) / 2;
+  const int flags = (Rf_asLogical(sronly_) ? LDW_SCAN_SR_ONLY : 0) | LDW_SCAN_SR_EXACT | LDW_SCAN_SR_ON_DEVICE;
+  ldw_ctx* c = ctx_for(first_gpu(gpus_));
+  ldw_links sr, lr, bd, rows;
+  memset(&sr, 0, sizeof(sr)); memset(&lr, 0, sizeof(lr)); memset(&bd, 0, sizeof(bd)); memset(&rows, 0, sizeof(rows));
+  ldw_sr_post post;
+  memset(&post, 0, sizeof(post));
+  ldw_scan_stats st;
+  SEXP thr = PROTECT(Rf_allocVector(REALSXP, nblk));
+  ldw_mi_plan* plan = nullptr;
+  int rc = ldw_mi_plan_create(c, RAW(codes_), n, S, REAL(hdw_), INTEGER(pos_), INTEGER(paint_), blk, &plan);
+  if (rc == 0)
+    rc = ldw_mi_scan(plan, Rf_asReal(g_), Rf_asReal(srd_), Rf_asReal(retain_), Rf_asReal(approx_), flags, 1, 0, &sr, &lr, &bd, REAL(thr),
+                     nullptr, &st);
+  if (rc == 0) rc = ldw_sr_postprocess_dev(c, Rf_asInteger(nclust_), Rf_asReal(srd_), Rf_asReal(cut_), &post, &rows);
+  if (plan) ldw_mi_plan_destroy(plan);
+  if (rc != 0) {
+    UNPROTECT(1);
+    Rf_error("%s", ldw_last_error());
+  }
+  SEXP v[4];
+  v[0] = PROTECT(links_to_list(&lr));
+  v[1] = PROTECT(links_to_list(&bd));
+  v[2] = thr;
+  SEXP pl = PROTECT(links_to_list(&rows));  // pos1 .. MI, block of the sr_links_df rows
+  SEXP cc = PROTECT(Rf_allocVector(INTSXP, post.n_df)), srp = PROTECT(Rf_allocVector(REALSXP, post.n_df));
+  SEXP red = PROTECT(Rf_allocVector(REALSXP, post.n_red)), chk = PROTECT(Rf_allocVector(REALSXP, post.n_chk));
+  for (int64_t i = 0; i < post.n_df; i++) { INTEGER(cc)[i] = post.clust_c[i]; REAL(srp)[i] = post.srp_max[i]; }
+  for (int64_t i = 0; i < post.n_red; i++) REAL(red)[i] = (double)(post.red[i] + 1);
+  for (int64_t i = 0; i < post.n_chk; i++) REAL(chk)[i] = (double)(post.chk[i] + 1);
+  ldw_sr_post_free(&post);  // rows' columns belonged to it: everything was copied above
+  const char* pn[] = {"rows", "clust_c", "srp_max", "red", "chk"};
+  SEXP pv[] = {pl, cc, srp, red, chk};
+  v[3] = PROTECT(named_list(5, pn, pv));
+  const char* nm[] = {"lr", "borderline", "thr", "post"};
+  SEXP out = named_list(4, nm, v);
+  UNPROTECT(9);
+  return out;
+}
+
 // .Call("_LDWeaver_ACGTN2num", nv, cv, ncores): the reference's own symbol (src/RcppExports.cpp:16; R stub `.ACGTN2num`,
 // R/RcppExports.R:4-6) with its in-place semantics (src/ACGTN2num_parallel.cpp:10-43, quirk Q11).  `ncores` is accepted
 // and ignored.  The device is the first of options(LDWeaver.gpus) / LDW_GPUS as resolved at load time (LDW_DEVICE), 0 otherwise.
@@ -287,6 +336,7 @@ static const R_CallMethodDef CallEntries[] = {
     {"_LDWeaver_gpu_encode", (DL_FUNC)&LDWeaver_gpu_encode, 5},
     {"_LDWeaver_gpu_hdw", (DL_FUNC)&LDWeaver_gpu_hdw, 5},
     {"_LDWeaver_gpu_mi_scan", (DL_FUNC)&LDWeaver_gpu_mi_scan, 14},
+    {"_LDWeaver_gpu_mi_scan_post", (DL_FUNC)&LDWeaver_gpu_mi_scan_post, 15},
     {"_LDWeaver_ACGTN2num", (DL_FUNC)&LDWeaver_ACGTN2num, 3},  // replaces the Rcpp entry of the same name (src/RcppExports.cpp:155)
     {"_LDWeaver_gpu_runARACNE", (DL_FUNC)&LDWeaver_gpu_runARACNE, 6},
     {"_LDWeaver_gpu_sr_post", (DL_FUNC)&LDWeaver_gpu_sr_post, 9},

@@ -452,3 +452,54 @@ def test_in_scan_exact_short_range_mi(fixture_snp, fixture_expected, sr_only):
                                          perform_SR_analysis_only=True, write_tsv=False, exact_sr="in_scan")
         np.testing.assert_array_equal(res.sr["pos1"], ref.sr["pos1"].astype(np.int32))
         assert np.abs(res.sr["MI"] - ref.sr["MI"]).max() < 1e-12
+
+
+def test_device_post_processing_matches_the_host_implementation(fixture_snp, fixture_expected, tmp_path):
+    """mergeNsort_sr_links on the device-resident short-range table (ldw_sr_postprocess_dev) against the native host code
+    (ldw_sr_postprocess) on the same table: same rows in the same order, same cluster attribution, per-length percentiles
+    bit for bit (order statistics), decay fits identical, beta shapes / srp_max to 1e-9 relative (sums formed in another
+    order), same sr_links_red / ARACNE check sets apart from listed borderline rows."""
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import api
+    e = fixture_expected
+    for g, sr_dist in ((50000, 20000.0), (2221315, 7000.0)):
+        snp = _snp(fixture_snp, g)
+        cds = ldw.CdsVar(e["paint"], 3)
+        plan = ldw.MIPlan(snp, e["hdw"], e["paint"], 1000)
+        sr, lr, bd, thr, prob, st = plan.scan(float(g), sr_dist, 1e4, 1e5, api.SCAN_SR_EXACT)   # rows on the host AND left on the device
+        host = api.mergeNsort_sr_links(cds, sr, sr_dist, None, 3.0)
+        dev = api.mergeNsort_sr_links_device(cds, sr_dist, None, 3.0)
+        plan.close()
+        np.testing.assert_array_equal(dev.df["row"], host.df["row"])
+        np.testing.assert_array_equal(dev.df["clust_c"], host.df["clust_c"])
+        for k in ("pos1", "pos2", "clust1", "clust2", "len", "MI"):
+            np.testing.assert_array_equal(dev.df[k], host.df[k], err_msg=k)
+        for fd, fh in zip(dev.fits, host.fits):
+            np.testing.assert_array_equal(fd["len"], fh["len"])
+            np.testing.assert_array_equal(fd["max"], fh["max"])          # type-7 percentiles: bit-exact
+            np.testing.assert_array_equal(fd["fit"], fh["fit"])
+            assert fd["n_pos"] == fh["n_pos"]
+            np.testing.assert_allclose(fd["start"], fh["start"], rtol=1e-9)
+            np.testing.assert_allclose(fd["shape"], fh["shape"], rtol=1e-7)
+        np.testing.assert_allclose(dev.df["srp_max"], host.df["srp_max"], rtol=1e-6, atol=1e-9)
+        diff_red = set(dev.red.tolist()) ^ set(host.red.tolist())
+        assert diff_red <= set(host.borderline_red.tolist()) | set(dev.borderline_red.tolist())
+        if not diff_red:
+            np.testing.assert_array_equal(dev.chk, host.chk)
+        print(f"g={g}: {len(sr['MI'])} links -> df {len(host.df['row'])}, red {len(host.red)}, chk {len(host.chk)}; max rel srp diff",
+              float(np.max(np.abs(dev.df["srp_max"] - host.df["srp_max"]) / np.maximum(host.df["srp_max"], 1e-300))))
+    # the whole call with the table kept on the device: same sr_links_red (values to 1e-9), same lr file
+    snp = _snp(fixture_snp, 50000)
+    outs = []
+    for tag, kw in (("host", dict(exact_sr="in_scan")), ("dev", dict(device_post=True))):
+        d = tmp_path / tag
+        d.mkdir()
+        res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), lr_save_path=str(d / "lr.tsv"), sr_save_path=str(d / "sr.tsv"),
+                                         plt_folder=str(d), lr_retain_links=1e4, max_blk_sz=1000, lr_links_approx=1e5, **kw)
+        outs.append((res, (d / "lr.tsv").read_bytes(), api.read_ShortRangeLinks(str(d / "sr.tsv"))))
+    (a, lra, sra), (b, lrb, srb) = outs
+    assert lra == lrb and len(b.sr["MI"]) == 0 and len(a.sr["MI"]) > 0
+    for k in ("clust_c", "pos1", "pos2", "clust1", "clust2", "len", "MI", "ARACNE"):
+        np.testing.assert_array_equal(a.sr_links_red[k], b.sr_links_red[k], err_msg=k)
+        np.testing.assert_array_equal(sra[k], srb[k], err_msg=k)
+    np.testing.assert_allclose(a.sr_links_red["srp_max"], b.sr_links_red["srp_max"], rtol=1e-6)
