@@ -84,14 +84,15 @@ __global__ void sr_group_q95_kernel(const double* sorted, const int64_t* goff, i
   const int64_t n = goff[g + 1] - goff[g];
   if (n <= 0) { gq[g] = 0.0; return; }
   const double* x = sorted + goff[g];
-  const double index = 1.0 + (double)(n - 1) * 0.95;
+  // every product and sum rounded on its own (no FMA contraction): the host evaluates the same expression that way
+  const double index = __dadd_rn(1.0, __dmul_rn((double)(n - 1), 0.95));
   const int64_t lo = (int64_t)floor(index), hi = (int64_t)ceil(index);
   double qs = x[lo - 1];
   if (hi > lo) {
     const double xhi = x[lo];  // smallest of the values above position lo
     if (index > (double)lo && xhi != qs) {
       const double h = index - (double)lo;
-      qs = (1.0 - h) * qs + h * xhi;
+      qs = __dadd_rn(__dmul_rn(1.0 - h, qs), __dmul_rn(h, xhi));
     }
   }
   gq[g] = qs;

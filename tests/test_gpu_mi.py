@@ -360,8 +360,11 @@ def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, t
     native mergeNsort_sr_links / runARACNE / ordering / sr_links.tsv + lr_links.tsv, against the oracle chain on the
     golden short-range table.  srp_max is a statistic of ALL short-range MI values (per-length percentiles, a decay fit,
     a beta fit whose likelihood weighs residuals near zero by their logarithm), so the 1e-6 tolerance on MI shows up
-    amplified: +-4e-7 on MI moves srp_max by up to ~2e-2 (tests/test_post_cpu.py covers the exact-input case).  That is
-    why the default is exact_sr=True (next test); here the fp32 column is kept on purpose."""
+    amplified: +-4e-7 on MI moves srp_max by up to ~2e-2, and one (cluster, length) group of this fixture has a 95th
+    percentile of +1e-8, which the fp32 epilogue's 3e-7 can turn negative -- log() of it then poisons the decay fit, in R as
+    here.  That is why the short-range MI is refined to fp64 whenever the post-processing runs; this test takes the values
+    from inside the scan (LDW_SCAN_SR_EXACT), the next one the host-driven way, and tests/test_post_cpu.py covers what
+    MI errors of the scan's size do to the chain."""
     import ldw_oracle as O
     import post_oracle as PO
     import ldweaver_b200 as ldw
@@ -371,7 +374,7 @@ def test_whole_perform_mi_computation_with_tsvs(fixture_snp, fixture_expected, t
     lr_path, sr_path = tmp_path / "lr_links.tsv", tmp_path / "sr_links.tsv"
     res = ldw.perform_MI_computation(snp, e["hdw"], ldw.CdsVar(e["paint"], 3), ncores=1, lr_save_path=str(lr_path),
                                      sr_save_path=str(sr_path), plt_folder=str(tmp_path), sr_dist=20000, lr_retain_links=1e4,
-                                     max_blk_sz=1000, srp_cutoff=3, runARACNE=True, lr_links_approx=1e5, exact_sr=False)
+                                     max_blk_sz=1000, srp_cutoff=3, runARACNE=True, lr_links_approx=1e5, exact_sr="in_scan")
     red = res.sr_links_red
     assert red is not None and len(red["row"]) > 0
     # oracle chain on the golden (fp64) short-range table
