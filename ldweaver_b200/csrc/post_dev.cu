@@ -17,12 +17,16 @@
 //                              sum log(1-d), sum d, sum d^2
 //      host: beta fit from those sufficient statistics (moment start + Nelder-Mead, :452; shared code)
 //   7. cub::DeviceSelect::Flagged per cluster: the links above the fit in scan order (the reference's row order)
-//   8. sr_srp_gather_kernel    srp_max = -pbeta(d, a, b, lower = F, log = T) in fp64 (continued fraction, :453) and the
-//                              link columns of those rows
-//      host: cross-cluster links kept once (:474-483), srp_max > cutoff, MI >= min (:494-495); shared code
+//   8. sr_srp_kernel           srp_max = -pbeta(d, a, b, lower = F, log = T) in fp64 (continued fraction, :453), and the smallest
+//                              MI among the same-cluster links with srp_max > cutoff
+//   9. sr_keep_kernel + select + sr_gather_kernel: ONLY the rows sr_links_red (srp_max > cutoff, :494) and
+//                              sr_links_ARACNE_check (MI >= min(sr_links_red$MI), :495) need -- a few 10^5 of the 4.5 x 10^6
+//                              links above the fit at 616 x 100k -- and the (few) cross-cluster links, which the host keeps
+//                              once each (:474-483; shared code), come to the host
 #include <cub/cub.cuh>
 #include <thrust/iterator/counting_iterator.h>
 
+#include <chrono>
 #include <cmath>
 #include <memory>
 
@@ -184,17 +188,48 @@ struct FullCols {
   const double* mi;
 };
 
-__global__ void sr_srp_gather_kernel(FullCols T, FitTab F, int c, double a, double b, double lbeta, const int64_t* rows, int64_t n,
-                                     double* srp, int32_t* o_pos1, int32_t* o_pos2, int32_t* o_c1, int32_t* o_c2, int32_t* o_len,
-                                     int32_t* o_blk, double* o_mi) {
+// order-preserving 64-bit key of a double (for atomicMin on MI values, which may be negative)
+__device__ __forceinline__ unsigned long long dbl_key(double v) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// srp_max of the links above the fit of cluster c (rows[k]); dup[k] = the link joins two clusters (it is listed under both
+// and de-duplicated on the host); *min_red_key = smallest MI among the same-cluster links that pass the cut-off.
+__global__ void sr_srp_kernel(FullCols T, FitTab F, int c, double a, double b, double lbeta, double cutoff, const int64_t* rows, int64_t n,
+                              double* srp, uint8_t* dup, unsigned long long* min_red_key) {
   int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int64_t i = rows[k];
-  const int l = T.len[i];
   const double mi = T.mi[i];
-  const double d = mi - F.val[F.off[c - 1] + l - 1];
-  srp[k] = d < 1.0 ? d_neg_log_upper_beta(d, a, b, lbeta) : INFINITY;
-  o_pos1[k] = T.pos1[i]; o_pos2[k] = T.pos2[i]; o_c1[k] = T.c1[i]; o_c2[k] = T.c2[i]; o_len[k] = l; o_blk[k] = T.blk[i]; o_mi[k] = mi;
+  const double d = mi - F.val[F.off[c - 1] + T.len[i] - 1];
+  const double v = d < 1.0 ? d_neg_log_upper_beta(d, a, b, lbeta) : INFINITY;
+  srp[k] = v;
+  const bool is_dup = T.c1[i] != T.c2[i];
+  dup[k] = is_dup ? 1 : 0;
+  if (!is_dup && v > cutoff) atomicMin(min_red_key, dbl_key(mi));  // NaN compares false: dropped as in :458
+}
+
+// which rows of the cluster's list travel to the host: every cross-cluster link (few; de-duplicated there), and the
+// same-cluster links that are in sr_links_red (srp_max > cutoff) or in sr_links_ARACNE_check (MI >= min_mi)
+__global__ void sr_keep_kernel(FullCols T, const int64_t* rows, const double* srp, const uint8_t* dup, int64_t n, double cutoff, double min_mi,
+                               int phase, uint8_t* keep) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const double v = srp[k];
+  bool kp;
+  if (phase == 0) kp = dup[k] != 0;
+  else kp = !dup[k] && !isnan(v) && (v > cutoff || T.mi[rows[k]] >= min_mi);
+  keep[k] = kp ? 1 : 0;
+}
+
+__global__ void sr_gather_kernel(FullCols T, const int64_t* rows, const double* srp, const int64_t* pick, int64_t n, int64_t* o_row, double* o_srp,
+                                 int32_t* o_pos1, int32_t* o_pos2, int32_t* o_c1, int32_t* o_c2, int32_t* o_len, int32_t* o_blk, double* o_mi) {
+  int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int64_t k = pick[t], i = rows[k];
+  o_row[t] = i; o_srp[t] = srp[k];
+  o_pos1[t] = T.pos1[i]; o_pos2[t] = T.pos2[i]; o_c1[t] = T.c1[i]; o_c2[t] = T.c2[i]; o_len[t] = T.len[i]; o_blk[t] = T.blk[i]; o_mi[t] = T.mi[i];
 }
 
 __global__ void max_len_kernel(SrCols T, double sr_dist, int nclust, int* out) {
@@ -226,6 +261,15 @@ extern "C" int ldw_sr_postprocess_dev(ldw_ctx* ctx, int32_t nclust, double sr_di
     std::unique_ptr<ldwpost::SrPostPriv> S(new ldwpost::SrPostPriv());
     S->fit_off.assign(1, 0);
     const int nb_stream = ctx->num_sms * 8;
+    const bool dbg_t = getenv("LDW_DBG_TIMING") != nullptr;  // phase times on stderr (never stdout)
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+      if (!dbg_t) return;
+      cudaStreamSynchronize(st);
+      const auto t = std::chrono::steady_clock::now();
+      fprintf(stderr, "[ldw_sr_postprocess_dev] %-34s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+      t_last = t;
+    };
 
     // ---- groups: (cluster, length) ----
     int32_t maxlen = 0;
@@ -265,6 +309,7 @@ extern "C" int ldw_sr_postprocess_dev(ldw_ctx* ctx, int32_t nclust, double sr_di
     LDW_CUDA(cudaMemcpyAsync(goff.data(), d_goff.p, (size_t)(G + 1) * 8, cudaMemcpyDeviceToHost, st));
     LDW_CUDA(cudaStreamSynchronize(st));
     const int64_t E = goff[G];
+    lap("group histogram + offsets");
     for (int32_t c = 1; c <= nclust; c++)
       if (goff[(int64_t)c * nl] == goff[(int64_t)(c - 1) * nl])
         return set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d holds no short-range link with 0 < len < sr_dist", (int)c);
@@ -283,6 +328,7 @@ extern "C" int ldw_sr_postprocess_dev(ldw_ctx* ctx, int32_t nclust, double sr_di
       LDW_TRY(tmp.alloc(tb));
       LDW_CUDA(cub::DeviceSegmentedSort::SortKeys(tmp.p, tb, d_keys.as<double>(), d_sorted.as<double>(), (int)E, (int)G,
                                                   d_goff.as<int64_t>(), d_goff.as<int64_t>() + 1, st));
+      lap("scatter + segmented sort");
       sr_group_q95_kernel<<<(unsigned)((G + 255) / 256), 256, 0, st>>>(d_sorted.as<double>(), d_goff.as<int64_t>(), G, d_gq.as<double>());
       LDW_CUDA(cudaGetLastError());
       LDW_CUDA(cudaMemcpyAsync(gq_all.data(), d_gq.p, (size_t)G * 8, cudaMemcpyDeviceToHost, st));
@@ -292,8 +338,10 @@ extern "C" int ldw_sr_postprocess_dev(ldw_ctx* ctx, int32_t nclust, double sr_di
     std::vector<double> gq;
     for (int64_t g = 0; g < G; g++)
       if (goff[g + 1] > goff[g]) { glist.push_back(g); gq.push_back(gq_all[g]); }
+    lap("percentiles to host");
     // ---- decay fits (host) ----
     LDW_TRY(ldwpost::decay_fits(*S, nclust, nl, glist, gq));
+    lap("decay fits (host)");
     // ---- residuals: flags + sufficient statistics ----
     FitTab F;
     memset(&F, 0, sizeof(F));
@@ -318,13 +366,16 @@ extern "C" int ldw_sr_postprocess_dev(ldw_ctx* ctx, int32_t nclust, double sr_di
     LDW_CUDA(cudaMemcpyAsync(&bad, d_bad.p, 4, cudaMemcpyDeviceToHost, st));
     LDW_CUDA(cudaStreamSynchronize(st));
     if (bad) return set_error(LDW_ERR_ARG, "ldw_sr_postprocess: cluster %d: values must be in [0-1] to fit a beta distribution", (int)bad);
+    lap("residual flags + sums");
 
     FullCols FT{D.pos1, D.pos2, D.c1, D.c2, D.len, D.blk, D.mi};
-    std::vector<int64_t> dup_row, dup_at, df_at;
-    std::vector<int32_t> dup_c;
-    std::vector<double> dup_srp;
-    DevBuf d_iota_tmp, d_rows, d_nsel, d_srp, g1, g2, g3, g4, g5, g6, g7;
+    // Per cluster: the links above the fit in scan order, their srp_max, the smallest MI of those that pass the cut-off.
+    struct PerC { DevBuf rows, srp, dup; int64_t npos = 0; };
+    std::vector<PerC> pc((size_t)nclust + 1);
+    DevBuf d_tmp, d_nsel, d_minkey, d_keep, d_pick;
     LDW_TRY(d_nsel.alloc(8));
+    LDW_TRY(d_minkey.alloc(8));
+    LDW_CUDA(cudaMemsetAsync(d_minkey.p, 0xFF, 8, st));
     for (int32_t c = 1; c <= nclust; c++) {
       long double cnt = 0, s1 = 0, s2 = 0, sm = 0, sq = 0;
       for (int64_t k = 0; k < nblocks; k++) {
@@ -338,65 +389,138 @@ extern "C" int ldw_sr_postprocess_dev(ldw_ctx* ctx, int32_t nclust, double sr_di
       double par[2];
       LDW_TRY(ldwpost::beta_fit(*S, c, npos, (double)s1, (double)s2, mean, v, par));
       const double lbeta = ldwpost::lbeta_fn(par[0], par[1]);
-      // ---- links above the fit, in scan order ----
-      LDW_TRY(d_rows.ensure((size_t)npos * 8));
+      PerC& P = pc[c];
+      P.npos = npos;
+      LDW_TRY(P.rows.alloc((size_t)npos * 8));
+      LDW_TRY(P.srp.alloc((size_t)npos * 8));
+      LDW_TRY(P.dup.alloc((size_t)npos));
       {
         thrust::counting_iterator<int64_t> it(0);
         size_t tb = 0;
-        cub::DeviceSelect::Flagged(nullptr, tb, it, d_flags.as<uint8_t>() + (size_t)(c - 1) * N, d_rows.as<int64_t>(), d_nsel.as<int64_t>(), (int)N, st);
-        LDW_TRY(d_iota_tmp.ensure(tb));
-        LDW_CUDA(cub::DeviceSelect::Flagged(d_iota_tmp.p, tb, it, d_flags.as<uint8_t>() + (size_t)(c - 1) * N, d_rows.as<int64_t>(),
+        cub::DeviceSelect::Flagged(nullptr, tb, it, d_flags.as<uint8_t>() + (size_t)(c - 1) * N, P.rows.as<int64_t>(), d_nsel.as<int64_t>(), (int)N, st);
+        LDW_TRY(d_tmp.ensure(tb));
+        LDW_CUDA(cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_flags.as<uint8_t>() + (size_t)(c - 1) * N, P.rows.as<int64_t>(),
                                             d_nsel.as<int64_t>(), (int)N, st));
       }
       int64_t nsel = 0;
       LDW_CUDA(cudaMemcpyAsync(&nsel, d_nsel.p, 8, cudaMemcpyDeviceToHost, st));
       LDW_CUDA(cudaStreamSynchronize(st));
       if (nsel != npos) return set_error(LDW_ERR_INTERNAL, "ldw_sr_postprocess_dev: %lld flagged links but %lld counted", (long long)nsel, (long long)npos);
-      LDW_TRY(d_srp.ensure((size_t)npos * 8));
-      LDW_TRY(g1.ensure((size_t)npos * 4)); LDW_TRY(g2.ensure((size_t)npos * 4)); LDW_TRY(g3.ensure((size_t)npos * 4));
-      LDW_TRY(g4.ensure((size_t)npos * 4)); LDW_TRY(g5.ensure((size_t)npos * 4)); LDW_TRY(g6.ensure((size_t)npos * 4));
-      LDW_TRY(g7.ensure((size_t)npos * 8));
-      sr_srp_gather_kernel<<<(unsigned)((npos + 127) / 128), 128, 0, st>>>(FT, F, c, par[0], par[1], lbeta, d_rows.as<int64_t>(), npos, d_srp.as<double>(),
-                                                                          g1.as<int32_t>(), g2.as<int32_t>(), g3.as<int32_t>(), g4.as<int32_t>(),
-                                                                          g5.as<int32_t>(), g6.as<int32_t>(), g7.as<double>());
+      sr_srp_kernel<<<(unsigned)((npos + 127) / 128), 128, 0, st>>>(FT, F, c, par[0], par[1], lbeta, srp_cutoff, P.rows.as<int64_t>(), npos,
+                                                                   P.srp.as<double>(), P.dup.as<uint8_t>(), d_minkey.as<unsigned long long>());
       LDW_CUDA(cudaGetLastError());
-      std::vector<int64_t> rows((size_t)npos);
-      std::vector<double> srp((size_t)npos);
-      const size_t base = S->g_mi.size();
-      for (auto* v32 : {&S->g_pos1, &S->g_pos2, &S->g_c1, &S->g_c2, &S->g_len, &S->g_blk}) v32->resize(base + (size_t)npos);
-      S->g_mi.resize(base + (size_t)npos);
-      LDW_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, (size_t)npos * 8, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(srp.data(), d_srp.p, (size_t)npos * 8, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(S->g_pos1.data() + base, g1.p, (size_t)npos * 4, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(S->g_pos2.data() + base, g2.p, (size_t)npos * 4, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(S->g_c1.data() + base, g3.p, (size_t)npos * 4, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(S->g_c2.data() + base, g4.p, (size_t)npos * 4, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(S->g_len.data() + base, g5.p, (size_t)npos * 4, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(S->g_blk.data() + base, g6.p, (size_t)npos * 4, cudaMemcpyDeviceToHost, st));
-      LDW_CUDA(cudaMemcpyAsync(S->g_mi.data() + base, g7.p, (size_t)npos * 8, cudaMemcpyDeviceToHost, st));
+    }
+    lap("select + srp_max (all clusters)");
+    // Only what sr_links_red / sr_links_ARACNE_check need comes to the host (sr_links_df itself -- every link above the fit,
+    // 4.5e6 rows at 616 x 100k -- stays on the device): first the cross-cluster links, whose de-duplication decides which of
+    // them are in sr_links_red and therefore min(sr_links_red$MI); then the same-cluster rows of the two sets.
+    struct Got { std::vector<int64_t> row; std::vector<double> srp, mi; std::vector<int32_t> pos1, pos2, c1, c2, len, blk; };
+    auto fetch = [&](int32_t c, int phase, double min_mi, Got& G) -> int {
+      PerC& P = pc[c];
+      const int64_t npos = P.npos;
+      LDW_TRY(d_keep.ensure((size_t)npos));
+      LDW_TRY(d_pick.ensure((size_t)npos * 8));
+      sr_keep_kernel<<<(unsigned)((npos + 255) / 256), 256, 0, st>>>(FT, P.rows.as<int64_t>(), P.srp.as<double>(), P.dup.as<uint8_t>(), npos, srp_cutoff,
+                                                                    min_mi, phase, d_keep.as<uint8_t>());
+      thrust::counting_iterator<int64_t> it(0);
+      size_t tb = 0;
+      cub::DeviceSelect::Flagged(nullptr, tb, it, d_keep.as<uint8_t>(), d_pick.as<int64_t>(), d_nsel.as<int64_t>(), (int)npos, st);
+      LDW_TRY(d_tmp.ensure(tb));
+      LDW_CUDA(cub::DeviceSelect::Flagged(d_tmp.p, tb, it, d_keep.as<uint8_t>(), d_pick.as<int64_t>(), d_nsel.as<int64_t>(), (int)npos, st));
+      int64_t m = 0;
+      LDW_CUDA(cudaMemcpyAsync(&m, d_nsel.p, 8, cudaMemcpyDeviceToHost, st));
       LDW_CUDA(cudaStreamSynchronize(st));
-      // ---- same-cluster links go to sr_links_df, links between clusters to duplink_df (:460-468) ----
-      for (int64_t i = 0; i < npos; i++) {
-        if (std::isnan(srp[i])) continue;  // :458
-        const int64_t at = (int64_t)base + i;  // position in the gathered table
-        if (S->g_c1[at] != S->g_c2[at]) { dup_row.push_back(rows[i]); dup_at.push_back(at); dup_c.push_back(c); dup_srp.push_back(srp[i]); }
-        else { S->row.push_back(rows[i]); df_at.push_back(at); S->clust_c.push_back(c); S->srp.push_back(srp[i]); }
+      G.row.resize((size_t)m); G.srp.resize((size_t)m); G.mi.resize((size_t)m);
+      for (auto* v32 : {&G.pos1, &G.pos2, &G.c1, &G.c2, &G.len, &G.blk}) v32->resize((size_t)m);
+      if (m == 0) return 0;
+      DevBuf o_row, o_srp, o1, o2, o3, o4, o5, o6, o7;
+      LDW_TRY(o_row.alloc((size_t)m * 8)); LDW_TRY(o_srp.alloc((size_t)m * 8)); LDW_TRY(o7.alloc((size_t)m * 8));
+      LDW_TRY(o1.alloc((size_t)m * 4)); LDW_TRY(o2.alloc((size_t)m * 4)); LDW_TRY(o3.alloc((size_t)m * 4));
+      LDW_TRY(o4.alloc((size_t)m * 4)); LDW_TRY(o5.alloc((size_t)m * 4)); LDW_TRY(o6.alloc((size_t)m * 4));
+      sr_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(FT, P.rows.as<int64_t>(), P.srp.as<double>(), d_pick.as<int64_t>(), m, o_row.as<int64_t>(),
+                                                                   o_srp.as<double>(), o1.as<int32_t>(), o2.as<int32_t>(), o3.as<int32_t>(), o4.as<int32_t>(),
+                                                                   o5.as<int32_t>(), o6.as<int32_t>(), o7.as<double>());
+      LDW_CUDA(cudaGetLastError());
+      LDW_CUDA(cudaMemcpyAsync(G.row.data(), o_row.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.srp.data(), o_srp.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.mi.data(), o7.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.pos1.data(), o1.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.pos2.data(), o2.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.c1.data(), o3.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.c2.data(), o4.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.len.data(), o5.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaMemcpyAsync(G.blk.data(), o6.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+      LDW_CUDA(cudaStreamSynchronize(st));
+      return 0;
+    };
+    auto append = [&](const Got& G, int64_t t) -> int64_t {  // one row into the gathered table; returns its position
+      S->g_pos1.push_back(G.pos1[t]); S->g_pos2.push_back(G.pos2[t]); S->g_c1.push_back(G.c1[t]); S->g_c2.push_back(G.c2[t]);
+      S->g_len.push_back(G.len[t]); S->g_blk.push_back(G.blk[t]); S->g_mi.push_back(G.mi[t]);
+      return (int64_t)S->g_mi.size() - 1;
+    };
+    // ---- phase 0: cross-cluster links -> de-duplicated (:474-483) ----
+    std::vector<int64_t> dup_row, dup_at, dup_keep_row, dup_keep_at;
+    std::vector<int32_t> dup_c, dup_keep_c;
+    std::vector<double> dup_srp, dup_keep_srp;
+    for (int32_t c = 1; c <= nclust; c++) {
+      Got G;
+      LDW_TRY(fetch(c, 0, 0.0, G));
+      for (size_t t = 0; t < G.row.size(); t++) {
+        if (std::isnan(G.srp[t])) continue;  // :458
+        dup_row.push_back(G.row[t]); dup_at.push_back(append(G, (int64_t)t)); dup_c.push_back(c); dup_srp.push_back(G.srp[t]);
       }
     }
-    ldwpost::LinkCols cols{S->g_pos1.data(), S->g_pos2.data(), S->g_c1.data(), S->g_c2.data(), S->g_len.data(), S->g_mi.data()};
-    ldwpost::dedup_and_select(*S, cols, dup_row, dup_at, dup_c, dup_srp, df_at, srp_cutoff);
-    // the gathered columns, reordered to the df rows (the gathered table also holds the losing copies of cross-cluster links)
     {
-      const int64_t ndf = (int64_t)df_at.size();
+      ldwpost::SrPostPriv tmp;  // run the shared de-duplication on the cross-cluster links alone
+      ldwpost::LinkCols cols{S->g_pos1.data(), S->g_pos2.data(), S->g_c1.data(), S->g_c2.data(), S->g_len.data(), S->g_mi.data()};
+      std::vector<int64_t> at;
+      ldwpost::dedup_and_select(tmp, cols, dup_row, dup_at, dup_c, dup_srp, at, INFINITY);
+      dup_keep_row = tmp.row; dup_keep_c = tmp.clust_c; dup_keep_srp = tmp.srp; dup_keep_at = at;
+    }
+    unsigned long long minkey = ~0ull;
+    LDW_CUDA(cudaMemcpyAsync(&minkey, d_minkey.p, 8, cudaMemcpyDeviceToHost, st));
+    LDW_CUDA(cudaStreamSynchronize(st));
+    double min_mi = INFINITY;  // min(sr_links_red$MI), :495
+    if (minkey != ~0ull) {
+      const unsigned long long bts = (minkey >> 63) ? (minkey & 0x7FFFFFFFFFFFFFFFull) : ~minkey;
+      memcpy(&min_mi, &bts, 8);
+    }
+    for (size_t k = 0; k < dup_keep_row.size(); k++)
+      if (dup_keep_srp[k] > srp_cutoff) min_mi = std::min(min_mi, S->g_mi[(size_t)dup_keep_at[k]]);
+    lap("cross-cluster links + min MI");
+    // ---- phase 1: same-cluster rows of sr_links_red / sr_links_ARACNE_check, cluster by cluster in scan order ----
+    std::vector<int64_t> df_at;
+    for (int32_t c = 1; c <= nclust; c++) {
+      Got G;
+      LDW_TRY(fetch(c, 1, min_mi, G));
+      for (size_t t = 0; t < G.row.size(); t++) {
+        S->row.push_back(G.row[t]); S->clust_c.push_back(c); S->srp.push_back(G.srp[t]);
+        df_at.push_back(append(G, (int64_t)t));
+      }
+    }
+    for (size_t k = 0; k < dup_keep_row.size(); k++) {  // the de-duplicated cross-cluster links follow (:483), those in either set
+      const double mi = S->g_mi[(size_t)dup_keep_at[k]];
+      if (!(dup_keep_srp[k] > srp_cutoff || mi >= min_mi)) continue;
+      S->row.push_back(dup_keep_row[k]); S->clust_c.push_back(dup_keep_c[k]); S->srp.push_back(dup_keep_srp[k]);
+      df_at.push_back(dup_keep_at[k]);
+    }
+    lap("rows of red / check sets");
+    const int64_t ndf = (int64_t)S->row.size();
+    for (int64_t i = 0; i < ndf; i++) {
+      if (S->srp[(size_t)i] > srp_cutoff) S->red.push_back(i);
+      if (S->g_mi[(size_t)df_at[(size_t)i]] >= min_mi) S->chk.push_back(i);
+    }
+    {  // the gathered columns in df order (the gathered table also holds the losing copies of cross-cluster links)
       std::vector<int32_t> a1(ndf), a2(ndf), a3(ndf), a4(ndf), a5(ndf), a6(ndf);
       std::vector<double> a7(ndf);
       for (int64_t k = 0; k < ndf; k++) {
-        const int64_t at = df_at[k];
+        const int64_t at = df_at[(size_t)k];
         a1[k] = S->g_pos1[at]; a2[k] = S->g_pos2[at]; a3[k] = S->g_c1[at]; a4[k] = S->g_c2[at]; a5[k] = S->g_len[at]; a6[k] = S->g_blk[at];
         a7[k] = S->g_mi[at];
       }
       S->g_pos1.swap(a1); S->g_pos2.swap(a2); S->g_c1.swap(a3); S->g_c2.swap(a4); S->g_len.swap(a5); S->g_blk.swap(a6); S->g_mi.swap(a7);
     }
+    lap("red / chk + reorder (host)");
     ldwpost::publish(*S, nclust, out);
     if (df_rows_out) {
       df_rows_out->n = out->n_df;

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Wall time "to sr/lr links" at BASELINE config #2 (616 x 100k synthetic), through the public API exactly as
 a user of the reference would call it: estimate_Hamming_distance_weights(), then perform_MI_computation() with both
-TSV files written (scan on the device; mergeNsort_sr_links, runARACNE, ordering and the writers in native host code).
-Prints one JSON line; the second of two calls is reported (the first one allocates the pinned link buffers)."""
+TSV files written.  `--host-post`: the short-range table comes to the host and mergeNsort_sr_links runs on host threads;
+default: the table stays on the device (ldw_sr_postprocess_dev).  LDW_DBG_TIMING=1 prints the library's phase times on
+stderr.  Prints one JSON line; the second of two calls is reported (the first one allocates buffers)."""
 import json
 import os
 import sys
@@ -20,9 +21,7 @@ def main():
     sy = synth.generate(S, n, seed, probs, nrate)
     snp = ldw.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
     lra = synth.exact_lr_links_approx(sy.POS, sy.g, 20000.0)
-    exact_sr = "--exact-sr" in sys.argv   # fp64 MI for every short-range link before the statistics are derived
-    if "--exact-sr-in-scan" in sys.argv:  # the same from inside the scan call (LDW_SCAN_SR_EXACT)
-        exact_sr = "in_scan"
+    kw = dict(exact_sr="in_scan") if "--host-post" in sys.argv else dict(device_post=True)
     out = None
     for it in range(2):
         with tempfile.TemporaryDirectory() as d:
@@ -31,15 +30,13 @@ def main():
             t1 = time.perf_counter()
             res = ldw.perform_MI_computation(snp, hdw, ldw.CdsVar(sy.paint, 3), ncores=1, lr_save_path=os.path.join(d, "lr_links.tsv"),
                                              sr_save_path=os.path.join(d, "sr_links.tsv"), plt_folder=d, sr_dist=20000,
-                                             lr_retain_links=1e6, max_blk_sz=10000, srp_cutoff=3, runARACNE=True, lr_links_approx=lra, exact_sr=exact_sr)
+                                             lr_retain_links=1e6, max_blk_sz=10000, srp_cutoff=3, runARACNE=True, lr_links_approx=lra, **kw)
             t2 = time.perf_counter()
             out = {"workload": "C2: synthetic 616 x 100000, sr_dist 20000, lr_retain_links 1e6, max_blk_sz 10000, srp_cutoff 3, ARACNE on",
-                   "exact_sr": exact_sr, "call": it, "hdw_s": t1 - t0, "perform_MI_computation_s": t2 - t1, "total_s": t2 - t0,
-                   "n_sr_links": int(len(res.sr["MI"])), "n_lr_links": int(len(res.lr["MI"])), "n_sr_links_red": int(len(res.sr_links_red["row"])),
-                   "aracne_kept": int(res.sr_links_red["ARACNE"].sum()), "lr_tsv_bytes": os.path.getsize(os.path.join(d, "lr_links.tsv")),
-                   "sr_tsv_bytes": os.path.getsize(os.path.join(d, "sr_links.tsv")), "scan_stats_ms": {k: res.stats[k] for k in ("t_pack_ms", "t_scan_ms", "t_select_ms", "t_d2h_ms")},
-                   "host_threads": os.cpu_count(),
-                   "includes": "hdw + plan upload/packing + scan + D2H of all links + copies into NumPy columns + lr_links.tsv + mergeNsort_sr_links + runARACNE + ordering + sr_links.tsv"}
+                   "variant": "host_post" if "--host-post" in sys.argv else "device_post", "call": it, "hdw_s": t1 - t0,
+                   "perform_MI_computation_s": t2 - t1, "total_s": t2 - t0, "n_sr_links": int(res.stats["n_sr"]), "n_lr_links": int(len(res.lr["MI"])),
+                   "n_sr_links_red": int(len(res.sr_links_red["row"])), "aracne_kept": int(res.sr_links_red["ARACNE"].sum()),
+                   "phases_s": res.stats.get("phases"), "host_threads": os.cpu_count()}
         del res
     print(json.dumps(out))
 
