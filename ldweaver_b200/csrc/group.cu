@@ -344,10 +344,11 @@ int ldw_group_mi_scan(ldw_group* G, const double* hdw, const int32_t* pos, const
     });
     if (rc != 0) { destroy_plans(); return rc; }
     if (t_plan_ms_out) *t_plan_ms_out = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
-    if (G->world == 1) {  // one device, one process: exactly ldw_mi_scan (its own sizing pass, its own tables, nothing to merge)
+    if (nl == 1) {  // one local member (a single device, or one rank of a multi-process job): exactly ldw_mi_scan over this rank's
+                    // share -- its own sizing pass over its own blocks, its own tables, nothing to merge
       ldw_scan_stats st1;
-      rc = mi_scan_impl(plans[0], g, sr_dist, lr_retain_links, lr_links_approx, flags, 1, 0, nullptr, sr_out, lr_out, borderline_out,
-                        thr_out, prob_out, &st1);
+      rc = mi_scan_impl(plans[0], g, sr_dist, lr_retain_links, lr_links_approx, flags, G->world, G->m[0].rank, nullptr, sr_out, lr_out,
+                        borderline_out, thr_out, prob_out, &st1);
       if (rc != 0) { std::string keep = last_error_ref(); destroy_plans(); return set_error(rc, "%s", keep.c_str()); }
       destroy_plans();
       if (stats_out) stats_out[0] = st1;

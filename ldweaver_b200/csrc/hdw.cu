@@ -439,14 +439,14 @@ int hdw_device(cudaStream_t st, const uint8_t* d_codes, int64_t n, int64_t S, in
       for (int tn = sn; tn < std::min(sn + SUP_N, p.tiles_n); tn++)
         for (int tm = sm; tm < std::min(sm + SUP_M, p.tiles_m); tm++)
           if ((int64_t)tm * HDW_BM <= (int64_t)tn * HDW_BN + HDW_BN - 1) tri.push_back(make_int2(tm, tn));
-  // Multi-GPU: when every rank still gets more than a wave of whole-K tiles, the triangle's tiles are
+  // Multi-GPU: when every rank still gets at least a wave of whole-K tiles, the triangle's tiles are
   // dealt round-robin, each rank counts the neighbours its tiles reveal and the partial counts are summed across ranks
   // (the `allreduce` callback: ncclAllReduce).  Smaller problems are computed whole on every rank -- identical results,
   // no collective -- because split-K (which they need to fill the SMs) leaves no per-rank share to count from.
   // The decision depends on S, the rank count and the SM count only, so all ranks of a homogeneous box agree.
   int n_parts = 1, part = 0;
   if (shard && shard->n_parts > 1 && d_dist == nullptr &&
-      (shard->force || (int64_t)tri.size() >= (int64_t)shard->n_parts * 2 * num_sms)) {
+      (shard->force || (int64_t)tri.size() >= (int64_t)shard->n_parts * num_sms)) {
     n_parts = shard->n_parts;
     part = shard->part;
   }
