@@ -209,9 +209,9 @@ LDW_API int ldw_mi_scan(ldw_mi_plan* plan, double g, double sr_dist, double lr_r
 
 /* ldw_write_lr_tsv writes the long-range rows exactly as perform_MI_computation_ACGTN appends them with
  *   write.table(MI_df_lr, lr_save_path, append = T, quote = F, row.names = F, col.names = F, sep = '\t')
- * (R/computePairwiseMI.R:362): tab-separated pos1 pos2 clust1 clust2 len MI, integers as digits, doubles the way
- * write.table encodes a single cell (15 significant digits, scientific notation only when strictly narrower, so a
- * len of 100000 is "1e+05").  Host only, no device needed.  ldw_format_r_real exposes the cell encoder (tests).
+ * (R/computePairwiseMI.R:362): tab-separated pos1 pos2 clust1 clust2 len MI, all of them doubles in the reference's
+ * data.frame (pos = as.numeric(POS), :176-177) and written the way write.table encodes a single cell (15 significant
+ * digits, scientific notation only when strictly narrower, so a position or a len of 100000 is "1e+05").  Host only, no device needed.  ldw_format_r_real exposes the cell encoder (tests).
  */
 LDW_API int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int append);
 LDW_API int ldw_format_r_real(double x, char* out, int cap);

@@ -3,9 +3,10 @@
 // (R/computePairwiseMI.R:362; columns pos1 pos2 clust1 clust2 len MI, :326-331; reader R/io_functions.R:34-35).
 // write.table encodes every cell on its own (utils:::writetable -> EncodeElement0): integers as plain digits, doubles
 // with up to 15 significant digits, in fixed notation unless scientific notation is strictly narrower (formatReal with
-// R_print.digits = DBL_DIG, scipen = 0).  pos1 / pos2 are integer columns (POS is an IntegerVector,
-// src/getACGTNsites.cpp:97,173), clust1 / clust2 / len / MI are doubles (paint is built by rep(0, n),
-// R/estimateCDSDiversity.R:152) -- so len = 100000 is written "1e+05", exactly as R does.
+// R_print.digits = DBL_DIG, scipen = 0).  Every column of MI_df is a double: pos1 / pos2 come from
+// POS_f = as.numeric(snp.dat$POS[from]) (R/computePairwiseMI.R:176-177), paint is built by rep(0, n)
+// (R/estimateCDSDiversity.R:152) -- so a position or a len of 100000 is written "1e+05", exactly as R does.  Only clust_c
+// of sr_links.tsv is an integer column (the loop index of :464-467).
 // Rows are formatted on a few host threads and written in order.
 #include <math.h>
 #include <stdint.h>
@@ -126,8 +127,8 @@ extern "C" int ldw_write_lr_tsv(const char* path, const ldw_links* lr, int appen
   if (!path || !lr) return ldw::set_error(LDW_ERR_ARG, "ldw_write_lr_tsv: null argument");
   return write_rows("ldw_write_lr_tsv", path, append, lr->n, [&](int64_t i, std::string& s) {
     char tmp[512];
-    s.append(tmp, format_int(lr->pos1[i], tmp)); s.push_back('\t');
-    s.append(tmp, format_int(lr->pos2[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(lr->pos1[i], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(lr->pos2[i], tmp)); s.push_back('\t');
     s.append(tmp, format_r_whole(lr->clust1[i], tmp)); s.push_back('\t');
     s.append(tmp, format_r_whole(lr->clust2[i], tmp)); s.push_back('\t');
     s.append(tmp, format_r_whole(lr->len[i], tmp)); s.push_back('\t');
@@ -148,8 +149,8 @@ extern "C" int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n
     char tmp[512];
     const int64_t r = rows[i];
     s.append(tmp, format_int(clust_c[i], tmp)); s.push_back('\t');
-    s.append(tmp, format_int(sr->pos1[r], tmp)); s.push_back('\t');
-    s.append(tmp, format_int(sr->pos2[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(sr->pos1[r], tmp)); s.push_back('\t');
+    s.append(tmp, format_r_whole(sr->pos2[r], tmp)); s.push_back('\t');
     s.append(tmp, format_r_whole(sr->clust1[r], tmp)); s.push_back('\t');
     s.append(tmp, format_r_whole(sr->clust2[r], tmp)); s.push_back('\t');
     s.append(tmp, format_r_whole(sr->len[r], tmp)); s.push_back('\t');

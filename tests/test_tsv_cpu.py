@@ -35,16 +35,19 @@ def test_write_lr_tsv_rows_and_append(tmp_path):
           "clust1": rng.integers(1, 4, n).astype(np.int32), "clust2": rng.integers(1, 4, n).astype(np.int32),
           "len": (rng.integers(2, 111, n) * 10000).astype(np.int32), "MI": rng.random(n) * 10.0 ** rng.integers(-7, 0, n),
           "block": np.zeros(n, np.int32)}
+    lr["pos1"][:3] = (100000, 2000000, 1200000)    # round positions take the scientific form, as in R
     p = str(tmp_path / "lr_links.tsv")
     api.write_lr_tsv(p, lr, append=True)          # the reference appends (file may not exist yet)
     api.write_lr_tsv(p, {k: v[:5] for k, v in lr.items()}, append=True)
     rows = open(p).read().split("\n")
     assert rows[-1] == "" and len(rows) == n + 5 + 1
     for i in list(rng.integers(0, n, 300)) + [0, n - 1]:
-        want = "\t".join([str(lr["pos1"][i]), str(lr["pos2"][i]), O.format_r_numeric(lr["clust1"][i]),
+        # pos1 / pos2 are doubles in the reference's data.frame (as.numeric(POS), R/computePairwiseMI.R:176-177): 100000 -> 1e+05
+        want = "\t".join([O.format_r_numeric(lr["pos1"][i]), O.format_r_numeric(lr["pos2"][i]), O.format_r_numeric(lr["clust1"][i]),
                           O.format_r_numeric(lr["clust2"][i]), O.format_r_numeric(lr["len"][i]), O.format_r_numeric(lr["MI"][i])])
         assert rows[i] == want
     assert rows[n] == rows[0]
+    assert [r.split("\t")[0] for r in rows[:3]] == ["1e+05", "2e+06", "1200000"]
     back = np.loadtxt(p, delimiter="\t")           # what read.table / read_LongRangeLinks would parse (R/io_functions.R:34-35)
     assert back.shape == (n + 5, 6)
     assert np.array_equal(back[:n, 4], lr["len"]) and np.allclose(back[:n, 5], lr["MI"], rtol=1e-14, atol=0)
