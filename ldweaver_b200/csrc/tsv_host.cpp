@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <charconv>
 #include <string>
 #include <vector>
 
@@ -23,33 +24,63 @@
 namespace {
 
 // One double the way write.table prints it.  Returns the number of characters written (no terminator needed).
+// The 15 correctly rounded significant digits come from std::to_chars (same rounding of the exact binary value as
+// printf's "%.14e", several times faster); both of R's candidate forms are then laid out from those digits: the fixed form
+// sprintf("%.*f", rgt, x) shows exactly the first nsig significant digits (digits nsig+1..15 are zeros after the 15-digit
+// rounding, so rounding x directly to rgt decimals cannot differ), the scientific one "%.*e" with nsig - 1 decimals.
 int format_r_real(double x, char* out) {
   if (isnan(x)) { memcpy(out, "NA", 2); return 2; }
   if (isinf(x)) { if (x > 0) { memcpy(out, "Inf", 3); return 3; } memcpy(out, "-Inf", 4); return 4; }
   if (x == 0.0) { out[0] = '0'; return 1; }
-  // 15 significant digits, correctly rounded: d.dddddddddddddde[+-]XX
-  char e15[40];
-  snprintf(e15, sizeof(e15), "%.14e", x);
-  const char* p = e15;
-  const int neg = (*p == '-');
-  if (neg) p++;
-  // mantissa digits: p[0], p[2..15]
+  const int neg = x < 0;
+  const double ax = fabs(x);
+  char e15[48];
+  const std::to_chars_result tr = std::to_chars(e15, e15 + sizeof(e15), ax, std::chars_format::scientific, 14);
+  *tr.ptr = 0;  // d.dddddddddddddde[+-]XX[X]
+  char dig[16];
+  dig[0] = e15[0];
+  memcpy(dig + 1, e15 + 2, 14);
   int nsig = 15;
-  while (nsig > 1 && p[nsig == 1 ? 0 : nsig] == '0') nsig--;  // digit k (k >= 2) sits at p[k]; stop at the first non-zero
-  const char* ep = strchr(p, 'e');
-  const int kpower = atoi(ep + 1);
+  while (nsig > 1 && dig[nsig - 1] == '0') nsig--;
+  const int kpower = atoi(e15 + 17);
   int left, rgt;
   if (kpower >= 0) {
     left = kpower + 1;
     rgt = nsig - kpower - 1;
     if (rgt < 0) rgt = 0;
-    if (kpower > 0 && kpower <= 22 && fabs(x) < pow(10.0, kpower)) left--;  // formatReal's `roundingwidens`
+    if (kpower > 0 && kpower <= 22 && ax < pow(10.0, kpower)) left--;  // formatReal's `roundingwidens`
   }
   else { left = 1; rgt = nsig - kpower - 1; }
   const int wF = neg + left + (rgt ? rgt + 1 : 0);
   const int wE = neg + (nsig > 1 ? nsig + 1 : 1) + ((kpower >= 100 || kpower <= -100) ? 5 : 4);
-  if (wF <= wE) return snprintf(out, 400, "%.*f", rgt, x);
-  return snprintf(out, 64, "%.*e", nsig - 1, x);
+  if (wF <= wE && kpower >= 15) return snprintf(out, 400, "%.*f", rgt, x);  // more integer digits than the 15 at hand: printf's exact expansion
+  int o = 0;
+  if (neg) out[o++] = '-';
+  if (wF <= wE) {  // fixed notation
+    if (kpower >= 0) {
+      for (int k = 0; k <= kpower; k++) out[o++] = k < 15 ? dig[k] : '0';
+      if (rgt > 0) {
+        out[o++] = '.';
+        for (int k = 0; k < rgt; k++) out[o++] = (kpower + 1 + k) < 15 ? dig[kpower + 1 + k] : '0';
+      }
+    } else {
+      out[o++] = '0';
+      out[o++] = '.';
+      for (int k = 0; k < -kpower - 1; k++) out[o++] = '0';
+      memcpy(out + o, dig, nsig);
+      o += nsig;
+    }
+    return o;
+  }
+  out[o++] = dig[0];
+  if (nsig > 1) { out[o++] = '.'; memcpy(out + o, dig + 1, nsig - 1); o += nsig - 1; }
+  out[o++] = 'e';
+  out[o++] = kpower < 0 ? '-' : '+';
+  const int ae = kpower < 0 ? -kpower : kpower;
+  if (ae >= 100) out[o++] = (char)('0' + ae / 100);
+  out[o++] = (char)('0' + (ae / 10) % 10);
+  out[o++] = (char)('0' + ae % 10);
+  return o;
 }
 
 int format_int(int64_t v, char* out) {
@@ -101,14 +132,14 @@ template <class RowFn>
 int write_rows(const char* who, const char* path, int append, int64_t n, RowFn row) {
   FILE* f = fopen(path, append ? "ab" : "wb");
   if (!f) return ldw::set_error(LDW_ERR_ARG, "%s: can't open %s", who, path);
-  const int64_t chunk = 1 << 16;
+  const int64_t chunk = 1 << 13;  // small enough that a few 10^5 rows (sr_links.tsv) already keep every thread busy
   const int64_t nchunks = (n + chunk - 1) / chunk;
-  const int64_t wave = 32;  // chunks formatted concurrently, then written in order
+  const int64_t wave = 256;  // chunks formatted concurrently, then written in order
   int rc = 0;
   for (int64_t c0 = 0; c0 < nchunks && rc == 0; c0 += wave) {
     const int64_t nc = std::min<int64_t>(wave, nchunks - c0);
     std::vector<std::string> bufs(nc);
-    ldw::parallel_for(nc, 8, [&](int64_t k) {
+    ldw::parallel_for(nc, 32, [&](int64_t k) {
       std::string& s = bufs[k];
       const int64_t lo = (c0 + k) * chunk, hi = std::min<int64_t>(n, lo + chunk);
       s.reserve((size_t)(hi - lo) * 96);
@@ -156,7 +187,8 @@ extern "C" int ldw_write_sr_tsv(const char* path, const ldw_links* sr, int64_t n
     s.append(tmp, format_r_whole(sr->len[r], tmp)); s.push_back('\t');
     s.append(tmp, format_r_real(sr->MI[r], tmp)); s.push_back('\t');
     s.append(tmp, format_r_real(srp_max[i], tmp)); s.push_back('\t');
-    s.append(tmp, format_r_real(aracne[i], tmp)); s.push_back('\n');
+    const double ar = aracne[i];  // 0 / 1 (as.numeric(logical)): no need to go through printf
+    s.append(tmp, (ar == 0.0 || ar == 1.0) ? format_r_whole((int64_t)ar, tmp) : format_r_real(ar, tmp)); s.push_back('\n');
   });
   });
 }
