@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldwgpu.so")
+# LDW_LIBRARY_PATH: developer override (same-box A/B of kernel variants, tools/kernel_ab.py); the product ships one library
+LIB_PATH = os.environ.get("LDW_LIBRARY_PATH") or os.path.join(_HERE, "libldwgpu.so")
 
 i64 = C.c_int64
 f64 = C.c_double

@@ -39,15 +39,23 @@ constexpr int MI_THREADS = 32 * (MI_EPI_WARP0 + MI_EPI_WARPS);
 #define MI_REGS_EPI 96
 // the CTA's pool is what the launch allocated: MI_THREADS x (65536 / MI_THREADS rounded down to a multiple of 8)
 static_assert(MI_EPI_WARP0 * 32 * MI_REGS_CTRL + MI_EPI_THREADS * MI_REGS_EPI <= MI_THREADS * ((65536 / MI_THREADS) & ~7), "register budget");
-constexpr int MI_MAX_STAGES = 3;
+constexpr int MI_MAX_STAGES = 4;
 constexpr uint32_t MI_ARR_BYTES = 128 * 128;              // one operand array slice: 128 rows x 128 K-bytes
-// The stage region is cut per tile kind: three 64 KB stages when the kind's planes fit (PA row planes + the 4 digit
-// copies of the PB column planes), otherwise two 96 KB stages (the largest kind needs 4 + 2 array slices).
+// CTA pairs (cta_group::2): a tile is 256 row SNPs (128 per CTA of the pair) x NJ column SNPs; each CTA stages its own row
+// planes and HALF of the column tile (NJ/2 columns, expanded into the four digit copies), and the pair's MMA reads the B
+// operand from both shared memories -- per SM that is 3/4 of the operand reads and half of the expansion traffic of a
+// one-CTA tile of the same size, which is what the kernel is bound by (shared-memory bandwidth).
+// The stage region is cut per tile kind: four 48 KB stages when the kind's planes fit (PA row planes + the 4 digit
+// copies of this CTA's half of the PB column planes), else three 64 KB stages, else two 96 KB stages.
 constexpr uint32_t MI_STAGE_REGION = 12 * MI_ARR_BYTES;
-constexpr uint32_t MI_STAGE_SMALL = 4 * MI_ARR_BYTES, MI_STAGE_LARGE = 6 * MI_ARR_BYTES;
 __host__ __device__ constexpr uint32_t mi_stage_need(int pa, int pb, int njlog2) {
-  return (uint32_t)pa * MI_ARR_BYTES + 4u * (uint32_t)pb * (128u << njlog2);
+  return (uint32_t)pa * MI_ARR_BYTES + 4u * (uint32_t)pb * (64u << njlog2);
 }
+__host__ __device__ constexpr int mi_stage_geo(int pa, int pb, int njlog2) {  // 0: 4 x 48 KB, 1: 3 x 64 KB, 2: 2 x 96 KB
+  return mi_stage_need(pa, pb, njlog2) <= 3 * MI_ARR_BYTES ? 0 : mi_stage_need(pa, pb, njlog2) <= 4 * MI_ARR_BYTES ? 1 : 2;
+}
+__host__ __device__ constexpr int mi_geo_stages(int geo) { return 4 - geo; }
+__host__ __device__ constexpr uint32_t mi_geo_bytes(int geo) { return geo == 0 ? 3 * MI_ARR_BYTES : geo == 1 ? 4 * MI_ARR_BYTES : 6 * MI_ARR_BYTES; }
 constexpr uint32_t MI_JREC_BYTES = 128 * sizeof(Rec);     // per j-buffer
 constexpr uint32_t MI_JDYN_BYTES = 128 * sizeof(ColDyn);
 constexpr uint32_t MI_SMEM_BYTES = MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + 256 + 1024;
@@ -113,7 +121,8 @@ __device__ __forceinline__ void timed_wait(uint64_t* bar, uint32_t parity, int t
 }
 
 struct EpiCtx {
-  int q, cg, lane;
+  int q, cg, lane, rank;
+  uint32_t tflags;      // this CTA's half of the tile (TileDesc::flags / flags1)
   uint32_t tmem_base;   // lane-quarter offset already applied, column of this tile's accumulators
   uint32_t jrec_saddr;  // shared-memory byte addresses of this tile's column records
   uint32_t jdyn_saddr;
@@ -230,15 +239,20 @@ struct TileRegs {
   float* sr_out;
 };
 
+// Accumulator columns of row plane a (2 PB NJ of them): [columns staged by CTA 0 | columns staged by CTA 1], each half
+// [H of plane 0 .. PB-1 | L of plane 0 .. PB-1] with NJ/2 columns per plane -- the order of the B rows in the two CTAs.
 template <int PA, int PB, int JC>
 __device__ __forceinline__ void epi_load(uint32_t tmem_base, int NJ, int j0, uint32_t (&H)[PA][PB][JC],
                                          uint32_t (&L)[PA][PB][JC]) {
+  const int NJh = NJ >> 1;
+  const int half = j0 >= NJh ? 1 : 0;
+  const uint32_t base = tmem_base + (uint32_t)(half * PB * NJ + (j0 - half * NJh));
 #pragma unroll
   for (int a = 0; a < PA; a++)
 #pragma unroll
     for (int b = 0; b < PB; b++) {
-      tmem_ldn<JC>(tmem_base + ((a * 2 + 0) * PB + b) * NJ + j0, H[a][b]);
-      tmem_ldn<JC>(tmem_base + ((a * 2 + 1) * PB + b) * NJ + j0, L[a][b]);
+      tmem_ldn<JC>(base + (uint32_t)(a * 2 * PB * NJ + b * NJh), H[a][b]);
+      tmem_ldn<JC>(base + (uint32_t)(a * 2 * PB * NJ + (PB + b) * NJh), L[a][b]);
     }
 }
 
@@ -373,7 +387,7 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   constexpr int NJ = 1 << mi_njlog2(PA, PB);
   constexpr int NB = (NJ / MI_EPI_GROUPS) / JC;  // batches per warp
   static_assert(NB >= 1 && NB * JC * MI_EPI_GROUPS == NJ, "column split must be exact");
-  const int row = c.q * 32 + c.lane;
+  const int row = c.rank * 128 + c.q * 32 + c.lane;  // this CTA's half of the pair's 256 row SNPs
   TileRegs<RA> k;
   const float den = p.den[RA - 2][RB - 2];
   const float rkT = 1.0f / p.kT;
@@ -384,7 +398,7 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   k.mul_a = 1u << p.sa; k.sb = p.sb;
   k.ragged = p.ragged != 0; k.dense = p.dense != 0;
   k.do_lr = !p.sr_only && !p.dense;
-  k.has_sr = (td.flags & TILE_HAS_SR) != 0;
+  k.has_sr = (c.tflags & TILE_HAS_SR) != 0;
   k.sr_out = p.sr_out;
   k.tcand = (k.do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
   {
@@ -441,82 +455,85 @@ __device__ __forceinline__ void epi_dispatch(const ScanParams& p, const TileDesc
 }
 
 template <bool DBG>
-__global__ void __launch_bounds__(MI_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MI_THREADS, 1)
 mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanParams p) {
   extern __shared__ uint8_t smem_raw[];
+  // (the dynamic shared-memory window starts at the same offset in both CTAs of the pair, so the aligned layout is identical)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* stage_base = smem;
   Rec* jrec = reinterpret_cast<Rec*>(smem + MI_STAGE_REGION);
   ColDyn* jdyn = reinterpret_cast<ColDyn*>(smem + MI_STAGE_REGION + 2 * MI_JREC_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES));
-  uint64_t* full = bars;            // [MI_MAX_STAGES]  raw planes landed (TMA)
-  uint64_t* empty = bars + 3;       // [MI_MAX_STAGES]  MMAs that read the stage have completed
-  uint64_t* ready = bars + 6;       // [MI_MAX_STAGES]  expanded operands written (expander warps)
-  uint64_t* tfull = bars + 9;       // [2]
-  uint64_t* tempty = bars + 11;     // [2]
-  uint64_t* jfull = bars + 13;      // [2]
-  uint64_t* jempty = bars + 15;     // [2]
-  uint64_t* drained = bars + 17;    // all MMAs of the tiles issued so far have completed (stage-geometry switch)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* full = bars;            // [MI_MAX_STAGES]  raw planes landed (TMA), per CTA
+  uint64_t* empty = bars + 4;       // [MI_MAX_STAGES]  MMAs that read the stage have completed (pair commit, both CTAs)
+  uint64_t* ready = bars + 8;       // [MI_MAX_STAGES]  LEADER's copy counts the expander warps of both CTAs
+  uint64_t* tfull = bars + 12;      // [2]  accumulators complete (pair commit, both CTAs)
+  uint64_t* tempty = bars + 14;     // [2]  LEADER's copy counts the epilogue warps of both CTAs
+  uint64_t* jfull = bars + 16;      // [2]
+  uint64_t* jempty = bars + 18;     // [2]
+  uint64_t* drained = bars + 20;    // all MMAs of the tiles issued so far have completed (stage-geometry switch; both CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader: issues the pair's MMAs
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm.a);
     for (int i = 0; i < MI_MAX_STAGES; i++) {
-      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], MI_EXP_WARPS);
+      mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], 2 * MI_EXP_WARPS);
     }
     mbar_init(drained, 1);
     for (int i = 0; i < 2; i++) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], MI_EPI_WARPS);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * MI_EPI_WARPS);
       mbar_init(&jfull[i], 1); mbar_init(&jempty[i], MI_EPI_WARPS);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / pair commit; also a CTA barrier
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // register budget: the control warps (0-7) give registers to the epilogue warps; setmaxnreg sits at the top of
   // each role's own branch so that ptxas allocates every role against its own budget
-  const int tile0 = (int)blockIdx.x, tstep = (int)gridDim.x;
+  const int tile0 = (int)(blockIdx.x >> 1), tstep = (int)(gridDim.x >> 1);  // one tile per CTA pair
 
   if (warp < MI_EPI_WARP0) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 " LDW_STR(MI_REGS_CTRL) ";");
   if (warp == 0) {
-    // ===================================================================== TMA producer
+    // ===================================================================== TMA producer (each CTA: its rows, its half of the columns)
     // Whole warp runs the loop (uniform registers), one elected lane issues the copies.
     // Stage ring: `st` walks the stages of the current geometry, bit i of `phb` is the parity of stage i's barriers
-    // (every role walks the same sequence, so the bits agree without communication).
+    // (every role of both CTAs walks the same sequence, so the bits agree without communication).
     int st = 0; uint32_t phb = 0; int geo = -1; uint32_t dph = 0;
     int it = 0;
     long long w_jempty = 0, w_empty = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
-      const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
-      const int njidx = 7 - td.njlog2;  // NJ 128,64,32,16 -> tm.b[0..3]
-      const int g3 = mi_stage_need(PA, PB, td.njlog2) <= MI_STAGE_SMALL ? 1 : 0;
-      const int nst = g3 ? 3 : 2;
-      const uint32_t sbytes = g3 ? MI_STAGE_SMALL : MI_STAGE_LARGE;
-      if (g3 != geo) {
+      const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2, NJh = NJ >> 1;
+      const int njidx = 7 - td.njlog2;  // NJ 128,64,32,16 -> tm.b[0..3] (boxes of NJ/2 rows)
+      const int g = mi_stage_geo(PA, PB, td.njlog2);
+      const int nst = mi_geo_stages(g);
+      const uint32_t sbytes = mi_geo_bytes(g);
+      if (g != geo) {
         // the stage region is re-cut: every stage of the old geometry must have been consumed
         if (geo >= 0) { mbar_wait(drained, dph, 12); dph ^= 1; }
-        geo = g3; st = 0;
+        geo = g; st = 0;
       }
-      // per stage: the raw planes of all PA row-tile planes and of all PB column planes (the latter into the first
-      // digit slot, expanded in place by the expander warps)
+      // per stage: the raw planes of this CTA's PA row-tile planes and of its half of all PB column planes (the latter
+      // into the first digit slot, expanded in place by the expander warps)
       {
-        const uint32_t stage_tx = (uint32_t)PA * MI_ARR_BYTES + (uint32_t)(PB * NJ * 128);
+        const uint32_t stage_tx = (uint32_t)PA * MI_ARR_BYTES + (uint32_t)(PB * NJh * 128);
+        const int a_row = td.a_row0 + (int)rank * 128, b_row = td.b_row0 + (int)rank * NJh;
         for (int kb = 0; kb < p.nkb; kb++) {
           timed_wait<DBG>(&empty[st], ((phb >> st) & 1) ^ 1, 11, w_empty);
           if (elect_one()) {
             uint8_t* sb = stage_base + st * sbytes;
             mbar_arrive_expect_tx(&full[st], stage_tx);
             for (int a = 0; a < PA; a++)
-              tma_load_2d(sb + a * MI_ARR_BYTES, &tm.a, &full[st], kb * 128, td.a_row0 + a * td.a_pstride);
+              tma_load_2d(sb + a * MI_ARR_BYTES, &tm.a, &full[st], kb * 128, a_row + a * td.a_pstride);
             uint8_t* sbB = sb + PA * MI_ARR_BYTES;
             for (int b = 0; b < PB; b++)
-              tma_load_2d(sbB + b * NJ * 128, &tm.b[njidx], &full[st], kb * 128, td.b_row0 + b * td.b_pstride);
+              tma_load_2d(sbB + b * NJh * 128, &tm.b[njidx], &full[st], kb * 128, b_row + b * td.b_pstride);
           }
           __syncwarp();
           phb ^= 1u << st;
@@ -540,29 +557,30 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       p.dbg[blockIdx.x * 16 + 2] = (unsigned long long)w_empty;
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
+    // ===================================================================== MMA issuer (leader CTA only)
     // The whole warp runs the loop (so addresses and descriptors live in uniform registers); one elected lane
-    // issues the tcgen05 instructions.
+    // issues the tcgen05 instructions for the pair.
+    if (rank == 0) {
     int st = 0; uint32_t phb = 0; int geo = -1; int as = 0; uint32_t aph = 0;
     long long w_tempty = 0, w_ready = 0, t_begin = DBG ? clock64() : 0;
     const uint32_t desc_hi = (uint32_t)(make_smem_desc_sw128(0) >> 32);
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const TileDesc td = p.tiles[t];
       const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
-      const int g3 = mi_stage_need(PA, PB, td.njlog2) <= MI_STAGE_SMALL ? 1 : 0;
-      const int nst = g3 ? 3 : 2;
-      const uint32_t sbytes = g3 ? MI_STAGE_SMALL : MI_STAGE_LARGE;
-      if (g3 != geo) { geo = g3; st = 0; }
-      // does this CTA's next tile use the other stage geometry?  Then the producer waits for `drained`.
+      const int g = mi_stage_geo(PA, PB, td.njlog2);
+      const int nst = mi_geo_stages(g);
+      const uint32_t sbytes = mi_geo_bytes(g);
+      if (g != geo) { geo = g; st = 0; }
+      // does this pair's next tile use another stage geometry?  Then the producers wait for `drained`.
       bool sw = false;
       if (t + tstep < p.n_tiles) {
         const TileDesc tn = p.tiles[t + tstep];
-        sw = (mi_stage_need(tn.PA, tn.PB, tn.njlog2) <= MI_STAGE_SMALL ? 1 : 0) != g3;
+        sw = mi_stage_geo(tn.PA, tn.PB, tn.njlog2) != g;
       }
       const bool big = 2 * PA * PB * NJ > 256;
-      const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA
-      const uint32_t idesc_u = make_idesc_u8(128, ncols);     // A bytes 0xFF read as +255
-      const uint32_t idesc_s = make_idesc_s8u8(128, ncols);   // A bytes 0xFF read as -1
+      const uint32_t ncols = (uint32_t)(2 * PB * NJ);  // [H | L] halves of all PB column planes in one MMA, NJ/2 columns from each CTA
+      const uint32_t idesc_u = make_idesc_u8(256, ncols);     // A bytes 0xFF read as +255
+      const uint32_t idesc_s = make_idesc_s8u8(256, ncols);   // A bytes 0xFF read as -1
       uint32_t dbase;
       if (big) {
         for (int s2 = 0; s2 < 2; s2++) {
@@ -576,8 +594,8 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       }
       tc_fence_after();
       {
-        const uint32_t boff = (uint32_t)PA * MI_ARR_BYTES;                // B region follows the A planes
-        const uint32_t b2off = boff + (uint32_t)(2 * PB * NJ * 128);      // bH | bL follow aH | aL
+        const uint32_t boff = (uint32_t)PA * MI_ARR_BYTES;               // B region follows the A planes
+        const uint32_t b2off = boff + (uint32_t)(PB * NJ * 128);         // bH | bL follow aH | aL (2 PB NJ/2 rows of 128 B)
         for (int kb = 0; kb < p.nkb; kb++) {
           timed_wait<DBG>(&ready[st], (phb >> st) & 1, 22, w_ready);
           tc_fence_after();
@@ -590,15 +608,15 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
             for (int a = 0; a < PA; a++) {
               const uint64_t dx = ((uint64_t)desc_hi << 32) | (lo + (uint32_t)((a * MI_ARR_BYTES) >> 4));
               const uint32_t dHL = dbase + (uint32_t)(a * 2 * PB * NJ);
-              umma_i8(dHL, dx, dBa, idesc_u, acc0);
-              umma_i8(dHL, dx, dBb, idesc_s, 1u);
+              umma_i8_pair(dHL, dx, dBa, idesc_u, acc0);
+              umma_i8_pair(dHL, dx, dBb, idesc_s, 1u);
 #pragma unroll
               for (int kk = 1; kk < 4; kk++) {
-                umma_i8(dHL, dx + 2 * kk, dBa + 2 * kk, idesc_u, 1u);
-                umma_i8(dHL, dx + 2 * kk, dBb + 2 * kk, idesc_s, 1u);
+                umma_i8_pair(dHL, dx + 2 * kk, dBa + 2 * kk, idesc_u, 1u);
+                umma_i8_pair(dHL, dx + 2 * kk, dBb + 2 * kk, idesc_s, 1u);
               }
             }
-            umma_commit(&empty[st]);
+            umma_commit_pair(&empty[st]);
           }
           __syncwarp();
           phb ^= 1u << st;
@@ -606,12 +624,12 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         }
       }
       if (elect_one()) {
-        if (sw) umma_commit(drained);
+        if (sw) umma_commit_pair(drained);
         if (big) {
-          umma_commit(&tfull[0]);
-          umma_commit(&tfull[1]);
+          umma_commit_pair(&tfull[0]);
+          umma_commit_pair(&tfull[1]);
         } else {
-          umma_commit(&tfull[as]);
+          umma_commit_pair(&tfull[as]);
         }
       }
       __syncwarp();
@@ -624,23 +642,24 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       p.dbg[blockIdx.x * 16 + 4] = (unsigned long long)w_tempty;
       p.dbg[blockIdx.x * 16 + 5] = (unsigned long long)w_ready;
     }
+    }
   } else {
-    // ===================================================================== operand expanders
-    // stage layout: PA row planes (raw, used as they are), then aH | aL | bH | bL digit copies of all PB column
-    // planes (the raw one-hot Y lands in the aH slot; aL, bH, bL are written, aH = Y & digit is formed in place).
-    // Elementwise on the swizzled image; only the digit lookup needs the logical K position, i.e. the 16-byte
+    // ===================================================================== operand expanders (each CTA: its half of the columns)
+    // stage layout: PA row planes (raw, used as they are), then aH | aL | bH | bL digit copies of this CTA's NJ/2 columns
+    // of all PB column planes (the raw one-hot Y lands in the aH slot; aL, bH, bL are written, aH = Y & digit is formed
+    // in place).  Elementwise on the swizzled image; only the digit lookup needs the logical K position, i.e. the 16-byte
     // chunk index XOR (row & 7).
     const int h = (warp - 2) * 32 + lane;  // 0..191
     int st = 0; uint32_t phb = 0; int geo = -1;
     long long w_full = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep) {
       const TileDesc td = p.tiles[t];
-      const int PA = td.PA, PB = td.PB, NJ = 1 << td.njlog2;
-      const int brows = PB * NJ;
-      const int g3 = mi_stage_need(PA, PB, td.njlog2) <= MI_STAGE_SMALL ? 1 : 0;
-      const int nst = g3 ? 3 : 2;
-      const uint32_t sbytes = g3 ? MI_STAGE_SMALL : MI_STAGE_LARGE;
-      if (g3 != geo) { geo = g3; st = 0; }
+      const int PA = td.PA, PB = td.PB, NJh = (1 << td.njlog2) >> 1;
+      const int brows = PB * NJh;
+      const int g = mi_stage_geo(PA, PB, td.njlog2);
+      const int nst = mi_geo_stages(g);
+      const uint32_t sbytes = mi_geo_bytes(g);
+      if (g != geo) { geo = g; st = 0; }
       for (int kb = 0; kb < p.nkb; kb++) {
         // this thread's digit chunks: logical chunk cl of K block kb
         const int cl = h & 7;
@@ -662,7 +681,9 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ready[st]);  // one arrival per warp: every arrival wakes the sleeping waiters
+        // one arrival per warp on the LEADER's barrier: the pair's MMA needs the stage of both CTAs (this CTA's row planes
+        // landed with the same `full` phase as its column planes)
+        if (lane == 0) mbar_arrive_cluster(&ready[st], 0);
         phb ^= 1u << st;
         if (++st == nst) st = 0;
       }
@@ -674,16 +695,18 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 " LDW_STR(MI_REGS_EPI) ";");
-    // ===================================================================== epilogue
+    // ===================================================================== epilogue (each CTA: its 128 rows x all NJ columns)
     EpiCtx c;
     c.q = warp & 3;
     c.cg = (warp - MI_EPI_WARP0) >> 2;
     c.lane = lane;
+    c.rank = (int)rank;
     int as = 0; uint32_t aph = 0;
     int it = 0;
     long long w_jfull = 0, w_tfull = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
+      c.tflags = rank ? td.flags1 : td.flags;
       const int NJ = 1 << td.njlog2;
       const bool big = 2 * td.PA * td.PB * NJ > 256;
       const int jb = it & 1;
@@ -705,18 +728,19 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       }
       if constexpr (DBG) w_tfull += clock64() - c1;
       tc_fence_after();
-      if (!(td.flags & TILE_NULL)) {
+      if (!(c.tflags & TILE_NULL)) {
         if (!p.qcorr) epi_dispatch<false, false>(p, td, c);
         else if (p.ragged) epi_dispatch<true, true>(p, td, c);
         else epi_dispatch<true, false>(p, td, c);
       }
       tc_fence_before();
       __syncwarp();
+      // the accumulators belong to the pair: release them on the leader's barrier
       if (big) {
-        if (lane == 0) { mbar_arrive(&tempty[0]); mbar_arrive(&tempty[1]); }
+        if (lane == 0) { mbar_arrive_cluster(&tempty[0], 0); mbar_arrive_cluster(&tempty[1], 0); }
         aph ^= 1;  // two ring slots consumed: phase flips once
       } else {
-        if (lane == 0) mbar_arrive(&tempty[as]);
+        if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);
         if (++as == 2) { as = 0; aph ^= 1; }
       }
       if (lane == 0) mbar_arrive(&jempty[jb]);
@@ -729,10 +753,10 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     }
   }
   tc_fence_before();
-  __syncthreads();
+  cluster_sync_all();  // neither CTA may exit (or free tensor memory) while its peer can still address it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc_pair(tmem_base, 512);
   }
 }
 

@@ -356,7 +356,7 @@ int build_plan(ldw_mi_plan* P, const uint8_t* codes, const uint8_t* codes_dev, c
   }
   uint64_t trows = (uint64_t)std::max<int64_t>(row, 128);
   LDW_TRY(make_tmap_u8_sw128(&P->tm.a, P->d_ops.p, trows, (uint64_t)P->Kpad, 128));
-  for (int j = 0; j < 4; j++) LDW_TRY(make_tmap_u8_sw128(&P->tm.b[j], P->d_ops.p, trows, (uint64_t)P->Kpad, 128u >> j));
+  for (int j = 0; j < 4; j++) LDW_TRY(make_tmap_u8_sw128(&P->tm.b[j], P->d_ops.p, trows, (uint64_t)P->Kpad, 64u >> j));
   {
     ScanWS* W = get_ws(ctx);
     if (!W->events_ready) {
@@ -596,10 +596,15 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
         flags = has_sr ? TILE_HAS_SR : 0;
         return true;
       };
-      for (int ti = 0; ti < n_ti; ti++)
+      // row tiles two at a time: one tile of a CTA pair (cta_group::2 MMAs, M = 256)
+      for (int ti = 0; ti < n_ti; ti += 2)
         for (int tj = 0; tj < n_tj; tj++) {
-          uint32_t fl = 0;
-          if (wanted(ti, tj, fl)) H.tiles.push_back(make_tile(ti, tj, fl));
+          uint32_t fl0 = 0, fl1 = 0;
+          const bool w0 = wanted(ti, tj, fl0), w1 = wanted(ti + 1, tj, fl1);
+          if (!w0 && !w1) continue;
+          TileDesc td = make_tile(ti, tj, w0 ? fl0 : (uint32_t)TILE_NULL);
+          td.flags1 = (uint8_t)(w1 ? fl1 : (uint32_t)TILE_NULL);
+          H.tiles.push_back(td);
         }
     }
   }
@@ -676,7 +681,8 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
 // SM they run on for the whole launch, so anything else would otherwise wait for the gap between two scans).
 int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st, int reserve = 0) {
   if (sp.n_tiles <= 0) return 0;
-  int grid = std::min<int>(sp.n_tiles, std::max(1, P->ctx->num_sms - reserve));
+  // one CTA pair (a cluster of two: the two SMs of a TPC) per tile
+  int grid = 2 * std::min<int>(sp.n_tiles, std::max(1, (P->ctx->num_sms - reserve) / 2));
   if (sp.dbg) mi_scan_kernel<true><<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
   else mi_scan_kernel<false><<<grid, MI_THREADS, MI_SMEM_BYTES, st>>>(P->tm, sp);
   LDW_CUDA(cudaGetLastError());
@@ -1184,11 +1190,12 @@ int ldw::mi_scan_impl(ldw_mi_plan* P, double g, double sr_dist, double lr_retain
       n_tiles += sp.n_tiles;
       for (int32_t ti = 0; ti < H.n_real_tiles; ti++) {  // 4 K-passes x 2 ops/MAC x 128 rows x (PA*PB*NJ) columns x Kpad
         const TileDesc& td = H.tiles[ti];
-        exec_ops += 8.0 * 128.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;  // 2 passes x 2 halves
-        // MUFU instructions of the epilogue, per lane-pair of the tile (all 128 x NJ lanes execute): one LG2 per cell of the
-        // (PA+1) x (PB+1) table, plus -- Q1 form, off-diagonal blocks -- one RCP per two cells of a row (mi_row)
+        exec_ops += 8.0 * 256.0 * (double)(td.PA * td.PB * (1 << td.njlog2)) * (double)P->Kpad;  // 2 passes x 2 halves, M = 256
+        // MUFU instructions of the epilogue, per lane-pair of the tile (all 128 x NJ lanes of a non-null half execute): one
+        // LG2 per cell of the (PA+1) x (PB+1) table, plus -- Q1 form, off-diagonal blocks -- one RCP per two cells of a row
         const int RA = td.PA + 1, RB = td.PB + 1;
-        exec_mufu += 128.0 * (double)(1 << td.njlog2) * (double)(RA * (RB + (sp.qcorr ? (RB + 1) / 2 : 0)));
+        const int halves = ((td.flags & TILE_NULL) ? 0 : 1) + ((td.flags1 & TILE_NULL) ? 0 : 1);
+        exec_mufu += halves * 128.0 * (double)(1 << td.njlog2) * (double)(RA * (RB + (sp.qcorr ? (RB + 1) / 2 : 0)));
       }
     }
     if (lr) {

@@ -43,14 +43,18 @@ static_assert(sizeof(ColDyn) == 32, "ColDyn must be 32 bytes");
 
 enum : uint32_t { TILE_HAS_SR = 1u, TILE_NULL = 2u };
 
-// One unit of work: 128 row SNPs (PA planes each) x NJ column SNPs (PB planes each).
+// One unit of work of a CTA pair: 2 x 128 row SNPs (PA planes each; CTA `rank` of the pair owns rows rank*128 ..) x NJ column
+// SNPs (PB planes each; CTA `rank` stages columns rank*NJ/2 ..).  The row-side fields name the first half; the second half
+// follows 128 slots / operand rows later.  A half that holds no wanted pair (or does not exist: odd number of row tiles)
+// is flagged TILE_NULL: its MMAs run with the pair's, its epilogue is skipped.
 struct __align__(16) TileDesc {
   int32_t a_row0, a_pstride;  // operand row of plane 0 of the row tile; rows between planes
   int32_t b_row0, b_pstride;
   int32_t i_slot0, j_slot0;   // global slot ids (index into Rec)
   int32_t i_dyn0, j_dyn0;     // offsets into RowDyn / ColDyn
-  uint8_t PA, PB, njlog2, flags;
-  int32_t pad[3];
+  uint8_t PA, PB, njlog2, flags;   // flags: rows 0..127 (CTA 0)
+  uint8_t flags1, pad8[3];         // flags1: rows 128..255 (CTA 1)
+  int32_t pad[2];
 };
 static_assert(sizeof(TileDesc) == 48, "TileDesc must be 48 bytes");
 
@@ -99,7 +103,7 @@ struct ScanParams {
 // inside shared memory by the expander warps.
 struct TmapSet {
   CUtensorMap a;      // box 128 rows
-  CUtensorMap b[4];   // box rows 128, 64, 32, 16
+  CUtensorMap b[4];   // box rows 64, 32, 16, 8: one CTA's half of a column tile of 128, 64, 32, 16 SNPs
 };
 
 }  // namespace ldw
