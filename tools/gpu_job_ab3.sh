@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_mi.py -x -q 2>&1 | tail -5 | tee gpurun_out/ab3_tests.log
+timeout 900 python tools/kernel_ab.py head rows2 r2_rcp3 head rows2 r2_rcp3 --nsnp 30000 2>&1 | tee gpurun_out/ab3.log
+LDW_DBG_BLOCK=4 LDW_LIBRARY_PATH=$PWD/ldweaver_b200/variants/libldwgpu_rows2.so timeout 300 python tools/kernel_ab.py --worker base --data /tmp/kernel_ab_data.npz --steps 1 2>&1 | grep -i "dbg" | cut -c1-600 | tail -1 | tee gpurun_out/ab3_dbg.log
