@@ -511,10 +511,14 @@ def main():
                 "traffic": traffic,
                 "peak_source": ("cuBLASLt int8 GEMM (torch._int_mm 8192^3, int32 accumulate) measured in this run on this GPU: burst %.0f, sustained %.0f TOP/s"
                                 % (i8[0], i8[1])) if i8 else "2 x MEASURED_PEAKS.json bf16_tflops (int8 microbenchmark not run at N > 1)",
+                "nominal_peak": 4500.0, "frac_of_nominal": exec_tops / 4500.0,
+                "peak_note": "the library GEMM does not reach the nominal dense int8 rate (4.5 POP/s) on this pool; when this kernel's tensor work "
+                             "runs faster than it (5000-sequence shapes) frac exceeds 1 and frac_of_nominal is the figure to read",
                 "kernel": "mi_scan_kernel", "avg_launch_ms": 1e3 * avg_launch_s, "launches": n_launch,
                 "kernel_share_of_step": kern_ms / dev_ms if dev_ms else None,
-                "what": "EXECUTED int8 tensor op/s of the scan kernel (2 x MACs of every UMMA it issues: (r_i-1)(r_j-1) plane pairs x 2 weight "
-                        "halves x 2 digit passes) over its CUDA-event time, against the measured int8 peak",
+                "what": "EXECUTED int8 tensor op/s of the scan kernel (2 x MACs of every cta_group::2 UMMA it issues, M = 256: (r_i-1)(r_j-1) plane "
+                        "pairs x 2 weight halves x 2 digit passes, halves of a pair tile without wanted pairs included) over its CUDA-event time, "
+                        "against the measured int8 peak",
                 "mufu": {"executed_per_s": mufu_rate, "peak_per_s": mufu_peak, "frac": mufu_rate / mufu_peak,
                          "what": "MUFU.LG2 / MUFU.RCP lane-results of the epilogue (counted per tile kind from the kernel's term loop) against "
                                  "16 / clk / SM x %d SMs at the sampled %.0f MHz" % (num_sms, sm_mhz)},

@@ -119,28 +119,96 @@ struct RefineParams {
   double neff;
 };
 
-// One warp per pair.  `acc` is this warp's scratch in shared memory: 32 lanes x 25 joint-count cells (doubles,
-// lane-major with a stride of 25 so lanes hit different banks).  Each lane adds the weights of its sequences into
-// its own row, then lanes 0..24 each reduce one cell over the 32 rows in a fixed order.
+// One warp per pair.  The joint table is built from the sequences that carry a NON-base class at BOTH sites (base class =
+// the heaviest class of a site, typically 5-10 % of the sequences); the cells of the base row / column follow from the
+// exact fp64 marginals p64 (sum_b c^ab = p_i^a), the corner from p_i^base.  Against summing all 25 cells directly this
+// moves the counts by a few ulp (both forms are fp64 sums of the same weights in a different association; the reference's
+// own order is that of a sparse matrix product), far inside the 1e-12 the fp64 paths are held to, and touches a
+// sixteenth of the (sequence, cell) updates.
+// `acc` is this warp's scratch in shared memory: 32 lanes x 25 cells (doubles, lane-major with a stride of 25 so lanes hit
+// different banks), ALL ZERO on entry and on return.  Each lane adds the weights of its sequences into its own row and
+// remembers which cells it touched; every touched cell is then reduced over the lanes by a fixed butterfly (deterministic).
 constexpr int REFINE_WARPS = 6;
+__device__ __forceinline__ int heaviest_class(const double (&p)[5]) {
+  int b = 0;
+#pragma unroll
+  for (int a = 1; a < 5; a++) b = p[a] > p[b] ? a : b;
+  return b;
+}
+__device__ __forceinline__ void refine_scratch_clear(double* acc, int lane) {  // once per kernel, before the first pair
+#pragma unroll
+  for (int k = 0; k < 25; k++) acc[lane * 25 + k] = 0.0;
+}
 __device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int jl, int lane, double* acc) {
   const int gi = P.from_idx[il], gj = P.to_idx[jl];
   const uint8_t* ci = P.codes + (int64_t)gi * P.S;
   const uint8_t* cj = P.codes + (int64_t)gj * P.S;
-  double* mine = acc + lane * 25;
+  double pi[5], pj[5];
 #pragma unroll
-  for (int k = 0; k < 25; k++) mine[k] = 0.0;
-  for (int64_t s = lane; s < P.S; s += 32) {
-    int idx = (int)ci[s] * 5 + (int)cj[s];
-    mine[idx] += P.w[s];
+  for (int a = 0; a < 5; a++) { pi[a] = P.p64[(int64_t)gi * 5 + a]; pj[a] = P.p64[(int64_t)gj * 5 + a]; }
+  const int bi = heaviest_class(pi), bj = heaviest_class(pj);
+  double* mine = acc + lane * 25;
+  uint32_t touched = 0;
+  if ((P.S & 3) == 0) {
+    // rows are 4-byte aligned (S % 4 == 0, cudaMalloc base): four sequences per load, most words hold no such sequence
+    const uint32_t* wi = reinterpret_cast<const uint32_t*>(ci);
+    const uint32_t* wj = reinterpret_cast<const uint32_t*>(cj);
+    const uint32_t vbi = 0x01010101u * (uint32_t)bi, vbj = 0x01010101u * (uint32_t)bj;
+    const int nw = (int)(P.S >> 2);
+    for (int q = lane; q < nw; q += 32) {
+      const uint32_t a4 = __ldg(wi + q), b4 = __ldg(wj + q);
+      uint32_t m = __vcmpne4(a4, vbi) & __vcmpne4(b4, vbj);  // 0xFF per byte where both classes differ from their base
+      while (m) {
+        const int k = (__ffs(m) - 1) >> 3;
+        m &= ~(0xFFu << (8 * k));
+        const int idx = (int)((a4 >> (8 * k)) & 0xFF) * 5 + (int)((b4 >> (8 * k)) & 0xFF);
+        mine[idx] += P.w[4 * q + k];
+        touched |= 1u << idx;
+      }
+    }
+  } else {
+    for (int64_t s = lane; s < P.S; s += 32) {
+      const int a = ci[s], b = cj[s];
+      if (a != bi && b != bj) {
+        mine[a * 5 + b] += P.w[s];
+        touched |= 1u << (a * 5 + b);
+      }
+    }
   }
-  __syncwarp();
+  const uint32_t any = __reduce_or_sync(0xffffffffu, touched);
+  // lane k < 25 ends up holding the reduced cell k of the non-base block (zero elsewhere)
   double cell = 0.0;
-  if (lane < 25) {
-#pragma unroll 8
-    for (int l = 0; l < 32; l++) cell += acc[l * 25 + lane];
+  for (uint32_t m = any; m; m &= m - 1) {
+    const int k = __ffs(m) - 1;
+    double v = mine[k];
+    if ((touched >> k) & 1) mine[k] = 0.0;  // leave the scratch clean for the next pair
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == k) cell = v;
   }
-  __syncwarp();
+  // row / column sums of the non-base block, then the base row, base column and corner from the marginals
+  const int a = lane < 25 ? lane / 5 : 0, b = lane < 25 ? lane % 5 : 0;
+  double rs = 0.0, cs = 0.0;
+#pragma unroll
+  for (int t = 0; t < 5; t++) {
+    rs += __shfl_sync(0xffffffffu, cell, a * 5 + t);
+    cs += __shfl_sync(0xffffffffu, cell, t * 5 + b);
+  }
+  double tot = 0.0;
+#pragma unroll
+  for (int t = 0; t < 5; t++) tot += __shfl_sync(0xffffffffu, rs, t * 5);
+  if (lane < 25) {
+    if (a == bi && b == bj) {
+      double o = 0.0;
+#pragma unroll
+      for (int t = 0; t < 5; t++) o += (t != bj) ? pj[t] : 0.0;
+      cell = pi[bi] - o + tot;
+    } else if (a == bi) {
+      cell = pj[b] - cs;
+    } else if (b == bj) {
+      cell = pi[a] - rs;
+    }
+  }
   const double ri = (double)P.r[gi], rj = (double)P.r[gj];
   const int mi_ = P.mask[gi], mj_ = P.mask[gj];
   const double den = P.neff + ri * rj * 0.5;
@@ -156,10 +224,9 @@ __device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int
   // (a-major, b-minor) by lane 0
   double term = 0.0;
   if (lane < 25) {
-    const int a = lane / 5, b = lane % 5;
     if (((mi_ >> a) & 1) && ((mj_ >> b) & 1)) {
       double pxy = cell + 0.5;
-      double pa = P.p64[(int64_t)gi * 5 + a], pb = P.p64[(int64_t)gj * 5 + b];
+      double pa = pi[a], pb = pj[b];
       double dsum = pa * pb + Q + pa * (0.5 * ri) + pb * (0.5 * rj);
       term = pxy / den * log(pxy / dsum * den);
     }
@@ -181,6 +248,7 @@ __global__ void mi_refine_cand_kernel(RefineParams P, const Cand* __restrict__ c
   const float tc = emit_all ? -3.0e38f : __uint_as_float(*tcand_bits);
   int lane = threadIdx.x & 31;
   double* acc = acc_s[threadIdx.x >> 5];
+  refine_scratch_clear(acc, threadIdx.x & 31);
   for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
     Cand c = cand[i];
     if (c.mi < tc) continue;
@@ -315,6 +383,7 @@ __global__ void mi_refine_list_kernel(RefineParams P, const Cand* __restrict__ l
   const uint32_t n = *n_ptr;
   const int lane = threadIdx.x & 31;
   double* acc = acc_s[threadIdx.x >> 5];
+  refine_scratch_clear(acc, threadIdx.x & 31);
   for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += gridDim.x * (blockDim.x >> 5)) {
     const Cand c = list[i];
     const double v = refine_pair(P, c.il, c.jl, lane, acc);
@@ -340,6 +409,7 @@ __global__ void mi_refine_pairs_kernel(RefineParams P, const int32_t* __restrict
   __shared__ double acc_s[REFINE_WARPS][32 * 25];
   int lane = threadIdx.x & 31;
   double* acc = acc_s[threadIdx.x >> 5];
+  refine_scratch_clear(acc, threadIdx.x & 31);
   for (int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n;
        i += (int64_t)gridDim.x * (blockDim.x >> 5)) {
     double v = refine_pair(P, il[i], jl[i], lane, acc);
@@ -620,6 +690,7 @@ __global__ void __launch_bounds__(32 * REFINE_WARPS) mi_sr_exact_kernel(SrMatPar
   const ColInfo c = P.col[jl];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* acc = acc_s[warp];
+  refine_scratch_clear(acc, lane);
   const int la = c.a1 - c.a0, lb = c.b1 - c.b0;
   const int bj = min(max(jl + 1 - c.a0, 0), la) + min(max(jl + 1 - c.b0, 0), lb);  // SR rows <= jl
   for (int k = warp; k < la + lb; k += REFINE_WARPS) {  // k is warp-uniform: refine_pair synchronises the warp
