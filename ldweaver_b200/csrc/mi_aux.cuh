@@ -216,12 +216,15 @@ __device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int
   if (P.ideal_q) {
     Q = ri * rj * 0.25;
   } else {
-    uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)P.nf;
-    uint32_t cdiv = (uint32_t)(lin / (uint32_t)P.nt), cmod = (uint32_t)(lin % (uint32_t)P.nt);
+    // quirk Q1: linear index il + jl * nf of the nf x nt matrix, read as (index / nt, index % nt); square blocks: (jl, il)
+    uint32_t cdiv = (uint32_t)jl, cmod = (uint32_t)il;
+    if (P.nf != P.nt) {
+      uint64_t lin = (uint64_t)il + (uint64_t)jl * (uint64_t)P.nf;
+      cdiv = (uint32_t)(lin / (uint32_t)P.nt); cmod = (uint32_t)(lin % (uint32_t)P.nt);
+    }
     Q = (double)P.rfl_arr[cdiv] * (double)P.rtl_arr[cmod] * 0.25;
   }
-  // lane k < 25 owns term (a, b) = (k / 5, k % 5); the 25 terms are then summed in the reference's order
-  // (a-major, b-minor) by lane 0
+  // lane k < 25 owns term (a, b) = (k / 5, k % 5); the 25 terms are summed by a fixed butterfly over the warp
   double term = 0.0;
   if (lane < 25) {
     if (((mi_ >> a) & 1) && ((mj_ >> b) & 1)) {
@@ -231,9 +234,9 @@ __device__ __forceinline__ double refine_pair(const RefineParams& P, int il, int
       term = pxy / den * log(pxy / dsum * den);
     }
   }
-  double mi = 0.0;
+  double mi = term;  // lanes 25..31 hold 0
 #pragma unroll
-  for (int k = 0; k < 25; k++) mi += __shfl_sync(0xffffffffu, term, k);
+  for (int o = 16; o > 0; o >>= 1) mi += __shfl_xor_sync(0xffffffffu, mi, o);
   return mi;
 }
 

@@ -389,10 +389,8 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   static_assert(NB >= 1 && NB * JC * MI_EPI_GROUPS == NJ, "column split must be exact");
   const int row = c.rank * 128 + c.q * 32 + c.lane;  // this CTA's half of the pair's 256 row SNPs
   TileRegs<RA> k;
-  const float den = p.den[RA - 2][RB - 2];
-  const float rkT = 1.0f / p.kT;
-  k.scale = p.ln2_over_den[RA - 2][RB - 2] * p.kT; k.q0 = p.q0[RA - 2][RB - 2] * rkT;
-  k.qod = p.quarter_over_den[RA - 2][RB - 2] * rkT;
+  k.scale = p.scale[RA - 2][RB - 2]; k.q0 = p.q0s[RA - 2][RB - 2];
+  k.qod = p.qod[RA - 2][RB - 2];
   k.M = p.M;
   k.nf = p.nf; k.nt = p.nt;
   k.mul_a = 1u << p.sa; k.sb = p.sb;
@@ -405,12 +403,12 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
     const uint4* rv = reinterpret_cast<const uint4*>(p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row);
     const uint4 v0 = __ldg(rv), v1 = __ldg(rv + (QC ? 2 : 1)), v3 = __ldg(rv + 3);
     const uint32_t tt[5] = {v0.x, v0.y, v0.z, v0.w, v3.x}, tr[5] = {v1.x, v1.y, v1.z, v1.w, QC ? v3.z : v3.y};
-    const float rden = 1.0f / den;
+    const float rf = QC ? p.rp_qc[RA - 2][RB - 2] : p.rp_plain[RA - 2][RB - 2];
 #pragma unroll
     for (int a = 0; a < RA; a++) {
       k.Ti[a] = tt[a];
       // Q1 form: (p + r'/2) / (kT den); plain form: kT den / (p + r'/2)
-      k.rpad[a] = QC ? __uint_as_float(tr[a]) * (rden * rkT) : __uint_as_float(tr[a]) * (den * p.kT);
+      k.rpad[a] = __uint_as_float(tr[a]) * rf;
     }
   }
   const RowDyn rd = p.rowdyn[td.i_dyn0 + row];

@@ -669,10 +669,12 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
     for (int b = 0; b < 4; b++) {
       double ri = a + 2, rj = b + 2;
       double den = P->neff + 0.5 * ri * rj;
-      sp.den[a][b] = (float)den;
-      sp.ln2_over_den[a][b] = (float)(M_LN2 / den);
-      sp.q0[a][b] = (float)(0.25 * ri * rj / den);
-      sp.quarter_over_den[a][b] = (float)(0.25 / den);
+      const float den_f = (float)den, rkT = 1.0f / sp.kT, rden = 1.0f / den_f;
+      sp.scale[a][b] = (float)(M_LN2 / den) * sp.kT;
+      sp.q0s[a][b] = (float)(0.25 * ri * rj / den) * rkT;
+      sp.qod[a][b] = (float)(0.25 / den) * rkT;
+      sp.rp_qc[a][b] = rden * rkT;
+      sp.rp_plain[a][b] = den_f * sp.kT;
     }
 }
 

@@ -80,10 +80,13 @@ struct ScanParams {
   float kT;               // joint count = t * kT with t = (H << sa) + (L >> sb) = floor(V / 2^sb)
   uint32_t sa, sb;
   uint32_t M;             // the pseudocount 0.5 in count units (kT = 0.5 / M exactly): cells are evaluated as t + M
-  float den[4][4];          // neff + 0.5 r_i r_j
-  float ln2_over_den[4][4];
-  float q0[4][4];           // 0.25 r_i r_j / den
-  float quarter_over_den[4][4];
+  // per tile kind [r_i - 2][r_j - 2], with den = neff + 0.5 r_i r_j: the epilogue's constants, formed on the host in the same
+  // single-precision operations the kernel used to run per tile (IEEE: identical bits)
+  float scale[4][4];        // (ln 2 / den) * kT
+  float q0s[4][4];          // (0.25 r_i r_j / den) / kT
+  float qod[4][4];          // (0.25 / den) / kT
+  float rp_qc[4][4];        // (1 / den) * (1 / kT): row factor of the Q1 form
+  float rp_plain[4][4];     // den * kT: row factor of the plain form
   float* sr_out;            // this block's SR slots
   float* dense_out;         // debug: nf x nt, column-major
   Cand* cand;
