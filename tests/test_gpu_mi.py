@@ -515,3 +515,27 @@ def test_device_post_processing_matches_the_host_implementation(fixture_snp, fix
             np.testing.assert_array_equal(x[k], y[k], err_msg=k)
         np.testing.assert_allclose(x["srp_max"], y["srp_max"], rtol=1e-6)
     assert np.all(np.diff(b.sr_links_red["srp_max"]) <= 0)
+
+
+def test_repeated_scans_of_multi_kind_ragged_blocks_are_bit_identical():
+    """The scan kernel's hand-over protocol (TMA -> expanders of both CTAs of a pair -> cta_group::2 MMAs -> epilogue, ring
+    of stages re-cut per tile kind) has no data race: repeated scans of blocks that mix every tile kind, a ragged range
+    and 3 K-blocks give bit-identical thresholds, short-range MI and long-range tables (tools/stress_determinism.py runs
+    the same check longer; a withdrawn kernel variant failed it in one run of four)."""
+    import ldweaver_b200 as ldw
+    from ldweaver_b200 import synth
+    sy = synth.generate(nseq=300, nsnp=2700, seed=11)
+    snp = ldw.snp_dat_from_codes(sy.codes, sy.POS, sy.g)
+    hdw = ldw.estimate_Hamming_distance_weights(snp, 0.1)
+    lra = synth.exact_lr_links_approx(sy.POS, sy.g, 20000)
+    first = None
+    for _ in range(6):
+        res = ldw.perform_MI_computation(snp, hdw, ldw.CdsVar(sy.paint, 3), sr_dist=20000, lr_retain_links=5e4, max_blk_sz=1000,
+                                         lr_links_approx=lra, write_tsv=False)
+        cur = (res.thr.copy(), res.sr["MI"].copy(), res.lr["MI"].copy(), res.lr["pos1"].copy(), res.lr["pos2"].copy())
+        if first is None:
+            first = cur
+            continue
+        np.testing.assert_array_equal(first[0], cur[0])
+        for a, b in zip(first[1:], cur[1:]):
+            np.testing.assert_array_equal(a, b)
