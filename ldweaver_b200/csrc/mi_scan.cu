@@ -608,6 +608,24 @@ int prepare_block(const ldw_mi_plan* P, int bf, int bt, const ScanCfg& cfg, Bloc
         }
     }
   }
+  // Order of the kinds: the large-stage geometries first, inside a geometry the rare kinds first, the most numerous last.  The CTA pairs take tiles round-robin, so the
+  // launch ends on many equal tiles instead of a handful of expensive odd ones (4 x 4 planes: both accumulator buffers, two
+  // 96 KB stages) that leave most SMs idle behind the last of them.  Tiles of a kind stay contiguous and in their order
+  // (neighbouring CTAs share a row tile through L2); results do not depend on the order.
+  {
+    size_t cnt[16] = {0}, beg[16];
+    for (const TileDesc& t : H.tiles) cnt[(t.PA - 1) * 4 + (t.PB - 1)]++;
+    int ord[16];
+    for (int k = 0; k < 16; k++) ord[k] = k;
+    // (kinds of one stage geometry stay together: a change of geometry drains the pipeline)
+    auto geo = [](int k) { return mi_stage_geo(k / 4 + 1, k % 4 + 1, mi_njlog2(k / 4 + 1, k % 4 + 1)); };
+    std::stable_sort(ord, ord + 16, [&](int a, int b) { return geo(a) != geo(b) ? geo(a) > geo(b) : cnt[a] < cnt[b]; });
+    size_t off = 0;
+    for (int k = 0; k < 16; k++) { beg[ord[k]] = off; off += cnt[ord[k]]; }
+    std::vector<TileDesc> sorted(H.tiles.size());
+    for (const TileDesc& t : H.tiles) sorted[beg[(t.PA - 1) * 4 + (t.PB - 1)]++] = t;
+    H.tiles.swap(sorted);
+  }
   // pilot sample: up to 64 tiles spread evenly over the list (kinds in proportion), appended as copies
   H.n_real_tiles = (int32_t)H.tiles.size();
   if (!cfg.dense && H.n_real_tiles >= 1024) {
