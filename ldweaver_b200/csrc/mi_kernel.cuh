@@ -10,7 +10,9 @@
 // digits a, b; each half is accumulated exactly in an int32 TMEM accumulator by two K-passes of kind::i8 UMMA over
 // the SAME one-hot operand (bytes 0xFF): an unsigned pass (x255, digit a) and a signed pass (x-1, digit b).  Only the r-1 non-complement allele planes of a site enter the GEMM; the remaining
 // counts follow from the exact integer marginals (sum_b c^ab = p^a).  SNPs are grouped by plane count so a tile is
-// 128 row SNPs x NJ column SNPs with uniform (PA, PB).  Sixteen epilogue warps (4 column groups x 4 TMEM lane quarters)
+// 2 x 128 row SNPs x NJ column SNPs with uniform (PA, PB), computed by a PAIR of CTAs with cta_group::2 MMAs (M = 256: each
+// CTA stages its 128 rows and half of the columns and owns the accumulators of its rows).  Per CTA, sixteen epilogue warps
+// (4 column groups x 4 TMEM lane quarters)
 // read the accumulators straight out of TMEM (thread = row SNP), rebuild the (PA+1)x(PB+1) table, evaluate
 //     MI = sum_ab x/den * ln(x den / D),  x = c + 0.5,  D = (p_i^a + r_j/2)(p_j^b + r_i/2) + dQ   (dQ: quirk Q1)
 // in fp32 with one MUFU.LG2 per term (two with the Q1 correction), and emit: short-range links to their final,
@@ -18,7 +20,8 @@
 // Only the raw one-hot planes travel from L2 to shared memory (the SM's inbound bandwidth, ~30 B/clk, is the scarce
 // resource): the expander warps build the four digit-weighted copies of the column tile in place, inside the stage,
 // before the MMA warp consumes it.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..7 = expanders (2 also owns TMEM), 8..23 = epilogue.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA of the pair only), 2..7 = expanders (2 also owns TMEM),
+// 8..23 = epilogue.
 #pragma once
 #include "mi_types.h"
 #include "umma.cuh"

@@ -696,7 +696,7 @@ void fill_scan_params(const ldw_mi_plan* P, const BlockDev& D, const BlockHost& 
     }
 }
 
-// Launch the scan kernel: persistent, one CTA per SM.
+// Launch the scan kernel: persistent, one CTA pair (cluster of two) per TPC.
 // `reserve`: SMs left free for the single-CTA selection kernels of earlier blocks (the persistent scan CTAs hold every
 // SM they run on for the whole launch, so anything else would otherwise wait for the gap between two scans).
 int launch_scan(const ldw_mi_plan* P, const ScanParams& sp, cudaStream_t st, int reserve = 0) {
