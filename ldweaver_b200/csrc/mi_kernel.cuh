@@ -61,7 +61,15 @@ __host__ __device__ constexpr int mi_geo_stages(int geo) { return 4 - geo; }
 __host__ __device__ constexpr uint32_t mi_geo_bytes(int geo) { return geo == 0 ? 3 * MI_ARR_BYTES : geo == 1 ? 4 * MI_ARR_BYTES : 6 * MI_ARR_BYTES; }
 constexpr uint32_t MI_JREC_BYTES = 128 * sizeof(Rec);     // per j-buffer
 constexpr uint32_t MI_JDYN_BYTES = 128 * sizeof(ColDyn);
-constexpr uint32_t MI_SMEM_BYTES = MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + 256 + 1024;
+// Row-side records of the tile the epilogue is about to start (Rec + RowDyn of this CTA's 128 row SNPs): ONE buffer, filled
+// by the producer warp with bulk copies and released by the epilogue as soon as its warps hold their row constants in
+// registers -- i.e. at the top of the tile, so the refill for the next tile runs under this tile's batches.  With the tile
+// header the producer leaves beside the barriers, the epilogue never waits for global memory at the top of a tile.
+constexpr uint32_t MI_IREC_BYTES = 128 * sizeof(Rec);
+constexpr uint32_t MI_IDYN_BYTES = 128 * sizeof(RowDyn);
+constexpr uint32_t MI_BAR_BYTES = 512;                    // mbarriers, TMEM slot, tile headers, per-warp scratch words
+constexpr uint32_t MI_SMEM_BYTES = MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + MI_IREC_BYTES + MI_IDYN_BYTES + MI_BAR_BYTES + 1024;
+static_assert(MI_SMEM_BYTES <= 232448, "shared memory budget (227 KB opt-in)");
 
 __device__ __forceinline__ float lg2_fast(float x) {
   float y;
@@ -129,6 +137,9 @@ struct EpiCtx {
   uint32_t tmem_base;   // lane-quarter offset already applied, column of this tile's accumulators
   uint32_t jrec_saddr;  // shared-memory byte addresses of this tile's column records
   uint32_t jdyn_saddr;
+  uint32_t irec_saddr, idyn_saddr;  // ... of its row records (single buffer, see MI_IREC_BYTES)
+  uint32_t rempty_saddr;            // barrier the warp arrives on once its lanes HOLD their row constants
+  uint32_t scr_saddr;               // this warp's scratch word (see epi_tile)
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
@@ -384,13 +395,13 @@ __device__ __forceinline__ void epi_batch(const ScanParams& p, const EpiCtx& c, 
 }
 
 template <int PA, int PB, bool QC, bool RG>
-__device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
+__device__ __forceinline__ void epi_tile(const ScanParams& p, const EpiCtx& c) {
   constexpr int RA = PA + 1, RB = PB + 1;
   constexpr int JC = mi_jc(PA, PB);
   constexpr int NJ = 1 << mi_njlog2(PA, PB);
   constexpr int NB = (NJ / MI_EPI_GROUPS) / JC;  // batches per warp
   static_assert(NB >= 1 && NB * JC * MI_EPI_GROUPS == NJ, "column split must be exact");
-  const int row = c.rank * 128 + c.q * 32 + c.lane;  // this CTA's half of the pair's 256 row SNPs
+  const int row = c.q * 32 + c.lane;  // within this CTA's half of the pair's 256 row SNPs
   TileRegs<RA> k;
   k.scale = p.scale[RA - 2][RB - 2]; k.q0 = p.q0s[RA - 2][RB - 2];
   k.qod = p.qod[RA - 2][RB - 2];
@@ -402,9 +413,24 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
   k.has_sr = (c.tflags & TILE_HAS_SR) != 0;
   k.sr_out = p.sr_out;
   k.tcand = (k.do_lr && !p.emit_all) ? __uint_as_float(ld_volatile_u32(p.tcand_bits)) : -3.0e38f;
+  uint32_t r0, r1;
   {
-    const uint4* rv = reinterpret_cast<const uint4*>(p.rec + (int64_t)(RB - 2) * p.rec_vstride + td.i_slot0 + row);
-    const uint4 v0 = __ldg(rv), v1 = __ldg(rv + (QC ? 2 : 1)), v3 = __ldg(rv + 3);
+    const uint32_t rv = c.irec_saddr + (uint32_t)row * (uint32_t)sizeof(Rec);
+    const uint4 v0 = lds128(rv), v1 = lds128(rv + (QC ? 32 : 16));
+    uint4 v3 = make_uint4(0, 0, 0, 0);
+    if (RA == 5) v3 = lds128(rv + 48);
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(c.idyn_saddr + (uint32_t)row * (uint32_t)sizeof(RowDyn)));
+    // Release the row buffer.  The arrive must not overtake the loads above: an mbarrier arrive issued right behind
+    // shared-memory loads whose results nobody has consumed yet can be performed before them, and the producer's next bulk
+    // copy (async proxy) then lands under the loads -- measured: one scan in four lost long-range candidates on multi-kind
+    // blocks.  So every lane first STORES a word made of what it loaded (the store cannot issue before the loads have
+    // returned), the warp synchronises, and lane 0 arrives (release: ordered after the stores).
+    {
+      const uint32_t dep = (v0.x ^ v0.y ^ v0.z ^ v0.w ^ v1.x ^ v1.y ^ v1.z ^ v1.w ^ v3.x ^ v3.y ^ v3.z ^ r0 ^ r1);
+      asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(c.scr_saddr), "r"(dep) : "memory");
+      __syncwarp();
+      if (c.lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c.rempty_saddr) : "memory");
+    }
     const uint32_t tt[5] = {v0.x, v0.y, v0.z, v0.w, v3.x}, tr[5] = {v1.x, v1.y, v1.z, v1.w, QC ? v3.z : v3.y};
     const float rf = QC ? p.rp_qc[RA - 2][RB - 2] : p.rp_plain[RA - 2][RB - 2];
 #pragma unroll
@@ -414,9 +440,8 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
       k.rpad[a] = __uint_as_float(tr[a]) * rf;
     }
   }
-  const RowDyn rd = p.rowdyn[td.i_dyn0 + row];
-  k.il = rd.il;
-  k.rtlq = rd.rtl * k.qod;
+  k.il = (int)r0;
+  k.rtlq = __uint_as_float(r1) * k.qod;
   // validity of a pair: diagonal block -> 0 <= jl < il; otherwise 0 <= jl < nt, jl != il (quirk Q2); il must exist
   k.jl_lim = k.il < 0 ? 0u : (p.diag ? (uint32_t)k.il : (uint32_t)p.nt);
 
@@ -433,24 +458,24 @@ __device__ __forceinline__ void epi_tile(const ScanParams& p, const TileDesc& td
 }
 
 template <bool QC, bool RG>
-__device__ __forceinline__ void epi_dispatch(const ScanParams& p, const TileDesc& td, const EpiCtx& c) {
-  switch (td.PA * 4 + td.PB - 5) {
-    case 0: epi_tile<1, 1, QC, RG>(p, td, c); break;
-    case 1: epi_tile<1, 2, QC, RG>(p, td, c); break;
-    case 2: epi_tile<1, 3, QC, RG>(p, td, c); break;
-    case 3: epi_tile<1, 4, QC, RG>(p, td, c); break;
-    case 4: epi_tile<2, 1, QC, RG>(p, td, c); break;
-    case 5: epi_tile<2, 2, QC, RG>(p, td, c); break;
-    case 6: epi_tile<2, 3, QC, RG>(p, td, c); break;
-    case 7: epi_tile<2, 4, QC, RG>(p, td, c); break;
-    case 8: epi_tile<3, 1, QC, RG>(p, td, c); break;
-    case 9: epi_tile<3, 2, QC, RG>(p, td, c); break;
-    case 10: epi_tile<3, 3, QC, RG>(p, td, c); break;
-    case 11: epi_tile<3, 4, QC, RG>(p, td, c); break;
-    case 12: epi_tile<4, 1, QC, RG>(p, td, c); break;
-    case 13: epi_tile<4, 2, QC, RG>(p, td, c); break;
-    case 14: epi_tile<4, 3, QC, RG>(p, td, c); break;
-    case 15: epi_tile<4, 4, QC, RG>(p, td, c); break;
+__device__ __forceinline__ void epi_dispatch(const ScanParams& p, int pa, int pb, const EpiCtx& c) {
+  switch (pa * 4 + pb - 5) {
+    case 0: epi_tile<1, 1, QC, RG>(p, c); break;
+    case 1: epi_tile<1, 2, QC, RG>(p, c); break;
+    case 2: epi_tile<1, 3, QC, RG>(p, c); break;
+    case 3: epi_tile<1, 4, QC, RG>(p, c); break;
+    case 4: epi_tile<2, 1, QC, RG>(p, c); break;
+    case 5: epi_tile<2, 2, QC, RG>(p, c); break;
+    case 6: epi_tile<2, 3, QC, RG>(p, c); break;
+    case 7: epi_tile<2, 4, QC, RG>(p, c); break;
+    case 8: epi_tile<3, 1, QC, RG>(p, c); break;
+    case 9: epi_tile<3, 2, QC, RG>(p, c); break;
+    case 10: epi_tile<3, 3, QC, RG>(p, c); break;
+    case 11: epi_tile<3, 4, QC, RG>(p, c); break;
+    case 12: epi_tile<4, 1, QC, RG>(p, c); break;
+    case 13: epi_tile<4, 2, QC, RG>(p, c); break;
+    case 14: epi_tile<4, 3, QC, RG>(p, c); break;
+    case 15: epi_tile<4, 4, QC, RG>(p, c); break;
     default: break;
   }
 }
@@ -464,7 +489,9 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   uint8_t* stage_base = smem;
   Rec* jrec = reinterpret_cast<Rec*>(smem + MI_STAGE_REGION);
   ColDyn* jdyn = reinterpret_cast<ColDyn*>(smem + MI_STAGE_REGION + 2 * MI_JREC_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES));
+  Rec* irec = reinterpret_cast<Rec*>(smem + MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES));
+  RowDyn* idyn = reinterpret_cast<RowDyn*>(smem + MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + MI_IREC_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + MI_STAGE_REGION + 2 * (MI_JREC_BYTES + MI_JDYN_BYTES) + MI_IREC_BYTES + MI_IDYN_BYTES);
   uint64_t* full = bars;            // [MI_MAX_STAGES]  raw planes landed (TMA), per CTA
   uint64_t* empty = bars + 4;       // [MI_MAX_STAGES]  MMAs that read the stage have completed (pair commit, both CTAs)
   uint64_t* ready = bars + 8;       // [MI_MAX_STAGES]  LEADER's copy counts the expander warps of both CTAs
@@ -473,7 +500,12 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
   uint64_t* jfull = bars + 16;      // [2]
   uint64_t* jempty = bars + 18;     // [2]
   uint64_t* drained = bars + 20;    // all MMAs of the tiles issued so far have completed (stage-geometry switch; both CTAs)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* rfull = bars + 21;      // row records of the next non-null tile landed
+  uint64_t* rempty = bars + 22;     // every epilogue warp holds its row constants
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  // per j-buffer tile header {PA | PB << 8 | njlog2 << 16 | this CTA's flags << 24}: written by the producer before it arms
+  // jfull, so the epilogue never touches the tile list in global memory; bars + 32 ..: one scratch word per epilogue warp
+  uint32_t* thdr = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();  // 0 = leader: issues the pair's MMAs
@@ -483,6 +515,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&ready[i], 2 * MI_EXP_WARPS);
     }
     mbar_init(drained, 1);
+    mbar_init(rfull, 1); mbar_init(rempty, MI_EPI_WARPS);
     for (int i = 0; i < 2; i++) {
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * MI_EPI_WARPS);
       mbar_init(&jfull[i], 1); mbar_init(&jempty[i], MI_EPI_WARPS);
@@ -506,7 +539,7 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     // Stage ring: `st` walks the stages of the current geometry, bit i of `phb` is the parity of stage i's barriers
     // (every role of both CTAs walks the same sequence, so the bits agree without communication).
     int st = 0; uint32_t phb = 0; int geo = -1; uint32_t dph = 0;
-    int it = 0;
+    int it = 0, rit = 0;  // tiles; tiles whose half of the rows is not null (phases of the row-record buffer)
     long long w_jempty = 0, w_empty = 0, t_begin = DBG ? clock64() : 0;
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
       const TileDesc td = p.tiles[t];
@@ -546,11 +579,24 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       const int jb = it & 1;
       timed_wait<DBG>(&jempty[jb], ((it >> 1) & 1) ^ 1, 10, w_jempty);
       if (elect_one()) {
+        thdr[jb] = (uint32_t)PA | ((uint32_t)PB << 8) | ((uint32_t)td.njlog2 << 16) | ((uint32_t)(rank ? td.flags1 : td.flags) << 24);
         mbar_arrive_expect_tx(&jfull[jb], (uint32_t)NJ * (uint32_t)(sizeof(Rec) + sizeof(ColDyn)));
         bulk_load_1d(jrec + jb * 128, p.rec + (int64_t)(PA + 1 - 2) * p.rec_vstride + td.j_slot0, NJ * sizeof(Rec), &jfull[jb]);
         bulk_load_1d(jdyn + jb * 128, p.coldyn + td.j_dyn0, NJ * sizeof(ColDyn), &jfull[jb]);
       }
       __syncwarp();
+      // row records (single buffer): free as soon as the epilogue has started the previous non-null tile.  A null half has
+      // none (its slots may lie beyond the group, even beyond the arrays).
+      if (!((rank ? td.flags1 : td.flags) & TILE_NULL)) {
+        timed_wait<DBG>(rempty, (uint32_t)(rit & 1) ^ 1, 13, w_jempty);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(rfull, MI_IREC_BYTES + MI_IDYN_BYTES);
+          bulk_load_1d(irec, p.rec + (int64_t)(PB + 1 - 2) * p.rec_vstride + td.i_slot0 + (int)rank * 128, MI_IREC_BYTES, rfull);
+          bulk_load_1d(idyn, p.rowdyn + td.i_dyn0 + (int)rank * 128, MI_IDYN_BYTES, rfull);
+        }
+        __syncwarp();
+        rit++;
+      }
     }
     if (DBG && p.dbg && lane == 0) {
       p.dbg[blockIdx.x * 16 + 0] = (unsigned long long)(clock64() - t_begin);
@@ -703,15 +749,22 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
     c.lane = lane;
     c.rank = (int)rank;
     int as = 0; uint32_t aph = 0;
-    int it = 0;
+    int it = 0, rit = 0;
     long long w_jfull = 0, w_tfull = 0, t_begin = DBG ? clock64() : 0;
+    c.irec_saddr = smem_u32(irec);
+    c.idyn_saddr = smem_u32(idyn);
+    c.rempty_saddr = smem_u32(rempty);
+    c.scr_saddr = smem_u32(bars + 32) + (uint32_t)(warp - MI_EPI_WARP0) * 4u;
     for (int t = tile0; t < p.n_tiles; t += tstep, it++) {
-      const TileDesc td = p.tiles[t];
-      c.tflags = rank ? td.flags1 : td.flags;
-      const int NJ = 1 << td.njlog2;
-      const bool big = 2 * td.PA * td.PB * NJ > 256;
       const int jb = it & 1;
       timed_wait<DBG>(&jfull[jb], (it >> 1) & 1, 30, w_jfull);
+      uint32_t hdr;  // tile header from shared memory (the tile list in global memory is read by the control warps only)
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hdr) : "r"(smem_u32(&thdr[jb])));
+      const int tPA = (int)(hdr & 0xFF), tPB = (int)((hdr >> 8) & 0xFF);
+      c.tflags = hdr >> 24;
+      const int NJ = 1 << ((hdr >> 16) & 0xFF);
+      const bool big = 2 * tPA * tPB * NJ > 256;
+      if (!(c.tflags & TILE_NULL)) { timed_wait<DBG>(rfull, (uint32_t)(rit & 1), 34, w_jfull); rit++; }
       long long c1 = DBG ? clock64() : 0;
       c.jrec_saddr = smem_u32(jrec + jb * 128);
       c.jdyn_saddr = smem_u32(jdyn + jb * 128);
@@ -730,9 +783,9 @@ mi_scan_kernel(const __grid_constant__ TmapSet tm, const __grid_constant__ ScanP
       if constexpr (DBG) w_tfull += clock64() - c1;
       tc_fence_after();
       if (!(c.tflags & TILE_NULL)) {
-        if (!p.qcorr) epi_dispatch<false, false>(p, td, c);
-        else if (p.ragged) epi_dispatch<true, true>(p, td, c);
-        else epi_dispatch<true, false>(p, td, c);
+        if (!p.qcorr) epi_dispatch<false, false>(p, tPA, tPB, c);
+        else if (p.ragged) epi_dispatch<true, true>(p, tPA, tPB, c);
+        else epi_dispatch<true, false>(p, tPA, tPB, c);
       }
       tc_fence_before();
       __syncwarp();
