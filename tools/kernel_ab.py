@@ -45,7 +45,7 @@ def worker(args):
            "digest": {"n_sr": int(sr.n), "n_lr": int(lr.n), "sr_MI_sum": float(np.sum(srv["MI"], dtype=np.float64)) if sr.n else 0.0,
                       "lr_MI_sum": float(np.sum(lrv["MI"], dtype=np.float64)) if lr.n else 0.0,
                       "lr_pos_sum": int(np.sum(lrv["pos1"].astype(np.int64) * 3 + lrv["pos2"])) if lr.n else 0,
-                      "thr_sum": float(np.sum(thr)), "eps": st[0]["eps_obs_max"], "reruns": st[0]["n_reruns"]}}
+                      "thr_sum": float(np.nansum(thr)), "eps": st[0]["eps_obs_max"], "reruns": st[0]["n_reruns"]}}
     print("AB " + json.dumps(out), flush=True)
 
 
